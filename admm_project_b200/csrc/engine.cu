@@ -1,0 +1,980 @@
+// engine.cu -- libadmm_b200.so: handle, one-time setup (Gram / Cholesky / inverse factor), the
+// device-resident ADMM loop and the C-ABI of include/admm_b200.h.  sm_100a only, no CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/admm_b200.h"
+#include "chol.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "gemv.cuh"
+#include "prox.cuh"
+#include "tri.cuh"
+
+namespace admmb200 {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// a device buffer the handle owns
+struct DBuf {
+  double* p = nullptr;
+  int64_t cap = 0;  // doubles
+  void ensure(int64_t n) {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    ADMM_CUDA(cudaMalloc(&p, (size_t)std::max<int64_t>(n, 1) * sizeof(double)));
+    cap = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct ColdotPlan {
+  int max_cols = 0, max_items = 0, grid = 0;
+  size_t smem = 0;
+};
+
+}  // namespace admmb200
+
+using namespace admmb200;
+
+struct admm_b200_handle {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[4] = {nullptr, nullptr, nullptr, nullptr};
+  double phase_ms[4] = {0, 0, 0, 0};  // gram (+Dts), cholesky, inverse factor (+transpose), total
+  int64_t launches = 0;
+
+  // problem
+  int kind = 0;
+  int64_t m = 0, n = 0;          // D is m x n
+  int64_t nA = 0, nB = 0, mc = 0;
+  const double* dD = nullptr;    // device D (ldD)
+  int64_t ldD = 0;
+  DBuf ownD;                     // backing store when D came from the host
+  DBuf s, dts;
+  bool tall = true;
+  double rho_setup = 1.0, lambda = 0.0;
+  int xsolve = ADMM_B200_XSOLVE_INVFACTOR;
+  double setup_ms = 0.0;
+
+  // cached factor (k x k, leading dimension ldf, multiple of 16)
+  int64_t k = 0, ldf = 0;
+  DBuf L, W, WT;
+  bool have_factor = false;
+
+  // iterates and work vectors
+  DBuf x, z, u, y, t1, t2;
+  bool have_init = false;
+  DBuf x0, z0, u0;
+
+  // loop control
+  LoopCtl* ctl = nullptr;
+  LoopCtl* h_ctl = nullptr;      // pinned
+  int* fail = nullptr;           // cholesky failure flag
+  DBuf partials, hist;           // hist: 6 x cap
+  int64_t hist_cap = 0;
+  DBuf xvals, zvals, uvals;
+  DBuf gemm_ws, gemv_ws, scratch;
+  bool iter_ready = false;
+  unsigned* tickets = nullptr;
+  int64_t tickets_cap = 0;
+};
+
+namespace admmb200 {
+
+static void check_handle(admm_b200_handle* h) {
+  ADMM_REQUIRE(h != nullptr, ADMM_B200_ERR_INVALID, "null handle");
+  ADMM_CUDA(cudaSetDevice(h->device));
+}
+
+static bool is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// copy `count` doubles from a host-or-device pointer into a device buffer (async on the stream)
+static void copy_in(admm_b200_handle* h, double* dst, const double* src, int64_t count) {
+  ADMM_CUDA(cudaMemcpyAsync(dst, src, (size_t)count * 8, cudaMemcpyDefault, h->stream));
+}
+static void copy_out(admm_b200_handle* h, double* dst, const double* src, int64_t count) {
+  if (!dst || count <= 0) return;
+  ADMM_CUDA(cudaMemcpyAsync(dst, src, (size_t)count * 8, cudaMemcpyDefault, h->stream));
+}
+
+static void ensure_tickets(admm_b200_handle* h, int64_t n) {
+  if (n <= h->tickets_cap) return;
+  if (h->tickets) cudaFree(h->tickets);
+  h->tickets = nullptr;
+  int64_t cap = std::max<int64_t>(n, 4096);
+  ADMM_CUDA(cudaMalloc(&h->tickets, (size_t)cap * sizeof(unsigned)));
+  ADMM_CUDA(cudaMemsetAsync(h->tickets, 0, (size_t)cap * sizeof(unsigned), h->stream));
+  h->tickets_cap = cap;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM launcher
+// ---------------------------------------------------------------------------------------------
+template <bool AK, bool BK, int VEC>
+static void gemm_launch_t(admm_b200_handle* h, const GemmArgs& g, dim3 grid) {
+  static bool configured = false;
+  if (!configured) {
+    ADMM_CUDA(cudaFuncSetAttribute(gemm_f64_dmma_kernel<AK, BK, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   GEMM_SMEM_BYTES));
+    configured = true;
+  }
+  gemm_f64_dmma_kernel<AK, BK, VEC><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(g);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+}
+
+struct GemmOpt {
+  int lower_only = 0;
+  double diag_add = 0.0;
+  int batch = 1;
+  int64_t strideA = 0, strideB = 0, strideC = 0;
+  int allow_splitk = 1;
+};
+
+static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
+                 const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+                 const GemmOpt& o = GemmOpt()) {
+  if (M <= 0 || N <= 0) return;
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.alpha = alpha; g.beta = beta; g.diag_add = o.diag_add;
+  g.lower_only = o.lower_only;
+  g.batch = o.batch; g.strideA = o.strideA; g.strideB = o.strideB; g.strideC = o.strideC;
+  g.splits = 1; g.k_per_split = std::max<int64_t>(K, 1); g.ws = nullptr;
+  const int64_t tm = (M + GEMM_BM - 1) / GEMM_BM, tn = (N + GEMM_BN - 1) / GEMM_BN;
+  int64_t tiles = o.lower_only ? tm * (tm + 1) / 2 : tm * tn;
+  tiles *= o.batch;
+  if (o.allow_splitk && tiles < kNumSM && K >= 4096) {
+    int64_t splits = std::min<int64_t>((2 * kNumSM + tiles - 1) / tiles, K / 1024);
+    splits = std::max<int64_t>(splits, 1);
+    if (splits > 1) {
+      g.k_per_split = round_up((K + splits - 1) / splits, GEMM_BK);
+      g.splits = (int)((K + g.k_per_split - 1) / g.k_per_split);
+      h->gemm_ws.ensure((int64_t)o.batch * g.splits * M * N);
+      g.ws = h->gemm_ws.p;
+    }
+  }
+  const bool vec_ok = (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
+                      (o.strideA % 2 == 0) && (o.strideB % 2 == 0);
+  dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)(o.batch * g.splits));
+  const bool AK = transa != 0;  // 'T': op(A)[i,k] = A[k + i*lda]  (K contiguous)
+  const bool BK = transb == 0;  // 'N': op(B)[k,j] = B[k + j*ldb]  (K contiguous)
+#define ADMM_GEMM_CASE(a, b)                                     \
+  if (AK == a && BK == b) {                                      \
+    if (vec_ok) gemm_launch_t<a, b, 2>(h, g, grid);              \
+    else gemm_launch_t<a, b, 1>(h, g, grid);                     \
+  }
+  ADMM_GEMM_CASE(true, true)
+  ADMM_GEMM_CASE(true, false)
+  ADMM_GEMM_CASE(false, true)
+  ADMM_GEMM_CASE(false, false)
+#undef ADMM_GEMM_CASE
+  if (g.splits > 1) {
+    int64_t total = M * N;
+    dim3 rg((unsigned)std::min<int64_t>((total + 255) / 256, 4 * kNumSM), (unsigned)o.batch);
+    gemm_splitk_reduce_kernel<<<rg, 256, 0, h->stream>>>(g);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+}
+
+static void symmetrize(admm_b200_handle* h, double* C, int64_t n, int64_t ldc) {
+  unsigned t = (unsigned)((n + 31) / 32);
+  symmetrize_lower_kernel<<<dim3(t, t), dim3(32, 8), 0, h->stream>>>(C, n, ldc);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+}
+
+static void transpose(admm_b200_handle* h, const double* in, int64_t rows, int64_t cols, int64_t ldi, double* out,
+                      int64_t ldo) {
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(in, rows, cols, ldi, out, ldo);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocked Cholesky (+ inverse factor by recursive doubling)
+// ---------------------------------------------------------------------------------------------
+// A: k x k, lower triangle holds the SPD matrix; on exit lower(A) = L, strict upper zero.
+// W (k x k, ldw) zero-filled by the caller's allocation step here; on exit W = inv(L) when
+// want_inverse, otherwise only its diagonal blocks are valid.
+static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda, double* W, int64_t ldw,
+                          bool want_inverse) {
+  static bool configured = false;
+  if (!configured) {
+    ADMM_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_DIAG_SMEM));
+    configured = true;
+  }
+  ADMM_CUDA(cudaMemsetAsync(h->fail, 0, sizeof(int), h->stream));
+  ADMM_CUDA(cudaMemset2DAsync(W, (size_t)ldw * 8, 0, (size_t)k * 8, (size_t)k, h->stream));
+  for (int64_t k0 = 0; k0 < k; k0 += CHOL_NB) {
+    const int nb = (int)std::min<int64_t>(CHOL_NB, k - k0);
+    double* A11 = A + k0 + k0 * lda;
+    double* W11 = W + k0 + k0 * ldw;
+    potrf_diag_kernel<<<1, CHOL_DIAG_THREADS, CHOL_DIAG_SMEM, h->stream>>>(A11, lda, nb, W11, ldw, h->fail, (int)k0);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+    const int64_t rem = k - k0 - nb;
+    if (rem > 0) {
+      double* A21 = A + (k0 + nb) + k0 * lda;
+      double* A22 = A + (k0 + nb) + (k0 + nb) * lda;
+      // L21 = A21 * inv(L11)'.  In place: N = nb <= one tile column, so every CTA reads only the
+      // rows it later writes, after its whole K loop.
+      GemmOpt po;
+      po.allow_splitk = 0;
+      gemm(h, 0, 1, rem, nb, nb, 1.0, A21, lda, W11, ldw, 0.0, A21, lda, po);
+      // A22 -= L21 * L21'  (lower tiles)
+      GemmOpt to;
+      to.lower_only = 1;
+      to.allow_splitk = 0;
+      gemm(h, 0, 1, rem, rem, nb, -1.0, A21, lda, A21, lda, 1.0, A22, lda, to);
+    }
+  }
+  {
+    dim3 grid((unsigned)((k + 255) / 256), (unsigned)k);
+    zero_upper_kernel<<<grid, 256, 0, h->stream>>>(A, k, lda);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+  int fail = 0;
+  ADMM_CUDA(cudaMemcpyAsync(&fail, h->fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  ADMM_REQUIRE(fail == 0, ADMM_B200_ERR_NOTPOSDEF, "Matrix must be positive definite. (pivot %d is not positive)", fail);
+  ADMM_CUDA(cudaEventRecord(h->evp[2], h->stream));
+  if (!want_inverse) return;
+  // inverse factor by recursive doubling: for [[A,0],[B,C]]: inv = [[Ai,0],[-Ci*B*Ai, Ci]]
+  for (int64_t b = CHOL_NB; b < k; b *= 2) {
+    const int64_t npairs_full = k / (2 * b);  // pairs whose second block is a full b
+    DBuf& T = h->scratch;  // T_p = B_p * inv(A_p), one b x b block per pair
+    T.ensure((k / (2 * b) + 1) * b * b);
+    if (npairs_full > 0) {
+      GemmOpt o1;
+      o1.batch = (int)npairs_full;
+      o1.strideA = 2 * b * (lda + 1);
+      o1.strideB = 2 * b * (ldw + 1);
+      o1.strideC = b * b;
+      o1.allow_splitk = 0;
+      // T_p = B_p * Ai_p      (b x b)
+      gemm(h, 0, 0, b, b, b, 1.0, A + b, lda, W, ldw, 0.0, T.p, b, o1);
+      GemmOpt o2;
+      o2.batch = (int)npairs_full;
+      o2.strideA = 2 * b * (ldw + 1);
+      o2.strideB = b * b;
+      o2.strideC = 2 * b * (ldw + 1);
+      o2.allow_splitk = 0;
+      // W21_p = -Ci_p * T_p
+      gemm(h, 0, 0, b, b, b, -1.0, W + b + b * ldw, ldw, T.p, b, 0.0, W + b, ldw, o2);
+    }
+    const int64_t start = npairs_full * 2 * b;
+    const int64_t cb = k - start - b;  // ragged last pair: second block has cb rows, 0 < cb < b
+    if (cb > 0) {
+      GemmOpt o;
+      o.allow_splitk = 0;
+      double* Tl = T.p + npairs_full * b * b;
+      gemm(h, 0, 0, cb, b, b, 1.0, A + (start + b) + start * lda, lda, W + start + start * ldw, ldw, 0.0, Tl, cb, o);
+      gemm(h, 0, 0, cb, b, cb, -1.0, W + (start + b) + (start + b) * ldw, ldw, Tl, cb, 0.0,
+           W + (start + b) + start * ldw, ldw, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// streaming products
+// ---------------------------------------------------------------------------------------------
+static int64_t coldot_area_host(int mode, int64_t rows, int64_t j) {
+  if (mode == COLDOT_FULL) return j * rows;
+  if (mode == COLDOT_LOWER) return j * rows - j * (j - 1) / 2;
+  return j * (j + 1) / 2;
+}
+static int64_t coldot_len_host(int mode, int64_t rows, int64_t j) {
+  return mode == COLDOT_FULL ? rows : (mode == COLDOT_LOWER ? rows - j : j + 1);
+}
+
+static ColdotPlan coldot_plan(int mode, int64_t rows, int64_t cols) {
+  ColdotPlan p;
+  const int64_t total = coldot_area_host(mode, rows, cols);
+  // enough CTAs to fill the machine twice over, but at least ~32 KB of matrix per CTA
+  int64_t grid = std::min<int64_t>(2 * kNumSM, std::max<int64_t>(1, total / 4096));
+  p.grid = (int)grid;
+  int64_t prev = 0;
+  for (int64_t b = 1; b <= grid; ++b) {
+    int64_t target = (int64_t)(((__int128)total * b) / grid);
+    int64_t lo = 0, hi = cols;
+    if (b >= grid) lo = cols;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (coldot_area_host(mode, rows, mid) >= target) hi = mid; else lo = mid + 1;
+    }
+    int64_t c0 = prev, c1 = lo;
+    prev = lo;
+    int64_t items = 0;
+    for (int64_t j = c0; j < c1; ++j) items += (coldot_len_host(mode, rows, j) + COLDOT_SEG - 1) / COLDOT_SEG;
+    p.max_cols = (int)std::max<int64_t>(p.max_cols, c1 - c0);
+    p.max_items = (int)std::max<int64_t>(p.max_items, items);
+  }
+  p.smem = (size_t)((((p.max_cols + 1) * 4 + 15) & ~15) + (size_t)p.max_items * 8);
+  return p;
+}
+
+static void coldot(admm_b200_handle* h, int mode, const double* M, int64_t ld, int64_t rows, int64_t cols,
+                   const double* v, double* out, double scale = 1.0, const double* addend = nullptr,
+                   double addscale = 0.0, const int* done = nullptr) {
+  ADMM_REQUIRE((ld % 2 == 0) && (((uintptr_t)M & 15) == 0) && (((uintptr_t)v & 15) == 0), ADMM_B200_ERR_UNSUPPORTED,
+               "coldot: matrix must be 16-byte aligned with an even leading dimension (ld=%lld)", (long long)ld);
+  // plans are cheap but not free (O(cols)); cache the last few shapes
+  struct Key { int mode; int64_t rows, cols; ColdotPlan plan; };
+  static thread_local std::vector<Key> cache;
+  const ColdotPlan* plan = nullptr;
+  for (auto& e : cache)
+    if (e.mode == mode && e.rows == rows && e.cols == cols) plan = &e.plan;
+  if (!plan) {
+    cache.push_back(Key{mode, rows, cols, coldot_plan(mode, rows, cols)});
+    plan = &cache.back().plan;
+  }
+  ADMM_REQUIRE(plan->smem <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED, "coldot: problem too large for the item table");
+  static size_t configured_smem = 0;
+  if (plan->smem > configured_smem) {
+    ADMM_CUDA(cudaFuncSetAttribute(coldot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
+    configured_smem = plan->smem;
+  }
+  ColdotArgs a;
+  a.M = M; a.ld = ld; a.rows = rows; a.cols = cols; a.mode = mode; a.v = v; a.out = out;
+  a.scale = scale; a.addend = addend; a.addscale = addscale; a.done = done;
+  a.max_cols_per_cta = plan->max_cols; a.max_items_per_cta = plan->max_items;
+  coldot_kernel<<<plan->grid, COLDOT_THREADS, plan->smem, h->stream>>>(a);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+}
+
+static void gemvn(admm_b200_handle* h, const double* D, int64_t ld, int64_t m, int64_t n, const double* v,
+                  double* out, double alpha = 1.0, double beta = 0.0, const double* w = nullptr,
+                  const int* done = nullptr) {
+  GemvNArgs a;
+  a.D = D; a.ld = ld; a.m = m; a.n = n; a.v = v; a.out = out; a.alpha = alpha; a.beta = beta; a.w = w; a.done = done;
+  const int64_t rb = (m + GEMVN_ROWS - 1) / GEMVN_ROWS;
+  int64_t chunks = 1;
+  if (rb < 2 * kNumSM) chunks = std::min<int64_t>((4 * kNumSM + rb - 1) / rb, std::max<int64_t>(1, n / 16));
+  a.cols_per_chunk = (n + chunks - 1) / chunks;
+  chunks = (n + a.cols_per_chunk - 1) / a.cols_per_chunk;
+  if (chunks > 1) {
+    h->gemv_ws.ensure(chunks * m);
+    ensure_tickets(h, rb);
+  }
+  a.ws = h->gemv_ws.p;
+  a.tickets = h->tickets;
+  dim3 grid((unsigned)rb, (unsigned)chunks);
+  const bool vec_ok = (((uintptr_t)D & 15) == 0) && (ld % 2 == 0);
+  if (vec_ok) gemvn_kernel<2><<<grid, GEMVN_THREADS, 0, h->stream>>>(a);
+  else gemvn_kernel<1><<<grid, GEMVN_THREADS, 0, h->stream>>>(a);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+}
+
+// x = L' \ (L \ b) with the cached factor (size k)
+static void factor_solve(admm_b200_handle* h, const double* b, double* tmp, double* x, int xsolve, const int* done) {
+  ADMM_REQUIRE(h->have_factor, ADMM_B200_ERR_STATE, "no cached factor: call a setup function first");
+  if (xsolve == ADMM_B200_XSOLVE_INVFACTOR) {
+    // t = W b : row i of W is column i of WT (rows 0..i)
+    coldot(h, COLDOT_UPPER, h->WT.p, h->ldf, h->k, h->k, b, tmp, 1.0, nullptr, 0.0, done);
+    // x = W' t : x_j = column j of W (rows j..k-1) . t
+    coldot(h, COLDOT_LOWER, h->W.p, h->ldf, h->k, h->k, tmp, x, 1.0, nullptr, 0.0, done);
+  } else {
+    ADMM_REQUIRE(false, ADMM_B200_ERR_UNSUPPORTED, "xsolve = SUBST (blocked substitution) is not built yet");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup
+// ---------------------------------------------------------------------------------------------
+static void stage_matrix(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD) {
+  if (is_device_ptr(D)) {
+    h->dD = D;
+    h->ldD = ldD;
+    h->ownD.release();
+  } else {
+    int64_t ld = round_up(m, 2);
+    h->ownD.ensure(ld * n);
+    ADMM_CUDA(cudaMemcpy2DAsync(h->ownD.p, (size_t)ld * 8, D, (size_t)ldD * 8, (size_t)m * 8, (size_t)n,
+                                cudaMemcpyHostToDevice, h->stream));
+    h->dD = h->ownD.p;
+    h->ldD = ld;
+  }
+  h->m = m;
+  h->n = n;
+}
+
+static void factor_current(admm_b200_handle* h, int64_t k, bool want_inverse) {
+  // h->L holds the lower triangle of the SPD matrix
+  h->W.ensure(h->ldf * k);
+  potrf_blocked(h, k, h->L.p, h->ldf, h->W.p, h->ldf, want_inverse);
+  if (want_inverse) {
+    h->WT.ensure(h->ldf * k);
+    transpose(h, h->W.p, k, k, h->ldf, h->WT.p, h->ldf);
+  }
+  h->k = k;
+  h->have_factor = true;
+}
+
+static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD, const double* s,
+                        double rho, int xsolve) {
+  ADMM_REQUIRE(m > 0 && n > 0 && D && s && ldD >= m, ADMM_B200_ERR_INVALID, "lasso: bad dimensions or null input");
+  ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
+  ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
+  h->have_factor = false;
+  stage_matrix(h, m, n, D, ldD);
+  h->s.ensure(round_up(m, 2));
+  copy_in(h, h->s.p, s, m);
+  h->dts.ensure(round_up(n, 2));
+  h->kind = ADMM_B200_LASSO;
+  h->tall = (m >= n);
+  h->rho_setup = rho;
+  h->xsolve = xsolve;
+  h->nA = h->nB = h->mc = n;
+  // Dts = D'*s  (lasso.m:160)
+  coldot(h, COLDOT_FULL, h->dD, h->ldD, m, n, h->s.p, h->dts.p);
+  const int64_t k = h->tall ? n : m;
+  h->ldf = round_up(k, 16);
+  h->L.ensure(h->ldf * k);
+  GemmOpt o;
+  o.lower_only = 1;
+  if (h->tall) {  // chol(D'*D + rho*I)  (lasso.m:168)
+    o.diag_add = rho;
+    gemm(h, 1, 0, n, n, m, 1.0, h->dD, h->ldD, h->dD, h->ldD, 0.0, h->L.p, h->ldf, o);
+  } else {        // chol(1/rho*(D*D') + I)  (lasso.m:172)
+    o.diag_add = 1.0;
+    gemm(h, 0, 1, m, m, n, 1.0 / rho, h->dD, h->ldD, h->dD, h->ldD, 0.0, h->L.p, h->ldf, o);
+  }
+  ADMM_CUDA(cudaEventRecord(h->evp[1], h->stream));
+  factor_current(h, k, xsolve == ADMM_B200_XSOLVE_INVFACTOR);
+  ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
+  ADMM_CUDA(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->setup_ms = ms;
+  h->phase_ms[3] = ms;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->evp[1]));
+  h->phase_ms[0] = ms;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->evp[1], h->evp[2]));
+  h->phase_ms[1] = ms;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->evp[2], h->ev1));
+  h->phase_ms[2] = ms;
+  h->have_init = false;
+  h->iter_ready = false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the loop
+// ---------------------------------------------------------------------------------------------
+static LoopParams make_loop_params(admm_b200_handle* h, const admm_b200_options& o, int64_t maxiters, int raw) {
+  LoopParams lp;
+  lp.rho = o.rho; lp.relax = o.relax; lp.abstol = o.abstol; lp.reltol = o.reltol; lp.convtol = o.convtol;
+  lp.hnormtol = o.hnormtol; lp.eps = 2.220446049250313e-16;
+  lp.maxiters = maxiters;
+  lp.domaxiters = o.domaxiters; lp.stopcond = o.stopcond; lp.nodualerror = o.nodualerror; lp.convtest = o.convtest;
+  lp.objevals = o.objevals;
+  lp.use_hnorm = (o.convtest || o.stopcond == ADMM_B200_STOP_HNORM || o.stopcond == ADMM_B200_STOP_BOTH) ? 1 : 0;
+  lp.raw = raw;
+  double* hp = h->hist.p;
+  lp.pnorm = hp; lp.dnorm = hp + h->hist_cap; lp.perr = hp + 2 * h->hist_cap; lp.derr = hp + 3 * h->hist_cap;
+  lp.hn = hp + 4 * h->hist_cap; lp.obj = hp + 5 * h->hist_cap;
+  return lp;
+}
+
+static int prox_grid(int64_t n) {
+  return (int)std::min<int64_t>(2 * kNumSM, std::max<int64_t>(1, (n + PROX_THREADS * 4 - 1) / (PROX_THREADS * 4)));
+}
+
+static void alloc_iterates(admm_b200_handle* h) {
+  const int64_t big = round_up(std::max(std::max(h->nA, h->nB), std::max(h->mc, std::max(h->m, h->n))), 2);
+  h->x.ensure(round_up(h->nA, 2));
+  h->z.ensure(round_up(h->nB, 2));
+  h->u.ensure(round_up(h->mc, 2));
+  h->y.ensure(big);
+  h->t1.ensure(big);
+  h->t2.ensure(big);
+  h->partials.ensure(2 * kNumSM * 16);
+}
+
+static void load_init(admm_b200_handle* h) {
+  if (h->have_init) {
+    ADMM_CUDA(cudaMemcpyAsync(h->x.p, h->x0.p, (size_t)h->nA * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(h->z.p, h->z0.p, (size_t)h->nB * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(h->u.p, h->u0.p, (size_t)h->mc * 8, cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    ADMM_CUDA(cudaMemsetAsync(h->x.p, 0, (size_t)h->nA * 8, h->stream));
+    ADMM_CUDA(cudaMemsetAsync(h->z.p, 0, (size_t)h->nB * 8, h->stream));
+    ADMM_CUDA(cudaMemsetAsync(h->u.p, 0, (size_t)h->mc * 8, h->stream));
+  }
+  ADMM_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(LoopCtl), h->stream));
+  h->iter_ready = true;
+}
+
+// which: 0 whole iteration, 1 x-update only, 2 fused pass only
+static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, int which,
+                              bool history) {
+  const int* done = &h->ctl->done;
+  if (h->kind == ADMM_B200_LASSO) {
+    const int64_t n = h->n, m = h->m;
+    if (which != 2) {
+      if (h->tall) {
+        // x = U \ (L \ y)   (getProxOps.m:1200)
+        factor_solve(h, h->y.p, h->t1.p, h->x.p, o.xsolve, done);
+      } else {
+        // x = y/rho - D'*(U \ (L \ (D*y)))/rho^2   (getProxOps.m:1204)
+        gemvn(h, h->dD, h->ldD, m, n, h->y.p, h->t1.p, 1.0, 0.0, nullptr, done);
+        factor_solve(h, h->t1.p, h->t2.p, h->t1.p, o.xsolve, done);
+        coldot(h, COLDOT_FULL, h->dD, h->ldD, m, n, h->t1.p, h->x.p, -1.0 / (o.rho * o.rho), h->y.p, 1.0 / o.rho, done);
+      }
+    }
+    if (which == 1) return;
+    if (o.objevals && which == 0) {
+      // obj = 1/2*norm(D*x - s)^2 + lambda*norm(z,1)   (lasso.m:227)
+      gemvn(h, h->dD, h->ldD, m, n, h->x.p, h->t2.p, 1.0, 0.0, nullptr, done);
+      half_sqdist_kernel<<<1, 1024, 0, h->stream>>>(h->t2.p, h->s.p, m, h->ctl);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+    }
+    ProxIdentArgs a;
+    a.n = n; a.x = h->x.p; a.z = h->z.p; a.u = h->u.p; a.dts = h->dts.p; a.y = h->y.p;
+    a.lb = a.ub = nullptr;
+    a.thresh = h->lambda / o.rho;
+    a.objscale = h->lambda;
+    a.kind = PROX_SOFT; a.next = NEXT_LASSO; a.obj_l1_of_x = 0;
+    a.partials = h->partials.p; a.ctl = h->ctl; a.lp = lp;
+    a.xvals = history ? h->xvals.p : nullptr;
+    a.zvals = history ? h->zvals.p : nullptr;
+    a.uvals = history ? h->uvals.p : nullptr;
+    prox_ident_kernel<<<prox_grid(n), PROX_THREADS, 0, h->stream>>>(a);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+  } else {
+    ADMM_REQUIRE(false, ADMM_B200_ERR_UNSUPPORTED, "problem kind %d has no iteration built yet", h->kind);
+  }
+}
+
+static void enqueue_first_rhs(admm_b200_handle* h, const admm_b200_options& o) {
+  if (h->kind == ADMM_B200_LASSO) {
+    const int64_t n = h->n;
+    first_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, h->z.p, h->u.p, h->dts.p, o.rho,
+                                                                         NEXT_LASSO, h->y.p);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+}
+
+static void validate_options(admm_b200_handle* h, const admm_b200_options& o) {
+  ADMM_REQUIRE(h->kind != 0, ADMM_B200_ERR_STATE, "no problem set up on this handle");
+  ADMM_REQUIRE(o.rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
+  ADMM_REQUIRE(o.stopcond >= 0 && o.stopcond <= 2, ADMM_B200_ERR_INVALID, "invalid stopcond %d", o.stopcond);
+  if (h->kind == ADMM_B200_LASSO)
+    ADMM_REQUIRE(o.rho == h->rho_setup, ADMM_B200_ERR_INVALID,
+                 "options.rho (%g) differs from the rho the factor was built with (%g); redo the setup", o.rho,
+                 h->rho_setup);
+}
+
+static void prepare_loop(admm_b200_handle* h, const admm_b200_options& o, int64_t maxiters, bool history) {
+  alloc_iterates(h);
+  if (maxiters > h->hist_cap) {
+    h->hist.release();
+    h->hist.ensure(6 * maxiters);
+    h->hist_cap = maxiters;
+  }
+  if (history) {
+    const int64_t need = std::max(std::max(h->nA, h->nB), h->mc) * maxiters;
+    ADMM_REQUIRE(need * 8 * 3 < (int64_t)60e9, ADMM_B200_ERR_UNSUPPORTED,
+                 "history of %lld iterations x %lld entries does not fit; set options.history = 0",
+                 (long long)maxiters, (long long)std::max(std::max(h->nA, h->nB), h->mc));
+    h->xvals.ensure(h->nA * maxiters);
+    h->zvals.ensure(h->nB * maxiters);
+    h->uvals.ensure(h->mc * maxiters);
+  }
+}
+
+static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_result* res) {
+  validate_options(h, o);
+  int64_t N = o.maxiters > 0 ? o.maxiters : 1000;  // admm.m:334-339
+  const bool history = o.history && res && res->xvals && res->zvals && res->uvals;
+  prepare_loop(h, o, N, history);
+  LoopParams lp = make_loop_params(h, o, N, 0);
+  ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
+  load_init(h);
+  enqueue_first_rhs(h, o);
+  const int check = std::max(1, o.check_every);
+  int64_t enq = 0;
+  while (true) {
+    int64_t burst = std::min<int64_t>(check, N - enq);
+    for (int64_t c = 0; c < burst; ++c) enqueue_iteration(h, o, lp, 0, history);
+    enq += burst;
+    ADMM_CUDA(cudaMemcpyAsync(h->h_ctl, h->ctl, sizeof(LoopCtl), cudaMemcpyDeviceToHost, h->stream));
+    ADMM_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->h_ctl->done || enq >= N) break;
+  }
+  ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
+  ADMM_CUDA(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (!res) return;
+  const int64_t steps = h->h_ctl->it;
+  res->steps = steps;
+  res->status = h->h_ctl->status;
+  res->setup_ms = h->setup_ms;
+  res->loop_ms = ms;
+  res->objopt = NAN;
+  const double* hp = h->hist.p;
+  copy_out(h, res->pnorm, hp, steps);
+  copy_out(h, res->dnorm, hp + h->hist_cap, steps);
+  copy_out(h, res->perr, hp + 2 * h->hist_cap, steps);
+  copy_out(h, res->derr, hp + 3 * h->hist_cap, steps);
+  if (lp.use_hnorm) copy_out(h, res->hnormsq, hp + 4 * h->hist_cap, steps);
+  if (o.objevals) {
+    copy_out(h, res->objevals, hp + 5 * h->hist_cap, steps);
+    if (steps > 0) ADMM_CUDA(cudaMemcpyAsync(&res->objopt, hp + 5 * h->hist_cap + steps - 1, 8, cudaMemcpyDeviceToHost, h->stream));
+  }
+  copy_out(h, res->xopt, h->x.p, h->nA);
+  copy_out(h, res->zopt, h->z.p, h->nB);
+  copy_out(h, res->uopt, h->u.p, h->mc);
+  if (history) {
+    copy_out(h, res->xvals, h->xvals.p, h->nA * steps);
+    copy_out(h, res->zvals, h->zvals.p, h->nB * steps);
+    copy_out(h, res->uvals, h->uvals.p, h->mc * steps);
+  }
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+}  // namespace admmb200
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+#define ADMM_API_BEGIN try {
+#define ADMM_API_END                                                        \
+  }                                                                         \
+  catch (const admmb200::CudaFail&) { return ADMM_B200_ERR_CUDA; }          \
+  catch (const admmb200::ArgFail& f) { return f.code; }                     \
+  catch (const std::exception& e) {                                         \
+    admmb200::set_error("internal error: %s", e.what());                    \
+    return ADMM_B200_ERR_CUDA;                                              \
+  }                                                                         \
+  return ADMM_B200_OK;
+
+extern "C" {
+
+int admm_b200_version(void) { return ADMM_B200_VERSION; }
+const char* admm_b200_last_error(void) { return admmb200::g_err; }
+
+void admm_b200_default_options(admm_b200_options* o) {
+  if (!o) return;
+  o->rho = 1.0; o->relax = 1.0; o->abstol = 1e-5; o->reltol = 1e-3; o->convtol = 1e-10; o->hnormtol = 1e-6;
+  o->maxiters = 1000; o->domaxiters = 0; o->stopcond = ADMM_B200_STOP_STANDARD; o->nodualerror = 0;
+  o->convtest = 0; o->objevals = 0; o->history = 1; o->xsolve = ADMM_B200_XSOLVE_INVFACTOR; o->check_every = 8;
+}
+
+int admm_b200_create(int device, admm_b200_handle** out) {
+  ADMM_API_BEGIN
+  ADMM_REQUIRE(out != nullptr, ADMM_B200_ERR_INVALID, "null output pointer");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    set_error("no usable CUDA device (%s); libadmm_b200 has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return ADMM_B200_ERR_CUDA;
+  }
+  ADMM_REQUIRE(device >= 0 && device < count, ADMM_B200_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
+  ADMM_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  ADMM_CUDA(cudaGetDeviceProperties(&prop, device));
+  ADMM_REQUIRE(prop.major == 10, ADMM_B200_ERR_UNSUPPORTED,
+               "device %d is sm_%d%d; libadmm_b200 is built for sm_100a (Blackwell B200) only", device, prop.major,
+               prop.minor);
+  admm_b200_handle* h = new admm_b200_handle();
+  h->device = device;
+  ADMM_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  ADMM_CUDA(cudaEventCreate(&h->ev0));
+  ADMM_CUDA(cudaEventCreate(&h->ev1));
+  for (auto& e : h->evp) ADMM_CUDA(cudaEventCreate(&e));
+  ADMM_CUDA(cudaMalloc(&h->ctl, sizeof(LoopCtl)));
+  ADMM_CUDA(cudaMemset(h->ctl, 0, sizeof(LoopCtl)));
+  ADMM_CUDA(cudaMalloc(&h->fail, sizeof(int)));
+  ADMM_CUDA(cudaMallocHost(&h->h_ctl, sizeof(LoopCtl)));
+  *out = h;
+  ADMM_API_END
+}
+
+int admm_b200_destroy(admm_b200_handle* h) {
+  ADMM_API_BEGIN
+  if (!h) return ADMM_B200_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  DBuf* bufs[] = {&h->ownD, &h->s, &h->dts, &h->L, &h->W, &h->WT, &h->x, &h->z, &h->u, &h->y, &h->t1, &h->t2,
+                  &h->x0, &h->z0, &h->u0, &h->partials, &h->hist, &h->xvals, &h->zvals, &h->uvals, &h->gemm_ws,
+                  &h->gemv_ws, &h->scratch};
+  for (DBuf* b : bufs) b->release();
+  if (h->tickets) cudaFree(h->tickets);
+  if (h->ctl) cudaFree(h->ctl);
+  if (h->fail) cudaFree(h->fail);
+  if (h->h_ctl) cudaFreeHost(h->h_ctl);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto& e : h->evp) if (e) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  ADMM_API_END
+}
+
+int admm_b200_set_stream(admm_b200_handle* h, void* cuda_stream) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+  ADMM_API_END
+}
+
+int admm_b200_synchronize(admm_b200_handle* h) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  ADMM_API_END
+}
+
+int admm_b200_setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD, const double* s,
+                          double rho, int32_t xsolve) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  setup_lasso(h, m, n, D, ldD, s, rho, xsolve);
+  ADMM_API_END
+}
+
+int admm_b200_set_lambda(admm_b200_handle* h, double lambda) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(lambda >= 0, ADMM_B200_ERR_INVALID, "Argument lambda is not a nonnegative real number!");
+  h->lambda = lambda;
+  ADMM_API_END
+}
+
+int admm_b200_set_init(admm_b200_handle* h, const double* x0, const double* z0, const double* u0) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(h->kind != 0, ADMM_B200_ERR_STATE, "no problem set up on this handle");
+  if (!x0 && !z0 && !u0) {
+    h->have_init = false;
+    return ADMM_B200_OK;
+  }
+  h->x0.ensure(h->nA); h->z0.ensure(h->nB); h->u0.ensure(h->mc);
+  if (x0) copy_in(h, h->x0.p, x0, h->nA); else ADMM_CUDA(cudaMemsetAsync(h->x0.p, 0, (size_t)h->nA * 8, h->stream));
+  if (z0) copy_in(h, h->z0.p, z0, h->nB); else ADMM_CUDA(cudaMemsetAsync(h->z0.p, 0, (size_t)h->nB * 8, h->stream));
+  if (u0) copy_in(h, h->u0.p, u0, h->mc); else ADMM_CUDA(cudaMemsetAsync(h->u0.p, 0, (size_t)h->mc * 8, h->stream));
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  h->have_init = true;
+  ADMM_API_END
+}
+
+int admm_b200_solve(admm_b200_handle* h, const admm_b200_options* opts, admm_b200_result* res) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(opts != nullptr, ADMM_B200_ERR_INVALID, "Given options is not a struct! At least pass empty struct!");
+  solve(h, *opts, res);
+  ADMM_API_END
+}
+
+int admm_b200_get_dims(admm_b200_handle* h, int64_t* nA, int64_t* nB, int64_t* m) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  if (nA) *nA = h->nA;
+  if (nB) *nB = h->nB;
+  if (m) *m = h->mc;
+  ADMM_API_END
+}
+
+int admm_b200_get_factor(admm_b200_handle* h, double* L, int64_t ldL, int64_t* k) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(h->have_factor, ADMM_B200_ERR_STATE, "no cached factor: call a setup function first");
+  if (k) *k = h->k;
+  if (L) {
+    ADMM_REQUIRE(ldL >= h->k, ADMM_B200_ERR_INVALID, "ldL too small");
+    ADMM_CUDA(cudaMemcpy2DAsync(L, (size_t)ldL * 8, h->L.p, (size_t)h->ldf * 8, (size_t)h->k * 8, (size_t)h->k,
+                                cudaMemcpyDefault, h->stream));
+    ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  ADMM_API_END
+}
+
+// stage a host-or-device matrix into a handle-owned scratch (returns device pointer + ld)
+namespace {
+struct Staged {
+  admmb200::DBuf buf;
+  const double* p = nullptr;
+  int64_t ld = 0;
+  ~Staged() { buf.release(); }
+};
+void stage_any(admm_b200_handle* h, Staged& st, const double* A, int64_t rows, int64_t cols, int64_t lda) {
+  if (admmb200::is_device_ptr(A)) {
+    st.p = A;
+    st.ld = lda;
+    return;
+  }
+  st.ld = admmb200::round_up(rows, 2);
+  st.buf.ensure(st.ld * std::max<int64_t>(cols, 1));
+  ADMM_CUDA(cudaMemcpy2DAsync(st.buf.p, (size_t)st.ld * 8, A, (size_t)lda * 8, (size_t)rows * 8, (size_t)cols,
+                              cudaMemcpyHostToDevice, h->stream));
+  st.p = st.buf.p;
+}
+void unstage(admm_b200_handle* h, Staged& st, double* A, int64_t rows, int64_t cols, int64_t lda) {
+  if (st.p == A) return;
+  ADMM_CUDA(cudaMemcpy2DAsync(A, (size_t)lda * 8, st.p, (size_t)st.ld * 8, (size_t)rows * 8, (size_t)cols,
+                              cudaMemcpyDeviceToHost, h->stream));
+}
+}  // namespace
+
+int admm_b200_dgemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
+                    const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+                    int lower_only) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(M >= 0 && N >= 0 && K >= 0 && A && B && C, ADMM_B200_ERR_INVALID, "dgemm: bad arguments");
+  Staged sa, sb, sc;
+  stage_any(h, sa, A, transa ? K : M, transa ? M : K, lda);
+  stage_any(h, sb, B, transb ? N : K, transb ? K : N, ldb);
+  stage_any(h, sc, C, M, N, ldc);
+  GemmOpt o;
+  o.lower_only = lower_only;
+  gemm(h, transa, transb, M, N, K, alpha, sa.p, sa.ld, sb.p, sb.ld, beta, const_cast<double*>(sc.p), sc.ld, o);
+  unstage(h, sc, C, M, N, ldc);
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  ADMM_API_END
+}
+
+int admm_b200_gram(admm_b200_handle* h, int trans, int64_t m, int64_t n, const double* D, int64_t ldD, double scale,
+                   double shift, double* G, int64_t ldG) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(m > 0 && n > 0 && D && G, ADMM_B200_ERR_INVALID, "gram: bad arguments");
+  const int64_t k = trans ? n : m;
+  Staged sd, sg;
+  stage_any(h, sd, D, m, n, ldD);
+  const bool gdev = admmb200::is_device_ptr(G);
+  if (gdev) { sg.p = G; sg.ld = ldG; }
+  else { sg.ld = admmb200::round_up(k, 2); sg.buf.ensure(sg.ld * k); sg.p = sg.buf.p; }
+  GemmOpt o;
+  o.lower_only = 1;
+  o.diag_add = shift;
+  if (trans) gemm(h, 1, 0, n, n, m, scale, sd.p, sd.ld, sd.p, sd.ld, 0.0, const_cast<double*>(sg.p), sg.ld, o);
+  else gemm(h, 0, 1, m, m, n, scale, sd.p, sd.ld, sd.p, sd.ld, 0.0, const_cast<double*>(sg.p), sg.ld, o);
+  symmetrize(h, const_cast<double*>(sg.p), k, sg.ld);
+  if (!gdev) unstage(h, sg, G, k, k, ldG);
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  ADMM_API_END
+}
+
+int admm_b200_potrf(admm_b200_handle* h, int64_t k, double* A, int64_t lda, double* Winv, int64_t ldw) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(k > 0 && A && lda >= k, ADMM_B200_ERR_INVALID, "potrf: bad arguments");
+  Staged sa;
+  stage_any(h, sa, A, k, k, lda);
+  admmb200::DBuf w;
+  const int64_t ldwi = admmb200::round_up(k, 16);
+  w.ensure(ldwi * k);
+  try {
+    potrf_blocked(h, k, const_cast<double*>(sa.p), sa.ld, w.p, ldwi, Winv != nullptr);
+  } catch (...) {
+    w.release();
+    throw;
+  }
+  unstage(h, sa, A, k, k, lda);
+  if (Winv) {
+    ADMM_CUDA(cudaMemcpy2DAsync(Winv, (size_t)ldw * 8, w.p, (size_t)ldwi * 8, (size_t)k * 8, (size_t)k,
+                                cudaMemcpyDefault, h->stream));
+  }
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  w.release();
+  ADMM_API_END
+}
+
+int admm_b200_factor_solve(admm_b200_handle* h, const double* b, double* x, int32_t xsolve) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(h->have_factor && b && x, ADMM_B200_ERR_STATE, "factor_solve: no cached factor or null argument");
+  alloc_iterates(h);
+  h->t1.ensure(admmb200::round_up(h->k, 2));
+  h->t2.ensure(admmb200::round_up(h->k, 2));
+  h->y.ensure(admmb200::round_up(h->k, 2));
+  copy_in(h, h->y.p, b, h->k);
+  factor_solve(h, h->y.p, h->t1.p, h->t2.p, xsolve, nullptr);
+  copy_out(h, x, h->t2.p, h->k);
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  ADMM_API_END
+}
+
+int admm_b200_iterate_raw(admm_b200_handle* h, const admm_b200_options* opts, int which, int reps) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(opts && reps >= 0 && which >= 0 && which <= 2, ADMM_B200_ERR_INVALID, "iterate_raw: bad arguments");
+  validate_options(h, *opts);
+  prepare_loop(h, *opts, std::max<int64_t>(h->hist_cap, 16), false);
+  LoopParams lp = make_loop_params(h, *opts, h->hist_cap, 1);
+  admm_b200_options o = *opts;
+  o.objevals = 0;
+  lp.objevals = 0;
+  if (!h->iter_ready) {
+    load_init(h);
+    enqueue_first_rhs(h, o);
+  }
+  ADMM_CUDA(cudaMemsetAsync(&h->ctl->done, 0, sizeof(int), h->stream));
+  for (int r = 0; r < reps; ++r) enqueue_iteration(h, o, lp, which, false);
+  ADMM_API_END
+}
+
+int64_t admm_b200_launch_count(admm_b200_handle* h) { return h ? h->launches : 0; }
+
+int admm_b200_get_setup_phases(admm_b200_handle* h, double* out4) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(out4 != nullptr, ADMM_B200_ERR_INVALID, "null output");
+  for (int i = 0; i < 4; ++i) out4[i] = h->phase_ms[i];
+  ADMM_API_END
+}
+
+int admm_b200_slicemaker(int64_t len, int64_t workers, int64_t* out) {
+  ADMM_API_BEGIN
+  ADMM_REQUIRE(len >= 0 && workers > 0 && out, ADMM_B200_ERR_INVALID, "slicemaker: bad arguments");
+  const int64_t rem = len % workers, base = len / workers;  // errorcheck.m:249-259
+  for (int64_t w = 0; w < workers; ++w) out[w] = base + (w < rem ? 1 : 0);
+  ADMM_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+// gemm.cuh -- FP64 GEMM / SYRK on the DMMA tensor pipe (mma.sync m8n8k4 f64; tcgen05 has no FP64
+// kind).  This is the only dense contraction on the reference's path: D'*D and D*D'
+// (solvers/lasso.m:168,172; huberfit.m:166; lad.m:134; unwrappedadmm.m:115), and it also carries
+// the Cholesky trailing update, the panel solves and the inverse-factor products.
+//
+// C(MxN, column-major) = alpha * op(A)(MxK) * op(B)(KxN) + beta * C [+ diag_add on the diagonal]
+//
+// CTA tile 128x128x16, 8 warps (2 along M x 4 along N, warp tile 64x32 = 8x4 DMMA tiles,
+// 64 FP64 accumulators per lane), 4-stage cp.async (LDGSTS) pipeline, padded shared memory so
+// every fragment LDS.64 is bank-conflict free.  Split-K (deterministic two-pass reduction) keeps
+// all 148 SMs busy when the output has few tiles (n = 784 / 1024 Gram matrices of tall D).
+#pragma once
+#include "common.cuh"
+
+namespace admmb200 {
+
+constexpr int GEMM_BM = 128, GEMM_BN = 128, GEMM_BK = 16, GEMM_STAGES = 4, GEMM_THREADS = 256;
+constexpr int GEMM_LDK = GEMM_BK + 4;    // K-major tile: [128][20]  (row stride 160 B = 32 mod 128)
+constexpr int GEMM_LDM = GEMM_BM + 4;    // M-major tile: [16][132]  (row stride 1056 B = 32 mod 128)
+constexpr int GEMM_TILE_DOUBLES = 128 * GEMM_LDK;  // 2560 >= 16*132 = 2112
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * 2 * GEMM_TILE_DOUBLES * 8;  // 163840
+
+struct GemmArgs {
+  int64_t M, N, K;
+  const double* A; int64_t lda;
+  const double* B; int64_t ldb;
+  double* C; int64_t ldc;
+  double alpha, beta, diag_add;
+  int lower_only;
+  int batch; int64_t strideA, strideB, strideC;
+  int splits; int64_t k_per_split; double* ws;   // ws: [batch][splits][M*N]
+};
+
+// Loads one 128 x 16 operand tile.  KMAJOR: element (r,k) at g[k + r*ld]; else at g[r + k*ld].
+template <bool KMAJOR, int VEC>
+__device__ __forceinline__ void gemm_load_tile(double* s, const double* __restrict__ g, int64_t ld,
+                                               int64_t r0, int64_t R, int64_t k0, int64_t Kend, int tid) {
+  if (KMAJOR) {
+    if (VEC == 2) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        int r = (tid >> 3) + 32 * it, c = (tid & 7) * 2;
+        int64_t gr = r0 + r, gk = k0 + c;
+        int64_t left = (gr < R) ? (Kend - gk) : 0;
+        int nb = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+        const double* src = nb ? (g + gk + gr * ld) : g;
+        cp_async16(&s[r * GEMM_LDK + c], src, nb);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        int r = (tid >> 4) + 16 * it, c = tid & 15;
+        int64_t gr = r0 + r, gk = k0 + c;
+        int nb = (gr < R && gk < Kend) ? 8 : 0;
+        const double* src = nb ? (g + gk + gr * ld) : g;
+        cp_async8(&s[r * GEMM_LDK + c], src, nb);
+      }
+    }
+  } else {
+    if (VEC == 2) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        int kk = (tid >> 6) + 4 * it, c = (tid & 63) * 2;
+        int64_t gr = r0 + c, gk = k0 + kk;
+        int64_t left = (gk < Kend) ? (R - gr) : 0;
+        int nb = left >= 2 ? 16 : (left == 1 ? 8 : 0);
+        const double* src = nb ? (g + gr + gk * ld) : g;
+        cp_async16(&s[kk * GEMM_LDM + c], src, nb);
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        int kk = (tid >> 7) + 2 * it, c = tid & 127;
+        int64_t gr = r0 + c, gk = k0 + kk;
+        int nb = (gr < R && gk < Kend) ? 8 : 0;
+        const double* src = nb ? (g + gr + gk * ld) : g;
+        cp_async8(&s[kk * GEMM_LDM + c], src, nb);
+      }
+    }
+  }
+}
+
+template <bool AK, bool BK, int VEC>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs p) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.x * GEMM_BM, n0 = (int64_t)blockIdx.y * GEMM_BN;
+  if (p.lower_only && n0 > m0) return;  // tile strictly above the diagonal
+  const int bz = blockIdx.z;
+  const int batch = bz / p.splits, split = bz - batch * p.splits;
+  const double* A = p.A + (int64_t)batch * p.strideA;
+  const double* B = p.B + (int64_t)batch * p.strideB;
+  const int64_t kbeg = (int64_t)split * p.k_per_split;
+  const int64_t kend = min(p.K, kbeg + p.k_per_split);
+  const int nk = (int)((kend - kbeg + GEMM_BK - 1) / GEMM_BK);
+
+  double* sA = smem;
+  double* sB = smem + GEMM_STAGES * GEMM_TILE_DOUBLES;
+
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp & 1, wn = warp >> 1;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+    if (s < nk) {
+      gemm_load_tile<AK, VEC>(sA + s * GEMM_TILE_DOUBLES, A, p.lda, m0, p.M, kbeg + (int64_t)s * GEMM_BK, kend, tid);
+      gemm_load_tile<BK, VEC>(sB + s * GEMM_TILE_DOUBLES, B, p.ldb, n0, p.N, kbeg + (int64_t)s * GEMM_BK, kend, tid);
+    }
+    cp_async_commit();
+  }
+
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<GEMM_STAGES - 2>();
+    __syncthreads();
+    {
+      int kn = kt + GEMM_STAGES - 1;
+      if (kn < nk) {
+        int slot = kn % GEMM_STAGES;
+        gemm_load_tile<AK, VEC>(sA + slot * GEMM_TILE_DOUBLES, A, p.lda, m0, p.M, kbeg + (int64_t)kn * GEMM_BK, kend, tid);
+        gemm_load_tile<BK, VEC>(sB + slot * GEMM_TILE_DOUBLES, B, p.ldb, n0, p.N, kbeg + (int64_t)kn * GEMM_BK, kend, tid);
+      }
+      cp_async_commit();
+    }
+    const double* a_s = sA + (kt % GEMM_STAGES) * GEMM_TILE_DOUBLES;
+    const double* b_s = sB + (kt % GEMM_STAGES) * GEMM_TILE_DOUBLES;
+#pragma unroll
+    for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
+      double a[8], b[4];
+      const int k = ks * 4 + t;
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi) {
+        int r = wm * 64 + mi * 8 + g;
+        a[mi] = AK ? a_s[r * GEMM_LDK + k] : a_s[k * GEMM_LDM + r];
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        int c = wn * 32 + ni * 8 + g;
+        b[ni] = BK ? b_s[c * GEMM_LDK + k] : b_s[k * GEMM_LDM + c];
+      }
+#pragma unroll
+      for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue
+  if (p.splits > 1) {
+    double* W = p.ws + ((int64_t)batch * p.splits + split) * p.M * p.N;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int64_t r = m0 + wm * 64 + mi * 8 + g, c = n0 + wn * 32 + ni * 8 + 2 * t + e;
+          if (r < p.M && c < p.N) W[r + c * p.M] = acc[mi][ni][e];
+        }
+  } else {
+    double* C = p.C + (int64_t)batch * p.strideC;
+#pragma unroll
+    for (int mi = 0; mi < 8; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int64_t r = m0 + wm * 64 + mi * 8 + g, c = n0 + wn * 32 + ni * 8 + 2 * t + e;
+          if (r < p.M && c < p.N) {
+            double v = p.alpha * acc[mi][ni][e];
+            if (p.beta != 0.0) v += p.beta * C[r + c * p.ldc];
+            if (r == c) v += p.diag_add;
+            C[r + c * p.ldc] = v;
+          }
+        }
+  }
+}
+
+// second pass of split-K: fixed summation order over the splits (deterministic)
+__global__ void gemm_splitk_reduce_kernel(GemmArgs p) {
+  const int64_t total = p.M * p.N;
+  const int batch = blockIdx.y;
+  const double* W = p.ws + (int64_t)batch * p.splits * total;
+  double* C = p.C + (int64_t)batch * p.strideC;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx % p.M, c = idx / p.M;
+    if (p.lower_only && (c / GEMM_BN) > (r / GEMM_BM)) continue;
+    double s = 0.0;
+    for (int k = 0; k < p.splits; ++k) s += W[(int64_t)k * total + idx];
+    double v = p.alpha * s;
+    if (p.beta != 0.0) v += p.beta * C[r + c * p.ldc];
+    if (r == c) v += p.diag_add;
+    C[r + c * p.ldc] = v;
+  }
+}
+
+// copy the lower triangle onto the upper one (full symmetric result of a lower-only SYRK)
+__global__ void symmetrize_lower_kernel(double* C, int64_t n, int64_t ldc) {
+  __shared__ double tile[32][33];
+  int bx = blockIdx.x, by = blockIdx.y;  // tile (row-block by, col-block bx) with by >= bx read
+  if (by < bx) return;
+  int64_t r = (int64_t)by * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t c = (int64_t)bx * 32 + j;
+    tile[j][threadIdx.x] = (r < n && c < n) ? C[r + c * ldc] : 0.0;
+  }
+  __syncthreads();
+  // write transposed: element (c, r) <- (r, c) for r > c
+  int64_t cc = (int64_t)bx * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t rr = (int64_t)by * 32 + j;
+    if (rr < n && cc < n && rr > cc) C[cc + rr * ldc] = tile[threadIdx.x][j];
+  }
+}
+
+// out (cols x rows, ldo) = in (rows x cols, ldi) transposed
+__global__ void transpose_kernel(const double* __restrict__ in, int64_t rows, int64_t cols, int64_t ldi,
+                                 double* __restrict__ out, int64_t ldo) {
+  __shared__ double tile[32][33];
+  int64_t r = (int64_t)blockIdx.x * 32 + threadIdx.x;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t c = (int64_t)blockIdx.y * 32 + j;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? in[r + c * ldi] : 0.0;
+  }
+  __syncthreads();
+  int64_t oc = (int64_t)blockIdx.y * 32 + threadIdx.x;  // row index in `out`
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int64_t orow = (int64_t)blockIdx.x * 32 + j;          // column index in `out`
+    if (oc < cols && orow < rows) out[oc + orow * ldo] = tile[threadIdx.x][j];
+  }
+}
+
+// zero the strict upper triangle
+__global__ void zero_upper_kernel(double* A, int64_t n, int64_t lda) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t c = blockIdx.y;
+  if (r < n && r < c) A[r + c * lda] = 0.0;
+}
+
+}  // namespace admmb200

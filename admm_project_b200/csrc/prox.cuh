@@ -1,0 +1,217 @@
+// prox.cuh -- the fused per-iteration pass of admm.m:515-560 + :603-722 for the problems whose
+// constraint is x - z = 0 (A = 1, B = -1, c = 0: lasso.m:231-239, basispursuit.m:130-137, and the
+// nonneg / box z-prox of getProxOps.m:1378-1382,1470-1474):
+//
+//   xhat = relax*x + (1-relax)*zprev            (admm.m:517, only when relax ~= 1)
+//   z    = prox(xhat + u)                       (getProxOps.m:933-938 soft threshold, ...)
+//   u    = u + (xhat - z)                       (admm.m:542/548)
+//   y    = rhs of the NEXT x-update             (getProxOps.m:1196: rho*(z-u) + Dts)
+//   partial sums of every norm admm.m:618-658,682 needs, reduced block -> grid in fixed order,
+//   and, in the last CTA to finish, the scalar epilogue: pnorm/dnorm/perr/derr/Hnormsq/objective
+//   history, H-norm divergence test (admm.m:686-701) and both stop tests (admm.m:706-722).
+//
+// One launch replaces ~8 interpreter temporaries and 5-7 separate norm passes of the reference.
+#pragma once
+#include "common.cuh"
+
+namespace admmb200 {
+
+// device-resident loop control (the host only polls `done` every check_every iterations)
+struct LoopCtl {
+  int it;            // iterations completed (MATLAB's i after the body ran)
+  int done;          // non-zero: every kernel of later iterations exits immediately
+  int status;        // ADMM_B200_CONVERGED_* ...
+  unsigned ticket;   // last-block election
+  double objpart;    // objective term produced by an earlier kernel of the iteration
+  double pad;
+};
+
+struct LoopParams {
+  double rho, relax, abstol, reltol, convtol, hnormtol, eps;
+  long long maxiters;
+  int domaxiters, stopcond, nodualerror, convtest, objevals, use_hnorm, raw;  // raw: no stop test
+  double *pnorm, *dnorm, *perr, *derr, *hn, *obj;  // device history, length maxiters
+};
+
+enum { PROX_SOFT = 0, PROX_NONNEG = 1, PROX_BOX = 2 };
+enum { NEXT_LASSO = 0, NEXT_DIFF = 1 };
+constexpr int PROX_NRED = 8;
+constexpr int PROX_THREADS = 256;
+
+struct ProxIdentArgs {
+  int64_t n;
+  const double* x;        // x-update result
+  double *z, *u;          // in/out
+  const double* dts;      // Dts (lasso) or NULL
+  double* y;              // rhs of the next x-update
+  const double *lb, *ub;  // box bounds (length n) or NULL
+  double thresh;          // lambda/rho (lasso), 1/rho (bp)
+  double objscale;        // objective = objpart + objscale * sum|z| (lasso: lambda) / sum|x| (bp)
+  int kind, next, obj_l1_of_x;
+  double* partials;       // [gridDim.x][PROX_NRED]
+  LoopCtl* ctl;
+  LoopParams lp;
+  double *xvals, *zvals, *uvals;  // optional history (n x maxiters)
+};
+
+__device__ __forceinline__ double soft_threshold(double v, double t) {
+  // sign(v).*subplus(abs(v) - t), getProxOps.m:937
+  double a = fabs(v) - t;
+  a = a > 0.0 ? a : 0.0;
+  return v > 0.0 ? a : (v < 0.0 ? -a : 0.0 * a);
+}
+
+template <int NRED>
+__device__ __forceinline__ void block_reduce_store(double (&r)[NRED], double* dst, double* sh /*[nwarps][NRED]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NRED; ++k) r[k] = warp_sum(r[k]);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NRED; ++k) sh[warp * NRED + k] = r[k];
+  __syncthreads();
+  if (threadIdx.x < NRED) {
+    double s = 0.0;
+    for (int w = 0; w < nw; ++w) s += sh[w * NRED + threadIdx.x];
+    dst[threadIdx.x] = s;
+  }
+}
+
+// Scalar epilogue shared by every problem family.  red[] holds:
+//  0 ||Ax+Bz-c||^2  1 ||Ax||^2  2 ||Bz||^2  3 ||c||^2  4 ||rho*At(B(z-zprev))||^2  5 ||rho*At(u)||^2
+//  6 ||B(z-zprev)||^2  7 ||u-uprev||^2 ;  M1 = numel(Ax), M2 = numel(Bz); obj = objective value.
+__device__ inline void loop_epilogue(LoopCtl* ctl, const LoopParams& lp, const double* red, double M1,
+                                     double M2, double obj) {
+  const int i = ctl->it + 1;  // MATLAB's i
+  const int slot = lp.raw ? 0 : i - 1;
+  const double pn = sqrt(red[0]);
+  const double dn = lp.nodualerror ? __longlong_as_double(0x7ff8000000000000LL) : sqrt(red[4]);
+  const double pe = sqrt(M1) * lp.abstol + lp.reltol * fmax(fmax(sqrt(red[1]), sqrt(red[2])), sqrt(red[3]));
+  const double de = lp.nodualerror ? __longlong_as_double(0x7ff8000000000000LL)
+                                   : sqrt(M2) * lp.abstol + lp.reltol * sqrt(red[5]);
+  const double hn = lp.rho * red[6] + lp.rho * (lp.rho * lp.rho * red[7]);  // admm.m:305-306 on w = [x;z;rho*u]
+  lp.pnorm[slot] = pn;
+  lp.dnorm[slot] = dn;
+  lp.perr[slot] = pe;
+  lp.derr[slot] = de;
+  if (lp.use_hnorm) lp.hn[slot] = hn;
+  if (lp.objevals) lp.obj[slot] = obj;
+  int done = 0, status = 0;
+  if (!lp.raw) {
+    if (lp.convtest && i >= 2) {  // admm.m:689-700
+      const double H2 = hn, H1 = lp.hn[i - 2];
+      if (H1 > lp.eps && H2 > H1 && !((H2 - H1) <= H1 * lp.convtol)) { done = 1; status = 4; }
+    }
+    if (!done && (lp.stopcond == 0 || lp.stopcond == 2) && !lp.domaxiters && pn < pe &&
+        (lp.nodualerror || dn < de)) { done = 1; status = 1; }  // admm.m:710-713
+    if (!done && (lp.stopcond == 1 || lp.stopcond == 2) && !lp.domaxiters && i > 2 && hn <= lp.hnormtol) {
+      done = 1; status = 2;                                    // admm.m:719-722
+    }
+    if (!done && i >= lp.maxiters) { done = 1; status = 3; }
+  }
+  ctl->it = lp.raw ? ctl->it : i;
+  ctl->status = status;
+  ctl->objpart = 0.0;
+  __threadfence();
+  ctl->done = done;
+}
+
+__global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs a) {
+  LoopCtl* ctl = a.ctl;
+  if (ctl->done) return;
+  __shared__ double sh[(PROX_THREADS / 32) * PROX_NRED];
+  __shared__ bool is_last;
+  const double rho = a.lp.rho, relax = a.lp.relax;
+  const int it = ctl->it;
+  double r[PROX_NRED];
+#pragma unroll
+  for (int k = 0; k < PROX_NRED; ++k) r[k] = 0.0;
+
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double x = a.x[i], zp = a.z[i], up = a.u[i];
+    double xh = x;
+    if (relax != 1.0) xh = relax * x - (1.0 - relax) * (-zp - 0.0);
+    const double v = xh + up;
+    double z;
+    if (a.kind == PROX_SOFT) z = soft_threshold(v, a.thresh);
+    else if (a.kind == PROX_NONNEG) z = fmax(v, 0.0);
+    else z = fmin(a.ub[i], fmax(a.lb[i], v));
+    const double u = up + (xh + (-z) - 0.0);
+    a.z[i] = z;
+    a.u[i] = u;
+    a.y[i] = (a.next == NEXT_LASSO) ? (rho * (z - u) + a.dts[i]) : (z - u);
+    if (a.xvals) {
+      a.xvals[(int64_t)it * a.n + i] = x;
+      a.zvals[(int64_t)it * a.n + i] = z;
+      a.uvals[(int64_t)it * a.n + i] = u;
+    }
+    const double pr = x + (-z) - 0.0, dz = z - zp, du = u - up;
+    r[0] = fma(pr, pr, r[0]);
+    r[1] = fma(x, x, r[1]);
+    r[2] = fma(z, z, r[2]);
+    r[3] = fma(dz, dz, r[3]);
+    r[4] = fma(u, u, r[4]);
+    r[5] = fma(du, du, r[5]);
+    r[6] += a.obj_l1_of_x ? fabs(x) : fabs(z);
+  }
+  block_reduce_store<PROX_NRED>(r, a.partials + (int64_t)blockIdx.x * PROX_NRED, sh);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(&ctl->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // fixed-order grid reduction by the last CTA
+  if (threadIdx.x < PROX_NRED) {
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(a.partials + (int64_t)b * PROX_NRED + threadIdx.x);
+    sh[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double red[8];
+    red[0] = sh[0];                  // ||x - z||^2
+    red[1] = sh[1];                  // ||A x||^2 = ||x||^2
+    red[2] = sh[2];                  // ||B z||^2 = ||z||^2
+    red[3] = 0.0;                    // c = 0
+    red[4] = rho * rho * sh[3];      // ||rho * At(B(dz))||^2, At = 1
+    red[5] = rho * rho * sh[4];      // ||rho * At(u)||^2
+    red[6] = sh[3];
+    red[7] = sh[5];
+    ctl->ticket = 0;
+    const double obj = ctl->objpart + a.objscale * sh[6];
+    loop_epilogue(ctl, a.lp, red, (double)a.n, (double)a.n, obj);
+  }
+}
+
+// objective term 0.5*||D x - s||^2 from r = D*x computed by the GEMV kernel (lasso.m:227)
+__global__ void half_sqdist_kernel(const double* __restrict__ r, const double* __restrict__ s, int64_t m,
+                                   LoopCtl* ctl) {
+  if (ctl->done) return;
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) {
+    double d = r[i] - s[i];
+    acc = fma(d, d, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
+    ctl->objpart = 0.5 * t;
+  }
+}
+
+// y0 = rho*(z0 - u0) + Dts  /  z0 - u0  before the first iteration
+__global__ void first_rhs_kernel(int64_t n, const double* z, const double* u, const double* dts, double rho,
+                                 int next, double* y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = (next == NEXT_LASSO) ? (rho * (z[i] - u[i]) + dts[i]) : (z[i] - u[i]);
+}
+
+}  // namespace admmb200

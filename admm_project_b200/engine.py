@@ -1,0 +1,166 @@
+"""Thin object wrapper over the C-ABI handle (include/admm_b200.h).  One Engine = one GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+class DeviceMatrix:
+    """A column-major FP64 matrix already resident in HBM (raw device pointer + shape + ld), e.g.
+    ``DeviceMatrix(t.data_ptr(), m, n, ld)`` for a torch tensor holding the column-major data.
+    The solvers accept it wherever the reference takes the data matrix D."""
+
+    def __init__(self, ptr, rows, cols, ld=None, keepalive=None):
+        self.ptr, self.shape, self.ld = int(ptr), (int(rows), int(cols)), int(ld or rows)
+        self.keepalive = keepalive
+
+
+class Engine:
+    def __init__(self, device=0):
+        lib = L.load()
+        h = C.c_void_p()
+        L.check(lib.admm_b200_create(int(device), C.byref(h)))
+        self._lib, self._h, self.device = lib, h, int(device)
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.admm_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- plumbing --------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        L.check(self._lib.admm_b200_set_stream(self._h, C.c_void_p(int(cuda_stream) if cuda_stream else None)))
+
+    def synchronize(self):
+        L.check(self._lib.admm_b200_synchronize(self._h))
+
+    def launch_count(self):
+        return int(self._lib.admm_b200_launch_count(self._h))
+
+    def setup_phases(self):
+        out = (C.c_double * 4)()
+        L.check(self._lib.admm_b200_get_setup_phases(self._h, out))
+        return dict(gram_ms=out[0], chol_ms=out[1], inverse_ms=out[2], total_ms=out[3])
+
+    def default_options(self):
+        o = L.Options()
+        self._lib.admm_b200_default_options(C.byref(o))
+        return o
+
+    @staticmethod
+    def _matrix(D):
+        if isinstance(D, DeviceMatrix):
+            return D.ptr, D.shape[0], D.shape[1], D.ld, D
+        a = L.fmat(D)
+        return a.ctypes.data, a.shape[0], a.shape[1], a.shape[0], a
+
+    # -- setup -----------------------------------------------------------------------------
+    def setup_lasso(self, D, s, rho, xsolve=L.XSOLVE_INVFACTOR):
+        p, m, n, ld, keep = self._matrix(D)
+        sv = s if isinstance(s, (int, np.integer)) else L.fvec(s, m, "s")
+        self._keep = [keep, sv]
+        L.check(self._lib.admm_b200_setup_lasso(self._h, m, n, C.c_void_p(p), ld, L.ptr(sv), float(rho), int(xsolve)))
+        return m, n
+
+    def set_lambda(self, lam):
+        L.check(self._lib.admm_b200_set_lambda(self._h, float(lam)))
+
+    def dims(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        L.check(self._lib.admm_b200_get_dims(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def set_init(self, x0=None, z0=None, u0=None):
+        nA, nB, m = self.dims()
+        x0 = None if x0 is None else L.fvec(x0, nA, "x0")
+        z0 = None if z0 is None else L.fvec(z0, nB, "z0")
+        u0 = None if u0 is None else L.fvec(u0, m, "u0")
+        L.check(self._lib.admm_b200_set_init(self._h, L.ptr(x0), L.ptr(z0), L.ptr(u0)))
+
+    def get_factor(self):
+        k = C.c_int64()
+        L.check(self._lib.admm_b200_get_factor(self._h, None, 0, C.byref(k)))
+        out = np.zeros((k.value, k.value), order="F")
+        L.check(self._lib.admm_b200_get_factor(self._h, L.ptr(out), k.value, C.byref(k)))
+        return out
+
+    # -- loop ------------------------------------------------------------------------------
+    def solve(self, opts, want_history=True):
+        """Runs admm.m's loop on the device; returns a dict with the reference's result fields."""
+        nA, nB, m = self.dims()
+        N = int(opts.maxiters) if opts.maxiters > 0 else 1000
+        res = L.Result()
+        bufs = {k: np.full(N, np.nan) for k in ("pnorm", "dnorm", "perr", "derr", "hnormsq", "objevals")}
+        xo, zo, uo = np.zeros(nA), np.zeros(nB), np.zeros(m)
+        res.xopt, res.zopt, res.uopt = (a.ctypes.data_as(L._dp) for a in (xo, zo, uo))
+        for k, a in bufs.items():
+            setattr(res, k, a.ctypes.data_as(L._dp))
+        hist = None
+        if want_history and opts.history:
+            hist = [np.zeros((nA, N), order="F"), np.zeros((nB, N), order="F"), np.zeros((m, N), order="F")]
+            res.xvals, res.zvals, res.uvals = (a.ctypes.data_as(L._dp) for a in hist)
+        L.check(self._lib.admm_b200_solve(self._h, C.byref(opts), C.byref(res)))
+        k = int(res.steps)
+        out = dict(steps=k, status=int(res.status), xopt=xo, zopt=zo, uopt=uo, objopt=float(res.objopt),
+                   setup_ms=float(res.setup_ms), loop_ms=float(res.loop_ms))
+        for name, a in bufs.items():
+            out[name] = a[:k].copy()
+        if hist is not None:
+            out["xvals"], out["zvals"], out["uvals"] = (np.ascontiguousarray(a[:, :k]) for a in hist)
+        return out
+
+    def iterate_raw(self, opts, which=0, reps=1):
+        L.check(self._lib.admm_b200_iterate_raw(self._h, C.byref(opts), int(which), int(reps)))
+
+    # -- building blocks -----------------------------------------------------------------------
+    def dgemm(self, transa, transb, alpha, A, B, beta=0.0, Cmat=None, lower_only=False):
+        A, B = L.fmat(A), L.fmat(B)
+        M = A.shape[1] if transa else A.shape[0]
+        K = A.shape[0] if transa else A.shape[1]
+        N = B.shape[0] if transb else B.shape[1]
+        Kb = B.shape[1] if transb else B.shape[0]
+        if K != Kb:
+            raise L.EngineError(L.ERR_INVALID, "dgemm: inner dimensions differ")
+        out = np.zeros((M, N), order="F") if Cmat is None else np.array(Cmat, dtype=np.float64, order="F")
+        L.check(self._lib.admm_b200_dgemm(self._h, int(bool(transa)), int(bool(transb)), M, N, K, float(alpha),
+                                          L.ptr(A), max(A.shape[0], 1), L.ptr(B), max(B.shape[0], 1), float(beta),
+                                          L.ptr(out), max(M, 1), int(bool(lower_only))))
+        return out
+
+    def gram(self, D, trans=True, scale=1.0, shift=0.0):
+        p, m, n, ld, keep = self._matrix(D)
+        k = n if trans else m
+        G = np.zeros((k, k), order="F")
+        L.check(self._lib.admm_b200_gram(self._h, int(bool(trans)), m, n, C.c_void_p(p), ld, float(scale),
+                                         float(shift), L.ptr(G), k))
+        return G
+
+    def potrf(self, A, want_inverse=False):
+        A = np.array(A, dtype=np.float64, order="F")
+        k = A.shape[0]
+        W = np.zeros((k, k), order="F") if want_inverse else None
+        L.check(self._lib.admm_b200_potrf(self._h, k, L.ptr(A), k, L.ptr(W), k))
+        return (A, W) if want_inverse else A
+
+    def factor_solve(self, b, xsolve=L.XSOLVE_INVFACTOR):
+        b = L.fvec(b)
+        x = np.zeros_like(b)
+        L.check(self._lib.admm_b200_factor_solve(self._h, L.ptr(b), L.ptr(x), int(xsolve)))
+        return x
+
+
+def slicemaker(length, workers):
+    """errorcheck.m:249-259 through the C-ABI (no GPU needed)."""
+    out = (C.c_int64 * int(workers))()
+    L.check(L.load().admm_b200_slicemaker(int(length), int(workers), out))
+    return [int(v) for v in out]

@@ -1,0 +1,187 @@
+/*
+ * admm_b200.h -- C-ABI of libadmm_b200.so, a Blackwell (sm_100a) FP64 engine for the hot path of
+ * PeterSutor/ADMM-Project: the scaled-dual ADMM loop of admm.m, the getProxOps.m proximal
+ * operators and the one-time setup of solvers/*.m.
+ *
+ * This is the drop-in boundary.  Everything is plain C: column-major
+ * `double*`, `int64_t` sizes, `int` status codes.  No torch / C++ types cross it.
+ *
+ * Conventions
+ *   - Every matrix is column-major FP64 (MATLAB layout) with an explicit leading dimension.
+ *   - A pointer argument may be a HOST pointer or a DEVICE pointer of the handle's GPU; the
+ *     library asks the CUDA runtime which (cudaPointerGetAttributes).  Host data is staged to
+ *     the device by the library, device data is used in place (D) or copied device-to-device.
+ *   - The caller owns every buffer it passes; the library owns every device buffer it creates
+ *     and frees them in admm_b200_destroy.
+ *   - A handle is not thread-safe; use one host thread per handle.  One handle drives one GPU
+ *     (one process per GPU for the row-sharded solvers, admm_b200_comm_init).
+ *   - Functions return ADMM_B200_OK (0) or a negative-free error code; the text of the last
+ *     error of the calling thread is returned by admm_b200_last_error().  The reference reports
+ *     errors with MATLAB error(...) strings (no codes); the host-side mirror
+ *     turns a non-zero status into an exception carrying that text.
+ *   - There is NO CPU fallback: without a usable CUDA device admm_b200_create fails.
+ *
+ * Each entry point cites the reference interface it replaces (file:line in PeterSutor/ADMM-Project).
+ */
+#ifndef ADMM_B200_H
+#define ADMM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADMM_B200_VERSION 100 /* 0.1.0 */
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+  ADMM_B200_OK = 0,
+  ADMM_B200_ERR_INVALID = 1,     /* bad argument (the reference's errorcheck.m / error(...) cases) */
+  ADMM_B200_ERR_CUDA = 2,        /* CUDA runtime failure, no device, out of memory */
+  ADMM_B200_ERR_STATE = 3,       /* call order (solve before setup, ...) */
+  ADMM_B200_ERR_NOTPOSDEF = 4,   /* chol(...) failed: matrix is not positive definite */
+  ADMM_B200_ERR_COMM = 5,        /* NCCL failure / NCCL not loadable */
+  ADMM_B200_ERR_UNSUPPORTED = 6  /* a combination the engine does not implement (fails loudly) */
+};
+
+/* ---- problem kinds: the in-scope entries of the getProxOps.m switch (getProxOps.m:52-917) - */
+enum {
+  ADMM_B200_LASSO = 1,          /* getProxOps.m:311-456, xminLASSO :1192-1206, soft threshold :933-938 */
+  ADMM_B200_BASISPURSUIT = 2,   /* getProxOps.m:126-142, xminBasisPursuit :1027-1032 */
+  ADMM_B200_TOTALVARIATION = 3, /* getProxOps.m:172-199, xminTotalVariation :1044-1048 */
+  ADMM_B200_SVM_HINGE = 4,      /* getProxOps.m:256-309, zminLinearSVM :1084-1103 (loss ~= '01') */
+  ADMM_B200_SVM_01 = 5,         /* same, loss == '01' -> minz01 :1158-1180 */
+  ADMM_B200_HUBERFIT = 6,       /* getProxOps.m:890-912, zminHuberSoftThresholding :1529-1539 */
+  ADMM_B200_LAD = 7,            /* getProxOps.m:780-810, xminLAD :1511-1515 */
+  ADMM_B200_PROX_NONNEG = 8,    /* z-prox of linearprogram / quadraticprogram: pos(x+u) :1378-1382 */
+  ADMM_B200_PROX_BOX = 9        /* z-prox of bounded QP: min(ub,max(lb,x+u)) :1470-1474 */
+};
+
+/* ---- stop conditions (admm.m:706-722) ------------------------------------------------------ */
+enum { ADMM_B200_STOP_STANDARD = 0, ADMM_B200_STOP_HNORM = 1, ADMM_B200_STOP_BOTH = 2 };
+
+/* ---- why the loop ended --------------------------------------------------------------------- */
+enum {
+  ADMM_B200_RUNNING = 0,
+  ADMM_B200_CONVERGED_STD = 1,   /* admm.m:710-713 */
+  ADMM_B200_CONVERGED_HNORM = 2, /* admm.m:719-722 */
+  ADMM_B200_MAXITERS = 3,        /* loop ran out, admm.m:496 */
+  ADMM_B200_DIVERGED_RETURN = 4  /* H-norm monotonicity test fired, the reference `return`s, admm.m:692-700 */
+};
+
+/* ---- x-update realisation ------------------------------------------------------------------- */
+enum {
+  ADMM_B200_XSOLVE_INVFACTOR = 0, /* L\ and L'\ applied as products with the cached inverse factor
+                                     (block-inverse triangular solve with one block); no dependency
+                                     chain, two streaming passes over one triangle each */
+  ADMM_B200_XSOLVE_SUBST = 1      /* blocked forward/back substitution on the cached factor L */
+};
+
+typedef struct admm_b200_handle admm_b200_handle;
+
+/* The options struct of admm.m (defaults admm.m:51-76; setopt admm.m:780-971), as plain data.
+ * Fill with admm_b200_default_options() first. */
+typedef struct admm_b200_options {
+  double rho;         /* admm.m:53  default 1.0 */
+  double relax;       /* admm.m:56  default 1.0 (over-relaxation alpha) */
+  double abstol;      /* admm.m:67  default 1e-5 */
+  double reltol;      /* admm.m:68  default 1e-3 */
+  double convtol;     /* admm.m:64  default 1e-10 */
+  double hnormtol;    /* admm.m:69  default 1e-6 */
+  int64_t maxiters;   /* admm.m:54  default 1000; <=0 becomes 1000 (admm.m:334-339) */
+  int32_t domaxiters; /* admm.m:55 */
+  int32_t stopcond;   /* admm.m:65  ADMM_B200_STOP_* */
+  int32_t nodualerror;/* admm.m:66 */
+  int32_t convtest;   /* admm.m:63 */
+  int32_t objevals;   /* admm.m:62  evaluate the solver's objective every iteration */
+  int32_t history;    /* extension: 1 = record xvals/zvals/uvals (admm.m:608-610), 0 = do not */
+  int32_t xsolve;     /* ADMM_B200_XSOLVE_* */
+  int32_t check_every;/* iterations enqueued between host polls of the device stop flag (>=1) */
+} admm_b200_options;
+
+/* What admm.m returns in `results` (admm.m:603-610, 618-658, 682, 746-767).  Every pointer is
+ * caller-owned and may be NULL (then that output is skipped).  Per-iteration arrays must hold
+ * `maxiters` doubles; xvals/zvals/uvals hold n x maxiters column-major. */
+typedef struct admm_b200_result {
+  int64_t steps;      /* results.steps */
+  int32_t status;     /* ADMM_B200_CONVERGED_* / MAXITERS / DIVERGED_RETURN */
+  int32_t reserved;
+  double objopt;      /* results.objopt (NaN unless objevals) */
+  double setup_ms;    /* device time of the one-time setup (Gram, Cholesky, inverse factor) */
+  double loop_ms;     /* device time of the iteration loop */
+  double *xopt, *zopt, *uopt;                   /* lengths nA, nB, m */
+  double *pnorm, *dnorm, *perr, *derr;          /* results.pnorm/dnorm/perr/derr */
+  double *hnormsq;                              /* results.Hnormsq */
+  double *objevals;                             /* results.objevals */
+  double *xvals, *zvals, *uvals;                /* results.xvals/zvals/uvals */
+} admm_b200_result;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int admm_b200_version(void);
+const char* admm_b200_last_error(void);
+void admm_b200_default_options(admm_b200_options* o);          /* admm.m:51-76 */
+
+/* ---- handle -------------------------------------------------------------------------------- */
+int admm_b200_create(int device, admm_b200_handle** out);
+int admm_b200_destroy(admm_b200_handle* h);
+/* Run the handle's work on a caller-supplied cudaStream_t (e.g. torch's current stream) so the
+ * caller's CUDA events bracket it.  NULL restores the handle's own stream. */
+int admm_b200_set_stream(admm_b200_handle* h, void* cuda_stream);
+int admm_b200_synchronize(admm_b200_handle* h);
+
+/* ---- one-time setup: solvers/*.m ------------------------------------------------------------ */
+/* solvers/lasso.m:159-192: Dts = D'*s; L = chol(D'D + rho I,'lower') (m >= n) or
+ * chol(DD'/rho + I,'lower') (m < n).  D is m x n, leading dimension ldD. */
+int admm_b200_setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD,
+                          const double* s, double rho, int32_t xsolve);
+/* getProxOps.m:455 -- lambda of the soft threshold; may be changed between solves without
+ * redoing the setup (the factor does not depend on lambda). */
+int admm_b200_set_lambda(admm_b200_handle* h, double lambda);
+/* options.x0 / z0 / u0 (admm.m:252-254); NULL means zeros. */
+int admm_b200_set_init(admm_b200_handle* h, const double* x0, const double* z0, const double* u0);
+
+/* ---- the loop: admm.m:496-767 ---------------------------------------------------------------- */
+int admm_b200_solve(admm_b200_handle* h, const admm_b200_options* opts, admm_b200_result* res);
+
+/* Sizes of the current problem: nA (x), nB (z), m (u) -- admm.m:74-76. */
+int admm_b200_get_dims(admm_b200_handle* h, int64_t* nA, int64_t* nB, int64_t* m);
+/* Lower Cholesky factor of the current setup (k x k, column-major, ldL >= k) for setup parity
+ * tests (lasso.m:168,172; huberfit.m:166; lad.m:134). */
+int admm_b200_get_factor(admm_b200_handle* h, double* L, int64_t ldL, int64_t* k);
+
+/* ---- building blocks (each is one hand-written kernel family; exposed for parity tests and
+ *      per-kernel roofline measurement) -------------------------------------------------------- */
+/* C = alpha*op(A)*op(B) + beta*C on FP64 DMMA tiles.  transa/transb: 0 = 'N', 1 = 'T'.
+ * lower_only != 0 computes only the tiles on/below the diagonal (SYRK use: D'*D lasso.m:168). */
+int admm_b200_dgemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K,
+                    double alpha, const double* A, int64_t lda, const double* B, int64_t ldb,
+                    double beta, double* C, int64_t ldc, int lower_only);
+/* G = D'*D + shift*I (trans = 1, k = n) or G = scale*D*D' + shift*I (trans = 0, k = m); full
+ * symmetric k x k result.  lasso.m:168,172; unwrappedadmm.m:115. */
+int admm_b200_gram(admm_b200_handle* h, int trans, int64_t m, int64_t n, const double* D, int64_t ldD,
+                   double scale, double shift, double* G, int64_t ldG);
+/* In-place lower Cholesky of the k x k matrix A (chol(A,'lower'), lasso.m:168); the strict
+ * upper triangle is zeroed.  Winv (may be NULL) receives inv(L), k x k. */
+int admm_b200_potrf(admm_b200_handle* h, int64_t k, double* A, int64_t lda, double* Winv, int64_t ldw);
+/* x = L' \ (L \ b) with the factor cached by the last setup (getProxOps.m:1200); b, x length k. */
+int admm_b200_factor_solve(admm_b200_handle* h, const double* b, double* x, int32_t xsolve);
+/* Run `reps` x-updates + fused z/u/residual passes of the current problem back to back on the
+ * handle's stream without the stop test (kernel timing; `which`: 0 = whole iteration,
+ * 1 = x-update only, 2 = fused prox pass only). */
+int admm_b200_iterate_raw(admm_b200_handle* h, const admm_b200_options* opts, int which, int reps);
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int64_t admm_b200_launch_count(admm_b200_handle* h);
+
+/* Device time (ms) of the last setup by phase: [0] Gram (+ D's), [1] Cholesky, [2] inverse factor,
+ * [3] total.  (The reference only has tic/toc: results.solverruntime, lasso.m:117,243.) */
+int admm_b200_get_setup_phases(admm_b200_handle* h, double* out4);
+
+/* errorcheck.m:216-267 slicemaker, balanced case (slices == 0, :249-259): out[w] = rows of
+ * worker w; this is the row partition of the multi-GPU solvers. */
+int admm_b200_slicemaker(int64_t len, int64_t workers, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADMM_B200_H */

@@ -1,0 +1,195 @@
+"""CPU tests of the oracle (the checker) itself.  The reference is MATLAB and ships no golden
+vectors, so the oracle is PARITY UNPINNED (oracle/__init__.py); what can be pinned is pinned here:
+hand-derived known answers of each operator, closed-form optima, KKT conditions of the problems
+the solvers claim to solve, the reference testers' own pass criteria (testers/*.m), and the quirks
+of admm.m that SURVEY.md section 5 lists."""
+import math
+
+import numpy as np
+import pytest
+import scipy.optimize as sopt
+
+import oracle
+from admm_project_b200 import generators as gen
+
+
+# ---- operators: hand-derived values ---------------------------------------------------------
+def test_soft_threshold_known_values():                      # getProxOps.m:933-938
+    v = np.array([-3.0, -1.0, -0.5, 0.0, 0.5, 1.0, 3.0])
+    assert np.array_equal(oracle.zminSoftThresholding(v, 1.0), [-2.0, 0.0, 0.0, 0.0, 0.0, 0.0, 2.0])
+
+
+def test_minz01_known_values():                              # getProxOps.m:1158-1180
+    s = np.array([2.0, 1.0, 0.99, 0.0, -0.5, -3.0])
+    # t = rho/C = 2 -> threshold 1 - sqrt(2/2) = 0: s >= 1 or s < 0 keep s, the rest become 1
+    assert np.array_equal(oracle.minz01(s, 2.0), [2.0, 1.0, 1.0, 1.0, -0.5, -3.0])
+
+
+def test_box_and_nonneg():                                   # getProxOps.m:1378-1382, 1470-1474
+    x, u = np.array([-2.0, 0.5, 3.0]), np.array([0.5, 0.5, 0.5])
+    assert np.array_equal(oracle.zminNonNegative(x, None, u, 1.0), [0.0, 1.0, 3.5])
+    box = oracle.make_zminBox(np.array([-1.0, -1.0, -1.0]), np.array([1.0, 0.75, 1.0]))
+    assert np.array_equal(box(x, None, u, 1.0), [-1.0, 0.75, 1.0])
+
+
+def test_huber_prox_is_the_minimiser():                      # getProxOps.m:1529-1539
+    # z = argmin 1/2*huber(z) + rho/2 (z - v)^2 checked by brute force on a grid
+    rho, s = 0.7, np.zeros(1)
+    _, minz, _ = oracle.getproxops("huberfit", dict(R=np.eye(1), D=np.eye(1), s=s))
+    for v in (-5.0, -0.3, 0.0, 0.9, 4.0):
+        z = minz(np.array([v]), None, np.zeros(1), rho)[0]
+        grid = np.linspace(-6, 6, 240001)
+        f = 0.5 * oracle.huber(grid) / 2 + rho / 2 * (grid - v) ** 2
+        # huberfit's objective is 1/2*sum(huber(z)) with CVX huber = z^2 inside |z|<=1: g(z) = z^2/2
+        f = 0.5 * oracle.huber(grid) + rho / 2 * (grid - v) ** 2
+        assert abs(z - grid[np.argmin(f)]) < 1e-4
+
+
+def test_slicemaker_cases():                                 # errorcheck.m:216-267
+    assert oracle.slicemaker(0, 3, 10) == [4, 3, 3]
+    assert oracle.slicemaker(0, 4, 8) == [2, 2, 2, 2]
+    assert oracle.slicemaker(3, 2, 10) == [3, 3, 3, 1]
+    assert oracle.slicemaker(5, 2, 10) == [5, 0]             # the reference's off-by-one, kept
+    assert oracle.slicemaker([6, 4], 2, 10) == [6, 4]
+    with pytest.raises(oracle.MatlabError):
+        oracle.slicemaker([6, 5], 2, 10)
+
+
+# ---- admm.m quirks ----------------------------------------------------------------------------
+def test_setopt_hnormtol_reads_hreltol():                    # admm.m:927-928
+    assert oracle.setopt({}, "Hnormtol", 1e-6) == 1e-6
+    assert oracle.setopt({"Hnormtol": 1, "Hreltol": 5e-3}, "Hnormtol", 1e-6) == 5e-3
+    with pytest.raises(oracle.MatlabError):
+        oracle.setopt({"Hnormtol": 1e-3}, "Hnormtol", 1e-6)
+
+
+def test_nonpositive_maxiters_becomes_1000():                # admm.m:334-339
+    D, s, lam, _ = gen.lasso_problem(0, 40, 10)
+    r = oracle.lasso(D, s, lam, {"maxiters": -5, "domaxiters": 1})
+    assert r["steps"] == 1000
+
+
+def test_divergence_return_leaves_results_unfinished():      # admm.m:692-700
+    # a broken x-prox (in the spirit of examples/convergencechecking.m:198) trips the H-norm test
+    n = 8
+    rs = np.random.RandomState(0)
+    q = rs.randn(n)
+    minx_broken = lambda x, z, u, rho: 2 * x + (z - u) + q
+    minz = lambda x, z, u, rho: oracle.zminSoftThresholding(x + u, 0.1)
+    r = oracle.admm(minx_broken, minz, dict(A=1, At=1, B=-1, c=0, m=n, nA=n, nB=n, convtest=1))
+    assert "steps" not in r and "xopt" not in r and len(r["Hnormsq"]) == 2
+
+
+def test_missing_constraint_fields_raise_reference_messages():
+    f = lambda x, z, u, rho: x
+    with pytest.raises(oracle.MatlabError, match="Must specify a matrix A"):
+        oracle.admm(f, f, dict(B=-1, c=0, m=3))
+    with pytest.raises(oracle.MatlabError, match="Must specify a vector c"):
+        oracle.admm(f, f, dict(A=1, B=-1))
+    with pytest.raises(oracle.MatlabError, match="not a struct"):
+        oracle.admm(f, f, None)
+
+
+# ---- closed forms and optimality conditions ------------------------------------------------------
+def test_lasso_identity_design_has_closed_form():
+    # D = I  =>  argmin 1/2||x - s||^2 + lam||x||_1 = soft(s, lam)
+    rs = np.random.RandomState(3)
+    s = rs.randn(30)
+    r = oracle.lasso(np.eye(30), s, 0.4, {"abstol": 1e-12, "reltol": 1e-12, "maxiters": 5000})
+    assert np.allclose(r["zopt"], oracle.zminSoftThresholding(s, 0.4), atol=1e-9)
+
+
+@pytest.mark.parametrize("rows,cols", [(256, 64), (60, 200)])
+def test_lasso_kkt_and_tester_criterion(rows, cols):        # lassotest.m:143-147
+    D, s, lam, testx = gen.lasso_problem(0, rows, cols)
+    r = oracle.lasso(D, s, lam, {"objevals": 1, "abstol": 1e-11, "reltol": 1e-11, "maxiters": 20000})
+    z = r["zopt"]
+    g = D.T @ (D @ z - s)
+    on = np.abs(z) > 1e-8
+    assert np.allclose(g[on], -lam * np.sign(z[on]), atol=1e-6)      # stationarity on the support
+    assert np.all(np.abs(g[~on]) <= lam + 1e-6)                       # subgradient bound off it
+    obj = lambda x: 0.5 * np.sum((D @ x - s) ** 2) + lam * np.sum(np.abs(x))
+    assert obj(r["xopt"]) < obj(testx)
+
+
+def test_lasso_fat_and_tall_branches_agree_on_square_problem():  # getProxOps.m:1199-1205 (Woodbury)
+    D, s, lam, _ = gen.lasso_problem(1, 50, 50)
+    tall = oracle.lasso(D, s, lam, {"domaxiters": 1, "maxiters": 25})
+    # force the fat branch by appending a zero column (m < n) -- the extra coordinate stays 0
+    D2 = np.hstack([D, np.zeros((50, 1))])
+    fat = oracle.lasso(D2, s, lam, {"domaxiters": 1, "maxiters": 25})
+    assert np.allclose(fat["xopt"][:50], tall["xopt"], rtol=1e-9, atol=1e-12)
+    assert abs(fat["xopt"][50]) < 1e-14
+
+
+def test_lad_matches_linear_program():                       # ladtest.m:149-168
+    D, s, xtrue = gen.lad_problem(0, 120, 6)
+    r = oracle.lad(D, s, {"abstol": 1e-10, "reltol": 1e-10, "maxiters": 20000})
+    m, n = D.shape
+    # min sum t  s.t. -t <= Dx - s <= t
+    c = np.concatenate([np.zeros(n), np.ones(m)])
+    A = np.block([[D, -np.eye(m)], [-D, -np.eye(m)]])
+    lp = sopt.linprog(c, A_ub=A, b_ub=np.concatenate([s, -s]), bounds=[(None, None)] * n + [(0, None)] * m)
+    assert lp.status == 0
+    assert abs(np.sum(np.abs(D @ r["xopt"] - s)) - lp.fun) <= 1e-5 * lp.fun
+    assert np.linalg.norm(r["xopt"] - xtrue) < 1e-3
+
+
+def test_huberfit_stationarity_and_tester_criterion():      # huberfittest.m:154-158
+    D, s, testx = gen.huber_problem(0, 400, 12)
+    r = oracle.huberfit(D, s, {"abstol": 1e-11, "reltol": 1e-11, "maxiters": 20000})
+    res = D @ r["xopt"] - s
+    psi = np.clip(res, -1.0, 1.0)            # derivative of 1/2*huber
+    assert np.linalg.norm(D.T @ psi) < 1e-6
+    f = lambda x: 0.5 * np.sum(oracle.huber(D @ x - s))
+    assert f(r["xopt"]) <= f(testx)
+
+
+def test_basispursuit_feasible_and_not_worse_than_truth():   # basispursuittest.m:136-143
+    D, s, testx = gen.bp_problem(0, 30, 90, density=0.05)
+    r = oracle.basispursuit(D, s, {"maxiters": 10000})
+    assert np.linalg.norm(D @ r["xopt"] - s) <= 1e-8 * np.linalg.norm(s)
+    assert np.sum(np.abs(r["zopt"])) <= np.sum(np.abs(testx)) * (1 + 1e-3)
+
+
+def test_totalvariation_beats_truth_and_tridiagonal_solve():  # totalvariationtest.m:151-155
+    s, truth = gen.tv_problem(0, 128)
+    lam = 5.0
+    r = oracle.totalvariation(s, lam, {"maxiters": 10000})
+    obj = lambda x: 0.5 * np.sum((x - s) ** 2) + lam * np.sum(np.abs(np.diff(x)))
+    assert obj(r["xopt"]) < obj(truth)
+    # x-update solves (I + rho D'D) x = s + rho D'(z-u) with D'D = tridiag(-1, 2, -1), (1,1) entry 1
+    n, rho = 6, 0.7
+    Dm = np.eye(n) - np.eye(n, k=1)
+    DtD = Dm.T @ Dm
+    assert DtD[0, 0] == 1 and DtD[1, 1] == 2 and DtD[n - 1, n - 1] == 2 and DtD[0, 1] == -1
+
+
+def test_linearsvm_serial_equals_transpose_reduction():      # unwrappedadmm.m:76-78 vs :96-141
+    D, ell = gen.svm_problem(0, 64, 64)
+    np.random.seed(1)
+    a = oracle.linearsvm(D, ell, 0.5, {"objevals": 1})
+    np.random.seed(1)
+    b = oracle.linearsvm(D, ell, 0.5, {"objevals": 1, "parallel": "both", "workers": 3})
+    assert a["steps"] == b["steps"]
+    assert np.allclose(a["xopt"], b["xopt"], rtol=1e-9, atol=1e-12)
+    x = a["xopt"]
+    assert abs(1 + x[1] / x[0]) <= 0.05                      # linearsvmtest.m:180-192 (errtol 0.05)
+
+
+def test_linearsvm_0_1_string_is_hinge():                    # getProxOps.m:1094 strcmp(loss,'01')
+    D, ell = gen.svm_problem(0, 32, 32)
+    np.random.seed(2)
+    a = oracle.linearsvm(D, ell, 0.5, {"lossfunction": "0-1"})
+    np.random.seed(2)
+    b = oracle.linearsvm(D, ell, 0.5, {"lossfunction": "hinge"})
+    assert a["steps"] == b["steps"] and np.array_equal(a["xopt"], b["xopt"])
+
+
+def test_unwrapped_forced_options():                         # unwrappedadmm.m:81-92
+    D, ell = gen.svm_problem(0, 16, 16)
+    np.random.seed(0)
+    r = oracle.linearsvm(D, ell, 0.5, {"maxiters": 5, "stopcond": "standard"})
+    o = r["options"]
+    assert o["maxiters"] == 1000 and o["stopcond"] == "both" and o["nodualerror"] == 1
+    assert np.all(np.isnan(r["dnorm"])) and np.all(np.isnan(r["derr"]))
