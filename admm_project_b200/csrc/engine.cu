@@ -48,8 +48,12 @@ struct DBuf {
 };
 
 struct ColdotPlan {
-  int max_cols = 0, max_items = 0, grid = 0;
+  int mode = 0;
+  int64_t rows = 0, cols = 0;
+  int grid = 0;
   size_t smem = 0;
+  int *d_cta_col = nullptr, *d_col_item = nullptr;
+  ColdotItem* d_items = nullptr;
 };
 
 }  // namespace admmb200
@@ -95,6 +99,7 @@ struct admm_b200_handle {
   DBuf xvals, zvals, uvals;
   DBuf gemm_ws, gemv_ws, scratch;
   bool iter_ready = false;
+  std::vector<ColdotPlan*> plans;
   unsigned* tickets = nullptr;
   int64_t tickets_cap = 0;
 };
@@ -316,33 +321,51 @@ static int64_t coldot_area_host(int mode, int64_t rows, int64_t j) {
   if (mode == COLDOT_LOWER) return j * rows - j * (j - 1) / 2;
   return j * (j + 1) / 2;
 }
-static int64_t coldot_len_host(int mode, int64_t rows, int64_t j) {
-  return mode == COLDOT_FULL ? rows : (mode == COLDOT_LOWER ? rows - j : j + 1);
-}
 
-static ColdotPlan coldot_plan(int mode, int64_t rows, int64_t cols) {
-  ColdotPlan p;
+// Work plan of one (mode, rows, cols) shape, built on the host once and kept on the device.
+static ColdotPlan* coldot_plan(admm_b200_handle* h, int mode, int64_t rows, int64_t cols) {
+  for (auto& e : h->plans)
+    if (e->mode == mode && e->rows == rows && e->cols == cols) return e;
+  ADMM_REQUIRE(rows < (1LL << 31) && cols < (1LL << 31), ADMM_B200_ERR_UNSUPPORTED, "coldot: dimension too large");
+  ColdotPlan* p = new ColdotPlan();
+  p->mode = mode; p->rows = rows; p->cols = cols;
   const int64_t total = coldot_area_host(mode, rows, cols);
-  // enough CTAs to fill the machine twice over, but at least ~32 KB of matrix per CTA
-  int64_t grid = std::min<int64_t>(2 * kNumSM, std::max<int64_t>(1, total / 4096));
-  p.grid = (int)grid;
-  int64_t prev = 0;
-  for (int64_t b = 1; b <= grid; ++b) {
-    int64_t target = (int64_t)(((__int128)total * b) / grid);
-    int64_t lo = 0, hi = cols;
-    if (b >= grid) lo = cols;
-    while (lo < hi) {
-      int64_t mid = (lo + hi) >> 1;
-      if (coldot_area_host(mode, rows, mid) >= target) hi = mid; else lo = mid + 1;
+  const int grid = (int)std::min<int64_t>(kNumSM, std::max<int64_t>(1, total / 8192));
+  p->grid = grid;
+  std::vector<int> cta_col(grid + 1), col_item(cols + 1);
+  std::vector<ColdotItem> items;
+  items.reserve((size_t)(total / COLDOT_ITEM + cols + 1));
+  for (int64_t j = 0; j < cols; ++j) {
+    const int64_t rlo = (mode == COLDOT_LOWER) ? j : 0;
+    const int64_t rhi = (mode == COLDOT_UPPER) ? j + 1 : rows;
+    col_item[j] = (int)items.size();
+    // item boundaries on absolute multiples of COLDOT_ITEM so interior items start 16-byte aligned
+    for (int64_t r = rlo; r < rhi;) {
+      int64_t e = std::min<int64_t>(rhi, (r / COLDOT_ITEM + 1) * COLDOT_ITEM);
+      items.push_back(ColdotItem{(int)j, (int)r, (int)(e - r), 0});
+      r = e;
     }
-    int64_t c0 = prev, c1 = lo;
-    prev = lo;
-    int64_t items = 0;
-    for (int64_t j = c0; j < c1; ++j) items += (coldot_len_host(mode, rows, j) + COLDOT_SEG - 1) / COLDOT_SEG;
-    p.max_cols = (int)std::max<int64_t>(p.max_cols, c1 - c0);
-    p.max_items = (int)std::max<int64_t>(p.max_items, items);
   }
-  p.smem = (size_t)((((p.max_cols + 1) * 4 + 15) & ~15) + (size_t)p.max_items * 8);
+  col_item[cols] = (int)items.size();
+  cta_col[0] = 0;
+  int64_t c = 0;
+  int max_items = 0;
+  for (int b = 1; b <= grid; ++b) {
+    const int64_t target = (int64_t)((double)total * b / grid);
+    while (c < cols && (b == grid || coldot_area_host(mode, rows, c) < target)) ++c;
+    cta_col[b] = (int)c;
+    max_items = std::max(max_items, col_item[cta_col[b]] - col_item[cta_col[b - 1]]);
+  }
+  cta_col[grid] = (int)cols;
+  p->smem = (size_t)std::max(max_items, 1) * 8;
+  ADMM_REQUIRE(p->smem <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED, "coldot: problem too large for the item table");
+  ADMM_CUDA(cudaMalloc(&p->d_cta_col, cta_col.size() * sizeof(int)));
+  ADMM_CUDA(cudaMalloc(&p->d_col_item, col_item.size() * sizeof(int)));
+  ADMM_CUDA(cudaMalloc(&p->d_items, std::max<size_t>(items.size(), 1) * sizeof(ColdotItem)));
+  ADMM_CUDA(cudaMemcpy(p->d_cta_col, cta_col.data(), cta_col.size() * sizeof(int), cudaMemcpyHostToDevice));
+  ADMM_CUDA(cudaMemcpy(p->d_col_item, col_item.data(), col_item.size() * sizeof(int), cudaMemcpyHostToDevice));
+  ADMM_CUDA(cudaMemcpy(p->d_items, items.data(), items.size() * sizeof(ColdotItem), cudaMemcpyHostToDevice));
+  h->plans.push_back(p);
   return p;
 }
 
@@ -351,26 +374,16 @@ static void coldot(admm_b200_handle* h, int mode, const double* M, int64_t ld, i
                    double addscale = 0.0, const int* done = nullptr) {
   ADMM_REQUIRE((ld % 2 == 0) && (((uintptr_t)M & 15) == 0) && (((uintptr_t)v & 15) == 0), ADMM_B200_ERR_UNSUPPORTED,
                "coldot: matrix must be 16-byte aligned with an even leading dimension (ld=%lld)", (long long)ld);
-  // plans are cheap but not free (O(cols)); cache the last few shapes
-  struct Key { int mode; int64_t rows, cols; ColdotPlan plan; };
-  static thread_local std::vector<Key> cache;
-  const ColdotPlan* plan = nullptr;
-  for (auto& e : cache)
-    if (e.mode == mode && e.rows == rows && e.cols == cols) plan = &e.plan;
-  if (!plan) {
-    cache.push_back(Key{mode, rows, cols, coldot_plan(mode, rows, cols)});
-    plan = &cache.back().plan;
-  }
-  ADMM_REQUIRE(plan->smem <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED, "coldot: problem too large for the item table");
+  const ColdotPlan* plan = coldot_plan(h, mode, rows, cols);
   static size_t configured_smem = 0;
   if (plan->smem > configured_smem) {
     ADMM_CUDA(cudaFuncSetAttribute(coldot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
     configured_smem = plan->smem;
   }
   ColdotArgs a;
-  a.M = M; a.ld = ld; a.rows = rows; a.cols = cols; a.mode = mode; a.v = v; a.out = out;
+  a.M = M; a.ld = ld; a.v = v; a.out = out;
   a.scale = scale; a.addend = addend; a.addscale = addscale; a.done = done;
-  a.max_cols_per_cta = plan->max_cols; a.max_items_per_cta = plan->max_items;
+  a.cta_col = plan->d_cta_col; a.col_item = plan->d_col_item; a.items = plan->d_items;
   coldot_kernel<<<plan->grid, COLDOT_THREADS, plan->smem, h->stream>>>(a);
   ADMM_CUDA(cudaGetLastError());
   h->launches++;
@@ -742,6 +755,10 @@ int admm_b200_destroy(admm_b200_handle* h) {
                   &h->x0, &h->z0, &h->u0, &h->partials, &h->hist, &h->xvals, &h->zvals, &h->uvals, &h->gemm_ws,
                   &h->gemv_ws, &h->scratch};
   for (DBuf* b : bufs) b->release();
+  for (ColdotPlan* p : h->plans) {
+    cudaFree(p->d_cta_col); cudaFree(p->d_col_item); cudaFree(p->d_items);
+    delete p;
+  }
   if (h->tickets) cudaFree(h->tickets);
   if (h->ctl) cudaFree(h->ctl);
   if (h->fail) cudaFree(h->fail);

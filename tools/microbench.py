@@ -12,16 +12,21 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from admm_project_b200 import DeviceMatrix, Engine  # noqa: E402
 
 
+STREAM = None
+
+
 def timed(stream_fn, reps, warm=3):
-    for _ in range(warm):
-        stream_fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        stream_fn()
-    e1.record()
-    torch.cuda.synchronize()
+    # a real (non-legacy) stream: admm_b200_set_stream(NULL) means "the handle's own stream"
+    with torch.cuda.stream(STREAM):
+        for _ in range(warm):
+            stream_fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            stream_fn()
+        e1.record()
+        torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
 
@@ -30,6 +35,8 @@ def main():
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
     torch.manual_seed(0)
     dev = torch.device("cuda:0")
+    global STREAM
+    STREAM = torch.cuda.Stream()
     out = {"m": m, "n": n}
     # fp64 dgemm peak probe (cuBLAS)
     a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
@@ -41,7 +48,8 @@ def main():
     Dt /= Dt.norm(dim=1, keepdim=True)
     s = torch.randn(m, dtype=torch.float64, device=dev)
     eng = Engine(0)
-    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    eng.set_stream(STREAM.cuda_stream)
     D = DeviceMatrix(Dt.data_ptr(), m, n, m, keepalive=Dt)
     t0 = time.perf_counter()
     eng.setup_lasso(D, s.data_ptr(), 1.0)
