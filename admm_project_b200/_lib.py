@@ -57,6 +57,11 @@ SYMBOLS = {
     "admm_b200_set_stream": (_int, [_vp, _vp]),
     "admm_b200_synchronize": (_int, [_vp]),
     "admm_b200_setup_lasso": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _d, _i32]),
+    "admm_b200_setup_unwrapped": (_int, [_vp, _i32, _i64, _i64, _i64, _vp, _i64, _vp, _d]),
+    "admm_b200_get_unique_id": (_int, [_vp]),
+    "admm_b200_comm_init": (_int, [_vp, _int, _int, _vp]),
+    "admm_b200_comm_destroy": (_int, [_vp]),
+    "admm_b200_allreduce": (_int, [_vp, _vp, _i64]),
     "admm_b200_set_lambda": (_int, [_vp, _d]),
     "admm_b200_set_init": (_int, [_vp, _vp, _vp, _vp]),
     "admm_b200_solve": (_int, [_vp, C.POINTER(Options), C.POINTER(Result)]),

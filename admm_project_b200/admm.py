@@ -12,6 +12,7 @@ import numpy as np
 from . import _lib as L
 from .errorcheck import MatlabError
 from .getproxops import EngineProx
+from .parallel import gather_rows
 
 
 def setopt(options, opttext, default):
@@ -77,17 +78,30 @@ def admm(xminf, zming, options):
             raise MatlabError("Must specify a %s in constraint Ax + Bz = c!" % what)
 
     x0, z0, u0 = options.get("x0"), options.get("z0"), options.get("u0")    # admm.m:252-254
-    eng.set_init(x0, z0, u0)
     nA, nB, m = eng.dims()
+    sharded = eng.nranks > 1 and eng.row_range is not None
+    lo, hi = eng.row_range if sharded else (0, None)
+    mt = eng.m_total if sharded else m
+
+    def rows(v, full):          # a full-length row vector is cut to this rank's rows
+        if v is None or not sharded:
+            return v
+        v = L.fvec(v)
+        return v[lo:hi] if v.size == full else v
+    eng.set_init(x0, rows(z0, mt), rows(u0, mt))
     results = {"x0": np.zeros(nA) if x0 is None else L.fvec(x0).copy(),
-               "z0": np.zeros(nB) if z0 is None else L.fvec(z0).copy(),
-               "u0": np.zeros(m) if u0 is None else L.fvec(u0).copy()}
+               "z0": np.zeros(mt if sharded else nB) if z0 is None else L.fvec(z0).copy(),
+               "u0": np.zeros(mt) if u0 is None else L.fvec(u0).copy()}
     use_hnorm = bool(o.convtest) or stopcond in ("hnorm", "both")
     if use_hnorm:
         results["Hnormtol"] = o.hnormtol
 
     start = time.perf_counter()
     r = eng.solve(o, want_history=bool(o.history))
+    if sharded:                                     # results carry full-length z / u like the reference's
+        for key in ("zopt", "uopt", "zvals", "uvals"):
+            if key in r:
+                r[key] = gather_rows(r[key], mt)
     results["pnorm"], results["dnorm"] = r["pnorm"], r["dnorm"]
     results["perr"], results["derr"] = r["perr"], r["derr"]
     if use_hnorm:

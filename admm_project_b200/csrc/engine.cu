@@ -15,6 +15,8 @@
 #include "gemv.cuh"
 #include "prox.cuh"
 #include "tri.cuh"
+#include "unwrapped.cuh"
+#include <dlfcn.h>
 
 namespace admmb200 {
 
@@ -50,9 +52,8 @@ struct DBuf {
 struct ColdotPlan {
   int mode = 0;
   int64_t rows = 0, cols = 0;
-  int grid = 0;
-  size_t smem = 0;
-  int *d_cta_col = nullptr, *d_col_item = nullptr;
+  int grid = 0, panels = 1, max_pos = 1;
+  int *d_cta_pos = nullptr, *d_pos_item = nullptr, *d_order = nullptr;
   ColdotItem* d_items = nullptr;
 };
 
@@ -97,8 +98,16 @@ struct admm_b200_handle {
   DBuf partials, hist;           // hist: 6 x cap
   int64_t hist_cap = 0;
   DBuf xvals, zvals, uvals;
-  DBuf gemm_ws, gemv_ws, scratch;
+  DBuf gemm_ws, gemv_ws, scratch, cd_ws;
   bool iter_ready = false;
+  // A = D family (svm / huber / lad)
+  DBuf aux, rvec, dzvec, cb, uw_partials;
+  unsigned* grid_ticket = nullptr;
+  int64_t m_total = 0;
+  double svmC = 0.0;
+  // row-sharded runs: one NCCL communicator per handle (one process per GPU)
+  void* comm = nullptr;
+  int rank = 0, nranks = 1;
   std::vector<ColdotPlan*> plans;
   unsigned* tickets = nullptr;
   int64_t tickets_cap = 0;
@@ -162,6 +171,7 @@ struct GemmOpt {
   int batch = 1;
   int64_t strideA = 0, strideB = 0, strideC = 0;
   int allow_splitk = 1;
+  int a_lower = 0, b_lower = 0;
 };
 
 static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
@@ -173,14 +183,26 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
   g.alpha = alpha; g.beta = beta; g.diag_add = o.diag_add;
   g.lower_only = o.lower_only;
+  g.a_lower = o.a_lower; g.b_lower = o.b_lower;
   g.batch = o.batch; g.strideA = o.strideA; g.strideB = o.strideB; g.strideC = o.strideC;
   g.splits = 1; g.k_per_split = std::max<int64_t>(K, 1); g.ws = nullptr;
   const int64_t tm = (M + GEMM_BM - 1) / GEMM_BM, tn = (N + GEMM_BN - 1) / GEMM_BN;
   int64_t tiles = o.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   tiles *= o.batch;
+  int64_t want_splits = 1;
   if (o.allow_splitk && tiles < kNumSM && K >= 4096) {
-    int64_t splits = std::min<int64_t>((2 * kNumSM + tiles - 1) / tiles, K / 1024);
-    splits = std::max<int64_t>(splits, 1);
+    // few output tiles (n = 784 / 1024 Gram of a tall D): fill the machine twice over
+    want_splits = std::min<int64_t>((2 * kNumSM + tiles - 1) / tiles, K / 1024);
+  } else if (o.allow_splitk && tiles >= kNumSM && K >= 16384) {
+    // wave quantisation: 2080 tiles on 148 SMs = 14.05 waves -> 15 (6.7% idle).  Splitting K by S
+    // makes the work items S times smaller, so the idle tail shrinks to ~1/S of a tile time.
+    auto waste = [&](int64_t S) { int64_t items = tiles * S; return (double)((items + kNumSM - 1) / kNumSM * kNumSM) / (double)items; };
+    double best = waste(1);
+    for (int64_t S = 2; S <= 4; ++S)
+      if (waste(S) < best - 0.01 && (int64_t)o.batch * S * M * N * 8 <= (int64_t)4 << 30) { best = waste(S); want_splits = S; }
+  }
+  if (want_splits > 1) {
+    int64_t splits = want_splits;
     if (splits > 1) {
       g.k_per_split = round_up((K + splits - 1) / splits, GEMM_BK);
       g.splits = (int)((K + g.k_per_split - 1) / g.k_per_split);
@@ -242,27 +264,41 @@ static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda
   }
   ADMM_CUDA(cudaMemsetAsync(h->fail, 0, sizeof(int), h->stream));
   ADMM_CUDA(cudaMemset2DAsync(W, (size_t)ldw * 8, 0, (size_t)k * 8, (size_t)k, h->stream));
-  for (int64_t k0 = 0; k0 < k; k0 += CHOL_NB) {
-    const int nb = (int)std::min<int64_t>(CHOL_NB, k - k0);
-    double* A11 = A + k0 + k0 * lda;
-    double* W11 = W + k0 + k0 * ldw;
-    potrf_diag_kernel<<<1, CHOL_DIAG_THREADS, CHOL_DIAG_SMEM, h->stream>>>(A11, lda, nb, W11, ldw, h->fail, (int)k0);
-    ADMM_CUDA(cudaGetLastError());
-    h->launches++;
-    const int64_t rem = k - k0 - nb;
-    if (rem > 0) {
+  // two-level right-looking blocking: 512-wide outer panels (so the big trailing update runs with
+  // K = 512 and near-Gram efficiency), 128-wide inner steps inside a panel.
+  for (int64_t K0 = 0; K0 < k; K0 += CHOL_NBO) {
+    const int64_t wb = std::min<int64_t>(CHOL_NBO, k - K0);
+    for (int64_t k0 = K0; k0 < K0 + wb; k0 += CHOL_NB) {
+      const int nb = (int)std::min<int64_t>(CHOL_NB, K0 + wb - k0);
+      double* A11 = A + k0 + k0 * lda;
+      double* W11 = W + k0 + k0 * ldw;
+      potrf_diag_kernel<<<1, CHOL_DIAG_THREADS, CHOL_DIAG_SMEM, h->stream>>>(A11, lda, nb, W11, ldw, h->fail, (int)k0);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+      const int64_t rem = k - k0 - nb;
+      if (rem <= 0) continue;
       double* A21 = A + (k0 + nb) + k0 * lda;
-      double* A22 = A + (k0 + nb) + (k0 + nb) * lda;
       // L21 = A21 * inv(L11)'.  In place: N = nb <= one tile column, so every CTA reads only the
       // rows it later writes, after its whole K loop.
       GemmOpt po;
       po.allow_splitk = 0;
       gemm(h, 0, 1, rem, nb, nb, 1.0, A21, lda, W11, ldw, 0.0, A21, lda, po);
-      // A22 -= L21 * L21'  (lower tiles)
+      // inner trailing update, remaining columns of this outer panel only
+      const int64_t pc = K0 + wb - k0 - nb;
+      if (pc > 0) {
+        GemmOpt to;
+        to.lower_only = 1;
+        to.allow_splitk = 0;
+        gemm(h, 0, 1, rem, pc, nb, -1.0, A21, lda, A21, lda, 1.0, A + (k0 + nb) + (k0 + nb) * lda, lda, to);
+      }
+    }
+    const int64_t rem2 = k - K0 - wb;
+    if (rem2 > 0) {  // A22 -= L21 * L21'  (lower tiles), K = wb
+      double* P = A + (K0 + wb) + K0 * lda;
       GemmOpt to;
       to.lower_only = 1;
       to.allow_splitk = 0;
-      gemm(h, 0, 1, rem, rem, nb, -1.0, A21, lda, A21, lda, 1.0, A22, lda, to);
+      gemm(h, 0, 1, rem2, rem2, wb, -1.0, P, lda, P, lda, 1.0, A + (K0 + wb) + (K0 + wb) * lda, lda, to);
     }
   }
   {
@@ -289,7 +325,8 @@ static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda
       o1.strideB = 2 * b * (ldw + 1);
       o1.strideC = b * b;
       o1.allow_splitk = 0;
-      // T_p = B_p * Ai_p      (b x b)
+      o1.b_lower = 1;
+      // T_p = B_p * Ai_p      (b x b), Ai_p lower triangular
       gemm(h, 0, 0, b, b, b, 1.0, A + b, lda, W, ldw, 0.0, T.p, b, o1);
       GemmOpt o2;
       o2.batch = (int)npairs_full;
@@ -297,18 +334,21 @@ static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda
       o2.strideB = b * b;
       o2.strideC = 2 * b * (ldw + 1);
       o2.allow_splitk = 0;
-      // W21_p = -Ci_p * T_p
+      o2.a_lower = 1;
+      // W21_p = -Ci_p * T_p, Ci_p lower triangular
       gemm(h, 0, 0, b, b, b, -1.0, W + b + b * ldw, ldw, T.p, b, 0.0, W + b, ldw, o2);
     }
     const int64_t start = npairs_full * 2 * b;
     const int64_t cb = k - start - b;  // ragged last pair: second block has cb rows, 0 < cb < b
     if (cb > 0) {
-      GemmOpt o;
-      o.allow_splitk = 0;
+      GemmOpt o, oa;
+      o.allow_splitk = oa.allow_splitk = 0;
+      o.b_lower = 1;
+      oa.a_lower = 1;
       double* Tl = T.p + npairs_full * b * b;
       gemm(h, 0, 0, cb, b, b, 1.0, A + (start + b) + start * lda, lda, W + start + start * ldw, ldw, 0.0, Tl, cb, o);
       gemm(h, 0, 0, cb, b, cb, -1.0, W + (start + b) + (start + b) * ldw, ldw, Tl, cb, 0.0,
-           W + (start + b) + start * ldw, ldw, o);
+           W + (start + b) + start * ldw, ldw, oa);
     }
   }
 }
@@ -316,77 +356,142 @@ static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda
 // ---------------------------------------------------------------------------------------------
 // streaming products
 // ---------------------------------------------------------------------------------------------
-static int64_t coldot_area_host(int mode, int64_t rows, int64_t j) {
-  if (mode == COLDOT_FULL) return j * rows;
-  if (mode == COLDOT_LOWER) return j * rows - j * (j - 1) / 2;
-  return j * (j + 1) / 2;
-}
-
 // Work plan of one (mode, rows, cols) shape, built on the host once and kept on the device.
 static ColdotPlan* coldot_plan(admm_b200_handle* h, int mode, int64_t rows, int64_t cols) {
   for (auto& e : h->plans)
     if (e->mode == mode && e->rows == rows && e->cols == cols) return e;
   ADMM_REQUIRE(rows < (1LL << 31) && cols < (1LL << 31), ADMM_B200_ERR_UNSUPPORTED, "coldot: dimension too large");
-  ColdotPlan* p = new ColdotPlan();
-  p->mode = mode; p->rows = rows; p->cols = cols;
-  const int64_t total = coldot_area_host(mode, rows, cols);
-  const int grid = (int)std::min<int64_t>(kNumSM, std::max<int64_t>(1, total / 8192));
-  p->grid = grid;
-  std::vector<int> cta_col(grid + 1), col_item(cols + 1);
+  ColdotPlan* pl = new ColdotPlan();
+  pl->mode = mode; pl->rows = rows; pl->cols = cols;
+  // row panels for tall rectangular matrices: enough virtual columns to balance 148 CTAs
+  int64_t P = 1;
+  if (mode == COLDOT_FULL && cols < 6000) P = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((6000 + cols - 1) / cols, 32), rows / 2048));
+  pl->panels = (int)P;
+  const int64_t nv = P * cols;
+  ADMM_REQUIRE(nv < (1LL << 31), ADMM_B200_ERR_UNSUPPORTED, "coldot: too many virtual columns");
+  // virtual column vc = p*cols + j covers rows [lo, hi) of column j
+  auto vrange = [&](int64_t vc, int64_t& j, int64_t& lo, int64_t& hi) {
+    const int64_t p = vc / cols;
+    j = vc % cols;
+    if (mode == COLDOT_LOWER) { lo = j; hi = rows; }
+    else if (mode == COLDOT_UPPER) { lo = 0; hi = j + 1; }
+    else {
+      const int64_t per = ((rows + P - 1) / P + COLDOT_ITEM - 1) / COLDOT_ITEM * COLDOT_ITEM;
+      lo = std::min(rows, p * per);
+      hi = std::min(rows, (p + 1) * per);
+    }
+  };
+  std::vector<int> order(nv), pos_item(nv + 1);
+  // folded visiting order: triangular modes pair the longest remaining column with the shortest
+  for (int64_t q = 0, lo = 0, hi = nv - 1; q < nv; ++q) {
+    if (mode == COLDOT_FULL) order[q] = (int)q;
+    else order[q] = (int)((q & 1) ? hi-- : lo++);
+  }
   std::vector<ColdotItem> items;
-  items.reserve((size_t)(total / COLDOT_ITEM + cols + 1));
-  for (int64_t j = 0; j < cols; ++j) {
-    const int64_t rlo = (mode == COLDOT_LOWER) ? j : 0;
-    const int64_t rhi = (mode == COLDOT_UPPER) ? j + 1 : rows;
-    col_item[j] = (int)items.size();
+  int64_t total = 0;
+  for (int64_t q = 0; q < nv; ++q) {
+    int64_t j, rlo, rhi;
+    vrange(order[q], j, rlo, rhi);
+    pos_item[q] = (int)items.size();
     // item boundaries on absolute multiples of COLDOT_ITEM so interior items start 16-byte aligned
     for (int64_t r = rlo; r < rhi;) {
       int64_t e = std::min<int64_t>(rhi, (r / COLDOT_ITEM + 1) * COLDOT_ITEM);
-      items.push_back(ColdotItem{(int)j, (int)r, (int)(e - r), 0});
+      items.push_back(ColdotItem{(int)j, (int)r, (int)(e - r), (int)q});
+      total += e - r;
       r = e;
     }
+    ADMM_REQUIRE(items.size() < (size_t)1 << 31, ADMM_B200_ERR_UNSUPPORTED, "coldot: too many items");
   }
-  col_item[cols] = (int)items.size();
-  cta_col[0] = 0;
+  pos_item[nv] = (int)items.size();
+  const int grid = (int)std::min<int64_t>(kNumSM, std::max<int64_t>(1, total / 8192));
+  pl->grid = grid;
+  // Equal COST split of the visiting sequence: a warp needs a few thousand cycles per item however
+  // short it is (descriptor + DRAM latency + shuffle reduction), worth ~4.5 KB of streaming --
+  // measured on B200 (profiles/r01_notes.md): an equal-area split of the natural column order left
+  // the CTA owning the ~670 shortest columns running 1.7x longer than the rest.
+  constexpr int64_t kItemFloorBytes = 4608;
+  std::vector<int64_t> cost(nv + 1, 0);
+  for (int64_t q = 0; q < nv; ++q) {
+    int64_t cst = 0;
+    for (int it = pos_item[q]; it < pos_item[q + 1]; ++it) cst += std::max<int64_t>((int64_t)items[it].nrows * 8, kItemFloorBytes);
+    cost[q + 1] = cost[q] + cst;
+  }
+  std::vector<int> cta_pos(grid + 1);
+  cta_pos[0] = 0;
   int64_t c = 0;
-  int max_items = 0;
+  int max_pos = 1;
   for (int b = 1; b <= grid; ++b) {
-    const int64_t target = (int64_t)((double)total * b / grid);
-    while (c < cols && (b == grid || coldot_area_host(mode, rows, c) < target)) ++c;
-    cta_col[b] = (int)c;
-    max_items = std::max(max_items, col_item[cta_col[b]] - col_item[cta_col[b - 1]]);
+    const int64_t target = (int64_t)((double)cost[nv] * b / grid);
+    while (c < nv && (b == grid || cost[c + 1] <= target)) ++c;
+    cta_pos[b] = (int)c;
+    max_pos = std::max(max_pos, cta_pos[b] - cta_pos[b - 1]);
   }
-  cta_col[grid] = (int)cols;
-  p->smem = (size_t)std::max(max_items, 1) * 8;
-  ADMM_REQUIRE(p->smem <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED, "coldot: problem too large for the item table");
-  ADMM_CUDA(cudaMalloc(&p->d_cta_col, cta_col.size() * sizeof(int)));
-  ADMM_CUDA(cudaMalloc(&p->d_col_item, col_item.size() * sizeof(int)));
-  ADMM_CUDA(cudaMalloc(&p->d_items, std::max<size_t>(items.size(), 1) * sizeof(ColdotItem)));
-  ADMM_CUDA(cudaMemcpy(p->d_cta_col, cta_col.data(), cta_col.size() * sizeof(int), cudaMemcpyHostToDevice));
-  ADMM_CUDA(cudaMemcpy(p->d_col_item, col_item.data(), col_item.size() * sizeof(int), cudaMemcpyHostToDevice));
-  ADMM_CUDA(cudaMemcpy(p->d_items, items.data(), items.size() * sizeof(ColdotItem), cudaMemcpyHostToDevice));
-  h->plans.push_back(p);
-  return p;
+  pl->max_pos = max_pos;
+  ADMM_REQUIRE((size_t)max_pos * 3 * COLDOT_WARPS * 8 <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED,
+               "coldot: too many columns per CTA (%d)", max_pos);
+  ADMM_CUDA(cudaMalloc(&pl->d_cta_pos, cta_pos.size() * sizeof(int)));
+  ADMM_CUDA(cudaMalloc(&pl->d_pos_item, pos_item.size() * sizeof(int)));
+  ADMM_CUDA(cudaMalloc(&pl->d_order, std::max<size_t>(order.size(), 1) * sizeof(int)));
+  ADMM_CUDA(cudaMalloc(&pl->d_items, std::max<size_t>(items.size(), 1) * sizeof(ColdotItem)));
+  ADMM_CUDA(cudaMemcpy(pl->d_cta_pos, cta_pos.data(), cta_pos.size() * sizeof(int), cudaMemcpyHostToDevice));
+  ADMM_CUDA(cudaMemcpy(pl->d_pos_item, pos_item.data(), pos_item.size() * sizeof(int), cudaMemcpyHostToDevice));
+  ADMM_CUDA(cudaMemcpy(pl->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
+  ADMM_CUDA(cudaMemcpy(pl->d_items, items.data(), items.size() * sizeof(ColdotItem), cudaMemcpyHostToDevice));
+  h->plans.push_back(pl);
+  return pl;
+}
+
+// out_k = scale * M' v_k (+ addscale*addend, NV == 1 only), k < nv
+static void coldot_multi(admm_b200_handle* h, int mode, const double* M, int64_t ld, int64_t rows, int64_t cols, int nv,
+                         const double* const* v, double* const* out, double scale, const double* addend,
+                         double addscale, const int* done) {
+  ADMM_REQUIRE(nv == 1 || nv == 3, ADMM_B200_ERR_INVALID, "coldot: nv must be 1 or 3");
+  bool ok = (ld % 2 == 0) && (((uintptr_t)M & 15) == 0);
+  for (int k = 0; k < nv; ++k) ok = ok && (((uintptr_t)v[k] & 15) == 0);
+  ADMM_REQUIRE(ok, ADMM_B200_ERR_UNSUPPORTED,
+               "coldot: matrix and vectors must be 16-byte aligned with an even leading dimension (ld=%lld)", (long long)ld);
+  const ColdotPlan* plan = coldot_plan(h, mode, rows, cols);
+  const size_t smem = (size_t)plan->max_pos * nv * COLDOT_WARPS * 8;
+  static size_t configured[2] = {0, 0};
+  size_t& conf = configured[nv == 3];
+  if (smem > conf && smem > 48 * 1024) {
+    if (nv == 1) ADMM_CUDA(cudaFuncSetAttribute(coldot_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else ADMM_CUDA(cudaFuncSetAttribute(coldot_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  ColdotArgs a;
+  a.M = M; a.ld = ld; a.done = done;
+  a.cta_pos = plan->d_cta_pos; a.pos_item = plan->d_pos_item; a.order = plan->d_order; a.items = plan->d_items;
+  const int P = plan->panels;
+  if (P == 1) {
+    for (int k = 0; k < 3; ++k) { a.v[k] = v[k < nv ? k : 0]; a.out[k] = out[k < nv ? k : 0]; }
+    a.scale = scale; a.addend = addend; a.addscale = addscale;
+  } else {
+    ADMM_REQUIRE(addend == nullptr, ADMM_B200_ERR_UNSUPPORTED, "coldot: addend with row panels");
+    h->cd_ws.ensure((int64_t)P * cols * nv);
+    for (int k = 0; k < 3; ++k) { a.v[k] = v[k < nv ? k : 0]; a.out[k] = h->cd_ws.p + (int64_t)(k < nv ? k : 0) * P * cols; }
+    a.scale = 1.0; a.addend = nullptr; a.addscale = 0.0;
+  }
+  if (nv == 1) coldot_kernel<1><<<plan->grid, COLDOT_THREADS, smem, h->stream>>>(a);
+  else coldot_kernel<3><<<plan->grid, COLDOT_THREADS, smem, h->stream>>>(a);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+  if (P > 1) {
+    PanelReduceArgs r;
+    for (int k = 0; k < 3; ++k) { r.ws[k] = a.out[k]; r.out[k] = out[k < nv ? k : 0]; }
+    r.nv = nv; r.panels = P; r.cols = cols; r.scale = scale; r.done = done;
+    panel_reduce_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, h->stream>>>(r);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+  }
 }
 
 static void coldot(admm_b200_handle* h, int mode, const double* M, int64_t ld, int64_t rows, int64_t cols,
                    const double* v, double* out, double scale = 1.0, const double* addend = nullptr,
                    double addscale = 0.0, const int* done = nullptr) {
-  ADMM_REQUIRE((ld % 2 == 0) && (((uintptr_t)M & 15) == 0) && (((uintptr_t)v & 15) == 0), ADMM_B200_ERR_UNSUPPORTED,
-               "coldot: matrix must be 16-byte aligned with an even leading dimension (ld=%lld)", (long long)ld);
-  const ColdotPlan* plan = coldot_plan(h, mode, rows, cols);
-  static size_t configured_smem = 0;
-  if (plan->smem > configured_smem) {
-    ADMM_CUDA(cudaFuncSetAttribute(coldot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
-    configured_smem = plan->smem;
-  }
-  ColdotArgs a;
-  a.M = M; a.ld = ld; a.v = v; a.out = out;
-  a.scale = scale; a.addend = addend; a.addscale = addscale; a.done = done;
-  a.cta_col = plan->d_cta_col; a.col_item = plan->d_col_item; a.items = plan->d_items;
-  coldot_kernel<<<plan->grid, COLDOT_THREADS, plan->smem, h->stream>>>(a);
-  ADMM_CUDA(cudaGetLastError());
-  h->launches++;
+  const double* vs[1] = {v};
+  double* os[1] = {out};
+  coldot_multi(h, mode, M, ld, rows, cols, 1, vs, os, scale, addend, addscale, done);
 }
 
 static void gemvn(admm_b200_handle* h, const double* D, int64_t ld, int64_t m, int64_t n, const double* v,
@@ -506,6 +611,110 @@ static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double*
 }
 
 // ---------------------------------------------------------------------------------------------
+// NCCL (loaded lazily with dlopen so single-GPU use needs no NCCL at all)
+// ---------------------------------------------------------------------------------------------
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static void nccl_load() {
+  if (g_nccl.lib) return;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  ADMM_REQUIRE(g_nccl.lib != nullptr, ADMM_B200_ERR_COMM, "cannot load libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  ADMM_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy, ADMM_B200_ERR_COMM,
+               "libnccl is missing a required symbol");
+}
+#define ADMM_NCCL(call)                                                                          \
+  do {                                                                                           \
+    int _r = (call);                                                                             \
+    ADMM_REQUIRE(_r == 0, ADMM_B200_ERR_COMM, "NCCL error %d at %s:%d: %s", _r, __FILE__, __LINE__, \
+                 g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?");                       \
+  } while (0)
+
+static void comm_destroy(admm_b200_handle* h) {
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr;
+  h->rank = 0;
+  h->nranks = 1;
+}
+
+// in-place sum over ranks of `count` doubles on the handle's stream (no-op for a single rank)
+static void allreduce_sum(admm_b200_handle* h, double* buf, int64_t count) {
+  if (h->nranks <= 1) return;
+  ADMM_NCCL(g_nccl.AllReduce(buf, buf, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->comm, h->stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup of the A = D problems: W = sum over ranks of D_g'*D_g, R = chol(W)
+// (unwrappedadmm.m:96-123 nodepreprocessing; huberfit.m:166; lad.m:134)
+// ---------------------------------------------------------------------------------------------
+static void setup_unwrapped(admm_b200_handle* h, int kind, int64_t m_local, int64_t m_total, int64_t n, const double* D,
+                            int64_t ldD, const double* aux, double C) {
+  ADMM_REQUIRE(kind == ADMM_B200_SVM_HINGE || kind == ADMM_B200_SVM_01 || kind == ADMM_B200_HUBERFIT ||
+                   kind == ADMM_B200_LAD, ADMM_B200_ERR_INVALID, "setup_unwrapped: kind %d is not an A = D problem", kind);
+  ADMM_REQUIRE(m_local > 0 && n > 0 && D && aux && ldD >= m_local && m_total >= m_local, ADMM_B200_ERR_INVALID,
+               "setup_unwrapped: bad dimensions or null input");
+  if (kind == ADMM_B200_SVM_HINGE || kind == ADMM_B200_SVM_01)
+    ADMM_REQUIRE(C >= 0, ADMM_B200_ERR_INVALID, "Given regularization parameter C is not a nonnegative number!");
+  ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
+  h->have_factor = false;
+  stage_matrix(h, m_local, n, D, ldD);
+  h->aux.ensure(round_up(m_local, 2));
+  copy_in(h, h->aux.p, aux, m_local);
+  h->kind = kind;
+  h->svmC = C;
+  h->m_total = m_total;
+  h->nA = n;
+  h->nB = h->mc = m_local;
+  h->ldf = round_up(n, 16);
+  h->L.ensure(h->ldf * n);
+  ADMM_CUDA(cudaMemsetAsync(h->L.p, 0, (size_t)h->ldf * n * 8, h->stream));
+  GemmOpt o;
+  o.lower_only = 1;
+  gemm(h, 1, 0, n, n, m_local, 1.0, h->dD, h->ldD, h->dD, h->ldD, 0.0, h->L.p, h->ldf, o);
+  allreduce_sum(h, h->L.p, h->ldf * n);
+  ADMM_CUDA(cudaEventRecord(h->evp[1], h->stream));
+  factor_current(h, n, true);
+  ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
+  ADMM_CUDA(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->setup_ms = h->phase_ms[3] = ms;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->evp[1]));
+  h->phase_ms[0] = ms;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->evp[1], h->evp[2]));
+  h->phase_ms[1] = ms;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->evp[2], h->ev1));
+  h->phase_ms[2] = ms;
+  h->have_init = false;
+  h->iter_ready = false;
+}
+
+static bool is_unwrapped(int kind) {
+  return kind == ADMM_B200_SVM_HINGE || kind == ADMM_B200_SVM_01 || kind == ADMM_B200_HUBERFIT || kind == ADMM_B200_LAD;
+}
+static int uw_kind(int kind) {
+  return kind == ADMM_B200_SVM_HINGE ? UW_SVM_HINGE : kind == ADMM_B200_SVM_01 ? UW_SVM_01
+         : kind == ADMM_B200_HUBERFIT ? UW_HUBER : UW_LAD;
+}
+
+// ---------------------------------------------------------------------------------------------
 // the loop
 // ---------------------------------------------------------------------------------------------
 static LoopParams make_loop_params(admm_b200_handle* h, const admm_b200_options& o, int64_t maxiters, int raw) {
@@ -536,6 +745,15 @@ static void alloc_iterates(admm_b200_handle* h) {
   h->t1.ensure(big);
   h->t2.ensure(big);
   h->partials.ensure(2 * kNumSM * 16);
+  if (is_unwrapped(h->kind)) {
+    const int64_t need = 3 * round_up(h->n, 2) + 16;
+    if (h->cb.cap < need) {
+      h->cb.ensure(need);
+      ADMM_CUDA(cudaMemsetAsync(h->cb.p, 0, (size_t)need * 8, h->stream));
+    }
+    h->rvec.ensure(round_up(h->m, 2));
+    h->dzvec.ensure(round_up(h->m, 2));
+  }
 }
 
 static void load_init(admm_b200_handle* h) {
@@ -590,6 +808,52 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     prox_ident_kernel<<<prox_grid(n), PROX_THREADS, 0, h->stream>>>(a);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
+  } else if (is_unwrapped(h->kind)) {
+    const int64_t n = h->n, m = h->m, npad = round_up(n, 2);
+    const int nv = o.nodualerror ? 1 : 3;
+    double* d = h->cb.p;
+    double* scal = h->cb.p + (int64_t)nv * npad;
+    if (which != 2) {
+      // x = W \ d (unwrappedadmm.m:139) / Rt \ (R \ d) (getProxOps.m:1514), d summed over ranks
+      factor_solve(h, d, h->t1.p, h->x.p, o.xsolve, done);
+    }
+    if (which == 1) return;
+    UwArgs a;
+    a.D = h->dD; a.ld = h->ldD; a.m = m; a.n = n; a.x = h->x.p; a.z = h->z.p; a.u = h->u.p; a.aux = h->aux.p;
+    a.rvec = h->rvec.p; a.dzvec = (nv == 3) ? h->dzvec.p : nullptr;
+    a.rho = o.rho; a.relax = o.relax; a.C = h->svmC; a.kind = uw_kind(h->kind);
+    const int64_t rb = (m + UW_ROWS - 1) / UW_ROWS;
+    int64_t chunks = 1;
+    if (rb < 2 * kNumSM) chunks = std::min<int64_t>((4 * kNumSM + rb - 1) / rb, std::max<int64_t>(1, n / 16));
+    a.cols_per_chunk = (n + chunks - 1) / chunks;
+    chunks = (n + a.cols_per_chunk - 1) / a.cols_per_chunk;
+    if (chunks > 1) {
+      h->gemv_ws.ensure(chunks * m);
+      ensure_tickets(h, rb);
+    }
+    a.ws = h->gemv_ws.p; a.tickets = h->tickets;
+    h->uw_partials.ensure(rb * UW_NRED);
+    a.partials = h->uw_partials.p; a.grid_ticket = h->grid_ticket; a.scalars = scal; a.ctl = h->ctl;
+    a.zvals = history ? h->zvals.p : nullptr;
+    a.uvals = history ? h->uvals.p : nullptr;
+    dim3 grid((unsigned)rb, (unsigned)chunks);
+    const bool vec_ok = (((uintptr_t)h->dD & 15) == 0) && (h->ldD % 2 == 0);
+    if (vec_ok) uw_gemv_prox_kernel<2><<<grid, UW_THREADS, 0, h->stream>>>(a);
+    else uw_gemv_prox_kernel<1><<<grid, UW_THREADS, 0, h->stream>>>(a);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+    // D_g' * [rhs, z - zprev, u] in one pass
+    const double* vs[3] = {h->rvec.p, h->dzvec.p, h->u.p};
+    double* os[3] = {d, d + npad, d + 2 * npad};
+    coldot_multi(h, COLDOT_FULL, h->dD, h->ldD, m, n, nv, vs, os, 1.0, nullptr, 0.0, done);
+    allreduce_sum(h, d, (int64_t)nv * npad + UW_NRED);
+    UwEpiArgs e;
+    e.n = n; e.x = h->x.p; e.dzv = (nv == 3) ? d + npad : nullptr; e.duv = (nv == 3) ? d + 2 * npad : nullptr;
+    e.scalars = scal; e.m_total = (double)h->m_total; e.kind = a.kind; e.C = h->svmC; e.ctl = h->ctl; e.lp = lp;
+    e.xvals = history ? h->xvals.p : nullptr;
+    uw_epilogue_kernel<<<1, 256, 0, h->stream>>>(e);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
   } else {
     ADMM_REQUIRE(false, ADMM_B200_ERR_UNSUPPORTED, "problem kind %d has no iteration built yet", h->kind);
   }
@@ -602,6 +866,14 @@ static void enqueue_first_rhs(admm_b200_handle* h, const admm_b200_options& o) {
                                                                          NEXT_LASSO, h->y.p);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
+  } else if (is_unwrapped(h->kind)) {
+    const int64_t n = h->n, m = h->m;
+    uw_first_rhs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, h->z.p, h->u.p, h->aux.p, uw_kind(h->kind),
+                                                                            h->rvec.p);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+    coldot(h, COLDOT_FULL, h->dD, h->ldD, m, n, h->rvec.p, h->cb.p);
+    allreduce_sum(h, h->cb.p, round_up(n, 2));
   }
 }
 
@@ -609,6 +881,10 @@ static void validate_options(admm_b200_handle* h, const admm_b200_options& o) {
   ADMM_REQUIRE(h->kind != 0, ADMM_B200_ERR_STATE, "no problem set up on this handle");
   ADMM_REQUIRE(o.rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
   ADMM_REQUIRE(o.stopcond >= 0 && o.stopcond <= 2, ADMM_B200_ERR_INVALID, "invalid stopcond %d", o.stopcond);
+  if (h->kind == ADMM_B200_SVM_HINGE || h->kind == ADMM_B200_SVM_01)
+    ADMM_REQUIRE(o.relax == 1.0, ADMM_B200_ERR_INVALID,
+                 "Inner matrix dimensions must agree. (linearsvm with relax ~= 1: the reference's zminLinearSVM "
+                 "multiplies D (m x n) by the relaxed m-vector, getProxOps.m:1088, admm.m:521)");
   if (h->kind == ADMM_B200_LASSO)
     ADMM_REQUIRE(o.rho == h->rho_setup, ADMM_B200_ERR_INVALID,
                  "options.rho (%g) differs from the rho the factor was built with (%g); redo the setup", o.rho,
@@ -741,6 +1017,8 @@ int admm_b200_create(int device, admm_b200_handle** out) {
   ADMM_CUDA(cudaMalloc(&h->ctl, sizeof(LoopCtl)));
   ADMM_CUDA(cudaMemset(h->ctl, 0, sizeof(LoopCtl)));
   ADMM_CUDA(cudaMalloc(&h->fail, sizeof(int)));
+  ADMM_CUDA(cudaMalloc(&h->grid_ticket, sizeof(unsigned)));
+  ADMM_CUDA(cudaMemset(h->grid_ticket, 0, sizeof(unsigned)));
   ADMM_CUDA(cudaMallocHost(&h->h_ctl, sizeof(LoopCtl)));
   *out = h;
   ADMM_API_END
@@ -753,13 +1031,15 @@ int admm_b200_destroy(admm_b200_handle* h) {
   cudaStreamSynchronize(h->stream);
   DBuf* bufs[] = {&h->ownD, &h->s, &h->dts, &h->L, &h->W, &h->WT, &h->x, &h->z, &h->u, &h->y, &h->t1, &h->t2,
                   &h->x0, &h->z0, &h->u0, &h->partials, &h->hist, &h->xvals, &h->zvals, &h->uvals, &h->gemm_ws,
-                  &h->gemv_ws, &h->scratch};
+                  &h->gemv_ws, &h->scratch, &h->cd_ws, &h->aux, &h->rvec, &h->dzvec, &h->cb, &h->uw_partials};
   for (DBuf* b : bufs) b->release();
   for (ColdotPlan* p : h->plans) {
-    cudaFree(p->d_cta_col); cudaFree(p->d_col_item); cudaFree(p->d_items);
+    cudaFree(p->d_cta_pos); cudaFree(p->d_pos_item); cudaFree(p->d_order); cudaFree(p->d_items);
     delete p;
   }
   if (h->tickets) cudaFree(h->tickets);
+  if (h->grid_ticket) cudaFree(h->grid_ticket);
+  comm_destroy(h);
   if (h->ctl) cudaFree(h->ctl);
   if (h->fail) cudaFree(h->fail);
   if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -791,6 +1071,65 @@ int admm_b200_setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const doubl
   ADMM_API_BEGIN
   check_handle(h);
   setup_lasso(h, m, n, D, ldD, s, rho, xsolve);
+  ADMM_API_END
+}
+
+int admm_b200_setup_unwrapped(admm_b200_handle* h, int32_t kind, int64_t m_local, int64_t m_total, int64_t n,
+                              const double* D, int64_t ldD, const double* aux, double C) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  setup_unwrapped(h, kind, m_local, m_total, n, D, ldD, aux, C);
+  ADMM_API_END
+}
+
+int admm_b200_get_unique_id(void* out128) {
+  ADMM_API_BEGIN
+  ADMM_REQUIRE(out128 != nullptr, ADMM_B200_ERR_INVALID, "null output");
+  nccl_load();
+  NcclId id;
+  ADMM_NCCL(g_nccl.GetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+  ADMM_API_END
+}
+
+int admm_b200_comm_init(admm_b200_handle* h, int rank, int nranks, const void* unique_id128) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && unique_id128, ADMM_B200_ERR_INVALID, "comm_init: bad arguments");
+  comm_destroy(h);
+  if (nranks == 1) return ADMM_B200_OK;
+  nccl_load();
+  NcclId id;
+  memcpy(&id, unique_id128, sizeof(id));
+  void* comm = nullptr;
+  ADMM_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+  h->comm = comm;
+  h->rank = rank;
+  h->nranks = nranks;
+  ADMM_API_END
+}
+
+int admm_b200_comm_destroy(admm_b200_handle* h) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  comm_destroy(h);
+  ADMM_API_END
+}
+
+int admm_b200_allreduce(admm_b200_handle* h, double* buf, int64_t count) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(buf && count >= 0, ADMM_B200_ERR_INVALID, "allreduce: bad arguments");
+  if (admmb200::is_device_ptr(buf)) {
+    allreduce_sum(h, buf, count);
+  } else {
+    h->scratch.ensure(count);
+    copy_in(h, h->scratch.p, buf, count);
+    allreduce_sum(h, h->scratch.p, count);
+    copy_out(h, buf, h->scratch.p, count);
+  }
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
   ADMM_API_END
 }
 

@@ -27,6 +27,7 @@ struct GemmArgs {
   double* C; int64_t ldc;
   double alpha, beta, diag_add;
   int lower_only;
+  int a_lower, b_lower;   // op(A) / op(B) is lower triangular: restrict the K range per tile
   int batch; int64_t strideA, strideB, strideC;
   int splits; int64_t k_per_split; double* ws;   // ws: [batch][splits][M*N]
 };
@@ -90,8 +91,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
   const int batch = bz / p.splits, split = bz - batch * p.splits;
   const double* A = p.A + (int64_t)batch * p.strideA;
   const double* B = p.B + (int64_t)batch * p.strideB;
-  const int64_t kbeg = (int64_t)split * p.k_per_split;
-  const int64_t kend = min(p.K, kbeg + p.k_per_split);
+  int64_t kbeg = (int64_t)split * p.k_per_split;
+  int64_t kend = min(p.K, kbeg + p.k_per_split);
+  if (p.b_lower) kbeg = max(kbeg, n0);                      // op(B)[k][j] = 0 for k < j
+  if (p.a_lower) kend = min(kend, m0 + (int64_t)GEMM_BM);   // op(A)[i][k] = 0 for k > i
   const int nk = (int)((kend - kbeg + GEMM_BK - 1) / GEMM_BK);
 
   double* sA = smem;

@@ -1,13 +1,21 @@
-// tri.cuh -- the per-iteration x-update kernels: streaming products with a cached triangular
-// factor (getProxOps.m:1200,1204 `U \ (L \ y)`; :1514 `Rt \ (R \ .)`; unwrappedadmm.m:139 `W \ d`).
+// tri.cuh -- streaming "column dot" products: the per-iteration x-update with a cached triangular
+// factor (getProxOps.m:1200,1204 `U \ (L \ y)`; :1514 `Rt \ (R \ .)`; unwrappedadmm.m:139 `W \ d`)
+// and every transposed product D'*v on the path (lasso.m:160, getProxOps.m:1204,1514,
+// unwrappedadmm.m:116-121,133, admm.m:624,654).
 //
-// coldot_kernel computes out[j] = sum_{r in rows(j)} M[r + j*ld] * v[r] for every column j, where
-// rows(j) is [0,m) (FULL: a GEMV with the transpose), [j,n) (LOWER) or [0,j] (UPPER).
-// HBM-bound: every matrix byte is read exactly once with 16-byte streaming loads (16 of them in
-// flight per lane), v stays in L1/L2.  The host builds a PLAN once per shape: columns are split
-// between CTAs by equal AREA (not equal count) and every column into items of <= 1024 rows; a warp
-// takes one item at a time, item partials are combined per column in a fixed order, so the result
-// is bitwise reproducible and independent of scheduling.
+// coldot_kernel<NV> computes out_k[j] = sum_{r in rows(j)} M[r + j*ld] * v_k[r], k < NV, for every
+// column j, where rows(j) is [0,m) (FULL), [j,n) (LOWER) or [0,j] (UPPER).  NV = 3 shares one pass
+// over D between the three transposed products an iteration of the A = D problems needs.
+// HBM-bound: every matrix byte is read exactly once with 16-byte streaming loads (16 in flight per
+// lane), the vectors stay in L1/L2.  The host builds a PLAN once per shape:
+//   - tall FULL matrices are cut into P row panels (a "virtual column" = one column of one panel,
+//     panel results are summed in a fixed order by panel_reduce_kernel);
+//   - virtual columns are visited in a folded order (longest, shortest, 2nd longest, ...) so every
+//     CTA gets the same mix of long and short columns, and split between CTAs by equal cost;
+//   - every virtual column is cut into items of <= 1024 rows; warp w of a CTA takes items
+//     w, w+16, ... (a static map), keeps a running sum per column and parks it in a
+//     (column, warp) slot; slots are combined in a fixed order.
+// The result is therefore bitwise reproducible and independent of scheduling.
 #pragma once
 #include "common.cuh"
 
@@ -16,47 +24,73 @@ namespace admmb200 {
 enum { COLDOT_FULL = 0, COLDOT_LOWER = 1, COLDOT_UPPER = 2 };
 constexpr int COLDOT_ITEM = 1024;      // rows per item (16 x LDG.128 per lane)
 constexpr int COLDOT_THREADS = 512;
+constexpr int COLDOT_WARPS = COLDOT_THREADS / 32;
 
 struct ColdotItem {
-  int col;      // column index
+  int col;      // matrix column
   int row0;     // first row of the item
   int nrows;    // 1..COLDOT_ITEM
-  int pad;
+  int pos;      // position of its virtual column in the visiting order
 };
 
 struct ColdotArgs {
   const double* M; int64_t ld;    // ld must be even and M 16-byte aligned
-  const double* v;                // 16-byte aligned
-  double* out;
-  double scale;                   // out = scale * dot (+ addscale * addend[j])
+  const double* v[3];             // 16-byte aligned
+  double* out[3];                 // length = number of virtual columns (panel-major when P > 1)
+  double scale;                   // out = scale * dot (+ addscale * addend[j]); only with P == 1
   const double* addend; double addscale;
   const int* done;                // device stop flag (may be NULL): kernel exits when *done != 0
-  const int* cta_col;             // [grid+1] column range of each CTA
-  const int* col_item;            // [cols+1] item range of each column
+  const int* cta_pos;             // [grid+1] range of positions of each CTA
+  const int* pos_item;            // [nvcols+1] item range of each position
+  const int* order;               // [nvcols] position -> output index (virtual column)
   const ColdotItem* items;
 };
 
+template <int NV>
 __global__ void __launch_bounds__(COLDOT_THREADS, 1) coldot_kernel(ColdotArgs a) {
   if (a.done && *a.done) return;
-  extern __shared__ __align__(16) double partial[];   // one slot per item of this CTA
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int c0 = a.cta_col[blockIdx.x], c1 = a.cta_col[blockIdx.x + 1];
-  if (c1 <= c0) return;
-  const int it0 = a.col_item[c0], it1 = a.col_item[c1];
+  extern __shared__ __align__(16) double slots[];   // [npos_of_cta][NV][COLDOT_WARPS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int p0 = a.cta_pos[blockIdx.x], p1 = a.cta_pos[blockIdx.x + 1];
+  if (p1 <= p0) return;
+  const int it0 = a.pos_item[p0], it1 = a.pos_item[p1];
+  for (int i = tid; i < (p1 - p0) * NV * COLDOT_WARPS; i += COLDOT_THREADS) slots[i] = 0.0;
+  __syncthreads();
 
-  for (int item = it0 + warp; item < it1; item += nwarps) {
-    const ColdotItem d = a.items[item];
+  int item = it0 + warp;
+  ColdotItem dnext = (item < it1) ? a.items[item] : ColdotItem{0, 0, 0, 0};
+  int cur_pos = -1;
+  double run[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) run[k] = 0.0;
+  for (; item < it1; item += COLDOT_WARPS) {
+    const ColdotItem d = dnext;
+    if (item + COLDOT_WARPS < it1) dnext = a.items[item + COLDOT_WARPS];   // next descriptor, off the critical path
+    if (d.pos != cur_pos) {
+      if (cur_pos >= 0 && lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) slots[((cur_pos - p0) * NV + k) * COLDOT_WARPS + warp] = run[k];
+      }
+      cur_pos = d.pos;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) run[k] = 0.0;
+    }
     const double* col = a.M + (int64_t)d.col * a.ld;
     int r0 = d.row0;
     const int r1 = d.row0 + d.nrows;
-    double s0 = 0.0, s1 = 0.0;
+    double s0[NV], s1[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s0[k] = s1[k] = 0.0;
     if (r0 & 1) {  // ld even and bases 16B-aligned: address parity == row parity
-      if (lane == 0) s0 = __ldcs(col + r0) * __ldg(a.v + r0);
+      if (lane == 0) {
+        const double mval = __ldcs(col + r0);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s0[k] = mval * __ldg(a.v[k] + r0);
+      }
       r0 += 1;
     }
     const int nvec = (r1 - r0) >> 1;
     const double2* mp = reinterpret_cast<const double2*>(col + r0);
-    const double2* vp = reinterpret_cast<const double2*>(a.v + r0);
     double2 mv[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -64,28 +98,66 @@ __global__ void __launch_bounds__(COLDOT_THREADS, 1) coldot_kernel(ColdotArgs a)
       mv[i] = (idx < nvec) ? __ldcs(mp + idx) : make_double2(0.0, 0.0);
     }
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      int idx = lane + 32 * i;
-      if (idx < nvec) {
-        double2 vv = __ldg(vp + idx);
-        s0 = fma(mv[i].x, vv.x, s0);
-        s1 = fma(mv[i].y, vv.y, s1);
+    for (int k = 0; k < NV; ++k) {
+      const double2* vp = reinterpret_cast<const double2*>(a.v[k] + r0);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        int idx = lane + 32 * i;
+        if (idx < nvec) {
+          double2 vv = __ldg(vp + idx);
+          s0[k] = fma(mv[i].x, vv.x, s0[k]);
+          s1[k] = fma(mv[i].y, vv.y, s1[k]);
+        }
       }
     }
     if (((r1 - r0) & 1) && lane == 31) {
       int r = r1 - 1;
-      s1 = fma(__ldcs(col + r), __ldg(a.v + r), s1);
+      const double mval = __ldcs(col + r);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) s1[k] = fma(mval, __ldg(a.v[k] + r), s1[k]);
     }
-    double s = warp_sum(s0 + s1);
-    if (lane == 0) partial[item - it0] = s;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) run[k] += warp_sum(s0[k] + s1[k]);
+  }
+  if (cur_pos >= 0 && lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) slots[((cur_pos - p0) * NV + k) * COLDOT_WARPS + warp] = run[k];
   }
   __syncthreads();
-  for (int c = c0 + tid; c < c1; c += blockDim.x) {
+  for (int i = tid; i < (p1 - p0) * NV; i += COLDOT_THREADS) {
+    const int pos = p0 + i / NV, k = i % NV;
+    const double* sl = slots + (int64_t)i * COLDOT_WARPS;
     double s = 0.0;
-    for (int it = a.col_item[c]; it < a.col_item[c + 1]; ++it) s += partial[it - it0];
+#pragma unroll
+    for (int w = 0; w < COLDOT_WARPS; ++w) s += sl[w];
     s *= a.scale;
+    const int c = a.order[pos];
     if (a.addend) s += a.addscale * a.addend[c];
-    a.out[c] = s;
+    double* o = (k == 0) ? a.out[0] : (k == 1 ? a.out[1] : a.out[2]);
+    o[c] = s;
+  }
+}
+
+// out_k[j] = scale * sum_p ws_k[p*cols + j]  (fixed order), k < nv
+struct PanelReduceArgs {
+  const double* ws[3];
+  double* out[3];
+  int nv, panels;
+  int64_t cols;
+  double scale;
+  const int* done;
+};
+__global__ void panel_reduce_kernel(PanelReduceArgs a) {
+  if (a.done && *a.done) return;
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.cols) return;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    if (k < a.nv) {
+      double s = 0.0;
+      for (int p = 0; p < a.panels; ++p) s += a.ws[k][(int64_t)p * a.cols + j];
+      a.out[k][j] = a.scale * s;
+    }
   }
 }
 

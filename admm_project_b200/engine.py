@@ -25,6 +25,9 @@ class Engine:
         L.check(lib.admm_b200_create(int(device), C.byref(h)))
         self._lib, self._h, self.device = lib, h, int(device)
         self._keep = []
+        self.rank, self.nranks = 0, 1
+        self.m_total = None          # global row count of a row-sharded A = D problem
+        self.row_range = None        # (lo, hi) rows of this rank
 
     def close(self):
         if getattr(self, "_h", None):
@@ -71,6 +74,37 @@ class Engine:
         self._keep = [keep, sv]
         L.check(self._lib.admm_b200_setup_lasso(self._h, m, n, C.c_void_p(p), ld, L.ptr(sv), float(rho), int(xsolve)))
         return m, n
+
+    def setup_unwrapped(self, kind, D_local, aux_local, Cval=0.0, m_total=None):
+        """admm_b200_setup_unwrapped: D_local / aux_local are THIS rank's rows."""
+        p, m, n, ld, keep = self._matrix(D_local)
+        av = aux_local if isinstance(aux_local, (int, np.integer)) else L.fvec(aux_local, m, "ell / s")
+        self._keep = [keep, av]
+        self.m_total = int(m_total) if m_total is not None else m
+        L.check(self._lib.admm_b200_setup_unwrapped(self._h, int(kind), m, self.m_total, n, C.c_void_p(p), ld,
+                                                    L.ptr(av), float(Cval)))
+        return m, n
+
+    # -- row-sharded runs (one process per GPU) ---------------------------------------------------
+    def comm_init(self, rank, nranks, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        L.check(self._lib.admm_b200_comm_init(self._h, int(rank), int(nranks), buf))
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    def comm_destroy(self):
+        L.check(self._lib.admm_b200_comm_destroy(self._h))
+        self.rank, self.nranks = 0, 1
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * 128)()
+        L.check(L.load().admm_b200_get_unique_id(buf))
+        return bytes(buf.raw)
+
+    def allreduce(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        L.check(self._lib.admm_b200_allreduce(self._h, L.ptr(a), a.size))
+        return a
 
     def set_lambda(self, lam):
         L.check(self._lib.admm_b200_set_lambda(self._h, float(lam)))

@@ -6,8 +6,12 @@ and runs the WHOLE loop on the GPU -- a per-iteration host round trip would dest
 (SURVEY.md section 8b).  Calling a descriptor on the host raises: there is no CPU fallback."""
 from __future__ import annotations
 
-from ._lib import EngineError, ERR_UNSUPPORTED
+import numpy as np
+
+from ._lib import EngineError, ERR_UNSUPPORTED, SVM_HINGE, SVM_01, HUBERFIT, LAD
+from .engine import DeviceMatrix
 from .errorcheck import MatlabError
+from .parallel import attach_comm, row_range
 
 
 class EngineProx:
@@ -22,6 +26,31 @@ class EngineProx:
 
     def __repr__(self):
         return "<EngineProx %s/%s>" % (self.problem, self.name)
+
+
+def _need_engine(eng, problem):
+    if eng is None:
+        raise EngineError(ERR_UNSUPPORTED, "getproxops('%s'): args.engine is missing -- the operators are "
+                          "device-resident (there is no CPU path)" % problem)
+    return eng
+
+
+def _setup_rows(eng, kind, D, aux, C):
+    """One-time device setup of an A = D problem.  Under torch.distributed (world > 1) every rank
+    keeps only its row block of D / aux (errorcheck.m:249-259) and W = sum_g D_g'D_g is allreduced
+    (unwrappedadmm.m:114-122).  A DeviceMatrix is taken as THIS rank's rows already."""
+    rank, world = attach_comm(eng)
+    if isinstance(D, DeviceMatrix):
+        m_total = int(getattr(D, "m_total", D.shape[0]))
+        lo, hi = getattr(D, "row_range", (0, D.shape[0]))
+        eng.setup_unwrapped(kind, D, aux, C, m_total=m_total)
+    else:
+        D = np.asarray(D, dtype=np.float64)
+        m_total = D.shape[0]
+        lo, hi = row_range(m_total, rank, world)
+        aux = np.asarray(aux, dtype=np.float64).reshape(-1)
+        eng.setup_unwrapped(kind, D[lo:hi, :], aux[lo:hi], C, m_total=m_total)
+    eng.row_range = (lo, hi)
 
 
 _OUT = ("model", "linearprogram", "quadraticprogram", "covarianceselection")
@@ -47,9 +76,24 @@ def getproxops(problem, args):
         eng.set_lambda(args["lambda"])
         minx = EngineProx("xminf", "lasso", "xminLASSO", eng, dict(m=args["m"], n=args["n"], rho=args["rho"]))
         minz = EngineProx("zming", "lasso", "zminSoftThresholding", eng, {"lambda": args["lambda"]})
+    elif problem == "linearsvm":                                            # getProxOps.m:256-309
+        D, ell, C, loss = args["D"], args["ell"], args["C"], args["lossfunction"]
+        eng = _need_engine(eng, problem)
+        kind = SVM_01 if loss == "01" else SVM_HINGE      # strcmp(loss,'01') -- '0-1' is hinge (:1094)
+        _setup_rows(eng, kind, D, ell, C)
+        minx = EngineProx("xminf", "linearsvm", "xminLinearSVM", eng, {})  # Dplus*(z-u) == W\D'(z-u)
+        name = "zminParallelLinearSVM" if "slices" in args else "zminLinearSVM"
+        minz = EngineProx("zming", "linearsvm", name, eng, {"C": C, "lossfunction": loss})
+    elif problem in ("lad", "huberfit"):                                    # getProxOps.m:780-912
+        D, s_ = args["D"], args["s"]
+        eng = _need_engine(eng, problem)
+        _setup_rows(eng, LAD if problem == "lad" else HUBERFIT, D, s_, 0.0)
+        minx = EngineProx("xminf", problem, "xminLAD", eng, {})
+        minz = EngineProx("zming", problem, "zminSoftThresholding" if problem == "lad" else
+                          "zminHuberSoftThresholding", eng, {"userelax": int(bool(args.get("userelax", 0)))})
     elif problem in _OUT:
         raise EngineError(ERR_UNSUPPORTED, "problem '%s' is outside the engine's hot path (SURVEY.md section 2)" % problem)
-    elif problem in ("basispursuit", "totalvariation", "linearsvm", "lad", "huberfit"):
+    elif problem in ("basispursuit", "totalvariation"):
         raise EngineError(ERR_UNSUPPORTED, "problem '%s' is not built yet in this engine" % problem)
     else:
         raise MatlabError("Invalid input for problem - given string is not a solver!")

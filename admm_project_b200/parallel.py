@@ -1,0 +1,59 @@
+"""Host-side plumbing of the row-sharded solvers: one process per GPU, torch.distributed only as
+the bootstrap channel (it carries the 128-byte NCCL id and gathers result shards); the data-path
+collective -- ONE allreduce of [D'r ; D'dz ; D'u ; 8 scalars] per iteration -- is issued by
+libadmm_b200 itself on the handle's stream.
+
+Replaces the reference's PCT pool (gcp / parfor, admm.m:343-408; unwrappedadmm.m:45-74).  The row
+partition is the reference's own balancing rule (errorcheck.m:249-259)."""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import slicemaker
+
+
+def dist_info():
+    """(rank, world) of the default torch.distributed group, (0, 1) when not initialised."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def row_range(m, rank, world):
+    """Rows [lo, hi) of `rank`: first mod(m, w) ranks get floor(m/w)+1 rows (errorcheck.m:249-259)."""
+    sizes = slicemaker(m, world)
+    lo = int(sum(sizes[:rank]))
+    return lo, lo + int(sizes[rank])
+
+
+def attach_comm(engine):
+    """Create the engine's NCCL communicator over the default torch.distributed group: rank 0
+    makes the id, everybody receives it (works over gloo or nccl)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist_info()
+    if world == 1:
+        return rank, world
+    if engine.nranks == world and engine.rank == rank:
+        return rank, world
+    payload = [engine.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(payload, src=0)
+    engine.comm_init(rank, world, payload[0])
+    return rank, world
+
+
+def gather_rows(local, m_total):
+    """Concatenate the per-rank row shards of a vector (or the rows x K history of one) in rank order."""
+    rank, world = dist_info()
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, np.ascontiguousarray(local))
+    out = np.concatenate(parts, axis=0)
+    assert out.shape[0] == m_total, (out.shape, m_total)
+    return out

@@ -1,7 +1,7 @@
 /*
  * admm_b200.h -- C-ABI of libadmm_b200.so, a Blackwell (sm_100a) FP64 engine for the hot path of
  * PeterSutor/ADMM-Project: the scaled-dual ADMM loop of admm.m, the getProxOps.m proximal
- * operators and the one-time setup of solvers/*.m.
+ * operators and the one-time setup of solvers/<name>.m.
  *
  * This is the drop-in boundary.  Everything is plain C: column-major
  * `double*`, `int64_t` sizes, `int` status codes.  No torch / C++ types cross it.
@@ -130,11 +130,31 @@ int admm_b200_destroy(admm_b200_handle* h);
 int admm_b200_set_stream(admm_b200_handle* h, void* cuda_stream);
 int admm_b200_synchronize(admm_b200_handle* h);
 
-/* ---- one-time setup: solvers/*.m ------------------------------------------------------------ */
+/* ---- one-time setup: solvers/<name>.m ------------------------------------------------------------ */
 /* solvers/lasso.m:159-192: Dts = D'*s; L = chol(D'D + rho I,'lower') (m >= n) or
  * chol(DD'/rho + I,'lower') (m < n).  D is m x n, leading dimension ldD. */
 int admm_b200_setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD,
                           const double* s, double rho, int32_t xsolve);
+/* The A = D problems (constraint D*x - z = c): linear SVM by unwrapped ADMM / transpose reduction
+ * (solvers/unwrappedadmm.m:43-141, linearsvm.m:154-243; c = 0, aux = labels ell, C = regularisation),
+ * Huber fitting and least absolute deviations (huberfit.m:155-183, lad.m:123-151; c = aux = s).
+ * kind is ADMM_B200_SVM_HINGE / SVM_01 / HUBERFIT / LAD.  D holds THIS rank's m_local rows
+ * (errorcheck.m:249-259 partition, admm_b200_slicemaker); m_total is the global row count.
+ * W = sum over ranks of D_g'*D_g (unwrappedadmm.m:114-122) is allreduced when a communicator is
+ * attached, then R = chol(W,'lower') is cached on every rank (huberfit.m:166, lad.m:134). */
+int admm_b200_setup_unwrapped(admm_b200_handle* h, int32_t kind, int64_t m_local, int64_t m_total, int64_t n,
+                              const double* D, int64_t ldD, const double* aux, double C);
+
+/* Row-sharded runs, one process per GPU.  Rank 0 calls admm_b200_get_unique_id (128 bytes, an
+ * ncclUniqueId), the host side broadcasts it (torch.distributed / MPI / a file), every rank calls
+ * admm_b200_comm_init before the setup.  Replaces the PCT worker pool of the reference
+ * (gcp / parfor, admm.m:343-408, unwrappedadmm.m:45-74).  nranks == 1 detaches. */
+int admm_b200_get_unique_id(void* out128);
+int admm_b200_comm_init(admm_b200_handle* h, int rank, int nranks, const void* unique_id128);
+int admm_b200_comm_destroy(admm_b200_handle* h);
+/* In-place sum over ranks of `count` doubles (host or device pointer); no-op for a single rank. */
+int admm_b200_allreduce(admm_b200_handle* h, double* buf, int64_t count);
+
 /* getProxOps.m:455 -- lambda of the soft threshold; may be changed between solves without
  * redoing the setup (the factor does not depend on lambda). */
 int admm_b200_set_lambda(admm_b200_handle* h, double lambda);
