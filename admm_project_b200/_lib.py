@@ -58,6 +58,7 @@ SYMBOLS = {
     "admm_b200_synchronize": (_int, [_vp]),
     "admm_b200_setup_lasso": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _d, _i32]),
     "admm_b200_setup_unwrapped": (_int, [_vp, _i32, _i64, _i64, _i64, _vp, _i64, _vp, _d]),
+    "admm_b200_setup_basispursuit": (_int, [_vp, _i64, _i64, _vp, _i64, _vp]),
     "admm_b200_get_unique_id": (_int, [_vp]),
     "admm_b200_comm_init": (_int, [_vp, _int, _int, _vp]),
     "admm_b200_comm_destroy": (_int, [_vp]),
@@ -65,6 +66,8 @@ SYMBOLS = {
     "admm_b200_set_lambda": (_int, [_vp, _d]),
     "admm_b200_set_init": (_int, [_vp, _vp, _vp, _vp]),
     "admm_b200_solve": (_int, [_vp, C.POINTER(Options), C.POINTER(Result)]),
+    "admm_b200_solve_lasso_batch": (_int, [_vp, C.POINTER(Options), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           _vp, C.POINTER(C.c_double)]),
     "admm_b200_get_dims": (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "admm_b200_get_factor": (_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "admm_b200_dgemm": (_int, [_vp, _int, _int, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64, _int]),

@@ -171,7 +171,7 @@ struct GemmOpt {
   int batch = 1;
   int64_t strideA = 0, strideB = 0, strideC = 0;
   int allow_splitk = 1;
-  int a_lower = 0, b_lower = 0;
+  int a_lower = 0, b_lower = 0, a_upper = 0;
 };
 
 static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
@@ -183,7 +183,7 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
   g.alpha = alpha; g.beta = beta; g.diag_add = o.diag_add;
   g.lower_only = o.lower_only;
-  g.a_lower = o.a_lower; g.b_lower = o.b_lower;
+  g.a_lower = o.a_lower; g.b_lower = o.b_lower; g.a_upper = o.a_upper;
   g.batch = o.batch; g.strideA = o.strideA; g.strideB = o.strideB; g.strideC = o.strideC;
   g.splits = 1; g.k_per_split = std::max<int64_t>(K, 1); g.ws = nullptr;
   const int64_t tm = (M + GEMM_BM - 1) / GEMM_BM, tn = (N + GEMM_BN - 1) / GEMM_BN;
@@ -365,7 +365,12 @@ static ColdotPlan* coldot_plan(admm_b200_handle* h, int mode, int64_t rows, int6
   pl->mode = mode; pl->rows = rows; pl->cols = cols;
   // row panels for tall rectangular matrices: enough virtual columns to balance 148 CTAs
   int64_t P = 1;
-  if (mode == COLDOT_FULL && cols < 6000) P = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((6000 + cols - 1) / cols, 32), rows / 2048));
+  int64_t per = rows;   // rows per panel, a multiple of COLDOT_ITEM
+  if (mode == COLDOT_FULL && cols < 6000) {
+    P = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((6000 + cols - 1) / cols, 32), rows / 2048));
+    per = ((rows + P - 1) / P + COLDOT_ITEM - 1) / COLDOT_ITEM * COLDOT_ITEM;
+    P = (rows + per - 1) / per;   // no empty panels after rounding
+  }
   pl->panels = (int)P;
   const int64_t nv = P * cols;
   ADMM_REQUIRE(nv < (1LL << 31), ADMM_B200_ERR_UNSUPPORTED, "coldot: too many virtual columns");
@@ -376,7 +381,6 @@ static ColdotPlan* coldot_plan(admm_b200_handle* h, int mode, int64_t rows, int6
     if (mode == COLDOT_LOWER) { lo = j; hi = rows; }
     else if (mode == COLDOT_UPPER) { lo = 0; hi = j + 1; }
     else {
-      const int64_t per = ((rows + P - 1) / P + COLDOT_ITEM - 1) / COLDOT_ITEM * COLDOT_ITEM;
       lo = std::min(rows, p * per);
       hi = std::min(rows, (p + 1) * per);
     }
@@ -610,6 +614,42 @@ static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double*
   h->iter_ready = false;
 }
 
+// Basis pursuit (solvers/basispursuit.m:116-120): the reference caches the dense n x n projector
+// P = I - D'(DD')\D and q = D'((DD')\s) (8 GiB at n = 32768).  The engine caches only
+// L = chol(D*D') (m x m) and applies  x = P v + q = v - D'((DD') \ (D v - s))  per iteration.
+static void setup_bp(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD, const double* s) {
+  ADMM_REQUIRE(m > 0 && n > 0 && D && s && ldD >= m, ADMM_B200_ERR_INVALID, "basispursuit: bad dimensions or null input");
+  ADMM_REQUIRE(m < n, ADMM_B200_ERR_INVALID, "basispursuit: D must have fewer rows than columns");
+  ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
+  h->have_factor = false;
+  stage_matrix(h, m, n, D, ldD);
+  h->s.ensure(round_up(m, 2));
+  copy_in(h, h->s.p, s, m);
+  h->kind = ADMM_B200_BASISPURSUIT;
+  h->tall = false;
+  h->nA = h->nB = h->mc = n;
+  h->ldf = round_up(m, 16);
+  h->L.ensure(h->ldf * m);
+  GemmOpt o;
+  o.lower_only = 1;
+  gemm(h, 0, 1, m, m, n, 1.0, h->dD, h->ldD, h->dD, h->ldD, 0.0, h->L.p, h->ldf, o);   // D*D'  (basispursuit.m:116)
+  ADMM_CUDA(cudaEventRecord(h->evp[1], h->stream));
+  factor_current(h, m, true);
+  ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
+  ADMM_CUDA(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->setup_ms = h->phase_ms[3] = ms;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->evp[1]));
+  h->phase_ms[0] = ms;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->evp[1], h->evp[2]));
+  h->phase_ms[1] = ms;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->evp[2], h->ev1));
+  h->phase_ms[2] = ms;
+  h->have_init = false;
+  h->iter_ready = false;
+}
+
 // ---------------------------------------------------------------------------------------------
 // NCCL (loaded lazily with dlopen so single-GPU use needs no NCCL at all)
 // ---------------------------------------------------------------------------------------------
@@ -774,7 +814,30 @@ static void load_init(admm_b200_handle* h) {
 static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, int which,
                               bool history) {
   const int* done = &h->ctl->done;
-  if (h->kind == ADMM_B200_LASSO) {
+  if (h->kind == ADMM_B200_BASISPURSUIT) {
+    const int64_t n = h->n, m = h->m;
+    if (which != 2) {
+      // x = P(z-u) + q (getProxOps.m:1031) as v - D'((DD') \ (D v - s)), v = z - u in h->y
+      gemvn(h, h->dD, h->ldD, m, n, h->y.p, h->t1.p, 1.0, -1.0, h->s.p, done);
+      factor_solve(h, h->t1.p, h->t2.p, h->t1.p, o.xsolve, done);
+      coldot(h, COLDOT_FULL, h->dD, h->ldD, m, n, h->t1.p, h->x.p, -1.0, h->y.p, 1.0, done);
+    }
+    if (which == 1) return;
+    ProxIdentArgs a;
+    a.n = n; a.x = h->x.p; a.z = h->z.p; a.u = h->u.p; a.dts = nullptr; a.y = h->y.p;
+    a.lb = a.ub = nullptr;
+    a.thresh = 1.0 / o.rho;                      // getProxOps.m:142
+    a.objscale = 1.0;                            // obj = norm(x,1), basispursuit.m:140
+    a.kind = PROX_SOFT; a.next = NEXT_DIFF; a.obj_l1_of_x = 1;
+    a.partials = h->partials.p; a.ctl = h->ctl; a.lp = lp;
+    a.ld = 0; a.thresh_v = a.objscale_v = nullptr; a.hist_stride = 0; a.done_count = nullptr; a.xkeep = nullptr;
+    a.xvals = history ? h->xvals.p : nullptr;
+    a.zvals = history ? h->zvals.p : nullptr;
+    a.uvals = history ? h->uvals.p : nullptr;
+    prox_ident_kernel<<<prox_grid(n), PROX_THREADS, 0, h->stream>>>(a);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+  } else if (h->kind == ADMM_B200_LASSO) {
     const int64_t n = h->n, m = h->m;
     if (which != 2) {
       if (h->tall) {
@@ -802,6 +865,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     a.objscale = h->lambda;
     a.kind = PROX_SOFT; a.next = NEXT_LASSO; a.obj_l1_of_x = 0;
     a.partials = h->partials.p; a.ctl = h->ctl; a.lp = lp;
+    a.ld = 0; a.thresh_v = a.objscale_v = nullptr; a.hist_stride = 0; a.done_count = nullptr; a.xkeep = nullptr;
     a.xvals = history ? h->xvals.p : nullptr;
     a.zvals = history ? h->zvals.p : nullptr;
     a.uvals = history ? h->uvals.p : nullptr;
@@ -860,10 +924,11 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
 }
 
 static void enqueue_first_rhs(admm_b200_handle* h, const admm_b200_options& o) {
-  if (h->kind == ADMM_B200_LASSO) {
+  if (h->kind == ADMM_B200_LASSO || h->kind == ADMM_B200_BASISPURSUIT) {
     const int64_t n = h->n;
-    first_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, h->z.p, h->u.p, h->dts.p, o.rho,
-                                                                         NEXT_LASSO, h->y.p);
+    const bool bp = h->kind == ADMM_B200_BASISPURSUIT;
+    first_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, h->z.p, h->u.p, bp ? nullptr : h->dts.p, o.rho,
+                                                                         bp ? NEXT_DIFF : NEXT_LASSO, h->y.p);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
   } else if (is_unwrapped(h->kind)) {
@@ -958,6 +1023,120 @@ static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_res
     copy_out(h, res->uvals, h->uvals.p, h->mc * steps);
   }
   ADMM_CUDA(cudaStreamSynchronize(h->stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// regularisation path: nb lambda values on one cached factor (BASELINE.json configs[1]).  The two
+// triangular solves become two triangular DMMA GEMMs with nb right-hand sides (multi-RHS TRSM on
+// the inverse factor); every column runs admm.m's iteration with its own lambda and stop test.
+// ---------------------------------------------------------------------------------------------
+struct BatchOut {
+  int64_t* steps; int32_t* status;
+  double *xopt, *zopt, *uopt;                   // n x nb (ld = n)
+  double *pnorm, *dnorm, *perr, *derr, *objevals;  // maxiters x nb (ld = maxiters), may be NULL
+  double* loop_ms;
+};
+
+static void solve_lasso_batch(admm_b200_handle* h, const admm_b200_options& o, int64_t nb, const double* lambdas,
+                              const BatchOut& out) {
+  validate_options(h, o);
+  ADMM_REQUIRE(h->kind == ADMM_B200_LASSO && h->tall, ADMM_B200_ERR_UNSUPPORTED,
+               "lasso batch: only the tall (m >= n) lasso is built");
+  ADMM_REQUIRE(nb >= 1 && nb <= 4096 && lambdas, ADMM_B200_ERR_INVALID, "lasso batch: bad batch size or null lambdas");
+  ADMM_REQUIRE(!o.objevals, ADMM_B200_ERR_UNSUPPORTED, "lasso batch: objevals is not built for a batch");
+  const int64_t n = h->n, ld = round_up(n, 2);
+  const int64_t N = o.maxiters > 0 ? o.maxiters : 1000;
+  DBuf X, Z, U, Y, T, XK, hist, thr, osc, part;
+  LoopCtl* ctl = nullptr;
+  int* done_count = nullptr;
+  std::vector<double> hthr(nb), hosc(nb);
+  for (int64_t j = 0; j < nb; ++j) {
+    ADMM_REQUIRE(lambdas[j] >= 0, ADMM_B200_ERR_INVALID, "Argument lambda is not a nonnegative real number!");
+    hthr[j] = lambdas[j] / o.rho;
+    hosc[j] = lambdas[j];
+  }
+  auto cleanup = [&]() {
+    X.release(); Z.release(); U.release(); Y.release(); T.release(); XK.release(); hist.release(); thr.release(); osc.release();
+    part.release();
+    if (ctl) cudaFree(ctl);
+    if (done_count) cudaFree(done_count);
+  };
+  try {
+    X.ensure(ld * nb); Z.ensure(ld * nb); U.ensure(ld * nb); Y.ensure(ld * nb); T.ensure(ld * nb); XK.ensure(ld * nb);
+    hist.ensure(6 * N * nb); thr.ensure(nb); osc.ensure(nb);
+    const int pg = prox_grid(n);
+    part.ensure((int64_t)pg * PROX_NRED * nb);
+    ADMM_CUDA(cudaMalloc(&ctl, sizeof(LoopCtl) * nb));
+    ADMM_CUDA(cudaMalloc(&done_count, sizeof(int)));
+    ADMM_CUDA(cudaMemsetAsync(ctl, 0, sizeof(LoopCtl) * nb, h->stream));
+    ADMM_CUDA(cudaMemsetAsync(done_count, 0, sizeof(int), h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(thr.p, hthr.data(), nb * 8, cudaMemcpyHostToDevice, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(osc.p, hosc.data(), nb * 8, cudaMemcpyHostToDevice, h->stream));
+    ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
+    // x0 = z0 = u0 = 0 (admm.m:252-254) for every column  ->  y0 = Dts
+    ADMM_CUDA(cudaMemsetAsync(X.p, 0, (size_t)ld * nb * 8, h->stream));
+    ADMM_CUDA(cudaMemsetAsync(Z.p, 0, (size_t)ld * nb * 8, h->stream));
+    ADMM_CUDA(cudaMemsetAsync(U.p, 0, (size_t)ld * nb * 8, h->stream));
+    for (int64_t j = 0; j < nb; ++j)
+      ADMM_CUDA(cudaMemcpyAsync(Y.p + j * ld, h->dts.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    LoopParams lp = make_loop_params(h, o, N, 0);
+    lp.pnorm = hist.p; lp.dnorm = hist.p + N * nb; lp.perr = hist.p + 2 * N * nb; lp.derr = hist.p + 3 * N * nb;
+    lp.hn = hist.p + 4 * N * nb; lp.obj = hist.p + 5 * N * nb;
+    const int check = std::max(1, o.check_every);
+    int64_t enq = 0;
+    int hdone = 0;
+    while (true) {
+      const int64_t burst = std::min<int64_t>(check, N - enq);
+      for (int64_t c = 0; c < burst; ++c) {
+        GemmOpt g1;           // T = W * Y, W lower triangular
+        g1.a_lower = 1;
+        gemm(h, 0, 0, n, nb, n, 1.0, h->W.p, h->ldf, Y.p, ld, 0.0, T.p, ld, g1);
+        GemmOpt g2;           // X = W' * T, W' upper triangular (operand read K-major from W)
+        g2.a_upper = 1;
+        gemm(h, 1, 0, n, nb, n, 1.0, h->W.p, h->ldf, T.p, ld, 0.0, X.p, ld, g2);
+        ProxIdentArgs a;
+        a.n = n; a.x = X.p; a.z = Z.p; a.u = U.p; a.dts = h->dts.p; a.y = Y.p;
+        a.lb = a.ub = nullptr;
+        a.thresh = 0.0; a.objscale = 0.0;
+        a.kind = PROX_SOFT; a.next = NEXT_LASSO; a.obj_l1_of_x = 0;
+        a.partials = part.p; a.ctl = ctl; a.lp = lp;
+        a.xvals = a.zvals = a.uvals = nullptr;
+        a.ld = ld; a.thresh_v = thr.p; a.objscale_v = osc.p; a.hist_stride = N; a.done_count = done_count; a.xkeep = XK.p;
+        prox_ident_kernel<<<dim3(pg, (unsigned)nb), PROX_THREADS, 0, h->stream>>>(a);
+        ADMM_CUDA(cudaGetLastError());
+        h->launches++;
+      }
+      enq += burst;
+      ADMM_CUDA(cudaMemcpyAsync(&hdone, done_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      ADMM_CUDA(cudaStreamSynchronize(h->stream));
+      if (hdone >= nb || enq >= N) break;
+    }
+    ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
+    ADMM_CUDA(cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (out.loop_ms) *out.loop_ms = ms;
+    std::vector<LoopCtl> hc(nb);
+    ADMM_CUDA(cudaMemcpy(hc.data(), ctl, sizeof(LoopCtl) * nb, cudaMemcpyDeviceToHost));
+    for (int64_t j = 0; j < nb; ++j) {
+      if (out.steps) out.steps[j] = hc[j].it;
+      if (out.status) out.status[j] = hc[j].status;
+    }
+    auto mat_out = [&](double* dst, const double* src) {
+      if (dst) ADMM_CUDA(cudaMemcpy2DAsync(dst, (size_t)n * 8, src, (size_t)ld * 8, (size_t)n * 8, (size_t)nb, cudaMemcpyDefault, h->stream));
+    };
+    mat_out(out.xopt, XK.p); mat_out(out.zopt, Z.p); mat_out(out.uopt, U.p);
+    copy_out(h, out.pnorm, hist.p, N * nb);
+    copy_out(h, out.dnorm, hist.p + N * nb, N * nb);
+    copy_out(h, out.perr, hist.p + 2 * N * nb, N * nb);
+    copy_out(h, out.derr, hist.p + 3 * N * nb, N * nb);
+    ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  } catch (...) {
+    cudaStreamSynchronize(h->stream);
+    cleanup();
+    throw;
+  }
+  cleanup();
 }
 
 }  // namespace admmb200
@@ -1082,6 +1261,14 @@ int admm_b200_setup_unwrapped(admm_b200_handle* h, int32_t kind, int64_t m_local
   ADMM_API_END
 }
 
+int admm_b200_setup_basispursuit(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD,
+                                 const double* s) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  setup_bp(h, m, n, D, ldD, s);
+  ADMM_API_END
+}
+
 int admm_b200_get_unique_id(void* out128) {
   ADMM_API_BEGIN
   ADMM_REQUIRE(out128 != nullptr, ADMM_B200_ERR_INVALID, "null output");
@@ -1163,6 +1350,17 @@ int admm_b200_solve(admm_b200_handle* h, const admm_b200_options* opts, admm_b20
   check_handle(h);
   ADMM_REQUIRE(opts != nullptr, ADMM_B200_ERR_INVALID, "Given options is not a struct! At least pass empty struct!");
   solve(h, *opts, res);
+  ADMM_API_END
+}
+
+int admm_b200_solve_lasso_batch(admm_b200_handle* h, const admm_b200_options* opts, int64_t nb, const double* lambdas,
+                                int64_t* steps, int32_t* status, double* xopt, double* zopt, double* uopt,
+                                double* pnorm, double* dnorm, double* perr, double* derr, double* loop_ms) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(opts != nullptr, ADMM_B200_ERR_INVALID, "Given options is not a struct! At least pass empty struct!");
+  BatchOut out{steps, status, xopt, zopt, uopt, pnorm, dnorm, perr, derr, nullptr, loop_ms};
+  solve_lasso_batch(h, *opts, nb, lambdas, out);
   ADMM_API_END
 }
 

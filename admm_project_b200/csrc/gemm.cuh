@@ -28,6 +28,7 @@ struct GemmArgs {
   double alpha, beta, diag_add;
   int lower_only;
   int a_lower, b_lower;   // op(A) / op(B) is lower triangular: restrict the K range per tile
+  int a_upper;            // op(A) is upper triangular
   int batch; int64_t strideA, strideB, strideC;
   int splits; int64_t k_per_split; double* ws;   // ws: [batch][splits][M*N]
 };
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
   int64_t kend = min(p.K, kbeg + p.k_per_split);
   if (p.b_lower) kbeg = max(kbeg, n0);                      // op(B)[k][j] = 0 for k < j
   if (p.a_lower) kend = min(kend, m0 + (int64_t)GEMM_BM);   // op(A)[i][k] = 0 for k > i
+  if (p.a_upper) kbeg = max(kbeg, m0);                      // op(A)[i][k] = 0 for k < i
   const int nk = (int)((kend - kbeg + GEMM_BK - 1) / GEMM_BK);
 
   double* sA = smem;

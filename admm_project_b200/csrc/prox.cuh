@@ -52,6 +52,13 @@ struct ProxIdentArgs {
   LoopCtl* ctl;
   LoopParams lp;
   double *xvals, *zvals, *uvals;  // optional history (n x maxiters)
+  // batch of independent columns (regularisation path): blockIdx.y = column
+  int64_t ld;                     // column stride of x, z, u, y (0 for a single problem)
+  const double* thresh_v;         // per-column threshold (NULL: thresh)
+  const double* objscale_v;       // per-column objective scale (NULL: objscale)
+  int64_t hist_stride;            // per-column stride of the scalar histories
+  int* done_count;                // number of columns whose loop has ended (NULL for a single problem)
+  double* xkeep;                  // batch: x of the last iteration a column ran (the GEMMs keep overwriting x)
 };
 
 __device__ __forceinline__ double soft_threshold(double v, double t) {
@@ -117,8 +124,19 @@ __device__ inline void loop_epilogue(LoopCtl* ctl, const LoopParams& lp, const d
 }
 
 __global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs a) {
-  LoopCtl* ctl = a.ctl;
-  if (ctl->done) return;
+  const int col = blockIdx.y;
+  LoopCtl* ctl = a.ctl + col;
+  if (ctl->done) return;   // a column that has stopped is frozen
+  if (col > 0 || a.ld) {
+    const int64_t off = (int64_t)col * a.ld;
+    a.x += off; a.z += off; a.u += off; a.y += off;
+    if (a.xkeep) a.xkeep += off;
+    a.partials += (int64_t)col * gridDim.x * PROX_NRED;
+    const int64_t ho = (int64_t)col * a.hist_stride;
+    a.lp.pnorm += ho; a.lp.dnorm += ho; a.lp.perr += ho; a.lp.derr += ho; a.lp.hn += ho; a.lp.obj += ho;
+    if (a.thresh_v) a.thresh = a.thresh_v[col];
+    if (a.objscale_v) a.objscale = a.objscale_v[col];
+  }
   __shared__ double sh[(PROX_THREADS / 32) * PROX_NRED];
   __shared__ bool is_last;
   const double rho = a.lp.rho, relax = a.lp.relax;
@@ -139,6 +157,7 @@ __global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs 
     const double u = up + (xh + (-z) - 0.0);
     a.z[i] = z;
     a.u[i] = u;
+    if (a.xkeep) a.xkeep[i] = x;
     a.y[i] = (a.next == NEXT_LASSO) ? (rho * (z - u) + a.dts[i]) : (z - u);
     if (a.xvals) {
       a.xvals[(int64_t)it * a.n + i] = x;
@@ -184,6 +203,7 @@ __global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs 
     ctl->ticket = 0;
     const double obj = ctl->objpart + a.objscale * sh[6];
     loop_epilogue(ctl, a.lp, red, (double)a.n, (double)a.n, obj);
+    if (a.done_count && ctl->done) atomicAdd(a.done_count, 1);
   }
 }
 

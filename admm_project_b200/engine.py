@@ -85,6 +85,13 @@ class Engine:
                                                     L.ptr(av), float(Cval)))
         return m, n
 
+    def setup_basispursuit(self, D, s):
+        p, m, n, ld, keep = self._matrix(D)
+        sv = s if isinstance(s, (int, np.integer)) else L.fvec(s, m, "s")
+        self._keep = [keep, sv]
+        L.check(self._lib.admm_b200_setup_basispursuit(self._h, m, n, C.c_void_p(p), ld, L.ptr(sv)))
+        return m, n
+
     # -- row-sharded runs (one process per GPU) ---------------------------------------------------
     def comm_init(self, rank, nranks, unique_id):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
@@ -151,6 +158,24 @@ class Engine:
             out[name] = a[:k].copy()
         if hist is not None:
             out["xvals"], out["zvals"], out["uvals"] = (np.ascontiguousarray(a[:, :k]) for a in hist)
+        return out
+
+    def solve_lasso_batch(self, opts, lambdas, want_history=True):
+        """nb lasso problems (one per lambda) on the cached factor; returns per-column results."""
+        nA, _, _ = self.dims()
+        lam = L.fvec(lambdas)
+        nb = lam.size
+        N = int(opts.maxiters) if opts.maxiters > 0 else 1000
+        steps = np.zeros(nb, dtype=np.int64)
+        status = np.zeros(nb, dtype=np.int32)
+        X, Z, U = (np.zeros((nA, nb), order="F") for _ in range(3))
+        hist = [np.full((N, nb), np.nan, order="F") for _ in range(4)] if want_history else [None] * 4
+        ms = C.c_double()
+        L.check(self._lib.admm_b200_solve_lasso_batch(self._h, C.byref(opts), nb, L.ptr(lam), L.ptr(steps), L.ptr(status),
+                                                      L.ptr(X), L.ptr(Z), L.ptr(U), *(L.ptr(a) for a in hist), C.byref(ms)))
+        out = dict(steps=steps, status=status, xopt=X, zopt=Z, uopt=U, loop_ms=ms.value)
+        if want_history:
+            out.update(pnorm=hist[0], dnorm=hist[1], perr=hist[2], derr=hist[3])
         return out
 
     def iterate_raw(self, opts, which=0, reps=1):

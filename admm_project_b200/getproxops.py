@@ -76,6 +76,12 @@ def getproxops(problem, args):
         eng.set_lambda(args["lambda"])
         minx = EngineProx("xminf", "lasso", "xminLASSO", eng, dict(m=args["m"], n=args["n"], rho=args["rho"]))
         minz = EngineProx("zming", "lasso", "zminSoftThresholding", eng, {"lambda": args["lambda"]})
+    elif problem == "basispursuit":                                         # getProxOps.m:126-142
+        eng = _need_engine(eng, problem)
+        if "D" in args:                    # the engine keeps chol(D*D') instead of the dense projector P, q
+            eng.setup_basispursuit(args["D"], args["s"])
+        minx = EngineProx("xminf", "basispursuit", "xminBasisPursuit", eng, {})
+        minz = EngineProx("zming", "basispursuit", "zminSoftThresholding", eng, {})
     elif problem == "linearsvm":                                            # getProxOps.m:256-309
         D, ell, C, loss = args["D"], args["ell"], args["C"], args["lossfunction"]
         eng = _need_engine(eng, problem)
@@ -93,7 +99,7 @@ def getproxops(problem, args):
                           "zminHuberSoftThresholding", eng, {"userelax": int(bool(args.get("userelax", 0)))})
     elif problem in _OUT:
         raise EngineError(ERR_UNSUPPORTED, "problem '%s' is outside the engine's hot path (SURVEY.md section 2)" % problem)
-    elif problem in ("basispursuit", "totalvariation"):
+    elif problem in ("totalvariation",):
         raise EngineError(ERR_UNSUPPORTED, "problem '%s' is not built yet in this engine" % problem)
     else:
         raise MatlabError("Invalid input for problem - given string is not a solver!")

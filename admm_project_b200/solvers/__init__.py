@@ -4,3 +4,4 @@ from .lasso import lasso                       # noqa: F401
 from .unwrappedadmm import unwrappedadmm       # noqa: F401
 from .linearsvm import linearsvm               # noqa: F401
 from .robustfit import huberfit, lad           # noqa: F401
+from .basispursuit import basispursuit        # noqa: F401

@@ -145,6 +145,12 @@ int admm_b200_setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const doubl
 int admm_b200_setup_unwrapped(admm_b200_handle* h, int32_t kind, int64_t m_local, int64_t m_total, int64_t n,
                               const double* D, int64_t ldD, const double* aux, double C);
 
+/* solvers/basispursuit.m:116-120 (D is m x n with m < n): caches L = chol(D*D','lower') instead of
+ * the reference's dense n x n projector P and applies x = P(z-u) + q (getProxOps.m:1031) as
+ * v - D'((DD') \ (D v - s)). */
+int admm_b200_setup_basispursuit(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD,
+                                 const double* s);
+
 /* Row-sharded runs, one process per GPU.  Rank 0 calls admm_b200_get_unique_id (128 bytes, an
  * ncclUniqueId), the host side broadcasts it (torch.distributed / MPI / a file), every rank calls
  * admm_b200_comm_init before the setup.  Replaces the PCT worker pool of the reference
@@ -163,6 +169,16 @@ int admm_b200_set_init(admm_b200_handle* h, const double* x0, const double* z0, 
 
 /* ---- the loop: admm.m:496-767 ---------------------------------------------------------------- */
 int admm_b200_solve(admm_b200_handle* h, const admm_b200_options* opts, admm_b200_result* res);
+
+/* Regularisation path on one cached factor (BASELINE.json configs[1]: "a batch of 64 lambda values
+ * as multi-RHS TRSM"): nb independent lasso problems sharing D, s, rho, started from zeros.  Column
+ * j runs admm.m:496-767 with lambda[j] and its own stop test; a stopped column is frozen.  The
+ * x-update of all columns is two triangular FP64 DMMA GEMMs on the cached inverse factor.
+ * steps/status: nb entries; xopt/zopt/uopt: n x nb column-major; pnorm..derr: maxiters x nb
+ * (column j at offset j*maxiters) or NULL.  Tall lasso (m >= n) only. */
+int admm_b200_solve_lasso_batch(admm_b200_handle* h, const admm_b200_options* opts, int64_t nb, const double* lambdas,
+                                int64_t* steps, int32_t* status, double* xopt, double* zopt, double* uopt,
+                                double* pnorm, double* dnorm, double* perr, double* derr, double* loop_ms);
 
 /* Sizes of the current problem: nA (x), nB (z), m (u) -- admm.m:74-76. */
 int admm_b200_get_dims(admm_b200_handle* h, int64_t* nA, int64_t* nB, int64_t* m);

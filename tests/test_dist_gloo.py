@@ -1,0 +1,85 @@
+"""CPU, world_size 2, gloo: the host-side logic of the row-sharded path -- the reference's balanced
+partition (errorcheck.m:249-259), shard gathering, the NCCL-id bootstrap payload, and the algebra the
+device path relies on: one summed message [D_g'r ; D_g'dz ; D_g'u ; scalars] per iteration
+reproduces the serial iteration (unwrappedadmm.m:96-141)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import torch
+        import oracle
+        from admm_project_b200 import generators as gen
+        from admm_project_b200.parallel import dist_info, gather_rows, row_range
+        assert dist_info() == (rank, world)
+        m, n = 1001, 12
+        lo, hi = row_range(m, rank, world)
+        sizes = oracle.slicemaker(0, world, m)
+        assert hi - lo == sizes[rank] and lo == sum(sizes[:rank])
+        # shard gathering restores the reference's full-length vectors
+        v = np.arange(m, dtype=np.float64)
+        assert np.array_equal(gather_rows(v[lo:hi], m), v)
+        H = np.arange(3 * m, dtype=np.float64).reshape(m, 3)
+        assert np.array_equal(gather_rows(H[lo:hi], m), H)
+        # bootstrap payload travels like the 128-byte NCCL id does
+        payload = [bytes(range(128)) if rank == 0 else None]
+        dist.broadcast_object_list(payload, src=0)
+        assert payload[0] == bytes(range(128))
+        # the sharded iteration (what the device does) equals the serial oracle iteration
+        D, s, _ = gen.lad_problem(0, m, n)
+        ref = oracle.lad(D, s, {"history": 1, "maxiters": 15, "domaxiters": 1})
+        Dg, sg = D[lo:hi], s[lo:hi]
+        W = torch.from_numpy(Dg.T @ Dg)
+        dist.all_reduce(W)                                         # setup: allreduce of the Gram
+        R = np.linalg.cholesky(W.numpy())
+        z, u, rho = np.zeros(hi - lo), np.zeros(hi - lo), 1.0
+        msg = torch.from_numpy(np.concatenate([Dg.T @ (sg + z - u), np.zeros(1)]))
+        dist.all_reduce(msg)
+        for it in range(15):
+            d = msg.numpy()[:n]
+            x = np.linalg.solve(R.T, np.linalg.solve(R, d))
+            Ax = Dg @ x
+            znew = oracle.zminSoftThresholding(Ax + u - sg, 1 / rho)
+            u = u + (Ax - znew - sg)
+            z = znew
+            msg = torch.from_numpy(np.concatenate([Dg.T @ (sg + z - u), [np.sum((Ax - z - sg) ** 2)]]))
+            dist.all_reduce(msg)                                   # ONE message per iteration
+            assert np.allclose(x, ref["xvals"][:, it], rtol=1e-9, atol=1e-12)
+            assert abs(np.sqrt(msg.numpy()[n]) - ref["pnorm"][it]) <= 1e-9 * ref["pnorm"][it] + 1e-10
+        assert np.allclose(gather_rows(z, m), ref["zopt"], rtol=1e-9, atol=1e-12)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL " + traceback.format_exc()[-600:]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_host_logic_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+    got = sorted(q.get(timeout=5) for _ in range(2))
+    assert got == [(0, "ok"), (1, "ok")], got

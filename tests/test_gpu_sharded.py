@@ -1,0 +1,27 @@
+"""Row-sharded solvers on 2 GPUs (skipped on a 1-GPU box): the sharded run must reproduce the
+SERIAL oracle -- same steps, iterates within 1e-9."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("problem", ["svm", "huber", "lad"])
+def test_two_rank_run_matches_serial_oracle(problem):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "run_sharded.py"), "--check",
+           "--problem", problem, "--rows", "5001", "--cols", "64"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("SHARDED ")]
+    assert line, p.stdout[-2000:] + p.stderr[-2000:]
+    out = json.loads(line[-1][8:])
+    assert out["ok"], out
+    assert out["zopt_len"] == 5001

@@ -1,0 +1,71 @@
+"""Row-sharded A = D solvers under torchrun (one process per GPU): parity against the SERIAL oracle
+and timing.  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 \
+    --master-port 29511 tools/run_sharded.py [--check] [--bench] [--problem svm|huber|lad]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from admm_project_b200 import Engine, huberfit, lad, linearsvm  # noqa: E402
+from admm_project_b200 import generators as gen  # noqa: E402
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--problem", default="svm")
+    ap.add_argument("--rows", type=int, default=6001)
+    ap.add_argument("--cols", type=int, default=96)
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = Engine(local)
+    out = {"problem": args.problem, "world": world, "rows": args.rows, "cols": args.cols}
+    if args.problem == "svm":
+        D, ell = gen.svm_mnist_like(0, args.rows, args.cols, nclass=3)
+        D = D + 1e-3 * np.random.RandomState(1).randn(*D.shape)
+        aux = ell[:, 1]
+        opts = {"objevals": 1, "history": 0}
+        np.random.seed(3)
+        res = linearsvm(D, aux, 0.5, opts, engine=eng)
+        if args.check and rank == 0:
+            np.random.seed(3)
+            ref = __import__("oracle").linearsvm(D, aux, 0.5, opts)
+    else:
+        D, s, _ = (gen.huber_problem if args.problem == "huber" else gen.lad_problem)(0, args.rows, args.cols)
+        opts = {"objevals": 1, "convtest": 1, "history": 0, "relax": 1.5}
+        fn = huberfit if args.problem == "huber" else lad
+        res = fn(D, s, opts, engine=eng)
+        if args.check and rank == 0:
+            import oracle
+            ref = (oracle.huberfit if args.problem == "huber" else oracle.lad)(D, s, opts)
+    out["steps"] = res["steps"]
+    out["loop_ms"] = res["engine"]["loop_ms"]
+    out["zopt_len"] = int(res["zopt"].shape[0])
+    if args.check and rank == 0:
+        out["ref_steps"] = ref["steps"]
+        out["err_x"], out["err_z"], out["err_u"] = rel(res["xopt"], ref["xopt"]), rel(res["zopt"], ref["zopt"]), rel(res["uopt"], ref["uopt"])
+        out["err_pnorm"] = rel(res["pnorm"], ref["pnorm"])
+        out["err_obj"] = rel(res["objevals"], ref["objevals"])
+        out["ok"] = bool(res["steps"] == ref["steps"] and max(out["err_x"], out["err_z"], out["err_u"], out["err_pnorm"], out["err_obj"]) < 1e-9)
+    if rank == 0:
+        print("SHARDED " + json.dumps(out))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
