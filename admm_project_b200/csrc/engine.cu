@@ -16,6 +16,7 @@
 #include "prox.cuh"
 #include "tri.cuh"
 #include "unwrapped.cuh"
+#include "tv.cuh"
 #include <dlfcn.h>
 
 namespace admmb200 {
@@ -105,6 +106,10 @@ struct admm_b200_handle {
   unsigned* grid_ticket = nullptr;
   int64_t m_total = 0;
   double svmC = 0.0;
+  // total variation: double-buffered z/u, pivot table of the constant tridiagonal
+  DBuf zz, uu, tvtab;
+  int tv_par = 0, tv_ntab = 0, tv_halo = 0;
+  double tv_rho = -1.0;
   // row-sharded runs: one NCCL communicator per handle (one process per GPU)
   void* comm = nullptr;
   int rank = 0, nranks = 1;
@@ -650,6 +655,55 @@ static void setup_bp(admm_b200_handle* h, int64_t m, int64_t n, const double* D,
   h->iter_ready = false;
 }
 
+// Total variation (solvers/totalvariation.m:122-164): only s and lambda are data; the operator D
+// is implicit.  The pivot table depends on rho and is (re)built when the loop starts.
+static void setup_tv(admm_b200_handle* h, int64_t n, const double* s, double lambda) {
+  ADMM_REQUIRE(n > 0 && s, ADMM_B200_ERR_INVALID, "totalvariation: bad dimensions or null input");
+  ADMM_REQUIRE(lambda >= 0, ADMM_B200_ERR_INVALID, "Given lambda parameter is not a nonnegative number!");
+  h->have_factor = false;
+  h->kind = ADMM_B200_TOTALVARIATION;
+  h->m = h->n = n;
+  h->nA = h->nB = h->mc = n;
+  h->lambda = lambda;
+  h->s.ensure(round_up(n, 2));
+  copy_in(h, h->s.p, s, n);
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  h->setup_ms = 0.0;
+  h->tv_rho = -1.0;
+  h->have_init = false;
+  h->iter_ready = false;
+}
+
+static void tv_prepare(admm_b200_handle* h, double rho) {
+  const int64_t n = h->n;
+  h->zz.ensure(2 * n);
+  h->uu.ensure(2 * n);
+  if (h->tv_rho == rho) return;
+  // pivots of I + rho*D'D: delta_0 = 1 + rho, delta_i = 1 + 2 rho - rho^2/delta_{i-1}; contraction
+  std::vector<double> inv;
+  const int64_t cap = std::min<int64_t>(n, 1 << 18);
+  double d = 1.0 + rho;
+  inv.push_back(1.0 / d);
+  for (int64_t i = 1; i < cap; ++i) {
+    const double dn = (1.0 + 2.0 * rho) - rho * rho / d;
+    inv.push_back(1.0 / dn);
+    if (dn == d) break;
+    d = dn;
+  }
+  const double astar = rho * inv.back();       // forward/backward multiplier at the fixed point
+  int64_t K = (astar > 0.0) ? (int64_t)ceil(40.0 / -log(astar)) : 1;
+  K = round_up(std::max<int64_t>(K, 16), 16);
+  ADMM_REQUIRE(4 * K <= TV_SEG, ADMM_B200_ERR_UNSUPPORTED,
+               "totalvariation: rho = %g needs a %lld-element halo, more than the windowed tridiagonal solve carries",
+               rho, (long long)K);
+  h->tvtab.ensure((int64_t)inv.size());
+  ADMM_CUDA(cudaMemcpyAsync(h->tvtab.p, inv.data(), inv.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  h->tv_ntab = (int)inv.size();
+  h->tv_halo = (int)K;
+  h->tv_rho = rho;
+}
+
 // ---------------------------------------------------------------------------------------------
 // NCCL (loaded lazily with dlopen so single-GPU use needs no NCCL at all)
 // ---------------------------------------------------------------------------------------------
@@ -814,7 +868,41 @@ static void load_init(admm_b200_handle* h) {
 static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, int which,
                               bool history) {
   const int* done = &h->ctl->done;
-  if (h->kind == ADMM_B200_BASISPURSUIT) {
+  if (h->kind == ADMM_B200_TOTALVARIATION) {
+    const int64_t n = h->n;
+    static bool configured = false;
+    if (!configured) {
+      ADMM_CUDA(cudaFuncSetAttribute(tv_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TV_SMEM_BYTES));
+      configured = true;
+    }
+    const double* zc = h->zz.p + (int64_t)h->tv_par * n;
+    const double* uc = h->uu.p + (int64_t)h->tv_par * n;
+    if (which != 2) {
+      TvSolveArgs a;
+      a.n = n; a.s = h->s.p; a.z = zc; a.u = uc; a.x = h->x.p; a.rho = o.rho; a.invdelta = h->tvtab.p;
+      a.ntab = h->tv_ntab; a.halo = h->tv_halo; a.done = done;
+      const int64_t S = TV_SEG - 2 * h->tv_halo;
+      tv_solve_kernel<<<(unsigned)((n + S - 1) / S), TV_THREADS, TV_SMEM_BYTES, h->stream>>>(a);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+    }
+    if (which == 1) return;
+    TvProxArgs p;
+    p.n = n; p.x = h->x.p; p.s = h->s.p; p.z = zc; p.u = uc;
+    p.znew = h->zz.p + (int64_t)(1 - h->tv_par) * n;
+    p.unew = h->uu.p + (int64_t)(1 - h->tv_par) * n;
+    p.lambda = h->lambda;
+    const int grid = (int)std::min<int64_t>(4 * kNumSM, std::max<int64_t>(1, (n + TVP_THREADS * TVP_E - 1) / (TVP_THREADS * TVP_E)));
+    h->partials.ensure((int64_t)grid * 8);
+    p.partials = h->partials.p; p.ctl = h->ctl; p.lp = lp;
+    p.xvals = history ? h->xvals.p : nullptr;
+    p.zvals = history ? h->zvals.p : nullptr;
+    p.uvals = history ? h->uvals.p : nullptr;
+    tv_prox_kernel<<<grid, TVP_THREADS, 0, h->stream>>>(p);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+    h->tv_par ^= 1;
+  } else if (h->kind == ADMM_B200_BASISPURSUIT) {
     const int64_t n = h->n, m = h->m;
     if (which != 2) {
       // x = P(z-u) + q (getProxOps.m:1031) as v - D'((DD') \ (D v - s)), v = z - u in h->y
@@ -931,6 +1019,12 @@ static void enqueue_first_rhs(admm_b200_handle* h, const admm_b200_options& o) {
                                                                          bp ? NEXT_DIFF : NEXT_LASSO, h->y.p);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
+  } else if (h->kind == ADMM_B200_TOTALVARIATION) {
+    const int64_t n = h->n;
+    tv_prepare(h, o.rho);
+    h->tv_par = 0;
+    ADMM_CUDA(cudaMemcpyAsync(h->zz.p, h->z.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(h->uu.p, h->u.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
   } else if (is_unwrapped(h->kind)) {
     const int64_t n = h->n, m = h->m;
     uw_first_rhs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, h->z.p, h->u.p, h->aux.p, uw_kind(h->kind),
@@ -997,6 +1091,12 @@ static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_res
   ADMM_CUDA(cudaEventSynchronize(h->ev1));
   float ms = 0;
   ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  if (h->kind == ADMM_B200_TOTALVARIATION) {   // the last iteration that ran wrote half (steps mod 2)
+    const int64_t half = h->h_ctl->it % 2, n = h->n;
+    ADMM_CUDA(cudaMemcpyAsync(h->z.p, h->zz.p + half * n, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(h->u.p, h->uu.p + half * n, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    h->tv_par = (int)half;
+  }
   if (!res) return;
   const int64_t steps = h->h_ctl->it;
   res->steps = steps;
@@ -1210,7 +1310,7 @@ int admm_b200_destroy(admm_b200_handle* h) {
   cudaStreamSynchronize(h->stream);
   DBuf* bufs[] = {&h->ownD, &h->s, &h->dts, &h->L, &h->W, &h->WT, &h->x, &h->z, &h->u, &h->y, &h->t1, &h->t2,
                   &h->x0, &h->z0, &h->u0, &h->partials, &h->hist, &h->xvals, &h->zvals, &h->uvals, &h->gemm_ws,
-                  &h->gemv_ws, &h->scratch, &h->cd_ws, &h->aux, &h->rvec, &h->dzvec, &h->cb, &h->uw_partials};
+                  &h->gemv_ws, &h->scratch, &h->cd_ws, &h->aux, &h->rvec, &h->dzvec, &h->cb, &h->uw_partials, &h->zz, &h->uu, &h->tvtab};
   for (DBuf* b : bufs) b->release();
   for (ColdotPlan* p : h->plans) {
     cudaFree(p->d_cta_pos); cudaFree(p->d_pos_item); cudaFree(p->d_order); cudaFree(p->d_items);
@@ -1266,6 +1366,13 @@ int admm_b200_setup_basispursuit(admm_b200_handle* h, int64_t m, int64_t n, cons
   ADMM_API_BEGIN
   check_handle(h);
   setup_bp(h, m, n, D, ldD, s);
+  ADMM_API_END
+}
+
+int admm_b200_setup_totalvariation(admm_b200_handle* h, int64_t n, const double* s, double lambda) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  setup_tv(h, n, s, lambda);
   ADMM_API_END
 }
 

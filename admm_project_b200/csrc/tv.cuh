@@ -1,0 +1,281 @@
+// tv.cuh -- 1-D total variation denoising (solvers/totalvariation.m:122-164, getProxOps.m:172-199,
+// xminTotalVariation :1044-1048).  Constraint D*x - z = 0 with the sparse difference operator
+// (D x)_i = x_i - x_{i+1} (i < n), (D x)_n = x_n.
+//
+// x-update: (I + rho*D'D) x = s + rho*D'(z - u).  The reference rebuilds and factorises the sparse
+// matrix every iteration (:1047); the matrix is the constant tridiagonal  diag = [1+rho, 1+2rho, ...],
+// off-diagonal -rho, so the engine runs the Thomas recurrences as two block-parallel affine scans
+//   forward :  y_i = r_i + (rho/delta_{i-1}) y_{i-1}        delta_i = t_i - rho^2/delta_{i-1}
+//   backward:  x_i = (y_i + rho x_{i+1}) / delta_i
+// in ONE kernel: each CTA owns a segment and starts both recurrences K elements outside it; the
+// recurrences are contractions (rho/delta < 1), so the influence of the unknown carry decays as
+// (rho/delta*)^K and K is chosen for < 4e-18.  1/delta_i comes from a host-built table (the pivot
+// sequence reaches its fixed point after a few dozen to a few thousand entries).
+// z/u pass: tv_prox_kernel fuses D*x, the relaxed soft threshold, the u-update and every norm
+// (including the D' stencils of the dual residual) into one sweep.
+#pragma once
+#include "common.cuh"
+#include "prox.cuh"
+
+namespace admmb200 {
+
+constexpr int TV_THREADS = 512;
+constexpr int TV_E = 16;                         // consecutive elements per thread
+constexpr int TV_SEG = TV_THREADS * TV_E;        // 8192 elements per CTA (segment + both halos)
+__host__ __device__ constexpr int TV_PAD(int i) { return i + (i >> 4); }
+constexpr int TV_SMEM_DOUBLES = TV_SEG + (TV_SEG >> 4) + 32;
+constexpr int TV_SMEM_BYTES = 2 * TV_SMEM_DOUBLES * 8 + 64 * 8 * 2;
+
+struct TvSolveArgs {
+  int64_t n;
+  const double *s, *z, *u;
+  double* x;
+  double rho;
+  const double* invdelta;   // table of 1/delta_i, i < ntab; beyond: invdelta[ntab-1]
+  int ntab;
+  int halo;                 // K
+  const int* done;
+};
+
+struct Affine { double A, B; };   // v -> A*v + B
+__device__ __forceinline__ Affine compose(const Affine& second, const Affine& first) {
+  return Affine{second.A * first.A, fma(second.A, first.B, second.B)};
+}
+
+// inclusive scan of per-thread affine maps over the CTA, returns the map of all threads BEFORE this
+// one (exclusive prefix) applied to a zero carry, i.e. the carry-in value of this thread.
+__device__ __forceinline__ double block_affine_carry(Affine mine, double* shA, double* shB) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Affine inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double pa = __shfl_up_sync(0xffffffffu, inc.A, d);
+    const double pb = __shfl_up_sync(0xffffffffu, inc.B, d);
+    if (lane >= d) inc = compose(inc, Affine{pa, pb});
+  }
+  if (lane == 31) { shA[warp] = inc.A; shB[warp] = inc.B; }
+  __syncthreads();
+  if (warp == 0) {
+    Affine w = (lane < TV_THREADS / 32) ? Affine{shA[lane], shB[lane]} : Affine{1.0, 0.0};
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double pa = __shfl_up_sync(0xffffffffu, w.A, d);
+      const double pb = __shfl_up_sync(0xffffffffu, w.B, d);
+      if (lane >= d) w = compose(w, Affine{pa, pb});
+    }
+    if (lane < TV_THREADS / 32) { shA[32 + lane] = w.A; shB[32 + lane] = w.B; }
+  }
+  __syncthreads();
+  // exclusive prefix of this thread: (inclusive of previous lane) after (inclusive of previous warps)
+  const double pa = __shfl_up_sync(0xffffffffu, inc.A, 1);
+  const double pb = __shfl_up_sync(0xffffffffu, inc.B, 1);
+  Affine excl = (lane > 0) ? Affine{pa, pb} : Affine{1.0, 0.0};
+  if (warp > 0) excl = compose(excl, Affine{shA[32 + warp - 1], shB[32 + warp - 1]});
+  __syncthreads();
+  return excl.B;   // carry-in of the whole CTA is 0
+}
+
+__global__ void __launch_bounds__(TV_THREADS, 1) tv_solve_kernel(TvSolveArgs a) {
+  if (a.done && *a.done) return;
+  extern __shared__ __align__(16) double sm[];
+  double* bufA = sm;                         // w = z - u, later y, later x
+  double* bufB = sm + TV_SMEM_DOUBLES;       // s
+  double* shA = sm + 2 * TV_SMEM_DOUBLES;    // 64 doubles
+  double* shB = shA + 64;
+  const int tid = threadIdx.x;
+  const int64_t S = TV_SEG - 2 * a.halo;                  // outputs per CTA
+  const int64_t out0 = (int64_t)blockIdx.x * S;
+  const int64_t g0 = out0 - a.halo;                       // global index of local element 0 (may be < 0)
+  const double rho = a.rho;
+
+  // coalesced load of w = z - u (with one extra element on the left) and s
+  for (int j = tid; j < TV_SEG + 1; j += TV_THREADS) {
+    const int64_t i = g0 + j - 1;                         // local slot j holds global i = g0 + j - 1
+    double w = 0.0;
+    if (i >= 0 && i < a.n) w = a.z[i] - a.u[i];
+    bufA[TV_PAD(j)] = w;
+  }
+  for (int j = tid; j < TV_SEG; j += TV_THREADS) {
+    const int64_t i = g0 + j;
+    bufB[TV_PAD(j)] = (i >= 0 && i < a.n) ? a.s[i] : 0.0;
+  }
+  __syncthreads();
+
+  auto invd = [&](int64_t i) -> double {                  // 1/delta_i
+    return a.invdelta[i < a.ntab ? i : a.ntab - 1];
+  };
+
+  // ---- forward: y_i = r_i + fa_i * y_{i-1},  fa_i = rho/delta_{i-1} (0 at i = 0 and outside [0,n))
+  double r[TV_E], fa[TV_E];
+  const int j0 = tid * TV_E;
+#pragma unroll
+  for (int e = 0; e < TV_E; ++e) {
+    const int j = j0 + e;
+    const int64_t i = g0 + j;
+    const bool in = (i >= 0 && i < a.n);
+    const double w = bufA[TV_PAD(j + 1)], wl = bufA[TV_PAD(j)];   // w_i, w_{i-1} (w_{-1} = 0)
+    r[e] = in ? fma(rho, w - wl, bufB[TV_PAD(j)]) : 0.0;           // s + rho*D'(z-u), totalvariation.m / :1047
+    fa[e] = (in && i > 0) ? rho * invd(i - 1) : 0.0;
+  }
+  Affine m{1.0, 0.0};
+#pragma unroll
+  for (int e = 0; e < TV_E; ++e) m = Affine{fa[e] * m.A, fma(fa[e], m.B, r[e])};
+  __syncthreads();   // everyone has read bufA/bufB
+  double carry = block_affine_carry(m, shA, shB);
+#pragma unroll
+  for (int e = 0; e < TV_E; ++e) {
+    carry = fma(fa[e], carry, r[e]);
+    bufA[TV_PAD(j0 + e)] = carry;                        // y_i at local slot j
+  }
+  __syncthreads();
+
+  // ---- backward: x_i = invd_i*y_i + (rho*invd_i) * x_{i+1}, scanned over reversed local order
+  double bb[TV_E], ba[TV_E];
+#pragma unroll
+  for (int e = 0; e < TV_E; ++e) {
+    const int j = TV_SEG - 1 - (j0 + e);
+    const int64_t i = g0 + j;
+    const bool in = (i >= 0 && i < a.n);
+    const double id = in ? invd(i) : 0.0;
+    bb[e] = id * bufA[TV_PAD(j)];
+    ba[e] = (in && i < a.n - 1) ? rho * id : 0.0;
+  }
+  Affine mb{1.0, 0.0};
+#pragma unroll
+  for (int e = 0; e < TV_E; ++e) mb = Affine{ba[e] * mb.A, fma(ba[e], mb.B, bb[e])};
+  __syncthreads();
+  carry = block_affine_carry(mb, shA, shB);
+#pragma unroll
+  for (int e = 0; e < TV_E; ++e) {
+    carry = fma(ba[e], carry, bb[e]);
+    bufB[TV_PAD(TV_SEG - 1 - (j0 + e))] = carry;         // x_i
+  }
+  __syncthreads();
+  for (int j = a.halo + tid; j < a.halo + S; j += TV_THREADS) {
+    const int64_t i = g0 + j;
+    if (i < a.n) a.x[i] = bufB[TV_PAD(j)];
+  }
+}
+
+constexpr int TVP_THREADS = 256;
+constexpr int TVP_E = 4;
+
+struct TvProxArgs {
+  int64_t n;
+  const double *x, *s;
+  const double *z, *u;     // current iterates (read by neighbours too, hence double-buffered)
+  double *znew, *unew;
+  double lambda;
+  double* partials;     // [gridDim.x][8]
+  LoopCtl* ctl;
+  LoopParams lp;
+  double *xvals, *zvals, *uvals;
+};
+
+// (D v)_i for v given by a callable
+#define TV_D(vi, vip1, i, n) (((i) < (n) - 1) ? ((vi) - (vip1)) : (vi))
+
+__global__ void __launch_bounds__(TVP_THREADS) tv_prox_kernel(TvProxArgs a) {
+  LoopCtl* ctl = a.ctl;
+  if (ctl->done) return;
+  __shared__ double sh[(TVP_THREADS / 32) * 8];
+  __shared__ bool is_last;
+  const int it = ctl->it;
+  const double rho = a.lp.rho, relax = a.lp.relax, thr = a.lambda / rho;
+  const int64_t n = a.n;
+  double r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = 0.0;
+
+  // new (z, u) of element i from the OLD iterates; needs x_i..x_{i+2}, zprev_i, zprev_{i+1}, u_i
+  auto update = [&](int64_t i, double& znew, double& unew, double& Dx, double& zp, double& up) {
+    const double x0 = a.x[i], x1 = (i + 1 < n) ? a.x[i + 1] : 0.0;
+    Dx = TV_D(x0, x1, i, n);
+    zp = a.z[i];
+    up = a.u[i];
+    double Axh = Dx, w;
+    if (relax != 1.0) {
+      // admm.m:517 Axhat = relax*A(x) - (1-relax)*(B(zprev) - c); the z-prox then applies D to the
+      // vector in x's slot (getProxOps.m:199 `u + D*x` with x := Axhat, admm.m:521)
+      Axh = relax * Dx - (1.0 - relax) * (-zp - 0.0);
+      double Axh1 = 0.0;
+      if (i + 1 < n) {
+        const double x2 = (i + 2 < n) ? a.x[i + 2] : 0.0;
+        const double Dx1 = TV_D(x1, x2, i + 1, n);
+        Axh1 = relax * Dx1 - (1.0 - relax) * (-a.z[i + 1] - 0.0);
+      }
+      w = up + TV_D(Axh, Axh1, i, n);
+    } else {
+      w = up + Dx;
+    }
+    znew = soft_threshold(w, thr);
+    unew = up + (Axh + (-znew) - 0.0);
+  };
+
+  for (int64_t base = ((int64_t)blockIdx.x * TVP_THREADS + threadIdx.x) * TVP_E; base < n;
+       base += (int64_t)gridDim.x * TVP_THREADS * TVP_E) {
+    // left neighbour (element base-1) recomputed for the D' stencils of the dual residual
+    double zl = 0.0, ul = 0.0, dzl = 0.0;
+    if (base > 0) {
+      double Dx, zp, up;
+      update(base - 1, zl, ul, Dx, zp, up);
+      dzl = zl - zp;
+    }
+    double zn[TVP_E], un[TVP_E];
+#pragma unroll
+    for (int e = 0; e < TVP_E; ++e) {
+      const int64_t i = base + e;
+      if (i >= n) break;
+      double Dx, zp, up;
+      update(i, zn[e], un[e], Dx, zp, up);
+      const double dz = zn[e] - zp, du = un[e] - up;
+      const double pr = Dx + (-zn[e]) - 0.0;
+      const double dtdz = rho * ((i > 0) ? (dz - dzl) : dz);          // rho*At(B(z-zprev)) up to sign
+      const double dtu = rho * ((i > 0) ? (un[e] - ul) : un[e]);      // rho*At(u)
+      const double xs = a.x[i] - a.s[i];
+      r[0] = fma(pr, pr, r[0]);
+      r[1] = fma(Dx, Dx, r[1]);
+      r[2] = fma(zn[e], zn[e], r[2]);
+      r[3] = fma(dtdz, dtdz, r[3]);
+      r[4] = fma(dtu, dtu, r[4]);
+      r[5] = fma(dz, dz, r[5]);
+      r[6] = fma(du, du, r[6]);
+      r[7] += 0.5 * xs * xs + ((i < n - 1) ? a.lambda * fabs(Dx) : 0.0);   // totalvariation.m objective
+      dzl = dz; zl = zn[e]; ul = un[e];
+      if (a.xvals) a.xvals[(int64_t)it * n + i] = a.x[i];
+    }
+    // neighbouring threads read the OLD values of these elements: the new iterate goes to the other
+    // half of the double buffer
+#pragma unroll
+    for (int e = 0; e < TVP_E; ++e) {
+      const int64_t i = base + e;
+      if (i >= n) break;
+      a.znew[i] = zn[e];
+      a.unew[i] = un[e];
+      if (a.zvals) { a.zvals[(int64_t)it * n + i] = zn[e]; a.uvals[(int64_t)it * n + i] = un[e]; }
+    }
+  }
+  block_reduce_store<8>(r, a.partials + (int64_t)blockIdx.x * 8, sh);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(&ctl->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < 8) {
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(a.partials + (int64_t)b * 8 + threadIdx.x);
+    sh[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double red[8] = {sh[0], sh[1], sh[2], 0.0, sh[3], sh[4], sh[5], sh[6]};
+    ctl->ticket = 0;
+    loop_epilogue(ctl, a.lp, red, (double)n, (double)n, sh[7]);
+  }
+}
+
+}  // namespace admmb200

@@ -92,6 +92,12 @@ class Engine:
         L.check(self._lib.admm_b200_setup_basispursuit(self._h, m, n, C.c_void_p(p), ld, L.ptr(sv)))
         return m, n
 
+    def setup_totalvariation(self, s, lam):
+        sv = L.fvec(s)
+        self._keep = [sv]
+        L.check(self._lib.admm_b200_setup_totalvariation(self._h, sv.size, L.ptr(sv), float(lam)))
+        return sv.size
+
     # -- row-sharded runs (one process per GPU) ---------------------------------------------------
     def comm_init(self, rank, nranks, unique_id):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))

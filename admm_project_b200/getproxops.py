@@ -82,6 +82,11 @@ def getproxops(problem, args):
             eng.setup_basispursuit(args["D"], args["s"])
         minx = EngineProx("xminf", "basispursuit", "xminBasisPursuit", eng, {})
         minz = EngineProx("zming", "basispursuit", "zminSoftThresholding", eng, {})
+    elif problem == "totalvariation":                                       # getProxOps.m:172-199
+        eng = _need_engine(eng, problem)
+        eng.setup_totalvariation(args["s"], args["lambda"])      # D, Dt, DtD stay implicit on the device
+        minx = EngineProx("xminf", "totalvariation", "xminTotalVariation", eng, {})
+        minz = EngineProx("zming", "totalvariation", "zminSoftThresholding", eng, {"lambda": args["lambda"]})
     elif problem == "linearsvm":                                            # getProxOps.m:256-309
         D, ell, C, loss = args["D"], args["ell"], args["C"], args["lossfunction"]
         eng = _need_engine(eng, problem)
@@ -99,8 +104,6 @@ def getproxops(problem, args):
                           "zminHuberSoftThresholding", eng, {"userelax": int(bool(args.get("userelax", 0)))})
     elif problem in _OUT:
         raise EngineError(ERR_UNSUPPORTED, "problem '%s' is outside the engine's hot path (SURVEY.md section 2)" % problem)
-    elif problem in ("totalvariation",):
-        raise EngineError(ERR_UNSUPPORTED, "problem '%s' is not built yet in this engine" % problem)
     else:
         raise MatlabError("Invalid input for problem - given string is not a solver!")
     return minx, minz, extra

@@ -5,3 +5,4 @@ from .unwrappedadmm import unwrappedadmm       # noqa: F401
 from .linearsvm import linearsvm               # noqa: F401
 from .robustfit import huberfit, lad           # noqa: F401
 from .basispursuit import basispursuit        # noqa: F401
+from .totalvariation import totalvariation    # noqa: F401

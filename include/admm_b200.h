@@ -151,6 +151,11 @@ int admm_b200_setup_unwrapped(admm_b200_handle* h, int32_t kind, int64_t m_local
 int admm_b200_setup_basispursuit(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD,
                                  const double* s);
 
+/* solvers/totalvariation.m:122-164: 1-D total variation denoising of s (length n) with the implicit
+ * difference operator D = spdiags([1 -1],0:1,n,n).  The x-update (getProxOps.m:1047) is a constant
+ * tridiagonal SPD solve run as two block-parallel scans; the sparse matrix is never formed. */
+int admm_b200_setup_totalvariation(admm_b200_handle* h, int64_t n, const double* s, double lambda);
+
 /* Row-sharded runs, one process per GPU.  Rank 0 calls admm_b200_get_unique_id (128 bytes, an
  * ncclUniqueId), the host side broadcasts it (torch.distributed / MPI / a file), every rank calls
  * admm_b200_comm_init before the setup.  Replaces the PCT worker pool of the reference
