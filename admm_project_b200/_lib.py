@@ -60,6 +60,7 @@ SYMBOLS = {
     "admm_b200_setup_unwrapped": (_int, [_vp, _i32, _i64, _i64, _i64, _vp, _i64, _vp, _d]),
     "admm_b200_setup_basispursuit": (_int, [_vp, _i64, _i64, _vp, _i64, _vp]),
     "admm_b200_setup_totalvariation": (_int, [_vp, _i64, _vp, _d]),
+    "admm_b200_setup_quadratic": (_int, [_vp, _i32, _i64, _vp, _i64, _vp, _d, _d, _vp, _vp]),
     "admm_b200_get_unique_id": (_int, [_vp]),
     "admm_b200_comm_init": (_int, [_vp, _int, _int, _vp]),
     "admm_b200_comm_destroy": (_int, [_vp]),

@@ -56,6 +56,20 @@ __device__ __forceinline__ double ldg_stream1(const double* p) {
   return v;
 }
 
+// read-only 16-byte / 8-byte loads through L1 (vectors that are re-read by many warps).  `asm volatile`
+// on purpose: a non-volatile asm load (as __ldcs / __ldg are in the CUDA headers) may be hoisted out
+// of its bounds guard and executed speculatively past the end of an allocation.
+__device__ __forceinline__ double2 ldg_nc2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ldg_nc1(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes));

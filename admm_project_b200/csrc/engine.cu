@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -53,7 +54,7 @@ struct DBuf {
 struct ColdotPlan {
   int mode = 0;
   int64_t rows = 0, cols = 0;
-  int grid = 0, panels = 1, max_pos = 1;
+  int grid = 0, panels = 1, max_pos = 1, nitems = 0, npos = 0;
   int *d_cta_pos = nullptr, *d_pos_item = nullptr, *d_order = nullptr;
   ColdotItem* d_items = nullptr;
 };
@@ -85,7 +86,7 @@ struct admm_b200_handle {
   // cached factor (k x k, leading dimension ldf, multiple of 16)
   int64_t k = 0, ldf = 0;
   DBuf L, W, WT;
-  bool have_factor = false;
+  bool have_factor = false, have_inverse = false;
 
   // iterates and work vectors
   DBuf x, z, u, y, t1, t2;
@@ -106,6 +107,9 @@ struct admm_b200_handle {
   unsigned* grid_ticket = nullptr;
   int64_t m_total = 0;
   double svmC = 0.0;
+  // quadratic objective with box / nonneg prox: P (full, for the objective), bounds, constant r
+  DBuf Pfull, lb, ub;
+  double qp_r = 0.0;
   // total variation: double-buffered z/u, pivot table of the constant tridiagonal
   DBuf zz, uu, tvtab;
   int tv_par = 0, tv_ntab = 0, tv_halo = 0;
@@ -198,7 +202,7 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   if (o.allow_splitk && tiles < kNumSM && K >= 4096) {
     // few output tiles (n = 784 / 1024 Gram of a tall D): fill the machine twice over
     want_splits = std::min<int64_t>((2 * kNumSM + tiles - 1) / tiles, K / 1024);
-  } else if (o.allow_splitk && tiles >= kNumSM && K >= 16384) {
+  } else if (o.allow_splitk && tiles >= kNumSM && K >= 16384 && !getenv("ADMM_B200_NO_TAIL_SPLIT")) {
     // wave quantisation: 2080 tiles on 148 SMs = 14.05 waves -> 15 (6.7% idle).  Splitting K by S
     // makes the work items S times smaller, so the idle tail shrinks to ~1/S of a tile time.
     auto waste = [&](int64_t S) { int64_t items = tiles * S; return (double)((items + kNumSM - 1) / kNumSM * kNumSM) / (double)items; };
@@ -319,10 +323,14 @@ static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda
   ADMM_CUDA(cudaEventRecord(h->evp[2], h->stream));
   if (!want_inverse) return;
   // inverse factor by recursive doubling: for [[A,0],[B,C]]: inv = [[Ai,0],[-Ci*B*Ai, Ci]]
+  DBuf& T = h->scratch;  // T_p = B_p * inv(A_p), one b x b block per pair; sized once for all levels
+  {
+    int64_t need = 1;
+    for (int64_t b = CHOL_NB; b < k; b *= 2) need = std::max(need, (k / (2 * b) + 1) * b * b);
+    T.ensure(need);
+  }
   for (int64_t b = CHOL_NB; b < k; b *= 2) {
     const int64_t npairs_full = k / (2 * b);  // pairs whose second block is a full b
-    DBuf& T = h->scratch;  // T_p = B_p * inv(A_p), one b x b block per pair
-    T.ensure((k / (2 * b) + 1) * b * b);
     if (npairs_full > 0) {
       GemmOpt o1;
       o1.batch = (int)npairs_full;
@@ -436,16 +444,24 @@ static ColdotPlan* coldot_plan(admm_b200_handle* h, int mode, int64_t rows, int6
     max_pos = std::max(max_pos, cta_pos[b] - cta_pos[b - 1]);
   }
   pl->max_pos = max_pos;
+  pl->nitems = (int)items.size();
+  pl->npos = (int)nv;
   ADMM_REQUIRE((size_t)max_pos * 3 * COLDOT_WARPS * 8 <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED,
                "coldot: too many columns per CTA (%d)", max_pos);
   ADMM_CUDA(cudaMalloc(&pl->d_cta_pos, cta_pos.size() * sizeof(int)));
   ADMM_CUDA(cudaMalloc(&pl->d_pos_item, pos_item.size() * sizeof(int)));
   ADMM_CUDA(cudaMalloc(&pl->d_order, std::max<size_t>(order.size(), 1) * sizeof(int)));
   ADMM_CUDA(cudaMalloc(&pl->d_items, std::max<size_t>(items.size(), 1) * sizeof(ColdotItem)));
-  ADMM_CUDA(cudaMemcpy(pl->d_cta_pos, cta_pos.data(), cta_pos.size() * sizeof(int), cudaMemcpyHostToDevice));
-  ADMM_CUDA(cudaMemcpy(pl->d_pos_item, pos_item.data(), pos_item.size() * sizeof(int), cudaMemcpyHostToDevice));
-  ADMM_CUDA(cudaMemcpy(pl->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice));
-  ADMM_CUDA(cudaMemcpy(pl->d_items, items.data(), items.size() * sizeof(ColdotItem), cudaMemcpyHostToDevice));
+  // Upload ON THE HANDLE'S STREAM and wait for it.  A plain cudaMemcpy from pageable memory returns
+  // once the data sits in the driver's staging buffer -- the DMA may still be in flight -- and it is
+  // ordered only against the legacy default stream, not against the handle's non-blocking stream: the
+  // first kernel using the plan then raced the upload (seen on B200 as a flaky
+  // cudaErrorIllegalAddress on the first x-update after a setup).
+  ADMM_CUDA(cudaMemcpyAsync(pl->d_cta_pos, cta_pos.data(), cta_pos.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  ADMM_CUDA(cudaMemcpyAsync(pl->d_pos_item, pos_item.data(), pos_item.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  ADMM_CUDA(cudaMemcpyAsync(pl->d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  ADMM_CUDA(cudaMemcpyAsync(pl->d_items, items.data(), items.size() * sizeof(ColdotItem), cudaMemcpyHostToDevice, h->stream));
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));   // the host vectors die at the end of this function
   h->plans.push_back(pl);
   return pl;
 }
@@ -471,6 +487,13 @@ static void coldot_multi(admm_b200_handle* h, int mode, const double* M, int64_t
   ColdotArgs a;
   a.M = M; a.ld = ld; a.done = done;
   a.cta_pos = plan->d_cta_pos; a.pos_item = plan->d_pos_item; a.order = plan->d_order; a.items = plan->d_items;
+  a.dbg_rows = (int)rows; a.dbg_cols = (int)cols; a.dbg_nitems = plan->nitems; a.dbg_npos = plan->npos;
+  a.dbg = nullptr;
+  static int* dbgbuf = nullptr;
+  if (getenv("ADMM_B200_DEBUG")) {
+    if (!dbgbuf) { ADMM_CUDA(cudaMalloc(&dbgbuf, 32)); ADMM_CUDA(cudaMemset(dbgbuf, 0, 32)); ADMM_CUDA(cudaDeviceSynchronize()); }
+    a.dbg = dbgbuf;
+  }
   const int P = plan->panels;
   if (P == 1) {
     for (int k = 0; k < 3; ++k) { a.v[k] = v[k < nv ? k : 0]; a.out[k] = out[k < nv ? k : 0]; }
@@ -485,6 +508,25 @@ static void coldot_multi(admm_b200_handle* h, int mode, const double* M, int64_t
   else coldot_kernel<3><<<plan->grid, COLDOT_THREADS, smem, h->stream>>>(a);
   ADMM_CUDA(cudaGetLastError());
   h->launches++;
+  if (a.dbg) {
+    int hd[8];
+    {
+      cudaError_t e = cudaStreamSynchronize(h->stream);
+      if (e != cudaSuccess) {
+        fprintf(stderr, "COLDOT FAULT mode=%d rows=%lld cols=%lld nv=%d M=%p ld=%lld v0=%p out0=%p grid=%d smem=%zu items=%p n=%d | W=%p WT=%p L=%p y=%p t1=%p x=%p dts=%p s=%p D=%p\n",
+                mode, (long long)rows, (long long)cols, nv, (const void*)M, (long long)ld, (const void*)v[0], (void*)out[0], plan->grid, smem,
+                (void*)plan->d_items, plan->nitems, (void*)h->W.p, (void*)h->WT.p, (void*)h->L.p, (void*)h->y.p, (void*)h->t1.p, (void*)h->x.p,
+                (void*)h->dts.p, (void*)h->s.p, (const void*)h->dD);
+      }
+    }
+    ADMM_CUDA(cudaStreamSynchronize(h->stream));
+    ADMM_CUDA(cudaMemcpy(hd, dbgbuf, 32, cudaMemcpyDeviceToHost));
+    if (hd[0]) {
+      fprintf(stderr, "COLDOT SELF-CHECK kind=%d mode=%d rows=%lld cols=%lld nv=%d: %d %d %d %d %d %d %d (nitems=%d npos=%d grid=%d)\n", hd[0],
+              mode, (long long)rows, (long long)cols, nv, hd[1], hd[2], hd[3], hd[4], hd[5], hd[6], hd[7], plan->nitems, plan->npos, plan->grid);
+      ADMM_CUDA(cudaMemset(dbgbuf, 0, 32));
+    }
+  }
   if (P > 1) {
     PanelReduceArgs r;
     for (int k = 0; k < 3; ++k) { r.ws[k] = a.out[k]; r.out[k] = out[k < nv ? k : 0]; }
@@ -531,12 +573,42 @@ static void gemvn(admm_b200_handle* h, const double* D, int64_t ld, int64_t m, i
 static void factor_solve(admm_b200_handle* h, const double* b, double* tmp, double* x, int xsolve, const int* done) {
   ADMM_REQUIRE(h->have_factor, ADMM_B200_ERR_STATE, "no cached factor: call a setup function first");
   if (xsolve == ADMM_B200_XSOLVE_INVFACTOR) {
+    ADMM_REQUIRE(h->have_inverse, ADMM_B200_ERR_STATE,
+                 "xsolve = INVFACTOR but the setup was done with xsolve = SUBST (no inverse factor was built)");
     // t = W b : row i of W is column i of WT (rows 0..i)
     coldot(h, COLDOT_UPPER, h->WT.p, h->ldf, h->k, h->k, b, tmp, 1.0, nullptr, 0.0, done);
     // x = W' t : x_j = column j of W (rows j..k-1) . t
     coldot(h, COLDOT_LOWER, h->W.p, h->ldf, h->k, h->k, tmp, x, 1.0, nullptr, 0.0, done);
+  } else if (xsolve == ADMM_B200_XSOLVE_SUBST) {
+    // Blocked forward / back substitution on the factor L itself (128-wide blocks, the inverted
+    // diagonal blocks are the diagonal blocks of W).  2 x (k/128) dependent steps of small launches:
+    // the exact-semantics reference path, not the fast one.
+    ADMM_REQUIRE(h->W.p != nullptr, ADMM_B200_ERR_STATE, "xsolve = SUBST needs the inverted diagonal blocks");
+    const int64_t k = h->k, ld = h->ldf;
+    double* y = tmp;
+    ADMM_CUDA(cudaMemcpyAsync(y, b, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
+    for (int64_t k0 = 0; k0 < k; k0 += CHOL_NB) {          // L y = b
+      const int nb = (int)std::min<int64_t>(CHOL_NB, k - k0);
+      tri_block_mv_kernel<<<1, 128, 0, h->stream>>>(h->W.p + k0 + k0 * ld, ld, nb, y + k0, 0, done);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+      const int64_t rem = k - k0 - nb;
+      if (rem > 0)   // y[k0+nb:] -= L[k0+nb:, k0:k0+nb] * y_k
+        gemvn(h, h->L.p + (k0 + nb) + k0 * ld, ld, rem, nb, y + k0, y + k0 + nb, -1.0, 1.0, y + k0 + nb, done);
+    }
+    const int64_t nblk = (k + CHOL_NB - 1) / CHOL_NB;
+    for (int64_t bi = nblk - 1; bi >= 0; --bi) {           // L' x = y
+      const int64_t k0 = bi * CHOL_NB;
+      const int nb = (int)std::min<int64_t>(CHOL_NB, k - k0);
+      tri_block_mv_kernel<<<1, 128, 0, h->stream>>>(h->W.p + k0 + k0 * ld, ld, nb, y + k0, 1, done);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+      if (k0 > 0)    // y[0:k0] -= L[k0:k0+nb, 0:k0]' * x_k
+        coldot(h, COLDOT_FULL, h->L.p + k0, ld, nb, k0, y + k0, y, -1.0, y, 1.0, done);
+    }
+    ADMM_CUDA(cudaMemcpyAsync(x, y, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
   } else {
-    ADMM_REQUIRE(false, ADMM_B200_ERR_UNSUPPORTED, "xsolve = SUBST (blocked substitution) is not built yet");
+    ADMM_REQUIRE(false, ADMM_B200_ERR_INVALID, "unknown xsolve mode %d", xsolve);
   }
 }
 
@@ -570,6 +642,7 @@ static void factor_current(admm_b200_handle* h, int64_t k, bool want_inverse) {
   }
   h->k = k;
   h->have_factor = true;
+  h->have_inverse = want_inverse;
 }
 
 static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD, const double* s,
@@ -651,6 +724,58 @@ static void setup_bp(admm_b200_handle* h, int64_t m, int64_t n, const double* D,
   h->phase_ms[1] = ms;
   ADMM_CUDA(cudaEventElapsedTime(&ms, h->evp[2], h->ev1));
   h->phase_ms[2] = ms;
+  h->have_init = false;
+  h->iter_ready = false;
+}
+
+// Quadratic objective 1/2 x'Px + q'x + r with a projection as z-prox (quadraticprogram.m 'bounded'
+// branch, getProxOps.m:1441-1474): R = chol(P + rho*I) once, x = R \ (R' \ (rho*(z-u) - q)), which is
+// the tall-lasso x-update with Dts := -q.  kind = PROX_BOX (min(ub,max(lb,x+u)), :1470-1474) or
+// PROX_NONNEG (pos(x+u), the z-prox of :1378-1382 / :1422-1426).
+static void setup_quadratic(admm_b200_handle* h, int kind, int64_t n, const double* P, int64_t ldP, const double* q,
+                            double r, double rho, const double* lb, const double* ub) {
+  ADMM_REQUIRE(kind == ADMM_B200_PROX_BOX || kind == ADMM_B200_PROX_NONNEG, ADMM_B200_ERR_INVALID,
+               "setup_quadratic: kind must be PROX_BOX or PROX_NONNEG");
+  ADMM_REQUIRE(n > 0 && P && q && ldP >= n, ADMM_B200_ERR_INVALID, "setup_quadratic: bad dimensions or null input");
+  ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
+  ADMM_REQUIRE(kind != ADMM_B200_PROX_BOX || (lb && ub), ADMM_B200_ERR_INVALID, "setup_quadratic: box bounds missing");
+  ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
+  h->have_factor = false;
+  h->kind = kind;
+  h->tall = true;
+  h->m = h->n = n;
+  h->nA = h->nB = h->mc = n;
+  h->rho_setup = rho;
+  h->qp_r = r;
+  h->lambda = 0.0;
+  const int64_t ldp = round_up(n, 2);
+  h->Pfull.ensure(ldp * n);
+  ADMM_CUDA(cudaMemcpy2DAsync(h->Pfull.p, (size_t)ldp * 8, P, (size_t)ldP * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDefault,
+                              h->stream));
+  h->dD = h->Pfull.p;
+  h->ldD = ldp;
+  h->ownD.release();
+  h->dts.ensure(round_up(n, 2));
+  copy_in(h, h->dts.p, q, n);
+  if (kind == ADMM_B200_PROX_BOX) {
+    h->lb.ensure(n); h->ub.ensure(n);
+    copy_in(h, h->lb.p, lb, n);
+    copy_in(h, h->ub.p, ub, n);
+  }
+  h->ldf = round_up(n, 16);
+  h->L.ensure(h->ldf * n);
+  ADMM_CUDA(cudaMemcpy2DAsync(h->L.p, (size_t)h->ldf * 8, h->Pfull.p, (size_t)ldp * 8, (size_t)n * 8, (size_t)n,
+                              cudaMemcpyDeviceToDevice, h->stream));
+  add_diag_negate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->L.p, h->ldf, n, rho, h->dts.p);   // P + rho*I, -q
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+  ADMM_CUDA(cudaEventRecord(h->evp[1], h->stream));
+  factor_current(h, n, true);
+  ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
+  ADMM_CUDA(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->setup_ms = h->phase_ms[3] = ms;
   h->have_init = false;
   h->iter_ready = false;
 }
@@ -925,8 +1050,9 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     prox_ident_kernel<<<prox_grid(n), PROX_THREADS, 0, h->stream>>>(a);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
-  } else if (h->kind == ADMM_B200_LASSO) {
+  } else if (h->kind == ADMM_B200_LASSO || h->kind == ADMM_B200_PROX_BOX || h->kind == ADMM_B200_PROX_NONNEG) {
     const int64_t n = h->n, m = h->m;
+    const bool qp = h->kind != ADMM_B200_LASSO;
     if (which != 2) {
       if (h->tall) {
         // x = U \ (L \ y)   (getProxOps.m:1200)
@@ -940,18 +1066,21 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     }
     if (which == 1) return;
     if (o.objevals && which == 0) {
-      // obj = 1/2*norm(D*x - s)^2 + lambda*norm(z,1)   (lasso.m:227)
+      // obj = 1/2*norm(D*x - s)^2 + lambda*norm(z,1)   (lasso.m:227)  /  1/2*x'*P*x + q'*x + r
       gemvn(h, h->dD, h->ldD, m, n, h->x.p, h->t2.p, 1.0, 0.0, nullptr, done);
-      half_sqdist_kernel<<<1, 1024, 0, h->stream>>>(h->t2.p, h->s.p, m, h->ctl);
+      if (qp) quad_obj_kernel<<<1, 1024, 0, h->stream>>>(h->x.p, h->t2.p, h->dts.p, h->qp_r, n, h->ctl);
+      else half_sqdist_kernel<<<1, 1024, 0, h->stream>>>(h->t2.p, h->s.p, m, h->ctl);
       ADMM_CUDA(cudaGetLastError());
       h->launches++;
     }
     ProxIdentArgs a;
     a.n = n; a.x = h->x.p; a.z = h->z.p; a.u = h->u.p; a.dts = h->dts.p; a.y = h->y.p;
-    a.lb = a.ub = nullptr;
+    a.lb = qp ? h->lb.p : nullptr;
+    a.ub = qp ? h->ub.p : nullptr;
     a.thresh = h->lambda / o.rho;
-    a.objscale = h->lambda;
-    a.kind = PROX_SOFT; a.next = NEXT_LASSO; a.obj_l1_of_x = 0;
+    a.objscale = qp ? 0.0 : h->lambda;
+    a.kind = h->kind == ADMM_B200_PROX_BOX ? PROX_BOX : (h->kind == ADMM_B200_PROX_NONNEG ? PROX_NONNEG : PROX_SOFT);
+    a.next = NEXT_LASSO; a.obj_l1_of_x = 0;
     a.partials = h->partials.p; a.ctl = h->ctl; a.lp = lp;
     a.ld = 0; a.thresh_v = a.objscale_v = nullptr; a.hist_stride = 0; a.done_count = nullptr; a.xkeep = nullptr;
     a.xvals = history ? h->xvals.p : nullptr;
@@ -1012,7 +1141,8 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
 }
 
 static void enqueue_first_rhs(admm_b200_handle* h, const admm_b200_options& o) {
-  if (h->kind == ADMM_B200_LASSO || h->kind == ADMM_B200_BASISPURSUIT) {
+  if (h->kind == ADMM_B200_LASSO || h->kind == ADMM_B200_BASISPURSUIT || h->kind == ADMM_B200_PROX_BOX ||
+      h->kind == ADMM_B200_PROX_NONNEG) {
     const int64_t n = h->n;
     const bool bp = h->kind == ADMM_B200_BASISPURSUIT;
     first_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, h->z.p, h->u.p, bp ? nullptr : h->dts.p, o.rho,
@@ -1044,7 +1174,7 @@ static void validate_options(admm_b200_handle* h, const admm_b200_options& o) {
     ADMM_REQUIRE(o.relax == 1.0, ADMM_B200_ERR_INVALID,
                  "Inner matrix dimensions must agree. (linearsvm with relax ~= 1: the reference's zminLinearSVM "
                  "multiplies D (m x n) by the relaxed m-vector, getProxOps.m:1088, admm.m:521)");
-  if (h->kind == ADMM_B200_LASSO)
+  if (h->kind == ADMM_B200_LASSO || h->kind == ADMM_B200_PROX_BOX || h->kind == ADMM_B200_PROX_NONNEG)
     ADMM_REQUIRE(o.rho == h->rho_setup, ADMM_B200_ERR_INVALID,
                  "options.rho (%g) differs from the rho the factor was built with (%g); redo the setup", o.rho,
                  h->rho_setup);
@@ -1299,6 +1429,7 @@ int admm_b200_create(int device, admm_b200_handle** out) {
   ADMM_CUDA(cudaMalloc(&h->grid_ticket, sizeof(unsigned)));
   ADMM_CUDA(cudaMemset(h->grid_ticket, 0, sizeof(unsigned)));
   ADMM_CUDA(cudaMallocHost(&h->h_ctl, sizeof(LoopCtl)));
+  ADMM_CUDA(cudaDeviceSynchronize());   // the memsets above ran on the legacy stream; the handle's stream is non-blocking
   *out = h;
   ADMM_API_END
 }
@@ -1310,7 +1441,7 @@ int admm_b200_destroy(admm_b200_handle* h) {
   cudaStreamSynchronize(h->stream);
   DBuf* bufs[] = {&h->ownD, &h->s, &h->dts, &h->L, &h->W, &h->WT, &h->x, &h->z, &h->u, &h->y, &h->t1, &h->t2,
                   &h->x0, &h->z0, &h->u0, &h->partials, &h->hist, &h->xvals, &h->zvals, &h->uvals, &h->gemm_ws,
-                  &h->gemv_ws, &h->scratch, &h->cd_ws, &h->aux, &h->rvec, &h->dzvec, &h->cb, &h->uw_partials, &h->zz, &h->uu, &h->tvtab};
+                  &h->gemv_ws, &h->scratch, &h->cd_ws, &h->aux, &h->rvec, &h->dzvec, &h->cb, &h->uw_partials, &h->zz, &h->uu, &h->tvtab, &h->Pfull, &h->lb, &h->ub};
   for (DBuf* b : bufs) b->release();
   for (ColdotPlan* p : h->plans) {
     cudaFree(p->d_cta_pos); cudaFree(p->d_pos_item); cudaFree(p->d_order); cudaFree(p->d_items);
@@ -1373,6 +1504,14 @@ int admm_b200_setup_totalvariation(admm_b200_handle* h, int64_t n, const double*
   ADMM_API_BEGIN
   check_handle(h);
   setup_tv(h, n, s, lambda);
+  ADMM_API_END
+}
+
+int admm_b200_setup_quadratic(admm_b200_handle* h, int32_t kind, int64_t n, const double* P, int64_t ldP, const double* q,
+                              double r, double rho, const double* lb, const double* ub) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  setup_quadratic(h, kind, n, P, ldP, q, r, rho, lb, ub);
   ADMM_API_END
 }
 

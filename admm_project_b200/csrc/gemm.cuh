@@ -86,7 +86,21 @@ template <bool AK, bool BK, int VEC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs p) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
-  const int64_t m0 = (int64_t)blockIdx.x * GEMM_BM, n0 = (int64_t)blockIdx.y * GEMM_BN;
+  // grouped tile order (GROUP x GROUP super-tiles): the ~148 CTAs resident at any time then share
+  // ~12 A panels and ~12 B panels instead of 64 + 3, which cuts the DRAM re-reads of the Gram ~3x
+  // (ncu: 69.6 GB for a 4.3 GB matrix with the natural order).
+  int64_t bm = blockIdx.x, bn = blockIdx.y;
+  {
+    constexpr int GROUP = 12;
+    const int64_t tm = gridDim.x, tn = gridDim.y;
+    const int64_t pid = (int64_t)blockIdx.y * tm + blockIdx.x;
+    const int64_t per_group = GROUP * tn;
+    const int64_t g = pid / per_group, first_m = g * GROUP;
+    const int64_t gsz = min((int64_t)GROUP, tm - first_m);
+    bm = first_m + (pid % per_group) % gsz;
+    bn = (pid % per_group) / gsz;
+  }
+  const int64_t m0 = bm * GEMM_BM, n0 = bn * GEMM_BN;
   if (p.lower_only && n0 > m0) return;  // tile strictly above the diagonal
   const int bz = blockIdx.z;
   const int batch = bz / p.splits, split = bz - batch * p.splits;

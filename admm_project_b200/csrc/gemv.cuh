@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(GEMVN_THREADS) gemvn_kernel(GemvNArgs a) {
         for (int k = 0; k < 8; ++k) d[k] = ldg_stream2(p + (int64_t)k * a.ld);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          double vv = __ldg(a.v + c + k);
+          double vv = ldg_nc1(a.v + c + k);
           s0 = fma(d[k].x, vv, s0);
           s1 = fma(d[k].y, vv, s1);
         }
@@ -49,14 +49,14 @@ __global__ void __launch_bounds__(GEMVN_THREADS) gemvn_kernel(GemvNArgs a) {
       }
       for (; c < cend; ++c) {
         double2 d = ldg_stream2(p);
-        double vv = __ldg(a.v + c);
+        double vv = ldg_nc1(a.v + c);
         s0 = fma(d.x, vv, s0);
         s1 = fma(d.y, vv, s1);
         p += a.ld;
       }
     } else {
       for (; c < cend; ++c) {
-        double vv = __ldg(a.v + c);
+        double vv = ldg_nc1(a.v + c);
         s0 = fma(ldg_stream1(p), vv, s0);
         if (two) s1 = fma(ldg_stream1(p + 1), vv, s1);
         p += a.ld;

@@ -227,6 +227,32 @@ __global__ void half_sqdist_kernel(const double* __restrict__ r, const double* _
   }
 }
 
+// objective 1/2*x'*P*x + q'*x + r from t = P*x (quadraticprogram.m: options.obj)
+__global__ void quad_obj_kernel(const double* __restrict__ x, const double* __restrict__ t, const double* __restrict__ negq,
+                                double r, int64_t n, LoopCtl* ctl) {
+  if (ctl->done) return;
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc = fma(x[i], 0.5 * t[i] - negq[i], acc);
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sh[w];
+    ctl->objpart = tot + r;
+  }
+}
+
+// A[i][i] += shift;  v = -v
+__global__ void add_diag_negate_kernel(double* A, int64_t lda, int64_t n, double shift, double* v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    A[i + i * lda] += shift;
+    v[i] = -v[i];
+  }
+}
+
 // y0 = rho*(z0 - u0) + Dts  /  z0 - u0  before the first iteration
 __global__ void first_rhs_kernel(int64_t n, const double* z, const double* u, const double* dts, double rho,
                                  int next, double* y) {

@@ -44,6 +44,8 @@ struct ColdotArgs {
   const int* pos_item;            // [nvcols+1] item range of each position
   const int* order;               // [nvcols] position -> output index (virtual column)
   const ColdotItem* items;
+  int dbg_rows, dbg_cols, dbg_nitems, dbg_npos;   // bounds for the self-check
+  int* dbg;                                        // [8] first violation
 };
 
 template <int NV>
@@ -54,6 +56,10 @@ __global__ void __launch_bounds__(COLDOT_THREADS, 1) coldot_kernel(ColdotArgs a)
   const int p0 = a.cta_pos[blockIdx.x], p1 = a.cta_pos[blockIdx.x + 1];
   if (p1 <= p0) return;
   const int it0 = a.pos_item[p0], it1 = a.pos_item[p1];
+  if (a.dbg && (p0 < 0 || p1 > a.dbg_npos || it0 < 0 || it1 > a.dbg_nitems || it1 < it0)) {
+    if (tid == 0 && atomicCAS(a.dbg, 0, 2) == 0) { a.dbg[1] = blockIdx.x; a.dbg[2] = p0; a.dbg[3] = p1; a.dbg[4] = it0; a.dbg[5] = it1; }
+    return;
+  }
   for (int i = tid; i < (p1 - p0) * NV * COLDOT_WARPS; i += COLDOT_THREADS) slots[i] = 0.0;
   __syncthreads();
 
@@ -75,6 +81,13 @@ __global__ void __launch_bounds__(COLDOT_THREADS, 1) coldot_kernel(ColdotArgs a)
 #pragma unroll
       for (int k = 0; k < NV; ++k) run[k] = 0.0;
     }
+    if (a.dbg && (d.col < 0 || d.col >= a.dbg_cols || d.row0 < 0 || d.nrows < 1 || d.nrows > COLDOT_ITEM ||
+                  d.row0 + d.nrows > a.dbg_rows || d.pos < p0 || d.pos >= p1 || item >= a.dbg_nitems)) {
+      if (lane == 0 && atomicCAS(a.dbg, 0, 1) == 0) {
+        a.dbg[1] = item; a.dbg[2] = d.col; a.dbg[3] = d.row0; a.dbg[4] = d.nrows; a.dbg[5] = d.pos; a.dbg[6] = p0; a.dbg[7] = p1;
+      }
+      continue;
+    }
     const double* col = a.M + (int64_t)d.col * a.ld;
     int r0 = d.row0;
     const int r1 = d.row0 + d.nrows;
@@ -83,19 +96,34 @@ __global__ void __launch_bounds__(COLDOT_THREADS, 1) coldot_kernel(ColdotArgs a)
     for (int k = 0; k < NV; ++k) s0[k] = s1[k] = 0.0;
     if (r0 & 1) {  // ld even and bases 16B-aligned: address parity == row parity
       if (lane == 0) {
-        const double mval = __ldcs(col + r0);
+        const double mval = ldg_stream1(col + r0);
 #pragma unroll
-        for (int k = 0; k < NV; ++k) s0[k] = mval * __ldg(a.v[k] + r0);
+        for (int k = 0; k < NV; ++k) s0[k] = mval * ldg_nc1(a.v[k] + r0);
       }
       r0 += 1;
     }
     const int nvec = (r1 - r0) >> 1;
+    if (a.dbg) {
+      const long long lastm = (long long)d.col * a.ld + r0 + 2LL * nvec;   // one past the last vector element
+      if (lastm > (long long)a.ld * a.dbg_cols || r0 + 2 * nvec > a.dbg_rows || ((uintptr_t)(col + r0) & 15) ||
+          ((uintptr_t)(a.v[0] + r0) & 15)) {
+        if (lane == 0 && atomicCAS(a.dbg, 0, 3) == 0) {
+          a.dbg[1] = item; a.dbg[2] = d.col; a.dbg[3] = r0; a.dbg[4] = nvec; a.dbg[5] = (int)(lastm >> 20); a.dbg[6] = (int)((uintptr_t)(col + r0) & 15); a.dbg[7] = (int)((uintptr_t)(a.v[0] + r0) & 15);
+        }
+        continue;
+      }
+    }
     const double2* mp = reinterpret_cast<const double2*>(col + r0);
+    // NB: the loads must be `asm volatile` (ldg_stream2): __ldcs is a NON-volatile asm in the CUDA
+    // headers, the compiler may hoist it out of the (idx < nvec) guard, and the speculated load then
+    // runs up to 8 KB past the end of a short column -- past the end of the allocation for the last
+    // columns of W (seen on B200 as a layout-dependent cudaErrorIllegalAddress).
     double2 mv[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       int idx = lane + 32 * i;
-      mv[i] = (idx < nvec) ? __ldcs(mp + idx) : make_double2(0.0, 0.0);
+      mv[i] = make_double2(0.0, 0.0);
+      if (idx < nvec) mv[i] = ldg_stream2(reinterpret_cast<const double*>(mp + idx));
     }
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -104,7 +132,7 @@ __global__ void __launch_bounds__(COLDOT_THREADS, 1) coldot_kernel(ColdotArgs a)
       for (int i = 0; i < 16; ++i) {
         int idx = lane + 32 * i;
         if (idx < nvec) {
-          double2 vv = __ldg(vp + idx);
+          double2 vv = ldg_nc2(reinterpret_cast<const double*>(vp + idx));
           s0[k] = fma(mv[i].x, vv.x, s0[k]);
           s1[k] = fma(mv[i].y, vv.y, s1[k]);
         }
@@ -112,9 +140,9 @@ __global__ void __launch_bounds__(COLDOT_THREADS, 1) coldot_kernel(ColdotArgs a)
     }
     if (((r1 - r0) & 1) && lane == 31) {
       int r = r1 - 1;
-      const double mval = __ldcs(col + r);
+      const double mval = ldg_stream1(col + r);
 #pragma unroll
-      for (int k = 0; k < NV; ++k) s1[k] = fma(mval, __ldg(a.v[k] + r), s1[k]);
+      for (int k = 0; k < NV; ++k) s1[k] = fma(mval, ldg_nc1(a.v[k] + r), s1[k]);
     }
 #pragma unroll
     for (int k = 0; k < NV; ++k) run[k] += warp_sum(s0[k] + s1[k]);
@@ -136,6 +164,26 @@ __global__ void __launch_bounds__(COLDOT_THREADS, 1) coldot_kernel(ColdotArgs a)
     double* o = (k == 0) ? a.out[0] : (k == 1 ? a.out[1] : a.out[2]);
     o[c] = s;
   }
+}
+
+// y = Wkk * y (trans = 0) or Wkk' * y (trans = 1) in place, Wkk an nb x nb (<= 128) lower-triangular
+// block (the inverted diagonal block of the factor): the diagonal step of the blocked substitution
+// (ADMM_B200_XSOLVE_SUBST).  One CTA of 128 threads.
+__global__ void __launch_bounds__(128) tri_block_mv_kernel(const double* __restrict__ Wkk, int64_t ld, int nb, double* y,
+                                                           int trans, const int* done) {
+  if (done && *done) return;
+  __shared__ double v[128];
+  const int i = threadIdx.x;
+  if (i < nb) v[i] = y[i];
+  __syncthreads();
+  if (i >= nb) return;
+  double s = 0.0;
+  if (!trans) {
+    for (int j = 0; j <= i; ++j) s = fma(Wkk[i + (int64_t)j * ld], v[j], s);        // row i of Wkk
+  } else {
+    for (int j = i; j < nb; ++j) s = fma(Wkk[j + (int64_t)i * ld], v[j], s);        // column i of Wkk
+  }
+  y[i] = s;
 }
 
 // out_k[j] = scale * sum_p ws_k[p*cols + j]  (fixed order), k < nv

@@ -107,27 +107,27 @@ __global__ void __launch_bounds__(UW_THREADS) uw_gemv_prox_kernel(UwArgs a) {
       for (; c + 8 <= cend; c += 8) {
         double2 d[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) d[k] = __ldcs(reinterpret_cast<const double2*>(p + (int64_t)k * a.ld));
+        for (int k = 0; k < 8; ++k) d[k] = ldg_stream2(p + (int64_t)k * a.ld);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const double vv = __ldg(a.x + c + k);
+          const double vv = ldg_nc1(a.x + c + k);
           s0 = fma(d[k].x, vv, s0);
           s1 = fma(d[k].y, vv, s1);
         }
         p += 8 * a.ld;
       }
       for (; c < cend; ++c) {
-        const double2 d = __ldcs(reinterpret_cast<const double2*>(p));
-        const double vv = __ldg(a.x + c);
+        const double2 d = ldg_stream2(p);
+        const double vv = ldg_nc1(a.x + c);
         s0 = fma(d.x, vv, s0);
         s1 = fma(d.y, vv, s1);
         p += a.ld;
       }
     } else {
       for (; c < cend; ++c) {
-        const double vv = __ldg(a.x + c);
-        s0 = fma(__ldcs(p), vv, s0);
-        if (two) s1 = fma(__ldcs(p + 1), vv, s1);
+        const double vv = ldg_nc1(a.x + c);
+        s0 = fma(ldg_stream1(p), vv, s0);
+        if (two) s1 = fma(ldg_stream1(p + 1), vv, s1);
         p += a.ld;
       }
     }

@@ -98,6 +98,17 @@ class Engine:
         L.check(self._lib.admm_b200_setup_totalvariation(self._h, sv.size, L.ptr(sv), float(lam)))
         return sv.size
 
+    def setup_quadratic(self, kind, P, q, r, rho, lb=None, ub=None):
+        P = L.fmat(P)
+        n = P.shape[0]
+        q = L.fvec(q, n, "q")
+        lb = None if lb is None else L.fvec(lb, n, "lb")
+        ub = None if ub is None else L.fvec(ub, n, "ub")
+        self._keep = [P, q, lb, ub]
+        L.check(self._lib.admm_b200_setup_quadratic(self._h, int(kind), n, L.ptr(P), n, L.ptr(q), float(r), float(rho),
+                                                    L.ptr(lb), L.ptr(ub)))
+        return n
+
     # -- row-sharded runs (one process per GPU) ---------------------------------------------------
     def comm_init(self, rank, nranks, unique_id):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from ._lib import EngineError, ERR_UNSUPPORTED, SVM_HINGE, SVM_01, HUBERFIT, LAD
+from ._lib import EngineError, ERR_UNSUPPORTED, SVM_HINGE, SVM_01, HUBERFIT, LAD, PROX_BOX
 from .engine import DeviceMatrix
 from .errorcheck import MatlabError
 from .parallel import attach_comm, row_range
@@ -102,6 +102,11 @@ def getproxops(problem, args):
         minx = EngineProx("xminf", problem, "xminLAD", eng, {})
         minz = EngineProx("zming", problem, "zminSoftThresholding" if problem == "lad" else
                           "zminHuberSoftThresholding", eng, {"userelax": int(bool(args.get("userelax", 0)))})
+    elif problem == "quadraticprogram" and args.get("constraint") == "bounded":     # getProxOps.m:1441-1474
+        eng = _need_engine(eng, problem)
+        eng.setup_quadratic(PROX_BOX, args["P"], args["q"], args.get("r", 0.0), args["rho"], args["lb"], args["ub"])
+        minx = EngineProx("xminf", "quadraticprogram", "xminQuadraticProgramBounded", eng, {})
+        minz = EngineProx("zming", "quadraticprogram", "zminQuadraticProgramBounded", eng, {})
     elif problem in _OUT:
         raise EngineError(ERR_UNSUPPORTED, "problem '%s' is outside the engine's hot path (SURVEY.md section 2)" % problem)
     else:

@@ -6,3 +6,4 @@ from .linearsvm import linearsvm               # noqa: F401
 from .robustfit import huberfit, lad           # noqa: F401
 from .basispursuit import basispursuit        # noqa: F401
 from .totalvariation import totalvariation    # noqa: F401
+from .quadraticprogram import quadraticprogram  # noqa: F401

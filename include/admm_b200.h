@@ -156,6 +156,15 @@ int admm_b200_setup_basispursuit(admm_b200_handle* h, int64_t m, int64_t n, cons
  * tridiagonal SPD solve run as two block-parallel scans; the sparse matrix is never formed. */
 int admm_b200_setup_totalvariation(admm_b200_handle* h, int64_t n, const double* s, double lambda);
 
+/* Quadratic objective 1/2 x'Px + q'x + r (P symmetric positive semidefinite, n x n) with a projection
+ * as z-prox -- the stand-alone prox catalogue entries of the reference on a cached-Cholesky x-update:
+ *   kind = ADMM_B200_PROX_BOX    quadraticprogram.m 'bounded' (:210-216), getProxOps.m:1441-1474:
+ *                                R = chol(P + rho*I), x = R \ (R' \ (rho*(z-u) - q)), z = min(ub,max(lb,x+u))
+ *   kind = ADMM_B200_PROX_NONNEG same x-update with z = pos(x+u) (getProxOps.m:1378-1382, 1422-1426);
+ *                                lb / ub may be NULL. */
+int admm_b200_setup_quadratic(admm_b200_handle* h, int32_t kind, int64_t n, const double* P, int64_t ldP, const double* q,
+                              double r, double rho, const double* lb, const double* ub);
+
 /* Row-sharded runs, one process per GPU.  Rank 0 calls admm_b200_get_unique_id (128 bytes, an
  * ncclUniqueId), the host side broadcasts it (torch.distributed / MPI / a file), every rank calls
  * admm_b200_comm_init before the setup.  Replaces the PCT worker pool of the reference

@@ -1,0 +1,184 @@
+/*
+ * admm_b200_mex.c -- MATLAB MEX / GNU Octave (mkoctfile --mex) gateway onto libadmm_b200.so.
+ * It owns no numerics: it marshals mxArray <-> the C-ABI of include/admm_b200.h.
+ *
+ *   h   = admm_b200_mex('create', device)
+ *         admm_b200_mex('destroy', h)
+ *         admm_b200_mex('setup_lasso', h, D, s, rho)               solvers/lasso.m:159-176
+ *         admm_b200_mex('setup_unwrapped', h, kind, D, aux, C)     unwrappedadmm.m:96-123, huberfit.m:166, lad.m:134
+ *         admm_b200_mex('setup_basispursuit', h, D, s)             basispursuit.m:116-120
+ *         admm_b200_mex('setup_totalvariation', h, s, lambda)      totalvariation.m:127-131
+ *         admm_b200_mex('set_lambda', h, lambda)                   getProxOps.m:455
+ *         admm_b200_mex('set_init', h, x0, z0, u0)                 admm.m:252-254 ([] = zeros)
+ *   res = admm_b200_mex('solve', h, opts)                          admm.m:496-767
+ *   res = admm_b200_mex('solve_lasso_batch', h, opts, lambdas)
+ *
+ * opts is a struct with the numeric fields of admm_b200_options (missing fields keep the defaults
+ * of admm.m:51-76); res carries the fields of admm.m's results struct that the engine fills.
+ * Errors become MATLAB errors with the text of admm_b200_last_error().
+ *
+ * Build:  mex -I../include admm_b200_mex.c -L../admm_project_b200 -ladmm_b200
+ *    or:  mkoctfile --mex -I../include admm_b200_mex.c -L../admm_project_b200 -ladmm_b200
+ * NOT run in this repository's image (no MATLAB / Octave); `make -C matlab check` only compiles it
+ * against matlab/stub/mex.h.
+ */
+#include <math.h>
+#include <string.h>
+
+#include "admm_b200.h"
+#include "mex.h"
+
+static void check(int status) {
+  if (status != ADMM_B200_OK) mexErrMsgIdAndTxt("admm_b200:engine", "%s", admm_b200_last_error());
+}
+
+static admm_b200_handle* get_handle(const mxArray* a) {
+  if (mxGetNumberOfElements(a) != 1) mexErrMsgIdAndTxt("admm_b200:handle", "invalid engine handle");
+  return (admm_b200_handle*)(uintptr_t)(*(uint64_t*)mxGetData(a));
+}
+
+static const double* dense(const mxArray* a, const char* what) {
+  if (!mxIsDouble(a) || mxIsComplex(a) || mxIsSparse(a))
+    mexErrMsgIdAndTxt("admm_b200:type", "%s must be a full real double array", what);
+  return mxGetPr(a);
+}
+
+static double field(const mxArray* s, const char* name, double dflt) {
+  const mxArray* f = mxIsStruct(s) ? mxGetField(s, 0, name) : NULL;
+  return (f && !mxIsEmpty(f)) ? mxGetScalar(f) : dflt;
+}
+
+static void read_options(const mxArray* s, admm_b200_options* o) {
+  admm_b200_default_options(o);
+  o->rho = field(s, "rho", o->rho);
+  o->relax = field(s, "relax", o->relax);
+  o->abstol = field(s, "abstol", o->abstol);
+  o->reltol = field(s, "reltol", o->reltol);
+  o->convtol = field(s, "convtol", o->convtol);
+  o->hnormtol = field(s, "hnormtol", o->hnormtol);
+  o->maxiters = (int64_t)field(s, "maxiters", (double)o->maxiters);
+  o->domaxiters = (int32_t)field(s, "domaxiters", 0);
+  o->stopcond = (int32_t)field(s, "stopcond", 0);
+  o->nodualerror = (int32_t)field(s, "nodualerror", 0);
+  o->convtest = (int32_t)field(s, "convtest", 0);
+  o->objevals = (int32_t)field(s, "objevals", 0);
+  o->history = (int32_t)field(s, "history", 1);
+  o->xsolve = (int32_t)field(s, "xsolve", 0);
+  o->check_every = (int32_t)field(s, "check_every", 8);
+}
+
+static mxArray* put(mxArray* s, const char* name, mwSize m, mwSize n) {
+  mxArray* a = mxCreateDoubleMatrix(m, n, mxREAL);
+  mxAddField(s, name);
+  mxSetField(s, 0, name, a);
+  return a;
+}
+
+static void cmd_solve(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  admm_b200_handle* h = get_handle(prhs[1]);
+  admm_b200_options o;
+  admm_b200_result r;
+  int64_t nA, nB, m, N, k;
+  mxArray* s = mxCreateStructMatrix(1, 1, 0, NULL);
+  mxArray *px, *pz, *pu, *pn, *dn, *pe, *de, *hn, *ob, *xv = NULL, *zv = NULL, *uv = NULL;
+  (void)nlhs;
+  if (nrhs < 3) mexErrMsgIdAndTxt("admm_b200:args", "solve needs (h, opts)");
+  read_options(prhs[2], &o);
+  check(admm_b200_get_dims(h, &nA, &nB, &m));
+  N = o.maxiters > 0 ? o.maxiters : 1000;
+  memset(&r, 0, sizeof(r));
+  px = put(s, "xopt", nA, 1); pz = put(s, "zopt", nB, 1); pu = put(s, "uopt", m, 1);
+  pn = put(s, "pnorm", 1, N); dn = put(s, "dnorm", 1, N); pe = put(s, "perr", 1, N); de = put(s, "derr", 1, N);
+  hn = put(s, "Hnormsq", 1, N); ob = put(s, "objevals", 1, N);
+  r.xopt = mxGetPr(px); r.zopt = mxGetPr(pz); r.uopt = mxGetPr(pu);
+  r.pnorm = mxGetPr(pn); r.dnorm = mxGetPr(dn); r.perr = mxGetPr(pe); r.derr = mxGetPr(de);
+  r.hnormsq = mxGetPr(hn); r.objevals = mxGetPr(ob);
+  if (o.history) {
+    xv = put(s, "xvals", nA, N); zv = put(s, "zvals", nB, N); uv = put(s, "uvals", m, N);
+    r.xvals = mxGetPr(xv); r.zvals = mxGetPr(zv); r.uvals = mxGetPr(uv);
+  }
+  check(admm_b200_solve(h, &o, &r));
+  k = r.steps;   /* the .m wrapper trims the per-iteration arrays to 1:steps */
+  mxAddField(s, "steps");     mxSetField(s, 0, "steps", mxCreateDoubleScalar((double)k));
+  mxAddField(s, "status");    mxSetField(s, 0, "status", mxCreateDoubleScalar((double)r.status));
+  mxAddField(s, "objopt");    mxSetField(s, 0, "objopt", mxCreateDoubleScalar(r.objopt));
+  mxAddField(s, "setup_ms");  mxSetField(s, 0, "setup_ms", mxCreateDoubleScalar(r.setup_ms));
+  mxAddField(s, "loop_ms");   mxSetField(s, 0, "loop_ms", mxCreateDoubleScalar(r.loop_ms));
+  plhs[0] = s;
+}
+
+static void cmd_batch(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  admm_b200_handle* h = get_handle(prhs[1]);
+  admm_b200_options o;
+  int64_t nA, nB, m, nb, N, j;
+  mxArray* s = mxCreateStructMatrix(1, 1, 0, NULL);
+  mxArray *px, *pz, *pu, *pn, *dn, *pe, *de, *st, *ss;
+  int64_t* steps;
+  int32_t* status;
+  double ms = 0.0;
+  (void)nlhs;
+  if (nrhs < 4) mexErrMsgIdAndTxt("admm_b200:args", "solve_lasso_batch needs (h, opts, lambdas)");
+  read_options(prhs[2], &o);
+  check(admm_b200_get_dims(h, &nA, &nB, &m));
+  nb = (int64_t)mxGetNumberOfElements(prhs[3]);
+  N = o.maxiters > 0 ? o.maxiters : 1000;
+  px = put(s, "xopt", nA, nb); pz = put(s, "zopt", nB, nb); pu = put(s, "uopt", m, nb);
+  pn = put(s, "pnorm", N, nb); dn = put(s, "dnorm", N, nb); pe = put(s, "perr", N, nb); de = put(s, "derr", N, nb);
+  st = mxCreateNumericMatrix(nb, 1, mxUINT64_CLASS, mxREAL);
+  ss = mxCreateNumericMatrix(nb, 1, mxUINT64_CLASS, mxREAL);
+  steps = (int64_t*)mxGetData(st);
+  status = (int32_t*)mxGetData(ss);
+  check(admm_b200_solve_lasso_batch(h, &o, nb, dense(prhs[3], "lambdas"), steps, status, mxGetPr(px), mxGetPr(pz),
+                                    mxGetPr(pu), mxGetPr(pn), mxGetPr(dn), mxGetPr(pe), mxGetPr(de), &ms));
+  {
+    mxArray* sd = put(s, "steps", nb, 1);
+    for (j = 0; j < nb; ++j) mxGetPr(sd)[j] = (double)steps[j];
+  }
+  mxAddField(s, "loop_ms");
+  mxSetField(s, 0, "loop_ms", mxCreateDoubleScalar(ms));
+  plhs[0] = s;
+}
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+  char* cmd;
+  if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("admm_b200:args", "first argument must be a command string");
+  cmd = mxArrayToString(prhs[0]);
+  if (!strcmp(cmd, "create")) {
+    admm_b200_handle* h = NULL;
+    check(admm_b200_create(nrhs > 1 ? (int)mxGetScalar(prhs[1]) : 0, &h));
+    plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+    *(uint64_t*)mxGetData(plhs[0]) = (uint64_t)(uintptr_t)h;
+    mexLock();
+  } else if (!strcmp(cmd, "destroy")) {
+    check(admm_b200_destroy(get_handle(prhs[1])));
+  } else if (!strcmp(cmd, "setup_lasso")) {              /* (h, D, s, rho) */
+    check(admm_b200_setup_lasso(get_handle(prhs[1]), (int64_t)mxGetM(prhs[2]), (int64_t)mxGetN(prhs[2]),
+                                dense(prhs[2], "D"), (int64_t)mxGetM(prhs[2]), dense(prhs[3], "s"),
+                                mxGetScalar(prhs[4]), ADMM_B200_XSOLVE_INVFACTOR));
+  } else if (!strcmp(cmd, "setup_unwrapped")) {          /* (h, kind, D, aux, C) */
+    int64_t m = (int64_t)mxGetM(prhs[3]);
+    check(admm_b200_setup_unwrapped(get_handle(prhs[1]), (int32_t)mxGetScalar(prhs[2]), m, m, (int64_t)mxGetN(prhs[3]),
+                                    dense(prhs[3], "D"), m, dense(prhs[4], "ell/s"), nrhs > 5 ? mxGetScalar(prhs[5]) : 0.0));
+  } else if (!strcmp(cmd, "setup_basispursuit")) {       /* (h, D, s) */
+    check(admm_b200_setup_basispursuit(get_handle(prhs[1]), (int64_t)mxGetM(prhs[2]), (int64_t)mxGetN(prhs[2]),
+                                       dense(prhs[2], "D"), (int64_t)mxGetM(prhs[2]), dense(prhs[3], "s")));
+  } else if (!strcmp(cmd, "setup_totalvariation")) {     /* (h, s, lambda) */
+    check(admm_b200_setup_totalvariation(get_handle(prhs[1]), (int64_t)mxGetNumberOfElements(prhs[2]),
+                                         dense(prhs[2], "s"), mxGetScalar(prhs[3])));
+  } else if (!strcmp(cmd, "set_lambda")) {
+    check(admm_b200_set_lambda(get_handle(prhs[1]), mxGetScalar(prhs[2])));
+  } else if (!strcmp(cmd, "set_init")) {                 /* (h, x0, z0, u0), [] = zeros */
+    const double* v[3] = {NULL, NULL, NULL};
+    int i;
+    for (i = 0; i < 3 && i + 2 < nrhs; ++i)
+      if (!mxIsEmpty(prhs[i + 2])) v[i] = dense(prhs[i + 2], "x0/z0/u0");
+    check(admm_b200_set_init(get_handle(prhs[1]), v[0], v[1], v[2]));
+  } else if (!strcmp(cmd, "solve")) {
+    cmd_solve(nlhs, plhs, nrhs, prhs);
+  } else if (!strcmp(cmd, "solve_lasso_batch")) {
+    cmd_batch(nlhs, plhs, nrhs, prhs);
+  } else {
+    mexErrMsgIdAndTxt("admm_b200:cmd", "unknown command '%s'", cmd);
+  }
+  mxFree(cmd);
+}

@@ -1,0 +1,13 @@
+function results = unwrappedadmm(zming, D, options)
+% UNWRAPPEDADMM  Drop-in for solvers/unwrappedadmm.m:1.  The x-update is always the transpose
+% reduction W \ D'(z-u) with one cached Cholesky of W = D'D (unwrappedadmm.m:96-141).  UNTESTED HERE.
+t = tic;
+[m, n] = size(D);
+xminf = zming;                                   % same descriptor; admm() only needs the engine handle
+options.A = 1; options.At = 1; options.B = -1; options.nB = m; options.c = 0; options.m = m;   % D lives on the device
+options.x0 = rand(n, 1); options.z0 = rand(m, 1); options.u0 = rand(m, 1);                      % :87-89
+options.maxiters = 1000; options.stopcond = 'both'; options.nodualerror = 1;                    % :90-92
+options.parallel = 'none';
+results = admm(xminf, zming, options);
+results.solverruntime = toc(t);
+end

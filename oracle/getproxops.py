@@ -158,6 +158,17 @@ def getproxops(problem, args):
             else:                                                           # :910-911
                 minz = lambda x, _z, u, rho: zminHuber(D @ x, u, rho)
 
+    elif problem == "quadraticprogram" and args.get("constraint") == "bounded":      # :1441-1474
+        P, q, lb, ub, n = args["P"], args["q"], args["lb"], args["ub"], args["n"]
+        state = {"rhoprev": None, "R": None}
+
+        def minx(_x, z, u, rho):                                            # xminQuadraticProgramBounded
+            if rho != state["rhoprev"]:
+                state["R"] = sla.cholesky(P + rho * np.eye(n), lower=False, check_finite=False)   # chol(Pnew): upper R
+                state["rhoprev"] = rho
+            R = state["R"]
+            return _tri_upper_solve(R, _tri_lower_solve(R.T, rho * (z - u) - q))
+        minz = make_zminBox(lb, ub)
     elif problem in ("model", "linearprogram", "quadraticprogram", "covarianceselection"):
         raise MatlabError("oracle: problem '%s' is out of scope (SURVEY.md section 2)" % problem)
     else:

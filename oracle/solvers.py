@@ -226,3 +226,37 @@ def basispursuit(D, s, options):
     results = admm(minx, minz, options)
     results["solverruntime"] = time.perf_counter() - t0
     return results
+
+
+def quadraticprogram(P, q, r, cons1, cons2, options):
+    """solvers/quadraticprogram.m:99-257, 'bounded' constraint branch only (:210-216; error checks
+    :259-366).  The 'standard' branch (dense KKT solve per iteration) is out of scope."""
+    t0 = time.perf_counter()
+    options = dict(options)
+    P = np.asarray(P, dtype=np.float64)
+    q = _col(q)
+    nP = P.shape[0]
+    if q.shape[0] != nP:
+        raise MatlabError("The dimensions of square matrix P and vector q do not match!")
+    c1, c2 = np.asarray(cons1, dtype=np.float64), np.asarray(cons2, dtype=np.float64)
+    isvec = lambda a: a.ndim <= 1 or 1 in a.shape
+    if not (isvec(c1) and isvec(c2)):
+        raise MatlabError("oracle: quadraticprogram 'standard' form is out of scope (SURVEY.md section 2)")
+    c1, c2 = c1.reshape(-1), c2.reshape(-1)
+    if c1.shape[0] != c2.shape[0]:
+        raise MatlabError("Lengths of lower and upper bound constraints on solution x do not match!")
+    if c1.shape[0] != nP:
+        raise MatlabError("Bound vectors do not match predicted length of solution x!")
+    if np.array_equal(np.maximum(c1, c2), c1):
+        c1, c2 = c2, c1
+    elif not np.array_equal(np.maximum(c1, c2), c2):
+        raise MatlabError("Given constraint variables do not specify an upper and lower bound on solution x!")
+    n = nP
+    rho = float(options["rho"]) if "rho" in options else 1.0
+    args = dict(P=P, q=q, lb=c1, ub=c2, rho=rho, n=n, constraint="bounded")
+    minx, minz, _ = getproxops("quadraticprogram", args)
+    options.update(A=1, B=-1, c=0, m=n, nA=n, nB=n)
+    options["obj"] = lambda x, z: 0.5 * float(x @ (P @ x)) + float(q @ x) + r
+    results = admm(minx, minz, options)
+    results["solverruntime"] = time.perf_counter() - t0
+    return results

@@ -82,3 +82,34 @@ def test_lasso_setup_factor_and_solve(engine, m, n):
     b = rs.randn(Lref.shape[0])
     xref = sla.solve_triangular(Lref.T, sla.solve_triangular(Lref, b, lower=True), lower=False)
     assert rel(engine.factor_solve(b), xref) < 1e-12
+
+
+@pytest.mark.parametrize("m,n", [(900, 300), (200, 515), (2000, 1027)])
+def test_substitution_mode_equals_inverse_factor_mode(engine, m, n):
+    """ADMM_B200_XSOLVE_SUBST (blocked forward/back substitution on L) and the default inverse-factor
+    products give the same x-update; both match SciPy's triangular solves."""
+    from admm_project_b200 import _lib as L
+    rs = np.random.RandomState(n)
+    D = rs.randn(m, n) / np.sqrt(m)
+    s = rs.randn(m)
+    engine.setup_lasso(D, s, 0.7)
+    Lref = engine.get_factor()
+    b = rs.randn(Lref.shape[0])
+    xref = sla.solve_triangular(Lref.T, sla.solve_triangular(Lref, b, lower=True), lower=False)
+    x_inv = engine.factor_solve(b, L.XSOLVE_INVFACTOR)
+    x_sub = engine.factor_solve(b, L.XSOLVE_SUBST)
+    assert rel(x_inv, xref) < 1e-12 and rel(x_sub, xref) < 1e-12
+    assert rel(x_inv, x_sub) < 1e-12
+
+
+def test_lasso_runs_in_substitution_mode(engine):
+    import oracle
+    from admm_project_b200 import lasso
+    from admm_project_b200.generators import lasso_problem
+    from admm_project_b200 import _lib as L
+    for rows, cols in ((600, 260), (150, 400)):
+        D, s, lam, _ = lasso_problem(0, rows, cols)
+        ref = oracle.lasso(D, s, lam, {"history": 0})
+        res = lasso(D, s, lam, {"history": 0, "xsolve": L.XSOLVE_SUBST}, engine=engine)
+        assert res["steps"] == ref["steps"]
+        assert rel(res["xopt"], ref["xopt"]) < 1e-9 and rel(res["uopt"], ref["uopt"]) < 1e-9
