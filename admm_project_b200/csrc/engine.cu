@@ -420,7 +420,8 @@ static ColdotPlan* coldot_plan(admm_b200_handle* h, int mode, int64_t rows, int6
     ADMM_REQUIRE(items.size() < (size_t)1 << 31, ADMM_B200_ERR_UNSUPPORTED, "coldot: too many items");
   }
   pos_item[nv] = (int)items.size();
-  const int grid = (int)std::min<int64_t>(kNumSM, std::max<int64_t>(1, total / 8192));
+  // enough CTAs that none owns more than ~256 (virtual) columns, at least ~64 KB of matrix per CTA otherwise
+  const int grid = (int)std::min<int64_t>(kNumSM, std::max<int64_t>(std::max<int64_t>(1, total / 8192), (nv + 255) / 256));
   pl->grid = grid;
   // Equal COST split of the visiting sequence: a warp needs a few thousand cycles per item however
   // short it is (descriptor + DRAM latency + shuffle reduction), worth ~4.5 KB of streaming --
@@ -446,8 +447,6 @@ static ColdotPlan* coldot_plan(admm_b200_handle* h, int mode, int64_t rows, int6
   pl->max_pos = max_pos;
   pl->nitems = (int)items.size();
   pl->npos = (int)nv;
-  ADMM_REQUIRE((size_t)max_pos * 3 * COLDOT_WARPS * 8 <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED,
-               "coldot: too many columns per CTA (%d)", max_pos);
   ADMM_CUDA(cudaMalloc(&pl->d_cta_pos, cta_pos.size() * sizeof(int)));
   ADMM_CUDA(cudaMalloc(&pl->d_pos_item, pos_item.size() * sizeof(int)));
   ADMM_CUDA(cudaMalloc(&pl->d_order, std::max<size_t>(order.size(), 1) * sizeof(int)));
@@ -477,6 +476,7 @@ static void coldot_multi(admm_b200_handle* h, int mode, const double* M, int64_t
                "coldot: matrix and vectors must be 16-byte aligned with an even leading dimension (ld=%lld)", (long long)ld);
   const ColdotPlan* plan = coldot_plan(h, mode, rows, cols);
   const size_t smem = (size_t)plan->max_pos * nv * COLDOT_WARPS * 8;
+  ADMM_REQUIRE(smem <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED, "coldot: too many columns per CTA (%d)", plan->max_pos);
   static size_t configured[2] = {0, 0};
   size_t& conf = configured[nv == 3];
   if (smem > conf && smem > 48 * 1024) {
@@ -586,7 +586,9 @@ static void factor_solve(admm_b200_handle* h, const double* b, double* tmp, doub
     ADMM_REQUIRE(h->W.p != nullptr, ADMM_B200_ERR_STATE, "xsolve = SUBST needs the inverted diagonal blocks");
     const int64_t k = h->k, ld = h->ldf;
     double* y = tmp;
-    ADMM_CUDA(cudaMemcpyAsync(y, b, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
+    vec_copy_kernel<<<(unsigned)((k + 255) / 256), 256, 0, h->stream>>>(y, b, k, done);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
     for (int64_t k0 = 0; k0 < k; k0 += CHOL_NB) {          // L y = b
       const int nb = (int)std::min<int64_t>(CHOL_NB, k - k0);
       tri_block_mv_kernel<<<1, 128, 0, h->stream>>>(h->W.p + k0 + k0 * ld, ld, nb, y + k0, 0, done);
@@ -606,7 +608,9 @@ static void factor_solve(admm_b200_handle* h, const double* b, double* tmp, doub
       if (k0 > 0)    // y[0:k0] -= L[k0:k0+nb, 0:k0]' * x_k
         coldot(h, COLDOT_FULL, h->L.p + k0, ld, nb, k0, y + k0, y, -1.0, y, 1.0, done);
     }
-    ADMM_CUDA(cudaMemcpyAsync(x, y, (size_t)k * 8, cudaMemcpyDeviceToDevice, h->stream));
+    vec_copy_kernel<<<(unsigned)((k + 255) / 256), 256, 0, h->stream>>>(x, y, k, done);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
   } else {
     ADMM_REQUIRE(false, ADMM_B200_ERR_INVALID, "unknown xsolve mode %d", xsolve);
   }

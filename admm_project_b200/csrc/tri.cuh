@@ -186,6 +186,13 @@ __global__ void __launch_bounds__(128) tri_block_mv_kernel(const double* __restr
   y[i] = s;
 }
 
+// dst = src unless the loop has ended (a plain memcpy would keep running after `done` and clobber x)
+__global__ void vec_copy_kernel(double* dst, const double* src, int64_t n, const int* done) {
+  if (done && *done) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
 // out_k[j] = scale * sum_p ws_k[p*cols + j]  (fixed order), k < nv
 struct PanelReduceArgs {
   const double* ws[3];
