@@ -113,6 +113,7 @@ struct admm_b200_handle {
   // total variation: double-buffered z/u, pivot table of the constant tridiagonal
   DBuf zz, uu, tvtab;
   int tv_par = 0, tv_ntab = 0, tv_halo = 0;
+  double tv_inv_star = 0.0;
   double tv_rho = -1.0;
   // row-sharded runs: one NCCL communicator per handle (one process per GPU)
   void* comm = nullptr;
@@ -805,8 +806,8 @@ static void setup_tv(admm_b200_handle* h, int64_t n, const double* s, double lam
 
 static void tv_prepare(admm_b200_handle* h, double rho) {
   const int64_t n = h->n;
-  h->zz.ensure(2 * n);
-  h->uu.ensure(2 * n);
+  h->zz.ensure(2 * round_up(n, 2));   // two halves at an even stride (16-byte loads)
+  h->uu.ensure(2 * round_up(n, 2));
   if (h->tv_rho == rho) return;
   // pivots of I + rho*D'D: delta_0 = 1 + rho, delta_i = 1 + 2 rho - rho^2/delta_{i-1}; contraction
   std::vector<double> inv;
@@ -822,13 +823,14 @@ static void tv_prepare(admm_b200_handle* h, double rho) {
   const double astar = rho * inv.back();       // forward/backward multiplier at the fixed point
   int64_t K = (astar > 0.0) ? (int64_t)ceil(40.0 / -log(astar)) : 1;
   K = round_up(std::max<int64_t>(K, 16), 16);
-  ADMM_REQUIRE(4 * K <= TV_SEG, ADMM_B200_ERR_UNSUPPORTED,
+  ADMM_REQUIRE(4 * K <= TvCfg<16>::SEG, ADMM_B200_ERR_UNSUPPORTED,
                "totalvariation: rho = %g needs a %lld-element halo, more than the windowed tridiagonal solve carries",
                rho, (long long)K);
   h->tvtab.ensure((int64_t)inv.size());
   ADMM_CUDA(cudaMemcpyAsync(h->tvtab.p, inv.data(), inv.size() * 8, cudaMemcpyHostToDevice, h->stream));
   ADMM_CUDA(cudaStreamSynchronize(h->stream));
   h->tv_ntab = (int)inv.size();
+  h->tv_inv_star = inv.back();
   h->tv_halo = (int)K;
   h->tv_rho = rho;
 }
@@ -1001,27 +1003,34 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     const int64_t n = h->n;
     static bool configured = false;
     if (!configured) {
-      ADMM_CUDA(cudaFuncSetAttribute(tv_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TV_SMEM_BYTES));
+      ADMM_CUDA(cudaFuncSetAttribute(tv_solve_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TvCfg<8>::SMEM_BYTES));
+      ADMM_CUDA(cudaFuncSetAttribute(tv_solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TvCfg<16>::SMEM_BYTES));
       configured = true;
     }
-    const double* zc = h->zz.p + (int64_t)h->tv_par * n;
-    const double* uc = h->uu.p + (int64_t)h->tv_par * n;
+    const int64_t npad = round_up(n, 2);
+    const double* zc = h->zz.p + (int64_t)h->tv_par * npad;
+    const double* uc = h->uu.p + (int64_t)h->tv_par * npad;
     if (which != 2) {
       TvSolveArgs a;
       a.n = n; a.s = h->s.p; a.z = zc; a.u = uc; a.x = h->x.p; a.rho = o.rho; a.invdelta = h->tvtab.p;
-      a.ntab = h->tv_ntab; a.halo = h->tv_halo; a.done = done;
-      const int64_t S = TV_SEG - 2 * h->tv_halo;
-      tv_solve_kernel<<<(unsigned)((n + S - 1) / S), TV_THREADS, TV_SMEM_BYTES, h->stream>>>(a);
+      a.inv_star = h->tv_inv_star; a.ntab = h->tv_ntab; a.halo = h->tv_halo; a.done = done;
+      if (8 * h->tv_halo <= TvCfg<8>::SEG) {      // halo overhead <= 25 %: small segments, 3 CTAs per SM
+        const int64_t S = TvCfg<8>::SEG - 2 * h->tv_halo;
+        tv_solve_kernel<8><<<(unsigned)((n + S - 1) / S), TV_THREADS, TvCfg<8>::SMEM_BYTES, h->stream>>>(a);
+      } else {
+        const int64_t S = TvCfg<16>::SEG - 2 * h->tv_halo;
+        tv_solve_kernel<16><<<(unsigned)((n + S - 1) / S), TV_THREADS, TvCfg<16>::SMEM_BYTES, h->stream>>>(a);
+      }
       ADMM_CUDA(cudaGetLastError());
       h->launches++;
     }
     if (which == 1) return;
     TvProxArgs p;
     p.n = n; p.x = h->x.p; p.s = h->s.p; p.z = zc; p.u = uc;
-    p.znew = h->zz.p + (int64_t)(1 - h->tv_par) * n;
-    p.unew = h->uu.p + (int64_t)(1 - h->tv_par) * n;
+    p.znew = h->zz.p + (int64_t)(1 - h->tv_par) * npad;
+    p.unew = h->uu.p + (int64_t)(1 - h->tv_par) * npad;
     p.lambda = h->lambda;
-    const int grid = (int)std::min<int64_t>(4 * kNumSM, std::max<int64_t>(1, (n + TVP_THREADS * TVP_E - 1) / (TVP_THREADS * TVP_E)));
+    const int grid = (int)std::min<int64_t>(2 * kNumSM, std::max<int64_t>(1, (n + TVP_THREADS * TVP_E - 1) / (TVP_THREADS * TVP_E)));
     h->partials.ensure((int64_t)grid * 8);
     p.partials = h->partials.p; p.ctl = h->ctl; p.lp = lp;
     p.xvals = history ? h->xvals.p : nullptr;
@@ -1227,8 +1236,8 @@ static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_res
   ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   if (h->kind == ADMM_B200_TOTALVARIATION) {   // the last iteration that ran wrote half (steps mod 2)
     const int64_t half = h->h_ctl->it % 2, n = h->n;
-    ADMM_CUDA(cudaMemcpyAsync(h->z.p, h->zz.p + half * n, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
-    ADMM_CUDA(cudaMemcpyAsync(h->u.p, h->uu.p + half * n, (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(h->z.p, h->zz.p + half * round_up(n, 2), (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(h->u.p, h->uu.p + half * round_up(n, 2), (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
     h->tv_par = (int)half;
   }
   if (!res) return;

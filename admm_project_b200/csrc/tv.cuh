@@ -20,18 +20,22 @@
 namespace admmb200 {
 
 constexpr int TV_THREADS = 512;
-constexpr int TV_E = 16;                         // consecutive elements per thread
-constexpr int TV_SEG = TV_THREADS * TV_E;        // 8192 elements per CTA (segment + both halos)
-__host__ __device__ constexpr int TV_PAD(int i) { return i + (i >> 4); }
-constexpr int TV_SMEM_DOUBLES = TV_SEG + (TV_SEG >> 4) + 32;
-constexpr int TV_SMEM_BYTES = 2 * TV_SMEM_DOUBLES * 8 + 64 * 8 * 2;
+// E consecutive elements per thread: E = 8 (4096-element segments, 70 KB of shared memory, two CTAs
+// per SM so one CTA's loads overlap another's scans) for small halos, E = 16 (8192) for large rho.
+template <int E> struct TvCfg {
+  static constexpr int SEG = TV_THREADS * E;                 // elements per CTA (segment + both halos)
+  static constexpr int SMEM_DOUBLES = SEG + SEG / E + 32;    // padded: one spare slot per thread chunk
+  static constexpr int SMEM_BYTES = 2 * SMEM_DOUBLES * 8 + 64 * 8 * 2;
+};
+template <int E> __host__ __device__ constexpr int TV_PAD(int i) { return i + i / E; }
 
 struct TvSolveArgs {
   int64_t n;
   const double *s, *z, *u;
   double* x;
   double rho;
-  const double* invdelta;   // table of 1/delta_i, i < ntab; beyond: invdelta[ntab-1]
+  const double* invdelta;   // table of 1/delta_i, i < ntab; beyond: inv_star (the fixed point)
+  double inv_star;
   int ntab;
   int halo;                 // K
   const int* done;
@@ -75,8 +79,12 @@ __device__ __forceinline__ double block_affine_carry(Affine mine, double* shA, d
   return excl.B;   // carry-in of the whole CTA is 0
 }
 
-__global__ void __launch_bounds__(TV_THREADS, 1) tv_solve_kernel(TvSolveArgs a) {
+template <int TV_E>
+__global__ void __launch_bounds__(TV_THREADS, (TV_E == 8 ? 2 : 1)) tv_solve_kernel(TvSolveArgs a) {
   if (a.done && *a.done) return;
+  constexpr int TV_SEG = TvCfg<TV_E>::SEG;
+  constexpr int TV_SMEM_DOUBLES = TvCfg<TV_E>::SMEM_DOUBLES;
+#define TV_PAD(i) TV_PAD<TV_E>(i)
   extern __shared__ __align__(16) double sm[];
   double* bufA = sm;                         // w = z - u, later y, later x
   double* bufB = sm + TV_SMEM_DOUBLES;       // s
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(TV_THREADS, 1) tv_solve_kernel(TvSolveArgs a) 
   __syncthreads();
 
   auto invd = [&](int64_t i) -> double {                  // 1/delta_i
-    return a.invdelta[i < a.ntab ? i : a.ntab - 1];
+    return i < a.ntab ? a.invdelta[i] : a.inv_star;
   };
 
   // ---- forward: y_i = r_i + fa_i * y_{i-1},  fa_i = rho/delta_{i-1} (0 at i = 0 and outside [0,n))
@@ -155,6 +163,7 @@ __global__ void __launch_bounds__(TV_THREADS, 1) tv_solve_kernel(TvSolveArgs a) 
     const int64_t i = g0 + j;
     if (i < a.n) a.x[i] = bufB[TV_PAD(j)];
   }
+#undef TV_PAD
 }
 
 constexpr int TVP_THREADS = 256;
@@ -172,10 +181,7 @@ struct TvProxArgs {
   double *xvals, *zvals, *uvals;
 };
 
-// (D v)_i for v given by a callable
-#define TV_D(vi, vip1, i, n) (((i) < (n) - 1) ? ((vi) - (vip1)) : (vi))
-
-__global__ void __launch_bounds__(TVP_THREADS) tv_prox_kernel(TvProxArgs a) {
+__global__ void __launch_bounds__(TVP_THREADS, 2) tv_prox_kernel(TvProxArgs a) {
   LoopCtl* ctl = a.ctl;
   if (ctl->done) return;
   __shared__ double sh[(TVP_THREADS / 32) * 8];
@@ -187,73 +193,87 @@ __global__ void __launch_bounds__(TVP_THREADS) tv_prox_kernel(TvProxArgs a) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) r[k] = 0.0;
 
-  // new (z, u) of element i from the OLD iterates; needs x_i..x_{i+2}, zprev_i, zprev_{i+1}, u_i
-  auto update = [&](int64_t i, double& znew, double& unew, double& Dx, double& zp, double& up) {
-    const double x0 = a.x[i], x1 = (i + 1 < n) ? a.x[i + 1] : 0.0;
-    Dx = TV_D(x0, x1, i, n);
-    zp = a.z[i];
-    up = a.u[i];
-    double Axh = Dx, w;
-    if (relax != 1.0) {
-      // admm.m:517 Axhat = relax*A(x) - (1-relax)*(B(zprev) - c); the z-prox then applies D to the
-      // vector in x's slot (getProxOps.m:199 `u + D*x` with x := Axhat, admm.m:521)
-      Axh = relax * Dx - (1.0 - relax) * (-zp - 0.0);
-      double Axh1 = 0.0;
-      if (i + 1 < n) {
-        const double x2 = (i + 2 < n) ? a.x[i + 2] : 0.0;
-        const double Dx1 = TV_D(x1, x2, i + 1, n);
-        Axh1 = relax * Dx1 - (1.0 - relax) * (-a.z[i + 1] - 0.0);
-      }
-      w = up + TV_D(Axh, Axh1, i, n);
-    } else {
-      w = up + Dx;
-    }
-    znew = soft_threshold(w, thr);
-    unew = up + (Axh + (-znew) - 0.0);
-  };
-
   for (int64_t base = ((int64_t)blockIdx.x * TVP_THREADS + threadIdx.x) * TVP_E; base < n;
        base += (int64_t)gridDim.x * TVP_THREADS * TVP_E) {
-    // left neighbour (element base-1) recomputed for the D' stencils of the dual residual
+    // registers: x[base-1 .. base+9], z[base-1 .. base+8], u[base-1 .. base+7], s[base .. base+7]
+    double xr[TVP_E + 3], zr[TVP_E + 2], ur[TVP_E + 1], sr[TVP_E];
+    if (base >= 2 && base + TVP_E + 2 <= n) {          // interior: 16-byte loads (base is a multiple of 8)
+      xr[0] = a.x[base - 1]; zr[0] = a.z[base - 1]; ur[0] = a.u[base - 1];
+#pragma unroll
+      for (int k = 0; k < TVP_E / 2 + 1; ++k) {
+        const double2 v = *reinterpret_cast<const double2*>(a.x + base + 2 * k);
+        xr[1 + 2 * k] = v.x; xr[2 + 2 * k] = v.y;
+      }
+#pragma unroll
+      for (int k = 0; k < TVP_E / 2; ++k) {
+        const double2 vz = *reinterpret_cast<const double2*>(a.z + base + 2 * k);
+        const double2 vu = *reinterpret_cast<const double2*>(a.u + base + 2 * k);
+        const double2 vs = *reinterpret_cast<const double2*>(a.s + base + 2 * k);
+        zr[1 + 2 * k] = vz.x; zr[2 + 2 * k] = vz.y;
+        ur[1 + 2 * k] = vu.x; ur[2 + 2 * k] = vu.y;
+        sr[2 * k] = vs.x; sr[2 * k + 1] = vs.y;
+      }
+      zr[TVP_E + 1] = a.z[base + TVP_E];
+    } else {
+#pragma unroll
+      for (int k = 0; k < TVP_E + 3; ++k) { const int64_t i = base - 1 + k; xr[k] = (i >= 0 && i < n) ? a.x[i] : 0.0; }
+#pragma unroll
+      for (int k = 0; k < TVP_E + 2; ++k) { const int64_t i = base - 1 + k; zr[k] = (i >= 0 && i < n) ? a.z[i] : 0.0; }
+#pragma unroll
+      for (int k = 0; k < TVP_E + 1; ++k) { const int64_t i = base - 1 + k; ur[k] = (i >= 0 && i < n) ? a.u[i] : 0.0; }
+#pragma unroll
+      for (int k = 0; k < TVP_E; ++k) { const int64_t i = base + k; sr[k] = (i < n) ? a.s[i] : 0.0; }
+    }
+    // element i = base - 1 + k; k = 0 is the left neighbour, recomputed only for the D' stencils of
+    // the dual residual.  Values of the previous element are carried in scalars (few live registers).
     double zl = 0.0, ul = 0.0, dzl = 0.0;
-    if (base > 0) {
-      double Dx, zp, up;
-      update(base - 1, zl, ul, Dx, zp, up);
-      dzl = zl - zp;
-    }
-    double zn[TVP_E], un[TVP_E];
 #pragma unroll
-    for (int e = 0; e < TVP_E; ++e) {
-      const int64_t i = base + e;
-      if (i >= n) break;
-      double Dx, zp, up;
-      update(i, zn[e], un[e], Dx, zp, up);
-      const double dz = zn[e] - zp, du = un[e] - up;
-      const double pr = Dx + (-zn[e]) - 0.0;
-      const double dtdz = rho * ((i > 0) ? (dz - dzl) : dz);          // rho*At(B(z-zprev)) up to sign
-      const double dtu = rho * ((i > 0) ? (un[e] - ul) : un[e]);      // rho*At(u)
-      const double xs = a.x[i] - a.s[i];
-      r[0] = fma(pr, pr, r[0]);
-      r[1] = fma(Dx, Dx, r[1]);
-      r[2] = fma(zn[e], zn[e], r[2]);
-      r[3] = fma(dtdz, dtdz, r[3]);
-      r[4] = fma(dtu, dtu, r[4]);
-      r[5] = fma(dz, dz, r[5]);
-      r[6] = fma(du, du, r[6]);
-      r[7] += 0.5 * xs * xs + ((i < n - 1) ? a.lambda * fabs(Dx) : 0.0);   // totalvariation.m objective
-      dzl = dz; zl = zn[e]; ul = un[e];
-      if (a.xvals) a.xvals[(int64_t)it * n + i] = a.x[i];
+    for (int k = 0; k < TVP_E + 1; ++k) {
+      const int64_t i = base - 1 + k;
+      const double x0 = xr[k], x1 = xr[k + 1], x2 = xr[k + 2];
+      const double Dx = (i < n - 1) ? (x0 - x1) : x0;
+      const double zp = zr[k], up = ur[k];
+      double Axh = Dx, w;
+      if (relax != 1.0) {
+        // admm.m:517 Axhat = relax*A(x) - (1-relax)*(B(zprev) - c); the z-prox then applies D to the
+        // vector in x's slot (getProxOps.m:199 `u + D*x` with x := Axhat, admm.m:521)
+        Axh = relax * Dx - (1.0 - relax) * (-zp - 0.0);
+        const double Dx1 = (i + 1 < n - 1) ? (x1 - x2) : x1;
+        const double Axh1 = relax * Dx1 - (1.0 - relax) * (-zr[k + 1] - 0.0);
+        w = up + ((i < n - 1) ? (Axh - Axh1) : Axh);
+      } else {
+        w = up + Dx;
+      }
+      const double zn = soft_threshold(w, thr);
+      const double un = up + (Axh + (-zn) - 0.0);
+      const double dz = zn - zp;
+      if (k >= 1 && i < n) {
+        const double du = un - up;
+        const double pr = Dx + (-zn) - 0.0;
+        const double dtdz = rho * ((i > 0) ? (dz - dzl) : dz);       // rho*At(B(z-zprev)) up to sign
+        const double dtu = rho * ((i > 0) ? (un - ul) : un);         // rho*At(u)
+        const double xs = x0 - sr[k - 1];
+        r[0] = fma(pr, pr, r[0]);
+        r[1] = fma(Dx, Dx, r[1]);
+        r[2] = fma(zn, zn, r[2]);
+        r[3] = fma(dtdz, dtdz, r[3]);
+        r[4] = fma(dtu, dtu, r[4]);
+        r[5] = fma(dz, dz, r[5]);
+        r[6] = fma(du, du, r[6]);
+        r[7] += 0.5 * xs * xs + ((i < n - 1) ? a.lambda * fabs(Dx) : 0.0);   // totalvariation.m objective
+        // neighbouring threads read the OLD values of these elements: the new iterate goes to the
+        // other half of the double buffer
+        a.znew[i] = zn;
+        a.unew[i] = un;
+        if (a.xvals) {
+          a.xvals[(int64_t)it * n + i] = x0;
+          a.zvals[(int64_t)it * n + i] = zn;
+          a.uvals[(int64_t)it * n + i] = un;
+        }
+      }
+      zl = zn; ul = un; dzl = dz;
     }
-    // neighbouring threads read the OLD values of these elements: the new iterate goes to the other
-    // half of the double buffer
-#pragma unroll
-    for (int e = 0; e < TVP_E; ++e) {
-      const int64_t i = base + e;
-      if (i >= n) break;
-      a.znew[i] = zn[e];
-      a.unew[i] = un[e];
-      if (a.zvals) { a.zvals[(int64_t)it * n + i] = zn[e]; a.uvals[(int64_t)it * n + i] = un[e]; }
-    }
+    (void)zl;
   }
   block_reduce_store<8>(r, a.partials + (int64_t)blockIdx.x * 8, sh);
   __threadfence();
