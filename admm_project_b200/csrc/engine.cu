@@ -16,6 +16,7 @@
 #include "gemv.cuh"
 #include "prox.cuh"
 #include "tri.cuh"
+#include "gemvt.cuh"
 #include "unwrapped.cuh"
 #include "tv.cuh"
 #include <dlfcn.h>
@@ -466,6 +467,54 @@ static ColdotPlan* coldot_plan(admm_b200_handle* h, int mode, int64_t rows, int6
   return pl;
 }
 
+// rectangular D' * [v_k]: 256-row x 4-column items (gemvt.cuh)
+static void gemvt_multi(admm_b200_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols, int nv,
+                        const double* const* v, double* const* out, double scale, const double* addend, double addscale,
+                        const int* done) {
+  GemvtArgs a;
+  a.M = M; a.ld = ld; a.rows = rows; a.cols = cols; a.done = done;
+  a.ngroups = (cols + GEMVT_CG - 1) / GEMVT_CG;
+  // enough (panel, column group) units to give every CTA ~8 of them, panels of at least 2048 rows
+  int64_t P = 1;
+  if (a.ngroups < 8 * kNumSM) P = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((8 * kNumSM + a.ngroups - 1) / a.ngroups, 64), rows / 2048));
+  if (addend) P = 1;
+  int64_t per = round_up((rows + P - 1) / P, GEMVT_ROWS);
+  P = (rows + per - 1) / per;
+  a.P = (int)P; a.per = per;
+  const int64_t nunits = P * a.ngroups;
+  const int grid = (int)std::min<int64_t>(kNumSM, nunits);
+  a.units_per_cta = (nunits + grid - 1) / grid;
+  const size_t smem = (size_t)a.units_per_cta * GEMVT_CG * nv * GEMVT_WARPS * 8;
+  ADMM_REQUIRE(smem <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED, "gemvt: too many column groups per CTA");
+  static size_t configured[2] = {0, 0};
+  size_t& conf = configured[nv == 3];
+  if (smem > conf && smem > 48 * 1024) {
+    if (nv == 1) ADMM_CUDA(cudaFuncSetAttribute(gemvt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else ADMM_CUDA(cudaFuncSetAttribute(gemvt_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  if (P == 1) {
+    for (int k = 0; k < 3; ++k) { a.v[k] = v[k < nv ? k : 0]; a.out[k] = out[k < nv ? k : 0]; }
+    a.scale = scale; a.addend = addend; a.addscale = addscale;
+  } else {
+    h->cd_ws.ensure(P * cols * nv);
+    for (int k = 0; k < 3; ++k) { a.v[k] = v[k < nv ? k : 0]; a.out[k] = h->cd_ws.p + (int64_t)(k < nv ? k : 0) * P * cols; }
+    a.scale = 1.0; a.addend = nullptr; a.addscale = 0.0;
+  }
+  if (nv == 1) gemvt_kernel<1><<<grid, GEMVT_THREADS, smem, h->stream>>>(a);
+  else gemvt_kernel<3><<<grid, GEMVT_THREADS, smem, h->stream>>>(a);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+  if (P > 1) {
+    PanelReduceArgs r;
+    for (int k = 0; k < 3; ++k) { r.ws[k] = a.out[k]; r.out[k] = out[k < nv ? k : 0]; }
+    r.nv = nv; r.panels = (int)P; r.cols = cols; r.scale = scale; r.done = done;
+    panel_reduce_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, h->stream>>>(r);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+}
+
 // out_k = scale * M' v_k (+ addscale*addend, NV == 1 only), k < nv
 static void coldot_multi(admm_b200_handle* h, int mode, const double* M, int64_t ld, int64_t rows, int64_t cols, int nv,
                          const double* const* v, double* const* out, double scale, const double* addend,
@@ -475,6 +524,10 @@ static void coldot_multi(admm_b200_handle* h, int mode, const double* M, int64_t
   for (int k = 0; k < nv; ++k) ok = ok && (((uintptr_t)v[k] & 15) == 0);
   ADMM_REQUIRE(ok, ADMM_B200_ERR_UNSUPPORTED,
                "coldot: matrix and vectors must be 16-byte aligned with an even leading dimension (ld=%lld)", (long long)ld);
+  if (mode == COLDOT_FULL && rows >= 1024 && !getenv("ADMM_B200_NO_GEMVT")) {
+    gemvt_multi(h, M, ld, rows, cols, nv, v, out, scale, addend, addscale, done);
+    return;
+  }
   const ColdotPlan* plan = coldot_plan(h, mode, rows, cols);
   const size_t smem = (size_t)plan->max_pos * nv * COLDOT_WARPS * 8;
   ADMM_REQUIRE(smem <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED, "coldot: too many columns per CTA (%d)", plan->max_pos);
