@@ -23,7 +23,7 @@ namespace admmb200 {
 
 enum { COLDOT_FULL = 0, COLDOT_LOWER = 1, COLDOT_UPPER = 2 };
 constexpr int COLDOT_ITEM = 1024;      // rows per item (16 x LDG.128 per lane)
-constexpr int COLDOT_THREADS = 512;
+constexpr int COLDOT_THREADS = 640;
 constexpr int COLDOT_WARPS = COLDOT_THREADS / 32;
 
 struct ColdotItem {
