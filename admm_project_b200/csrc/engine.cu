@@ -163,15 +163,15 @@ static void ensure_tickets(admm_b200_handle* h, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 // GEMM launcher
 // ---------------------------------------------------------------------------------------------
-template <bool AK, bool BK, int VEC>
+template <bool AK, bool BK, int VEC, int BN>
 static void gemm_launch_t(admm_b200_handle* h, const GemmArgs& g, dim3 grid) {
   static bool configured = false;
   if (!configured) {
-    ADMM_CUDA(cudaFuncSetAttribute(gemm_f64_dmma_kernel<AK, BK, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ADMM_CUDA(cudaFuncSetAttribute(gemm_f64_dmma_kernel<AK, BK, VEC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    GEMM_SMEM_BYTES));
     configured = true;
   }
-  gemm_f64_dmma_kernel<AK, BK, VEC><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(g);
+  gemm_f64_dmma_kernel<AK, BK, VEC, BN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(g);
   ADMM_CUDA(cudaGetLastError());
   h->launches++;
 }
@@ -197,7 +197,9 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   g.a_lower = o.a_lower; g.b_lower = o.b_lower; g.a_upper = o.a_upper;
   g.batch = o.batch; g.strideA = o.strideA; g.strideB = o.strideB; g.strideC = o.strideC;
   g.splits = 1; g.k_per_split = std::max<int64_t>(K, 1); g.ws = nullptr;
-  const int64_t tm = (M + GEMM_BM - 1) / GEMM_BM, tn = (N + GEMM_BN - 1) / GEMM_BN;
+  const bool skinny = (N <= 64) && !o.lower_only;   // 128 x 64 tiles for few right-hand sides
+  const int64_t bnsz = skinny ? 64 : GEMM_BN;
+  const int64_t tm = (M + GEMM_BM - 1) / GEMM_BM, tn = (N + bnsz - 1) / bnsz;
   int64_t tiles = o.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   tiles *= o.batch;
   int64_t want_splits = 1;
@@ -228,8 +230,11 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   const bool BK = transb == 0;  // 'N': op(B)[k,j] = B[k + j*ldb]  (K contiguous)
 #define ADMM_GEMM_CASE(a, b)                                     \
   if (AK == a && BK == b) {                                      \
-    if (vec_ok) gemm_launch_t<a, b, 2>(h, g, grid);              \
-    else gemm_launch_t<a, b, 1>(h, g, grid);                     \
+    if (skinny) {                                                \
+      if (vec_ok) gemm_launch_t<a, b, 2, 64>(h, g, grid);        \
+      else gemm_launch_t<a, b, 1, 64>(h, g, grid);               \
+    } else if (vec_ok) gemm_launch_t<a, b, 2, 128>(h, g, grid);  \
+    else gemm_launch_t<a, b, 1, 128>(h, g, grid);                \
   }
   ADMM_GEMM_CASE(true, true)
   ADMM_GEMM_CASE(true, false)

@@ -33,14 +33,14 @@ struct GemmArgs {
   int splits; int64_t k_per_split; double* ws;   // ws: [batch][splits][M*N]
 };
 
-// Loads one 128 x 16 operand tile.  KMAJOR: element (r,k) at g[k + r*ld]; else at g[r + k*ld].
-template <bool KMAJOR, int VEC>
+// Loads one ROWS x 16 operand tile (ROWS = 128 or 64).  KMAJOR: element (r,k) at g[k + r*ld]; else at g[r + k*ld].
+template <bool KMAJOR, int VEC, int ROWS>
 __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restrict__ g, int64_t ld,
                                                int64_t r0, int64_t R, int64_t k0, int64_t Kend, int tid) {
   if (KMAJOR) {
     if (VEC == 2) {
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
+      for (int it = 0; it < ROWS / 32; ++it) {
         int r = (tid >> 3) + 32 * it, c = (tid & 7) * 2;
         int64_t gr = r0 + r, gk = k0 + c;
         int64_t left = (gr < R) ? (Kend - gk) : 0;
@@ -50,7 +50,7 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
       }
     } else {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
+      for (int it = 0; it < ROWS / 16; ++it) {
         int r = (tid >> 4) + 16 * it, c = tid & 15;
         int64_t gr = r0 + r, gk = k0 + c;
         int nb = (gr < R && gk < Kend) ? 8 : 0;
@@ -59,10 +59,12 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
       }
     }
   } else {
+    constexpr int CH2 = ROWS / 2;            // 16-byte chunks per k-row
+    constexpr int KR2 = GEMM_THREADS / CH2;  // k-rows per pass
     if (VEC == 2) {
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        int kk = (tid >> 6) + 4 * it, c = (tid & 63) * 2;
+      for (int it = 0; it < GEMM_BK / KR2; ++it) {
+        int kk = tid / CH2 + KR2 * it, c = (tid % CH2) * 2;
         int64_t gr = r0 + c, gk = k0 + kk;
         int64_t left = (gk < Kend) ? (R - gr) : 0;
         int nb = left >= 2 ? 16 : (left == 1 ? 8 : 0);
@@ -70,9 +72,10 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
         cp_async16(&s[kk * GEMM_LDM + c], src, nb);
       }
     } else {
+      constexpr int KR1 = GEMM_THREADS / ROWS;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        int kk = (tid >> 7) + 2 * it, c = tid & 127;
+      for (int it = 0; it < GEMM_BK / KR1; ++it) {
+        int kk = tid / ROWS + KR1 * it, c = tid % ROWS;
         int64_t gr = r0 + c, gk = k0 + kk;
         int nb = (gr < R && gk < Kend) ? 8 : 0;
         const double* src = nb ? (g + gr + gk * ld) : g;
@@ -82,8 +85,11 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
   }
 }
 
-template <bool AK, bool BK, int VEC>
+// BN = 128: 8 warps as 2 (M) x 4 (N), warp tile 64 x 32.  BN = 64 (skinny right-hand sides, e.g. the
+// 64-lambda batch): 8 warps as 4 (M) x 2 (N), warp tile 32 x 32, so no DMMA is spent on padding columns.
+template <bool AK, bool BK, int VEC, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs p) {
+  constexpr int MI = (BN == 128) ? 8 : 4;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   // grouped tile order (GROUP x GROUP super-tiles): the ~148 CTAs resident at any time then share
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
     bm = first_m + (pid % per_group) % gsz;
     bn = (pid % per_group) / gsz;
   }
-  const int64_t m0 = bm * GEMM_BM, n0 = bn * GEMM_BN;
+  const int64_t m0 = bm * GEMM_BM, n0 = bn * BN;
   if (p.lower_only && n0 > m0) return;  // tile strictly above the diagonal
   const int bz = blockIdx.z;
   const int batch = bz / p.splits, split = bz - batch * p.splits;
@@ -118,19 +124,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
 
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = warp & 1, wn = warp >> 1;
+  const int wm = (BN == 128) ? (warp & 1) : (warp & 3), wn = (BN == 128) ? (warp >> 1) : (warp >> 2);
+  const int wrow = wm * (MI * 8);
 
-  double acc[8][4][2];
+  double acc[MI][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < GEMM_STAGES - 1; ++s) {
     if (s < nk) {
-      gemm_load_tile<AK, VEC>(sA + s * GEMM_TILE_DOUBLES, A, p.lda, m0, p.M, kbeg + (int64_t)s * GEMM_BK, kend, tid);
-      gemm_load_tile<BK, VEC>(sB + s * GEMM_TILE_DOUBLES, B, p.ldb, n0, p.N, kbeg + (int64_t)s * GEMM_BK, kend, tid);
+      gemm_load_tile<AK, VEC, GEMM_BM>(sA + s * GEMM_TILE_DOUBLES, A, p.lda, m0, p.M, kbeg + (int64_t)s * GEMM_BK, kend, tid);
+      gemm_load_tile<BK, VEC, BN>(sB + s * GEMM_TILE_DOUBLES, B, p.ldb, n0, p.N, kbeg + (int64_t)s * GEMM_BK, kend, tid);
     }
     cp_async_commit();
   }
@@ -142,8 +149,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
       int kn = kt + GEMM_STAGES - 1;
       if (kn < nk) {
         int slot = kn % GEMM_STAGES;
-        gemm_load_tile<AK, VEC>(sA + slot * GEMM_TILE_DOUBLES, A, p.lda, m0, p.M, kbeg + (int64_t)kn * GEMM_BK, kend, tid);
-        gemm_load_tile<BK, VEC>(sB + slot * GEMM_TILE_DOUBLES, B, p.ldb, n0, p.N, kbeg + (int64_t)kn * GEMM_BK, kend, tid);
+        gemm_load_tile<AK, VEC, GEMM_BM>(sA + slot * GEMM_TILE_DOUBLES, A, p.lda, m0, p.M, kbeg + (int64_t)kn * GEMM_BK, kend, tid);
+        gemm_load_tile<BK, VEC, BN>(sB + slot * GEMM_TILE_DOUBLES, B, p.ldb, n0, p.N, kbeg + (int64_t)kn * GEMM_BK, kend, tid);
       }
       cp_async_commit();
     }
@@ -151,11 +158,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
     const double* b_s = sB + (kt % GEMM_STAGES) * GEMM_TILE_DOUBLES;
 #pragma unroll
     for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
-      double a[8], b[4];
+      double a[MI], b[4];
       const int k = ks * 4 + t;
 #pragma unroll
-      for (int mi = 0; mi < 8; ++mi) {
-        int r = wm * 64 + mi * 8 + g;
+      for (int mi = 0; mi < MI; ++mi) {
+        int r = wrow + mi * 8 + g;
         a[mi] = AK ? a_s[r * GEMM_LDK + k] : a_s[k * GEMM_LDM + r];
       }
 #pragma unroll
@@ -164,7 +171,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
         b[ni] = BK ? b_s[c * GEMM_LDK + k] : b_s[k * GEMM_LDM + c];
       }
 #pragma unroll
-      for (int mi = 0; mi < 8; ++mi)
+      for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
@@ -175,23 +182,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
   if (p.splits > 1) {
     double* W = p.ws + ((int64_t)batch * p.splits + split) * p.M * p.N;
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          int64_t r = m0 + wm * 64 + mi * 8 + g, c = n0 + wn * 32 + ni * 8 + 2 * t + e;
+          int64_t r = m0 + wrow + mi * 8 + g, c = n0 + wn * 32 + ni * 8 + 2 * t + e;
           if (r < p.M && c < p.N) W[r + c * p.M] = acc[mi][ni][e];
         }
   } else {
     double* C = p.C + (int64_t)batch * p.strideC;
 #pragma unroll
-    for (int mi = 0; mi < 8; ++mi)
+    for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          int64_t r = m0 + wm * 64 + mi * 8 + g, c = n0 + wn * 32 + ni * 8 + 2 * t + e;
+          int64_t r = m0 + wrow + mi * 8 + g, c = n0 + wn * 32 + ni * 8 + 2 * t + e;
           if (r < p.M && c < p.N) {
             double v = p.alpha * acc[mi][ni][e];
             if (p.beta != 0.0) v += p.beta * C[r + c * p.ldc];
@@ -211,7 +218,7 @@ __global__ void gemm_splitk_reduce_kernel(GemmArgs p) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = idx % p.M, c = idx / p.M;
-    if (p.lower_only && (c / GEMM_BN) > (r / GEMM_BM)) continue;
+    if (p.lower_only && (c / GEMM_BM) > (r / GEMM_BM)) continue;   // lower_only is used with BN = 128 only
     double s = 0.0;
     for (int k = 0; k < p.splits; ++k) s += W[(int64_t)k * total + idx];
     double v = p.alpha * s;
