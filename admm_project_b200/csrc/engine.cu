@@ -66,7 +66,8 @@ using namespace admmb200;
 
 struct admm_b200_handle {
   int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaStream_t own_stream = nullptr, stream = nullptr, stream2 = nullptr;   // stream2: Cholesky look-ahead
+  cudaEvent_t ev_la[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[4] = {nullptr, nullptr, nullptr, nullptr};
   double phase_ms[4] = {0, 0, 0, 0};  // gram (+Dts), cholesky, inverse factor (+transpose), total
   int64_t launches = 0;
@@ -280,6 +281,9 @@ static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda
   }
   ADMM_CUDA(cudaMemsetAsync(h->fail, 0, sizeof(int), h->stream));
   ADMM_CUDA(cudaMemset2DAsync(W, (size_t)ldw * 8, 0, (size_t)k * 8, (size_t)k, h->stream));
+  cudaStream_t sA = h->stream, sB = h->stream2;
+  ADMM_CUDA(cudaEventRecord(h->ev_la[0], sA));
+  ADMM_CUDA(cudaStreamWaitEvent(sB, h->ev_la[0], 0));
   // two-level right-looking blocking: 512-wide outer panels (so the big trailing update runs with
   // K = 512 and near-Gram efficiency), 128-wide inner steps inside a panel.
   for (int64_t K0 = 0; K0 < k; K0 += CHOL_NBO) {
@@ -310,13 +314,28 @@ static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda
     }
     const int64_t rem2 = k - K0 - wb;
     if (rem2 > 0) {  // A22 -= L21 * L21'  (lower tiles), K = wb
+      // Look-ahead on a second stream: first the columns of the NEXT outer panel (so its latency-bound
+      // factorisation chain can start), then the rest of the trailing matrix, which overlaps that chain.
       double* P = A + (K0 + wb) + K0 * lda;
+      const int64_t K1 = K0 + wb, n1 = std::min<int64_t>(CHOL_NBO, rem2);
       GemmOpt to;
       to.lower_only = 1;
       to.allow_splitk = 0;
-      gemm(h, 0, 1, rem2, rem2, wb, -1.0, P, lda, P, lda, 1.0, A + (K0 + wb) + (K0 + wb) * lda, lda, to);
+      ADMM_CUDA(cudaEventRecord(h->ev_la[0], sA));
+      ADMM_CUDA(cudaStreamWaitEvent(sB, h->ev_la[0], 0));
+      h->stream = sB;
+      gemm(h, 0, 1, rem2, n1, wb, -1.0, P, lda, P, lda, 1.0, A + K1 + K1 * lda, lda, to);
+      ADMM_CUDA(cudaEventRecord(h->ev_la[1], sB));
+      if (rem2 > n1) {
+        double* P2 = P + n1;   // rows K1+n1.. of the panel
+        gemm(h, 0, 1, rem2 - n1, rem2 - n1, wb, -1.0, P2, lda, P2, lda, 1.0, A + (K1 + n1) + (K1 + n1) * lda, lda, to);
+      }
+      h->stream = sA;
+      ADMM_CUDA(cudaStreamWaitEvent(sA, h->ev_la[1], 0));
     }
   }
+  ADMM_CUDA(cudaEventRecord(h->ev_la[0], sB));
+  ADMM_CUDA(cudaStreamWaitEvent(sA, h->ev_la[0], 0));
   {
     dim3 grid((unsigned)((k + 255) / 256), (unsigned)k);
     zero_upper_kernel<<<grid, 256, 0, h->stream>>>(A, k, lda);
@@ -1490,6 +1509,8 @@ int admm_b200_create(int device, admm_b200_handle** out) {
   admm_b200_handle* h = new admm_b200_handle();
   h->device = device;
   ADMM_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  ADMM_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  for (auto& e : h->ev_la) ADMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   h->stream = h->own_stream;
   ADMM_CUDA(cudaEventCreate(&h->ev0));
   ADMM_CUDA(cudaEventCreate(&h->ev1));
@@ -1528,6 +1549,8 @@ int admm_b200_destroy(admm_b200_handle* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto& e : h->evp) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
+  for (auto& e : h->ev_la) if (e) cudaEventDestroy(e);
   delete h;
   ADMM_API_END
 }
