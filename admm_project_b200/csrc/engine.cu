@@ -733,28 +733,52 @@ static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double*
   ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
   h->have_factor = false;
-  stage_matrix(h, m, n, D, ldD);
-  h->s.ensure(round_up(m, 2));
-  copy_in(h, h->s.p, s, m);
-  h->dts.ensure(round_up(n, 2));
   h->kind = ADMM_B200_LASSO;
   h->tall = (m >= n);
   h->rho_setup = rho;
   h->xsolve = xsolve;
   h->nA = h->nB = h->mc = n;
-  // Dts = D'*s  (lasso.m:160)
-  coldot(h, COLDOT_FULL, h->dD, h->ldD, m, n, h->s.p, h->dts.p);
+  h->s.ensure(round_up(m, 2));
+  copy_in(h, h->s.p, s, m);
+  h->dts.ensure(round_up(n, 2));
   const int64_t k = h->tall ? n : m;
   h->ldf = round_up(k, 16);
   h->L.ensure(h->ldf * k);
   GemmOpt o;
   o.lower_only = 1;
+  constexpr int64_t kPanelRows = 16384;
+  if (h->tall && !is_device_ptr(D) && m >= 2 * kPanelRows) {
+    // HOST matrix, tall: pipeline the upload with the Gram.  Row panels of D are copied on the second
+    // stream while the previous panel's D_p'D_p (and D_p's_p) accumulate on the compute stream, so the
+    // 4.3 GB H2D of config C2 hides behind the DMMA SYRK instead of preceding it.
+    const int64_t ld = round_up(m, 2);
+    h->ownD.ensure(ld * n);
+    h->dD = h->ownD.p; h->ldD = ld; h->m = m; h->n = n;
+    cudaStream_t sC = h->stream, sX = h->stream2;
+    ADMM_CUDA(cudaEventRecord(h->ev_la[0], sC));
+    ADMM_CUDA(cudaStreamWaitEvent(sX, h->ev_la[0], 0));   // ownD may still be read by earlier work
+    const int64_t npanels = (m + kPanelRows - 1) / kPanelRows;
+    for (int64_t p = 0; p < npanels; ++p) {
+      const int64_t r0 = p * kPanelRows, rows = std::min(kPanelRows, m - r0);
+      ADMM_CUDA(cudaMemcpy2DAsync(h->ownD.p + r0, (size_t)ld * 8, D + r0, (size_t)ldD * 8, (size_t)rows * 8, (size_t)n,
+                                  cudaMemcpyHostToDevice, sX));
+      ADMM_CUDA(cudaEventRecord(h->ev_la[p & 1], sX));
+      ADMM_CUDA(cudaStreamWaitEvent(sC, h->ev_la[p & 1], 0));
+      o.diag_add = (p == npanels - 1) ? rho : 0.0;
+      gemm(h, 1, 0, n, n, rows, 1.0, h->ownD.p + r0, ld, h->ownD.p + r0, ld, p ? 1.0 : 0.0, h->L.p, h->ldf, o);
+      coldot(h, COLDOT_FULL, h->ownD.p + r0, ld, rows, n, h->s.p + r0, h->dts.p, 1.0, p ? h->dts.p : nullptr, 1.0);
+    }
+  } else {
+  stage_matrix(h, m, n, D, ldD);
+  // Dts = D'*s  (lasso.m:160)
+  coldot(h, COLDOT_FULL, h->dD, h->ldD, m, n, h->s.p, h->dts.p);
   if (h->tall) {  // chol(D'*D + rho*I)  (lasso.m:168)
     o.diag_add = rho;
     gemm(h, 1, 0, n, n, m, 1.0, h->dD, h->ldD, h->dD, h->ldD, 0.0, h->L.p, h->ldf, o);
   } else {        // chol(1/rho*(D*D') + I)  (lasso.m:172)
     o.diag_add = 1.0;
     gemm(h, 0, 1, m, m, n, 1.0 / rho, h->dD, h->ldD, h->dD, h->ldD, 0.0, h->L.p, h->ldf, o);
+  }
   }
   ADMM_CUDA(cudaEventRecord(h->evp[1], h->stream));
   factor_current(h, k, xsolve == ADMM_B200_XSOLVE_INVFACTOR);

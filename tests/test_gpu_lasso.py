@@ -100,3 +100,14 @@ def test_lasso_errors_match_reference_messages(engine):
         lasso(D, s, lam, {"Hnormtol": 1e-3}, engine=engine)
     with pytest.raises(EngineError):
         lasso(D, s, lam, {"parallel": "both"}, engine=engine)
+
+
+def test_lasso_tall_host_matrix_pipelined_upload(engine):
+    """m >= 32768 with a HOST matrix takes the panel-pipelined path (H2D of row panels overlapped with
+    the accumulation of D_p'D_p and D_p's_p); the result must not depend on it."""
+    D, s, lam, _ = lasso_problem(6, 40000, 48)      # 3 panels: 16384 + 16384 + 7232 rows
+    ref = oracle.lasso(D, s, lam, {"history": 0, "objevals": 1})
+    res = lasso(D, s, lam, {"history": 0, "objevals": 1}, engine=engine)
+    compare(res, ref, hist=False)
+    G = D.T @ D + np.eye(48)
+    assert rel(engine.get_factor(), np.linalg.cholesky(G)) < 1e-12
