@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libadmm_b200.so")
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOTPOSDEF, ERR_COMM, ERR_UNSUPPORTED = range(7)
 LASSO, BASISPURSUIT, TOTALVARIATION, SVM_HINGE, SVM_01, HUBERFIT, LAD, PROX_NONNEG, PROX_BOX = range(1, 10)
 STOP_STANDARD, STOP_HNORM, STOP_BOTH = 0, 1, 2
-RUNNING, CONVERGED_STD, CONVERGED_HNORM, MAXITERS, DIVERGED_RETURN = range(5)
+RUNNING, CONVERGED_STD, CONVERGED_HNORM, MAXITERS, DIVERGED_RETURN, CONVERGED_DVAL = range(6)
 XSOLVE_INVFACTOR, XSOLVE_SUBST = 0, 1
 
 _dp = C.POINTER(C.c_double)
@@ -34,7 +34,8 @@ class Options(C.Structure):
                 ("reltol", C.c_double), ("convtol", C.c_double), ("hnormtol", C.c_double),
                 ("maxiters", C.c_int64), ("domaxiters", C.c_int32), ("stopcond", C.c_int32),
                 ("nodualerror", C.c_int32), ("convtest", C.c_int32), ("objevals", C.c_int32),
-                ("history", C.c_int32), ("xsolve", C.c_int32), ("check_every", C.c_int32)]
+                ("history", C.c_int32), ("xsolve", C.c_int32), ("check_every", C.c_int32),
+                ("fast", C.c_int32), ("fasttype", C.c_int32), ("restart", C.c_double), ("dvaltol", C.c_double)]
 
 
 class Result(C.Structure):
@@ -43,7 +44,8 @@ class Result(C.Structure):
                 ("xopt", _dp), ("zopt", _dp), ("uopt", _dp),
                 ("pnorm", _dp), ("dnorm", _dp), ("perr", _dp), ("derr", _dp),
                 ("hnormsq", _dp), ("objevals", _dp),
-                ("xvals", _dp), ("zvals", _dp), ("uvals", _dp)]
+                ("xvals", _dp), ("zvals", _dp), ("uvals", _dp),
+                ("dvals", _dp), ("avals", _dp), ("restarted", _dp)]
 
 
 # every symbol include/admm_b200.h declares: name -> (restype, argtypes)

@@ -45,8 +45,6 @@ def admm(xminf, zming, options):
     if setopt(options, "adaptive", 0):
         raise L.EngineError(L.ERR_UNSUPPORTED, "options.adaptive is an unfinished experiment in the reference "
                             "(admm.m:724-741) and is not built")
-    if setopt(options, "fast", 0):
-        raise L.EngineError(L.ERR_UNSUPPORTED, "options.fast (fast/accelerated ADMM, admm.m:267-298) is not built yet")
     quiet = setopt(options, "quiet", 1)
     o = eng.default_options()
     o.rho = float(setopt(options, "rho", 1.0))
@@ -72,6 +70,13 @@ def admm(xminf, zming, options):
     o.history = int(bool(setopt(options, "history", 1)))                    # extension
     o.xsolve = int(setopt(options, "xsolve", L.XSOLVE_INVFACTOR))
     o.check_every = int(setopt(options, "check_every", 8))
+    o.fast = int(bool(setopt(options, "fast", 0)))                          # admm.m:59-60, 267-298
+    o.fasttype = int(setopt(options, "fasttype", "weak") == "weak")
+    alg = (2 if o.fasttype else 1) if o.fast else 0
+    if alg == 2:
+        nrestart = setopt(options, "restart", 0.999)
+        o.restart = float(nrestart) if 0 < nrestart < 1 else 0.999
+        o.dvaltol = float(setopt(options, "dvaltol", 1e-8))
     for key in ("A", "B", "c"):                                             # admm.m:79-245
         if key not in options and not (key == "c" and options.get("m", 0) > 0):
             what = "vector c" if key == "c" else "matrix " + key
@@ -102,8 +107,15 @@ def admm(xminf, zming, options):
         for key in ("zopt", "uopt", "zvals", "uvals"):
             if key in r:
                 r[key] = gather_rows(r[key], mt)
-    results["pnorm"], results["dnorm"] = r["pnorm"], r["dnorm"]
-    results["perr"], results["derr"] = r["perr"], r["derr"]
+    if alg == 2:                            # the accelerated variant records d, not residual norms
+        results["dvaltol"] = o.dvaltol
+        results["pnorm"], results["dnorm"] = np.zeros(0), np.zeros(0)
+        results["dvals"], results["restarted"] = r["dvals"], r["restarted"]
+    else:
+        results["pnorm"], results["dnorm"] = r["pnorm"], r["dnorm"]
+        results["perr"], results["derr"] = r["perr"], r["derr"]
+    if alg:
+        results["avals"] = r["avals"]
     if use_hnorm:
         results["Hnormsq"] = r["hnormsq"]
     if o.objevals:

@@ -104,6 +104,7 @@ struct admm_b200_handle {
   DBuf xvals, zvals, uvals;
   DBuf gemm_ws, gemv_ws, scratch, cd_ws;
   bool iter_ready = false;
+  DBuf fv, fuhat, fzprev, fuprev;   // fast / accelerated ADMM state
   // A = D family (svm / huber / lad)
   DBuf aux, rvec, dzvec, cb, uw_partials;
   unsigned* grid_ticket = nullptr;
@@ -1052,9 +1053,13 @@ static LoopParams make_loop_params(admm_b200_handle* h, const admm_b200_options&
   lp.objevals = o.objevals;
   lp.use_hnorm = (o.convtest || o.stopcond == ADMM_B200_STOP_HNORM || o.stopcond == ADMM_B200_STOP_BOTH) ? 1 : 0;
   lp.raw = raw;
+  lp.alg = o.fast ? (o.fasttype ? 2 : 1) : 0;
+  lp.nrestart = (o.restart > 0.0 && o.restart < 1.0) ? o.restart : 0.999;   // admm.m:287-290
+  lp.dvaltol = o.dvaltol;
   double* hp = h->hist.p;
   lp.pnorm = hp; lp.dnorm = hp + h->hist_cap; lp.perr = hp + 2 * h->hist_cap; lp.derr = hp + 3 * h->hist_cap;
   lp.hn = hp + 4 * h->hist_cap; lp.obj = hp + 5 * h->hist_cap;
+  lp.dvals = hp + 6 * h->hist_cap; lp.avals = hp + 7 * h->hist_cap; lp.rst = hp + 8 * h->hist_cap;
   return lp;
 }
 
@@ -1071,6 +1076,8 @@ static void alloc_iterates(admm_b200_handle* h) {
   h->t1.ensure(big);
   h->t2.ensure(big);
   h->partials.ensure(2 * kNumSM * 16);
+  h->fv.ensure(round_up(h->nB, 2)); h->fuhat.ensure(round_up(h->mc, 2));
+  h->fzprev.ensure(round_up(h->nB, 2)); h->fuprev.ensure(round_up(h->mc, 2));
   if (is_unwrapped(h->kind)) {
     const int64_t need = 3 * round_up(h->n, 2) + 16;
     if (h->cb.cap < need) {
@@ -1092,7 +1099,12 @@ static void load_init(admm_b200_handle* h) {
     ADMM_CUDA(cudaMemsetAsync(h->z.p, 0, (size_t)h->nB * 8, h->stream));
     ADMM_CUDA(cudaMemsetAsync(h->u.p, 0, (size_t)h->mc * 8, h->stream));
   }
-  ADMM_CUDA(cudaMemsetAsync(h->ctl, 0, sizeof(LoopCtl), h->stream));
+  // v = z0, uhat = u0 (admm.m:268-269)
+  ADMM_CUDA(cudaMemcpyAsync(h->fv.p, h->z.p, (size_t)h->nB * 8, cudaMemcpyDeviceToDevice, h->stream));
+  ADMM_CUDA(cudaMemcpyAsync(h->fuhat.p, h->u.p, (size_t)h->mc * 8, cudaMemcpyDeviceToDevice, h->stream));
+  ctl_init_kernel<<<1, 32, 0, h->stream>>>(h->ctl, 1);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
   h->iter_ready = true;
 }
 
@@ -1161,9 +1173,19 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     a.xvals = history ? h->xvals.p : nullptr;
     a.zvals = history ? h->zvals.p : nullptr;
     a.uvals = history ? h->uvals.p : nullptr;
+    a.v = h->fv.p; a.uhat = h->fuhat.p; a.zprev = h->fzprev.p; a.uprev = h->fuprev.p;
     prox_ident_kernel<<<prox_grid(n), PROX_THREADS, 0, h->stream>>>(a);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
+    if (lp.alg != 0) {   // acceleration pass (admm.m:562-600) + scalar epilogue
+      AccelIdentArgs b;
+      b.n = n; b.z = h->z.p; b.u = h->u.p; b.zprev = h->fzprev.p; b.uprev = h->fuprev.p; b.dts = a.dts;
+      b.v = h->fv.p; b.uhat = h->fuhat.p; b.y = h->y.p; b.next = a.next;
+      b.partials = h->partials.p; b.ctl = h->ctl; b.lp = lp;
+      accel_ident_kernel<<<prox_grid(n), PROX_THREADS, 0, h->stream>>>(b);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+    }
   } else if (h->kind == ADMM_B200_LASSO || h->kind == ADMM_B200_PROX_BOX || h->kind == ADMM_B200_PROX_NONNEG) {
     const int64_t n = h->n, m = h->m;
     const bool qp = h->kind != ADMM_B200_LASSO;
@@ -1200,9 +1222,19 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     a.xvals = history ? h->xvals.p : nullptr;
     a.zvals = history ? h->zvals.p : nullptr;
     a.uvals = history ? h->uvals.p : nullptr;
+    a.v = h->fv.p; a.uhat = h->fuhat.p; a.zprev = h->fzprev.p; a.uprev = h->fuprev.p;
     prox_ident_kernel<<<prox_grid(n), PROX_THREADS, 0, h->stream>>>(a);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
+    if (lp.alg != 0) {   // acceleration pass (admm.m:562-600) + scalar epilogue
+      AccelIdentArgs b;
+      b.n = n; b.z = h->z.p; b.u = h->u.p; b.zprev = h->fzprev.p; b.uprev = h->fuprev.p; b.dts = a.dts;
+      b.v = h->fv.p; b.uhat = h->fuhat.p; b.y = h->y.p; b.next = a.next;
+      b.partials = h->partials.p; b.ctl = h->ctl; b.lp = lp;
+      accel_ident_kernel<<<prox_grid(n), PROX_THREADS, 0, h->stream>>>(b);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+    }
   } else if (is_unwrapped(h->kind)) {
     const int64_t n = h->n, m = h->m, npad = round_up(n, 2);
     const int nv = o.nodualerror ? 1 : 3;
@@ -1231,17 +1263,30 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     a.partials = h->uw_partials.p; a.grid_ticket = h->grid_ticket; a.scalars = scal; a.ctl = h->ctl;
     a.zvals = history ? h->zvals.p : nullptr;
     a.uvals = history ? h->uvals.p : nullptr;
+    a.alg = lp.alg; a.v = h->fv.p; a.uhat = h->fuhat.p; a.zprev = h->fzprev.p; a.uprev = h->fuprev.p;
     dim3 grid((unsigned)rb, (unsigned)chunks);
     const bool vec_ok = (((uintptr_t)h->dD & 15) == 0) && (h->ldD % 2 == 0);
     if (vec_ok) uw_gemv_prox_kernel<2><<<grid, UW_THREADS, 0, h->stream>>>(a);
     else uw_gemv_prox_kernel<1><<<grid, UW_THREADS, 0, h->stream>>>(a);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
-    // D_g' * [rhs, z - zprev, u] in one pass
+    if (lp.alg != 0) {
+      // fast variants: the restart decision needs the rank-summed ||u-uhat||^2, ||z-v||^2 BEFORE the
+      // acceleration pass, so the scalars travel in their own (tiny) allreduce
+      allreduce_sum(h, scal, UW_NRED);
+      uw_accel_decide_kernel<<<1, 1, 0, h->stream>>>(h->ctl, lp, scal);
+      ADMM_CUDA(cudaGetLastError());
+      uw_accel_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, h->z.p, h->u.p, h->fzprev.p, h->fuprev.p,
+                                                                          h->aux.p, a.kind, h->fv.p, h->fuhat.p, h->rvec.p,
+                                                                          (nv == 3) ? h->dzvec.p : nullptr, h->ctl);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches += 2;
+    }
+    // D_g' * [rhs, z - zprev (or z - v), u] in one pass
     const double* vs[3] = {h->rvec.p, h->dzvec.p, h->u.p};
     double* os[3] = {d, d + npad, d + 2 * npad};
     coldot_multi(h, COLDOT_FULL, h->dD, h->ldD, m, n, nv, vs, os, 1.0, nullptr, 0.0, done);
-    allreduce_sum(h, d, (int64_t)nv * npad + UW_NRED);
+    allreduce_sum(h, d, (int64_t)nv * npad + (lp.alg == 0 ? UW_NRED : 0));
     UwEpiArgs e;
     e.n = n; e.x = h->x.p; e.dzv = (nv == 3) ? d + npad : nullptr; e.duv = (nv == 3) ? d + 2 * npad : nullptr;
     e.scalars = scal; e.m_total = (double)h->m_total; e.kind = a.kind; e.C = h->svmC; e.ctl = h->ctl; e.lp = lp;
@@ -1284,6 +1329,9 @@ static void validate_options(admm_b200_handle* h, const admm_b200_options& o) {
   ADMM_REQUIRE(h->kind != 0, ADMM_B200_ERR_STATE, "no problem set up on this handle");
   ADMM_REQUIRE(o.rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
   ADMM_REQUIRE(o.stopcond >= 0 && o.stopcond <= 2, ADMM_B200_ERR_INVALID, "invalid stopcond %d", o.stopcond);
+  if (o.fast)
+    ADMM_REQUIRE(h->kind != ADMM_B200_TOTALVARIATION, ADMM_B200_ERR_UNSUPPORTED,
+                 "options.fast is not built for totalvariation");
   if (h->kind == ADMM_B200_SVM_HINGE || h->kind == ADMM_B200_SVM_01)
     ADMM_REQUIRE(o.relax == 1.0, ADMM_B200_ERR_INVALID,
                  "Inner matrix dimensions must agree. (linearsvm with relax ~= 1: the reference's zminLinearSVM "
@@ -1298,7 +1346,7 @@ static void prepare_loop(admm_b200_handle* h, const admm_b200_options& o, int64_
   alloc_iterates(h);
   if (maxiters > h->hist_cap) {
     h->hist.release();
-    h->hist.ensure(6 * maxiters);
+    h->hist.ensure(9 * maxiters);
     h->hist_cap = maxiters;
   }
   if (history) {
@@ -1349,10 +1397,17 @@ static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_res
   res->loop_ms = ms;
   res->objopt = NAN;
   const double* hp = h->hist.p;
-  copy_out(h, res->pnorm, hp, steps);
-  copy_out(h, res->dnorm, hp + h->hist_cap, steps);
-  copy_out(h, res->perr, hp + 2 * h->hist_cap, steps);
-  copy_out(h, res->derr, hp + 3 * h->hist_cap, steps);
+  if (lp.alg != 2) {
+    copy_out(h, res->pnorm, hp, steps);
+    copy_out(h, res->dnorm, hp + h->hist_cap, steps);
+    copy_out(h, res->perr, hp + 2 * h->hist_cap, steps);
+    copy_out(h, res->derr, hp + 3 * h->hist_cap, steps);
+  }
+  if (lp.alg == 2) {
+    copy_out(h, res->dvals, hp + 6 * h->hist_cap, steps);
+    copy_out(h, res->restarted, hp + 8 * h->hist_cap, steps);
+  }
+  if (lp.alg != 0) copy_out(h, res->avals, hp + 7 * h->hist_cap, steps);
   if (lp.use_hnorm) copy_out(h, res->hnormsq, hp + 4 * h->hist_cap, steps);
   if (o.objevals) {
     copy_out(h, res->objevals, hp + 5 * h->hist_cap, steps);
@@ -1407,12 +1462,13 @@ static void solve_lasso_batch(admm_b200_handle* h, const admm_b200_options& o, i
   };
   try {
     X.ensure(ld * nb); Z.ensure(ld * nb); U.ensure(ld * nb); Y.ensure(ld * nb); T.ensure(ld * nb); XK.ensure(ld * nb);
-    hist.ensure(6 * N * nb); thr.ensure(nb); osc.ensure(nb);
+    hist.ensure(9 * N * nb); thr.ensure(nb); osc.ensure(nb);
     const int pg = prox_grid(n);
     part.ensure((int64_t)pg * PROX_NRED * nb);
     ADMM_CUDA(cudaMalloc(&ctl, sizeof(LoopCtl) * nb));
     ADMM_CUDA(cudaMalloc(&done_count, sizeof(int)));
-    ADMM_CUDA(cudaMemsetAsync(ctl, 0, sizeof(LoopCtl) * nb, h->stream));
+    ctl_init_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, h->stream>>>(ctl, (int)nb);
+    ADMM_CUDA(cudaGetLastError());
     ADMM_CUDA(cudaMemsetAsync(done_count, 0, sizeof(int), h->stream));
     ADMM_CUDA(cudaMemcpyAsync(thr.p, hthr.data(), nb * 8, cudaMemcpyHostToDevice, h->stream));
     ADMM_CUDA(cudaMemcpyAsync(osc.p, hosc.data(), nb * 8, cudaMemcpyHostToDevice, h->stream));
@@ -1426,6 +1482,8 @@ static void solve_lasso_batch(admm_b200_handle* h, const admm_b200_options& o, i
     LoopParams lp = make_loop_params(h, o, N, 0);
     lp.pnorm = hist.p; lp.dnorm = hist.p + N * nb; lp.perr = hist.p + 2 * N * nb; lp.derr = hist.p + 3 * N * nb;
     lp.hn = hist.p + 4 * N * nb; lp.obj = hist.p + 5 * N * nb;
+    lp.dvals = hist.p + 6 * N * nb; lp.avals = hist.p + 7 * N * nb; lp.rst = hist.p + 8 * N * nb;
+    ADMM_REQUIRE(lp.alg == 0, ADMM_B200_ERR_UNSUPPORTED, "lasso batch: options.fast is not built for a batch");
     const int check = std::max(1, o.check_every);
     int64_t enq = 0;
     int hdone = 0;
@@ -1446,6 +1504,7 @@ static void solve_lasso_batch(admm_b200_handle* h, const admm_b200_options& o, i
         a.partials = part.p; a.ctl = ctl; a.lp = lp;
         a.xvals = a.zvals = a.uvals = nullptr;
         a.ld = ld; a.thresh_v = thr.p; a.objscale_v = osc.p; a.hist_stride = N; a.done_count = done_count; a.xkeep = XK.p;
+        a.v = a.uhat = nullptr; a.zprev = a.uprev = nullptr;
         prox_ident_kernel<<<dim3(pg, (unsigned)nb), PROX_THREADS, 0, h->stream>>>(a);
         ADMM_CUDA(cudaGetLastError());
         h->launches++;
@@ -1509,6 +1568,7 @@ void admm_b200_default_options(admm_b200_options* o) {
   o->rho = 1.0; o->relax = 1.0; o->abstol = 1e-5; o->reltol = 1e-3; o->convtol = 1e-10; o->hnormtol = 1e-6;
   o->maxiters = 1000; o->domaxiters = 0; o->stopcond = ADMM_B200_STOP_STANDARD; o->nodualerror = 0;
   o->convtest = 0; o->objevals = 0; o->history = 1; o->xsolve = ADMM_B200_XSOLVE_INVFACTOR; o->check_every = 8;
+  o->fast = 0; o->fasttype = 1; o->restart = 0.999; o->dvaltol = 1e-8;
 }
 
 int admm_b200_create(int device, admm_b200_handle** out) {
@@ -1557,7 +1617,7 @@ int admm_b200_destroy(admm_b200_handle* h) {
   cudaStreamSynchronize(h->stream);
   DBuf* bufs[] = {&h->ownD, &h->s, &h->dts, &h->L, &h->W, &h->WT, &h->x, &h->z, &h->u, &h->y, &h->t1, &h->t2,
                   &h->x0, &h->z0, &h->u0, &h->partials, &h->hist, &h->xvals, &h->zvals, &h->uvals, &h->gemm_ws,
-                  &h->gemv_ws, &h->scratch, &h->cd_ws, &h->aux, &h->rvec, &h->dzvec, &h->cb, &h->uw_partials, &h->zz, &h->uu, &h->tvtab, &h->Pfull, &h->lb, &h->ub};
+                  &h->gemv_ws, &h->scratch, &h->cd_ws, &h->aux, &h->rvec, &h->dzvec, &h->cb, &h->uw_partials, &h->zz, &h->uu, &h->tvtab, &h->Pfull, &h->lb, &h->ub, &h->fv, &h->fuhat, &h->fzprev, &h->fuprev};
   for (DBuf* b : bufs) b->release();
   for (ColdotPlan* p : h->plans) {
     cudaFree(p->d_cta_pos); cudaFree(p->d_pos_item); cudaFree(p->d_order); cudaFree(p->d_items);

@@ -24,18 +24,25 @@ struct LoopCtl {
   unsigned ticket;   // last-block election
   double objpart;    // objective term produced by an earlier kernel of the iteration
   double pad;
+  // fast / accelerated ADMM (admm.m:267-298, 562-600)
+  double acurr, d, dprev, gamma;   // alpha_k, d_k, d_{k-1}, (alpha_{k-1} - 1) / alpha_k
+  int restart, pad2;
+  double sums[8];                  // norm sums of the z/u pass, consumed by the acceleration pass
 };
 
 struct LoopParams {
   double rho, relax, abstol, reltol, convtol, hnormtol, eps;
   long long maxiters;
   int domaxiters, stopcond, nodualerror, convtest, objevals, use_hnorm, raw;  // raw: no stop test
+  int alg;                                         // 0 ADMM, 1 fast ADMM, 2 accelerated ADMM with restart
+  double nrestart, dvaltol;
   double *pnorm, *dnorm, *perr, *derr, *hn, *obj;  // device history, length maxiters
+  double *dvals, *avals, *rst;
 };
 
 enum { PROX_SOFT = 0, PROX_NONNEG = 1, PROX_BOX = 2 };
 enum { NEXT_LASSO = 0, NEXT_DIFF = 1 };
-constexpr int PROX_NRED = 8;
+constexpr int PROX_NRED = 10;
 constexpr int PROX_THREADS = 256;
 
 struct ProxIdentArgs {
@@ -59,6 +66,9 @@ struct ProxIdentArgs {
   int64_t hist_stride;            // per-column stride of the scalar histories
   int* done_count;                // number of columns whose loop has ended (NULL for a single problem)
   double* xkeep;                  // batch: x of the last iteration a column ran (the GEMMs keep overwriting x)
+  // fast / accelerated ADMM: the prox uses uhat, z/u of the previous iteration are kept for the acceleration pass
+  const double *v, *uhat;
+  double *zprev, *uprev;
 };
 
 __device__ __forceinline__ double soft_threshold(double v, double t) {
@@ -97,20 +107,24 @@ __device__ inline void loop_epilogue(LoopCtl* ctl, const LoopParams& lp, const d
   const double de = lp.nodualerror ? __longlong_as_double(0x7ff8000000000000LL)
                                    : sqrt(M2) * lp.abstol + lp.reltol * sqrt(red[5]);
   const double hn = lp.rho * red[6] + lp.rho * (lp.rho * lp.rho * red[7]);  // admm.m:305-306 on w = [x;z;rho*u]
-  lp.pnorm[slot] = pn;
-  lp.dnorm[slot] = dn;
-  lp.perr[slot] = pe;
-  lp.derr[slot] = de;
+  if (lp.alg != 2) {          // admm.m:618-658: the accelerated variant records no residual norms
+    lp.pnorm[slot] = pn;
+    lp.dnorm[slot] = dn;
+    lp.perr[slot] = pe;
+    lp.derr[slot] = de;
+  }
   if (lp.use_hnorm) lp.hn[slot] = hn;
   if (lp.objevals) lp.obj[slot] = obj;
   int done = 0, status = 0;
   if (!lp.raw) {
-    if (lp.convtest && i >= 2) {  // admm.m:689-700
+    if (lp.convtest && i >= 2 && lp.alg == 0) {  // admm.m:689-700
       const double H2 = hn, H1 = lp.hn[i - 2];
       if (H1 > lp.eps && H2 > H1 && !((H2 - H1) <= H1 * lp.convtol)) { done = 1; status = 4; }
     }
-    if (!done && (lp.stopcond == 0 || lp.stopcond == 2) && !lp.domaxiters && pn < pe &&
-        (lp.nodualerror || dn < de)) { done = 1; status = 1; }  // admm.m:710-713
+    if (lp.alg == 2) {                                          // admm.m:706-707
+      if (!done && i >= 2 && fabs(ctl->d - ctl->dprev) <= lp.dvaltol * ctl->dprev) { done = 1; status = 5; }
+    } else if (!done && (lp.stopcond == 0 || lp.stopcond == 2) && !lp.domaxiters && pn < pe &&
+               (lp.nodualerror || dn < de)) { done = 1; status = 1; }  // admm.m:710-713
     if (!done && (lp.stopcond == 1 || lp.stopcond == 2) && !lp.domaxiters && i > 2 && hn <= lp.hnormtol) {
       done = 1; status = 2;                                    // admm.m:719-722
     }
@@ -121,6 +135,43 @@ __device__ inline void loop_epilogue(LoopCtl* ctl, const LoopParams& lp, const d
   ctl->objpart = 0.0;
   __threadfence();
   ctl->done = done;
+}
+
+// admm.m:562-600: predictor/corrector weight of this iteration (one thread).  s_uuh = ||u - uhat||^2,
+// s_zv = ||B(z - v)||^2 with the v / uhat the iteration started from.
+__device__ inline void accel_decide(LoopCtl* ctl, const LoopParams& lp, double s_uuh, double s_zv) {
+  const int slot = lp.raw ? 0 : ctl->it;
+  const double aprev = ctl->acurr;
+  double acurr = 0.5 * (1.0 + sqrt(1.0 + 4.0 * aprev * aprev));
+  int restart = 0;
+  if (lp.alg == 2) {
+    const double dprev = ctl->d;
+    double d = 1.0 / lp.rho * s_uuh + lp.rho * s_zv;
+    if (!(d < lp.nrestart * dprev)) {       // restart (admm.m:591-596)
+      acurr = 1.0;
+      restart = 1;
+      d = dprev / lp.nrestart;
+    }
+    ctl->dprev = dprev;
+    ctl->d = d;
+    lp.dvals[slot] = d;
+    lp.rst[slot] = (double)restart;
+  }
+  ctl->gamma = (aprev - 1.0) / acurr;
+  ctl->acurr = acurr;
+  ctl->restart = restart;
+  lp.avals[slot] = acurr;
+}
+
+__global__ void ctl_init_kernel(LoopCtl* ctl, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LoopCtl c;
+  memset(&c, 0, sizeof(c));
+  c.acurr = 1.0;
+  c.d = __longlong_as_double(0x7ff0000000000000LL);      // Inf (admm.m:283-284)
+  c.dprev = c.d;
+  ctl[i] = c;
 }
 
 __global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs a) {
@@ -145,8 +196,10 @@ __global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs 
 #pragma unroll
   for (int k = 0; k < PROX_NRED; ++k) r[k] = 0.0;
 
+  const bool fastmode = a.lp.alg != 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
-    const double x = a.x[i], zp = a.z[i], up = a.u[i];
+    const double x = a.x[i], zp = a.z[i], uold = a.u[i];
+    const double up = fastmode ? a.uhat[i] : uold;      // admm.m:506-529: the fast variants use uhat
     double xh = x;
     if (relax != 1.0) xh = relax * x - (1.0 - relax) * (-zp - 0.0);
     const double v = xh + up;
@@ -158,13 +211,13 @@ __global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs 
     a.z[i] = z;
     a.u[i] = u;
     if (a.xkeep) a.xkeep[i] = x;
-    a.y[i] = (a.next == NEXT_LASSO) ? (rho * (z - u) + a.dts[i]) : (z - u);
+    if (!fastmode) a.y[i] = (a.next == NEXT_LASSO) ? (rho * (z - u) + a.dts[i]) : (z - u);
     if (a.xvals) {
       a.xvals[(int64_t)it * a.n + i] = x;
       a.zvals[(int64_t)it * a.n + i] = z;
       a.uvals[(int64_t)it * a.n + i] = u;
     }
-    const double pr = x + (-z) - 0.0, dz = z - zp, du = u - up;
+    const double pr = x + (-z) - 0.0, dz = z - zp, du = u - uold;
     r[0] = fma(pr, pr, r[0]);
     r[1] = fma(x, x, r[1]);
     r[2] = fma(z, z, r[2]);
@@ -172,6 +225,13 @@ __global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs 
     r[4] = fma(u, u, r[4]);
     r[5] = fma(du, du, r[5]);
     r[6] += a.obj_l1_of_x ? fabs(x) : fabs(z);
+    if (fastmode) {
+      a.zprev[i] = zp;
+      a.uprev[i] = uold;
+      const double e1 = u - up, e2 = z - a.v[i];
+      r[7] = fma(e1, e1, r[7]);                 // ||u - uhat||^2
+      r[8] = fma(e2, e2, r[8]);                 // ||B(z - v)||^2
+    }
   }
   block_reduce_store<PROX_NRED>(r, a.partials + (int64_t)blockIdx.x * PROX_NRED, sh);
   __threadfence();
@@ -191,6 +251,16 @@ __global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs 
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    ctl->ticket = 0;
+    if (fastmode) {
+      // the residual norms need the NEW v (admm.m:629-633), so the epilogue runs in the acceleration
+      // pass; here: keep the sums and fix this iteration's predictor weight / restart
+#pragma unroll
+      for (int k = 0; k < 7; ++k) ctl->sums[k] = sh[k];
+      ctl->sums[7] = ctl->objpart + a.objscale * sh[6];
+      accel_decide(ctl, a.lp, sh[7], sh[8]);
+      return;
+    }
     double red[8];
     red[0] = sh[0];                  // ||x - z||^2
     red[1] = sh[1];                  // ||A x||^2 = ||x||^2
@@ -200,11 +270,68 @@ __global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs 
     red[5] = rho * rho * sh[4];      // ||rho * At(u)||^2
     red[6] = sh[3];
     red[7] = sh[5];
-    ctl->ticket = 0;
     const double obj = ctl->objpart + a.objscale * sh[6];
     loop_epilogue(ctl, a.lp, red, (double)a.n, (double)a.n, obj);
     if (a.done_count && ctl->done) atomicAdd(a.done_count, 1);
   }
+}
+
+// Acceleration pass of the fast variants for the x - z = 0 problems (admm.m:562-600):
+//   v = z + gamma*(z - zprev), uhat = u + gamma*(u - uprev)   or, on a restart, v = zprev, uhat = uprev;
+//   y = rhs of the next x-update from (v, uhat) (admm.m:506); sum ||z - v||^2 for the dual residual of
+//   the fast variant (admm.m:629-633); last CTA: the scalar epilogue.
+struct AccelIdentArgs {
+  int64_t n;
+  const double *z, *u, *zprev, *uprev, *dts;
+  double *v, *uhat, *y;
+  int next;
+  double* partials;       // [gridDim.x]
+  LoopCtl* ctl;
+  LoopParams lp;
+};
+
+__global__ void __launch_bounds__(PROX_THREADS) accel_ident_kernel(AccelIdentArgs a) {
+  LoopCtl* ctl = a.ctl;
+  if (ctl->done) return;
+  __shared__ double sh[PROX_THREADS / 32];
+  __shared__ bool is_last;
+  const double gamma = ctl->gamma, rho = a.lp.rho;
+  const int restart = ctl->restart;
+  double r1[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double z = a.z[i], u = a.u[i], zp = a.zprev[i], up = a.uprev[i];
+    const double v = restart ? zp : z + gamma * (z - zp);
+    const double uh = restart ? up : u + gamma * (u - up);
+    a.v[i] = v;
+    a.uhat[i] = uh;
+    a.y[i] = (a.next == NEXT_LASSO) ? (rho * (v - uh) + a.dts[i]) : (v - uh);
+    const double e = z - v;
+    r1[0] = fma(e, e, r1[0]);
+  }
+  block_reduce_store<1>(r1, a.partials + blockIdx.x, sh);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(&ctl->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  double szv = 0.0;
+  for (unsigned b = 0; b < gridDim.x; ++b) szv += __ldcg(a.partials + b);
+  ctl->ticket = 0;
+  const double* sm = ctl->sums;
+  double red[8];
+  red[0] = sm[0];
+  red[1] = sm[1];
+  red[2] = sm[2];
+  red[3] = 0.0;
+  red[4] = rho * rho * szv;        // rho*norm(At(B(z - v))), At = 1 (admm.m:631)
+  red[5] = rho * rho * sm[4];
+  red[6] = sm[3];
+  red[7] = sm[5];
+  loop_epilogue(ctl, a.lp, red, (double)a.n, (double)a.n, sm[7]);
 }
 
 // objective term 0.5*||D x - s||^2 from r = D*x computed by the GEMV kernel (lasso.m:227)

@@ -18,7 +18,7 @@
 namespace admmb200 {
 
 enum { UW_SVM_HINGE = 0, UW_SVM_01 = 1, UW_HUBER = 2, UW_LAD = 3 };
-constexpr int UW_NRED = 8;
+constexpr int UW_NRED = 10;
 constexpr int UW_THREADS = 256;
 constexpr int UW_ROWS = 2 * UW_THREADS;
 
@@ -38,6 +38,11 @@ struct UwArgs {
   double* scalars;                     // [UW_NRED] sums over this rank's rows
   const LoopCtl* ctl;
   double *zvals, *uvals;               // optional history (m x maxiters)
+  // fast / accelerated ADMM (admm.m:506-529): prox and u-update use uhat; z/u of the previous
+  // iteration are kept for the acceleration pass, which also writes rvec / dzvec
+  int alg;
+  const double *v, *uhat;
+  double *zprev, *uprev;
 };
 
 __device__ __forceinline__ double huber1(double v) {  // CVX huber(v, 1)
@@ -47,7 +52,8 @@ __device__ __forceinline__ double huber1(double v) {  // CVX huber(v, 1)
 
 // z-prox, u-update and norm terms of one row (admm.m:515-548 with A = D, B = -1)
 __device__ __forceinline__ void uw_row(const UwArgs& a, int64_t i, double Ax, int it, double (&r)[UW_NRED]) {
-  const double zp = a.z[i], up = a.u[i], aux = a.aux[i];
+  const double zp = a.z[i], uold = a.u[i], aux = a.aux[i];
+  const double up = a.alg ? a.uhat[i] : uold;
   const double c = (a.kind >= UW_HUBER) ? aux : 0.0;
   double xh = Ax;
   if (a.relax != 1.0) xh = a.relax * Ax - (1.0 - a.relax) * (-zp - c);   // admm.m:517
@@ -72,9 +78,17 @@ __device__ __forceinline__ void uw_row(const UwArgs& a, int64_t i, double Ax, in
   const double u = up + (xh + (-z) - c);   // admm.m:542/548
   a.z[i] = z;
   a.u[i] = u;
-  a.rvec[i] = (a.kind >= UW_HUBER) ? (aux + z - u) : (z - u);
-  const double dz = z - zp, du = u - up, pr = Ax + (-z) - c;
-  if (a.dzvec) a.dzvec[i] = dz;
+  const double dz = z - zp, du = u - uold, pr = Ax + (-z) - c;
+  if (a.alg == 0) {
+    a.rvec[i] = (a.kind >= UW_HUBER) ? (aux + z - u) : (z - u);
+    if (a.dzvec) a.dzvec[i] = dz;
+  } else {
+    a.zprev[i] = zp;
+    a.uprev[i] = uold;
+    const double e1 = u - up, e2 = z - a.v[i];
+    r[7] = fma(e1, e1, r[7]);      // ||u - uhat||^2
+    r[8] = fma(e2, e2, r[8]);      // ||B(z - v)||^2
+  }
   if (a.zvals) {
     a.zvals[(int64_t)it * a.m + i] = z;
     a.uvals[(int64_t)it * a.m + i] = u;
@@ -183,6 +197,29 @@ __global__ void uw_first_rhs_kernel(int64_t m, const double* z, const double* u,
                                     double* rvec) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) rvec[i] = (kind >= UW_HUBER) ? (aux[i] + z[i] - u[i]) : (z[i] - u[i]);
+}
+
+// one thread: predictor weight / restart of this iteration from the (rank-summed) scalars
+__global__ void uw_accel_decide_kernel(LoopCtl* ctl, LoopParams lp, const double* scalars) {
+  if (ctl->done) return;
+  accel_decide(ctl, lp, scalars[7], scalars[8]);
+}
+
+// acceleration pass over this rank's rows (admm.m:562-600) + rhs of the next x-update from (v, uhat)
+__global__ void uw_accel_kernel(int64_t m, const double* z, const double* u, const double* zprev, const double* uprev,
+                                const double* aux, int kind, double* v, double* uhat, double* rvec, double* dzvec,
+                                const LoopCtl* ctl) {
+  if (ctl->done) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double gamma = ctl->gamma;
+  const double zi = z[i], ui = u[i], zp = zprev[i], up = uprev[i];
+  const double vn = ctl->restart ? zp : zi + gamma * (zi - zp);
+  const double uh = ctl->restart ? up : ui + gamma * (ui - up);
+  v[i] = vn;
+  uhat[i] = uh;
+  rvec[i] = (kind >= UW_HUBER) ? (aux[i] + vn - uh) : (vn - uh);
+  if (dzvec) dzvec[i] = zi - vn;       // B(z - v) up to sign, admm.m:631
 }
 
 struct UwEpiArgs {

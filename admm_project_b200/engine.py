@@ -158,7 +158,8 @@ class Engine:
         nA, nB, m = self.dims()
         N = int(opts.maxiters) if opts.maxiters > 0 else 1000
         res = L.Result()
-        bufs = {k: np.full(N, np.nan) for k in ("pnorm", "dnorm", "perr", "derr", "hnormsq", "objevals")}
+        bufs = {k: np.full(N, np.nan) for k in ("pnorm", "dnorm", "perr", "derr", "hnormsq", "objevals", "dvals", "avals",
+                                                "restarted")}
         xo, zo, uo = np.zeros(nA), np.zeros(nB), np.zeros(m)
         res.xopt, res.zopt, res.uopt = (a.ctypes.data_as(L._dp) for a in (xo, zo, uo))
         for k, a in bufs.items():

@@ -67,7 +67,8 @@ enum {
   ADMM_B200_CONVERGED_STD = 1,   /* admm.m:710-713 */
   ADMM_B200_CONVERGED_HNORM = 2, /* admm.m:719-722 */
   ADMM_B200_MAXITERS = 3,        /* loop ran out, admm.m:496 */
-  ADMM_B200_DIVERGED_RETURN = 4  /* H-norm monotonicity test fired, the reference `return`s, admm.m:692-700 */
+  ADMM_B200_DIVERGED_RETURN = 4, /* H-norm monotonicity test fired, the reference `return`s, admm.m:692-700 */
+  ADMM_B200_CONVERGED_DVAL = 5   /* accelerated ADMM: abs(d - dprev) <= dvaltol*dprev, admm.m:706-707 */
 };
 
 /* ---- x-update realisation ------------------------------------------------------------------- */
@@ -98,6 +99,10 @@ typedef struct admm_b200_options {
   int32_t history;    /* extension: 1 = record xvals/zvals/uvals (admm.m:608-610), 0 = do not */
   int32_t xsolve;     /* ADMM_B200_XSOLVE_* */
   int32_t check_every;/* iterations enqueued between host polls of the device stop flag (>=1) */
+  int32_t fast;       /* admm.m:59  fast / accelerated ADMM of Goldstein et al. (admm.m:267-298, 562-600) */
+  int32_t fasttype;   /* admm.m:60  1 = 'weak' (default): accelerated ADMM with restart (alg 2); 0 = fast ADMM (alg 1) */
+  double restart;     /* admm.m:287 options.restart, default 0.999 (values outside (0,1) become 0.999) */
+  double dvaltol;     /* admm.m:291 options.dvaltol, default 1e-8 */
 } admm_b200_options;
 
 /* What admm.m returns in `results` (admm.m:603-610, 618-658, 682, 746-767).  Every pointer is
@@ -115,6 +120,7 @@ typedef struct admm_b200_result {
   double *hnormsq;                              /* results.Hnormsq */
   double *objevals;                             /* results.objevals */
   double *xvals, *zvals, *uvals;                /* results.xvals/zvals/uvals */
+  double *dvals, *avals, *restarted;            /* fast modes: results.dvals / avals / restarted (admm.m:586-599) */
 } admm_b200_result;
 
 /* ---- library ------------------------------------------------------------------------------- */

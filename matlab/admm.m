@@ -12,8 +12,8 @@ dx = b200_descriptor(xminf); dz = b200_descriptor(zming);
 if isempty(dx) || isempty(dz) || dx.h ~= dz.h
     error('admm_b200: xminf/zming must come from getproxops (device-resident operators; no CPU path).');
 end
-if getopt(options, 'adaptive', 0) || getopt(options, 'fast', 0)
-    error('admm_b200: options.adaptive / options.fast are not built.');
+if getopt(options, 'adaptive', 0)
+    error('admm_b200: options.adaptive is not built (unfinished experiment in the reference, admm.m:724-741).');
 end
 stopnames = {'standard', 'hnorm', 'both'};
 o = struct();
@@ -28,6 +28,11 @@ o.nodualerror = getopt(options, 'nodualerror', 0);
 o.abstol = getopt(options, 'abstol', 1e-5);     o.reltol = getopt(options, 'reltol', 1e-3);
 if isfield(options, 'Hnormtol'), o.hnormtol = options.Hreltol; else, o.hnormtol = 1e-6; end  % admm.m:927-928 quirk
 o.history = getopt(options, 'history', 1);
+o.fast = double(getopt(options, 'fast', 0) ~= 0);                       % admm.m:59-60, 267-298
+o.fasttype = double(strcmp(getopt(options, 'fasttype', 'weak'), 'weak'));
+o.restart = getopt(options, 'restart', 0.999); if o.restart <= 0 || o.restart >= 1, o.restart = 0.999; end
+o.dvaltol = getopt(options, 'dvaltol', 1e-8);
+alg = o.fast*(1 + o.fasttype);
 for f = {'A', 'B'}
     if ~isfield(options, f{1}), error('Must specify a matrix %s in constraint Ax + Bz = c!', f{1}); end
 end
@@ -35,7 +40,12 @@ admm_b200_mex('set_init', dx.h, getopt(options, 'x0', []), getopt(options, 'z0',
 t = tic;
 r = admm_b200_mex('solve', dx.h, o);
 k = r.steps;
-results = struct('pnorm', r.pnorm(1:k), 'dnorm', r.dnorm(1:k), 'perr', r.perr(1:k), 'derr', r.derr(1:k));
+if alg == 2     % accelerated ADMM records d, alpha and restarts instead of residual norms (admm.m:586-599)
+    results = struct('dvals', r.dvals(1:k), 'restarted', r.restarted(1:k), 'dvaltol', o.dvaltol);
+else
+    results = struct('pnorm', r.pnorm(1:k), 'dnorm', r.dnorm(1:k), 'perr', r.perr(1:k), 'derr', r.derr(1:k));
+end
+if alg > 0, results.avals = r.avals(1:k); end
 usesH = o.convtest || any(strcmp(sc, {'hnorm', 'both'}));
 if usesH, results.Hnormsq = r.Hnormsq(1:k); results.Hnormtol = o.hnormtol; end
 if o.objevals, results.objevals = r.objevals(1:k); end

@@ -65,6 +65,10 @@ static void read_options(const mxArray* s, admm_b200_options* o) {
   o->history = (int32_t)field(s, "history", 1);
   o->xsolve = (int32_t)field(s, "xsolve", 0);
   o->check_every = (int32_t)field(s, "check_every", 8);
+  o->fast = (int32_t)field(s, "fast", 0);
+  o->fasttype = (int32_t)field(s, "fasttype", 1);   /* 1 = 'weak' (accelerated, restart), 0 = fast ADMM */
+  o->restart = field(s, "restart", 0.999);
+  o->dvaltol = field(s, "dvaltol", 1e-8);
 }
 
 static mxArray* put(mxArray* s, const char* name, mwSize m, mwSize n) {
@@ -80,7 +84,7 @@ static void cmd_solve(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]
   admm_b200_result r;
   int64_t nA, nB, m, N, k;
   mxArray* s = mxCreateStructMatrix(1, 1, 0, NULL);
-  mxArray *px, *pz, *pu, *pn, *dn, *pe, *de, *hn, *ob, *xv = NULL, *zv = NULL, *uv = NULL;
+  mxArray *px, *pz, *pu, *pn, *dn, *pe, *de, *hn, *ob, *dv, *av, *rs, *xv = NULL, *zv = NULL, *uv = NULL;
   (void)nlhs;
   if (nrhs < 3) mexErrMsgIdAndTxt("admm_b200:args", "solve needs (h, opts)");
   read_options(prhs[2], &o);
@@ -90,9 +94,11 @@ static void cmd_solve(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]
   px = put(s, "xopt", nA, 1); pz = put(s, "zopt", nB, 1); pu = put(s, "uopt", m, 1);
   pn = put(s, "pnorm", 1, N); dn = put(s, "dnorm", 1, N); pe = put(s, "perr", 1, N); de = put(s, "derr", 1, N);
   hn = put(s, "Hnormsq", 1, N); ob = put(s, "objevals", 1, N);
+  dv = put(s, "dvals", 1, N); av = put(s, "avals", 1, N); rs = put(s, "restarted", 1, N);
   r.xopt = mxGetPr(px); r.zopt = mxGetPr(pz); r.uopt = mxGetPr(pu);
   r.pnorm = mxGetPr(pn); r.dnorm = mxGetPr(dn); r.perr = mxGetPr(pe); r.derr = mxGetPr(de);
   r.hnormsq = mxGetPr(hn); r.objevals = mxGetPr(ob);
+  r.dvals = mxGetPr(dv); r.avals = mxGetPr(av); r.restarted = mxGetPr(rs);
   if (o.history) {
     xv = put(s, "xvals", nA, N); zv = put(s, "zvals", nB, N); uv = put(s, "uvals", m, N);
     r.xvals = mxGetPr(xv); r.zvals = mxGetPr(zv); r.uvals = mxGetPr(uv);

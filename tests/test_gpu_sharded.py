@@ -11,14 +11,14 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("problem", ["svm", "huber", "lad"])
-def test_two_rank_run_matches_serial_oracle(problem):
+@pytest.mark.parametrize("problem,fast", [("svm", ""), ("huber", ""), ("lad", ""), ("huber", "weak"), ("lad", "strong")])
+def test_two_rank_run_matches_serial_oracle(problem, fast):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "run_sharded.py"), "--check",
-           "--problem", problem, "--rows", "5001", "--cols", "64"]
+           "--problem", problem, "--rows", "5001", "--cols", "64"] + (["--fast", fast] if fast else [])
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("SHARDED ")]
     assert line, p.stdout[-2000:] + p.stderr[-2000:]

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--rows", type=int, default=6001)
     ap.add_argument("--cols", type=int, default=96)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--fast", default="", help="'' | weak | strong: fast / accelerated ADMM variant")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -38,6 +39,8 @@ def main():
         D = D + 1e-3 * np.random.RandomState(1).randn(*D.shape)
         aux = ell[:, 1]
         opts = {"objevals": 1, "history": 0}
+        if args.fast:
+            opts.update(fast=1, fasttype=args.fast, maxiters=30)
         np.random.seed(3)
         res = linearsvm(D, aux, 0.5, opts, engine=eng)
         if args.check and rank == 0:
@@ -46,6 +49,8 @@ def main():
     else:
         D, s, _ = (gen.huber_problem if args.problem == "huber" else gen.lad_problem)(0, args.rows, args.cols)
         opts = {"objevals": 1, "convtest": 1, "history": 0, "relax": 1.5}
+        if args.fast:
+            opts.update(fast=1, fasttype=args.fast, maxiters=30, restart=0.9, relax=1.0)
         fn = huberfit if args.problem == "huber" else lad
         res = fn(D, s, opts, engine=eng)
         if args.check and rank == 0:
@@ -57,7 +62,7 @@ def main():
     if args.check and rank == 0:
         out["ref_steps"] = ref["steps"]
         out["err_x"], out["err_z"], out["err_u"] = rel(res["xopt"], ref["xopt"]), rel(res["zopt"], ref["zopt"]), rel(res["uopt"], ref["uopt"])
-        out["err_pnorm"] = rel(res["pnorm"], ref["pnorm"])
+        out["err_pnorm"] = rel(res["pnorm"], ref["pnorm"]) if len(ref["pnorm"]) else 0.0
         out["err_obj"] = rel(res["objevals"], ref["objevals"])
         out["ok"] = bool(res["steps"] == ref["steps"] and max(out["err_x"], out["err_z"], out["err_u"], out["err_pnorm"], out["err_obj"]) < 1e-9)
     if rank == 0:
