@@ -72,6 +72,8 @@ SYMBOLS = {
     "admm_b200_solve": (_int, [_vp, C.POINTER(Options), C.POINTER(Result)]),
     "admm_b200_solve_lasso_batch": (_int, [_vp, C.POINTER(Options), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                            _vp, C.POINTER(C.c_double)]),
+    "admm_b200_solve_unwrapped_batch": (_int, [_vp, C.POINTER(Options), _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                               _vp, _vp, _vp, _vp, C.POINTER(C.c_double)]),
     "admm_b200_get_dims": (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "admm_b200_get_factor": (_int, [_vp, _vp, _i64, C.POINTER(_i64)]),
     "admm_b200_dgemm": (_int, [_vp, _int, _int, _i64, _i64, _i64, _d, _vp, _i64, _vp, _i64, _d, _vp, _i64, _int]),

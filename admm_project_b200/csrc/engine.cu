@@ -18,6 +18,7 @@
 #include "tri.cuh"
 #include "gemvt.cuh"
 #include "unwrapped.cuh"
+#include "uwbatch.cuh"
 #include "tv.cuh"
 #include <dlfcn.h>
 
@@ -208,6 +209,10 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   if (o.allow_splitk && tiles < kNumSM && K >= 4096) {
     // few output tiles (n = 784 / 1024 Gram of a tall D): fill the machine twice over
     want_splits = std::min<int64_t>((2 * kNumSM + tiles - 1) / tiles, K / 1024);
+  } else if (o.allow_splitk && tiles * 8 <= kNumSM && K >= 256) {
+    // a handful of tiles and a short K (the n x nb x n products of the class / lambda batches on a small
+    // factor): 7 CTAs marching through K one after the other is pure latency; split K ~64 wide
+    want_splits = std::min<int64_t>(kNumSM / tiles, K / 64);
   } else if (o.allow_splitk && tiles >= kNumSM && K >= 16384 && !getenv("ADMM_B200_NO_TAIL_SPLIT")) {
     // wave quantisation: 2080 tiles on 148 SMs = 14.05 waves -> 15 (6.7% idle).  Splitting K by S
     // makes the work items S times smaller, so the idle tail shrinks to ~1/S of a tile time.
@@ -1542,6 +1547,203 @@ static void solve_lasso_batch(admm_b200_handle* h, const admm_b200_options& o, i
   cleanup();
 }
 
+// ---------------------------------------------------------------------------------------------
+// class batch of A = D problems sharing D (one-vs-all linear SVM, examples/mnistsvm.m:121-156)
+// ---------------------------------------------------------------------------------------------
+template <int NV>
+static void gemvt_strided_t(admm_b200_handle* h, GemvtArgs& a, int grid, size_t smem) {
+  static size_t conf = 0;
+  if (smem > conf && smem > 48 * 1024) {
+    ADMM_CUDA(cudaFuncSetAttribute(gemvt_kernel<NV, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  gemvt_kernel<NV, 256><<<grid, 256, smem, h->stream>>>(a);
+}
+
+// out[k*ostride + j] = sum_r M[r + j*ld] * v[k*vstride + r], k < nvt (nvt in {2,4,8,10,16}; only nv are real)
+static void gemvt_strided(admm_b200_handle* h, const double* M, int64_t ld, int64_t rows, int64_t cols, int nvt,
+                          const double* vbase, int64_t vstride, double* obase, int64_t ostride) {
+  GemvtArgs a;
+  a.M = M; a.ld = ld; a.rows = rows; a.cols = cols; a.done = nullptr;
+  a.ngroups = (cols + GEMVT_CG - 1) / GEMVT_CG;
+  int64_t P = 1;
+  if (a.ngroups < 8 * kNumSM) P = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((8 * kNumSM + a.ngroups - 1) / a.ngroups, 64), rows / 2048));
+  int64_t per = round_up((rows + P - 1) / P, GEMVT_ROWS);
+  P = (rows + per - 1) / per;
+  a.P = (int)P; a.per = per;
+  const int64_t nunits = P * a.ngroups;
+  const int grid = (int)std::min<int64_t>(kNumSM, nunits);
+  a.units_per_cta = (nunits + grid - 1) / grid;
+  const size_t smem = (size_t)a.units_per_cta * GEMVT_CG * nvt * (256 / 32) * 8;
+  ADMM_REQUIRE(smem <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED, "gemvt: too many column groups per CTA");
+  for (int k = 0; k < 3; ++k) { a.v[k] = vbase; a.out[k] = obase; }
+  a.vbase = vbase; a.vstride = vstride;
+  a.scale = 1.0; a.addend = nullptr; a.addscale = 0.0;
+  if (P == 1) { a.obase = obase; a.ostride = ostride; }
+  else { h->cd_ws.ensure(P * cols * nvt); a.obase = h->cd_ws.p; a.ostride = P * cols; }
+  switch (nvt) {
+    case 2: gemvt_strided_t<2>(h, a, grid, smem); break;
+    case 4: gemvt_strided_t<4>(h, a, grid, smem); break;
+    case 8: gemvt_strided_t<8>(h, a, grid, smem); break;
+    case 10: gemvt_strided_t<10>(h, a, grid, smem); break;
+    default: gemvt_strided_t<16>(h, a, grid, smem); break;
+  }
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+  if (P > 1) {
+    panel_reduce_strided_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)nvt), 256, 0, h->stream>>>(
+        h->cd_ws.p, obase, ostride, nvt, (int)P, cols, 1.0);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+}
+
+struct UwBatchOut {
+  int64_t* steps; int32_t* status;
+  double *xopt, *zopt, *uopt;            // n x nb, m_local x nb, m_local x nb (ld = n / m_local)
+  double *pnorm, *perr, *objevals;       // maxiters x nb or NULL
+  double* loop_ms;
+};
+
+template <int NB>
+static void uwb_pass1_t(admm_b200_handle* h, const UwbArgs& a, dim3 grid, size_t smem) {
+  static bool configured = false;
+  if (!configured) {
+    ADMM_CUDA(cudaFuncSetAttribute(uwb_gemm_prox_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    configured = true;
+  }
+  uwb_gemm_prox_kernel<NB><<<grid, UW_THREADS, smem, h->stream>>>(a);
+}
+
+static void solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options& o, int64_t nb, const double* AUX,
+                                  int64_t ldaux, const double* X0, const double* Z0, const double* U0,
+                                  const UwBatchOut& out) {
+  validate_options(h, o);
+  ADMM_REQUIRE(is_unwrapped(h->kind) && h->have_inverse, ADMM_B200_ERR_STATE, "unwrapped batch: call admm_b200_setup_unwrapped first");
+  ADMM_REQUIRE(nb >= 1 && nb <= 16 && AUX && ldaux >= h->m, ADMM_B200_ERR_INVALID, "unwrapped batch: 1 <= nb <= 16 label / target columns");
+  ADMM_REQUIRE(o.nodualerror && o.relax == 1.0 && !o.fast && !o.convtest, ADMM_B200_ERR_UNSUPPORTED,
+               "unwrapped batch: built for the unwrappedadmm.m configuration (nodualerror = 1, relax = 1, no fast / convtest)");
+  const int64_t n = h->n, m = h->m, npad = round_up(n, 2), mpad = round_up(m, 2);
+  const int64_t N = o.maxiters > 0 ? o.maxiters : 1000;
+  const int nbt = nb <= 2 ? 2 : nb <= 4 ? 4 : nb <= 8 ? 8 : nb <= 10 ? 10 : 16;   // template width
+  const int64_t cbs = npad + 16;
+  DBuf X, XK, T, Z, U, R, A, CB, hist, part, ws;
+  LoopCtl* ctl = nullptr;
+  int* done_count = nullptr;
+  auto cleanup = [&]() {
+    DBuf* bs[] = {&X, &XK, &T, &Z, &U, &R, &A, &CB, &hist, &part, &ws};
+    for (DBuf* b : bs) b->release();
+    if (ctl) cudaFree(ctl);
+    if (done_count) cudaFree(done_count);
+  };
+  try {
+    X.ensure(npad * nbt); XK.ensure(npad * nbt); T.ensure(npad * nbt);
+    Z.ensure(mpad * nbt); U.ensure(mpad * nbt); R.ensure(mpad * nbt); A.ensure(mpad * nbt);
+    CB.ensure(cbs * nbt); hist.ensure(9 * N * nbt);
+    ADMM_CUDA(cudaMalloc(&ctl, sizeof(LoopCtl) * nbt));
+    ADMM_CUDA(cudaMalloc(&done_count, sizeof(int)));
+    cudaStream_t st = h->stream;
+    for (DBuf* b : {&X, &XK, &T, &Z, &U, &R, &A, &CB}) ADMM_CUDA(cudaMemsetAsync(b->p, 0, (size_t)b->cap * 8, st));
+    ADMM_CUDA(cudaMemsetAsync(done_count, 0, sizeof(int), st));
+    ctl_init_kernel<<<1, 32, 0, st>>>(ctl, nbt);
+    ADMM_CUDA(cudaGetLastError());
+    auto mat_in = [&](double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows) {
+      if (src) ADMM_CUDA(cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)nb, cudaMemcpyDefault, st));
+    };
+    mat_in(A.p, mpad, AUX, ldaux, m);
+    mat_in(X.p, npad, X0, n, n);
+    mat_in(Z.p, mpad, Z0, m, m);
+    mat_in(U.p, mpad, U0, m, m);
+    LoopParams lp = make_loop_params(h, o, N, 0);
+    lp.pnorm = hist.p; lp.dnorm = hist.p + N * nbt; lp.perr = hist.p + 2 * N * nbt; lp.derr = hist.p + 3 * N * nbt;
+    lp.hn = hist.p + 4 * N * nbt; lp.obj = hist.p + 5 * N * nbt;
+    lp.dvals = hist.p + 6 * N * nbt; lp.avals = hist.p + 7 * N * nbt; lp.rst = hist.p + 8 * N * nbt;
+    // pass-1 launch geometry
+    const int64_t rb = (m + UW_ROWS - 1) / UW_ROWS;
+    // columns are swept in 128-wide chunks INSIDE a CTA; the grid is split over columns (partials through
+    // a workspace) only when there are too few row blocks to fill the machine
+    int64_t chunks = 1;
+    if (rb < 3 * kNumSM) chunks = std::min<int64_t>((3 * kNumSM + rb - 1) / rb, std::max<int64_t>(1, n / 128));
+    const int64_t cpc = (n + chunks - 1) / chunks;
+    chunks = (n + cpc - 1) / cpc;
+    part.ensure(rb * nb * UW_NRED);
+    if (chunks > 1) { ws.ensure(chunks * nb * m); ensure_tickets(h, rb); }
+    UwbArgs a;
+    a.D = h->dD; a.ld = h->ldD; a.m = m; a.n = n; a.X = X.p; a.ldx = npad; a.Z = Z.p; a.U = U.p; a.R = R.p; a.AUX = A.p;
+    a.ldm = mpad; a.nb = (int)nb; a.rho = o.rho; a.C = h->svmC; a.kind = uw_kind(h->kind); a.cols_per_chunk = cpc;
+    a.ws = ws.p; a.tickets = h->tickets; a.partials = part.p; a.grid_ticket = h->grid_ticket;
+    a.cb = CB.p; a.cb_stride = cbs; a.scal_off = npad; a.ctl = ctl;
+    const size_t smem1 = (size_t)128 * (nbt + (nbt & 1)) * 8;   // one 128-column chunk of X, classes in pairs
+    UwbEpiArgs e;
+    e.n = n; e.X = X.p; e.ldx = npad; e.XK = XK.p; e.cb = CB.p; e.cb_stride = cbs; e.scal_off = npad;
+    e.m_total = (double)h->m_total; e.kind = a.kind; e.C = h->svmC; e.ctl = ctl; e.lp = lp; e.hist_stride = N;
+    e.done_count = done_count;
+    ADMM_CUDA(cudaEventRecord(h->ev0, st));
+    // rhs of the first x-update: d_k = D'(z0_k - u0_k)
+    uwb_first_rhs_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)nb), 256, 0, st>>>(m, (int)nb, mpad, Z.p, U.p, A.p, a.kind, R.p);
+    ADMM_CUDA(cudaGetLastError());
+    gemvt_strided(h, h->dD, h->ldD, m, n, nbt, R.p, mpad, CB.p, cbs);
+    allreduce_sum(h, CB.p, cbs * nbt);
+    const int check = std::max(1, o.check_every);
+    int64_t enq = 0;
+    int hdone = 0;
+    while (true) {
+      const int64_t burst = std::min<int64_t>(check, N - enq);
+      for (int64_t c = 0; c < burst; ++c) {
+        GemmOpt g1; g1.a_lower = 1;      // T = W * [d_1 .. d_nb]
+        gemm(h, 0, 0, n, nb, n, 1.0, h->W.p, h->ldf, CB.p, cbs, 0.0, T.p, npad, g1);
+        GemmOpt g2; g2.a_upper = 1;      // X = W' * T
+        gemm(h, 1, 0, n, nb, n, 1.0, h->W.p, h->ldf, T.p, npad, 0.0, X.p, npad, g2);
+        dim3 grid((unsigned)rb, (unsigned)chunks);
+        switch (nbt) {
+          case 2: uwb_pass1_t<2>(h, a, grid, smem1); break;
+          case 4: uwb_pass1_t<4>(h, a, grid, smem1); break;
+          case 8: uwb_pass1_t<8>(h, a, grid, smem1); break;
+          case 10: uwb_pass1_t<10>(h, a, grid, smem1); break;
+          default: uwb_pass1_t<16>(h, a, grid, smem1); break;
+        }
+        ADMM_CUDA(cudaGetLastError());
+        h->launches++;
+        gemvt_strided(h, h->dD, h->ldD, m, n, nbt, R.p, mpad, CB.p, cbs);
+        allreduce_sum(h, CB.p, cbs * nbt);
+        uwb_epilogue_kernel<<<(unsigned)nb, 256, 0, st>>>(e);
+        ADMM_CUDA(cudaGetLastError());
+        h->launches++;
+      }
+      enq += burst;
+      ADMM_CUDA(cudaMemcpyAsync(&hdone, done_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+      ADMM_CUDA(cudaStreamSynchronize(st));
+      if (hdone >= nb || enq >= N) break;
+    }
+    ADMM_CUDA(cudaEventRecord(h->ev1, st));
+    ADMM_CUDA(cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    if (out.loop_ms) *out.loop_ms = ms;
+    std::vector<LoopCtl> hc(nb);
+    ADMM_CUDA(cudaMemcpy(hc.data(), ctl, sizeof(LoopCtl) * nb, cudaMemcpyDeviceToHost));
+    for (int64_t j = 0; j < nb; ++j) {
+      if (out.steps) out.steps[j] = hc[j].it;
+      if (out.status) out.status[j] = hc[j].status;
+    }
+    auto mat_out = [&](double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows) {
+      if (dst) ADMM_CUDA(cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)rows * 8, (size_t)nb, cudaMemcpyDefault, st));
+    };
+    mat_out(out.xopt, n, XK.p, npad, n);
+    mat_out(out.zopt, m, Z.p, mpad, m);
+    mat_out(out.uopt, m, U.p, mpad, m);
+    copy_out(h, out.pnorm, hist.p, N * nb);
+    copy_out(h, out.perr, hist.p + 2 * N * nbt, N * nb);
+    if (o.objevals) copy_out(h, out.objevals, hist.p + 5 * N * nbt, N * nb);
+    ADMM_CUDA(cudaStreamSynchronize(st));
+  } catch (...) {
+    cudaStreamSynchronize(h->stream);
+    cleanup();
+    throw;
+  }
+  cleanup();
+}
+
 }  // namespace admmb200
 
 // ---------------------------------------------------------------------------------------------
@@ -1785,6 +1987,18 @@ int admm_b200_solve_lasso_batch(admm_b200_handle* h, const admm_b200_options* op
   ADMM_REQUIRE(opts != nullptr, ADMM_B200_ERR_INVALID, "Given options is not a struct! At least pass empty struct!");
   BatchOut out{steps, status, xopt, zopt, uopt, pnorm, dnorm, perr, derr, nullptr, loop_ms};
   solve_lasso_batch(h, *opts, nb, lambdas, out);
+  ADMM_API_END
+}
+
+int admm_b200_solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options* opts, int64_t nb, const double* aux,
+                                    int64_t ldaux, const double* X0, const double* Z0, const double* U0, int64_t* steps,
+                                    int32_t* status, double* xopt, double* zopt, double* uopt, double* pnorm, double* perr,
+                                    double* objevals, double* loop_ms) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(opts != nullptr, ADMM_B200_ERR_INVALID, "Given options is not a struct! At least pass empty struct!");
+  UwBatchOut out{steps, status, xopt, zopt, uopt, pnorm, perr, objevals, loop_ms};
+  solve_unwrapped_batch(h, *opts, nb, aux, ldaux, X0, Z0, U0, out);
   ADMM_API_END
 }
 

@@ -25,6 +25,9 @@ struct GemvtArgs {
   int64_t rows, cols;
   const double* v[3];
   double* out[3];                  // P == 1: the result (cols); P > 1: workspace [P][cols] per vector
+  // NV > 3 (class batches): vector k at vbase + k*vstride, output k at obase + k*ostride
+  const double* vbase; int64_t vstride;
+  double* obase; int64_t ostride;
   int P; int64_t per;              // row panels of `per` rows (multiple of GEMVT_ROWS)
   int64_t ngroups;                 // ceil(cols / GEMVT_CG)
   int64_t units_per_cta;           // ceil(P * ngroups / gridDim.x)
@@ -32,8 +35,9 @@ struct GemvtArgs {
   const int* done;
 };
 
-template <int NV>
-__global__ void __launch_bounds__(GEMVT_THREADS, 1) gemvt_kernel(GemvtArgs a) {
+template <int NV, int THREADS = GEMVT_THREADS>
+__global__ void __launch_bounds__(THREADS, 1) gemvt_kernel(GemvtArgs a) {
+  constexpr int GEMVT_WARPS = THREADS / 32;     // shadows the namespace constant: slots are sized per launch
   if (a.done && *a.done) return;
   extern __shared__ __align__(16) double slots[];   // [units_of_cta][GEMVT_CG][NV][GEMVT_WARPS]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -42,7 +46,7 @@ __global__ void __launch_bounds__(GEMVT_THREADS, 1) gemvt_kernel(GemvtArgs a) {
   const int64_t u1 = min(nunits, u0 + a.units_per_cta);
   if (u1 <= u0) return;
   const int nu = (int)(u1 - u0);
-  for (int i = tid; i < nu * GEMVT_CG * NV * GEMVT_WARPS; i += GEMVT_THREADS) slots[i] = 0.0;
+  for (int i = tid; i < nu * GEMVT_CG * NV * GEMVT_WARPS; i += THREADS) slots[i] = 0.0;
   __syncthreads();
   const int64_t ipu = a.per / GEMVT_ROWS;           // items per unit (the last panel may have empty ones)
   const int64_t nitems = (int64_t)nu * ipu;
@@ -88,22 +92,24 @@ __global__ void __launch_bounds__(GEMVT_THREADS, 1) gemvt_kernel(GemvtArgs a) {
         if (c < ncols && idx < nvec) mv[c][i] = ldg_stream2(base + (int64_t)c * a.ld + 2 * idx);
       }
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
+    for (int i = 0; i < 4; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        double2 vv[NV];                       // all NV vector loads of this row pair in flight together
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < nvec) {
-          const double2 vv = ldg_nc2(a.v[k] + r0 + 2 * idx);
+        for (int k = 0; k < NV; ++k)
+          vv[k] = ldg_nc2((NV > 3 ? a.vbase + (int64_t)k * a.vstride : a.v[k < 3 ? k : 0]) + r0 + 2 * idx);
 #pragma unroll
-          for (int c = 0; c < GEMVT_CG; ++c) acc[c][k] = fma(mv[c][i].y, vv.y, fma(mv[c][i].x, vv.x, acc[c][k]));
-        }
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+          for (int c = 0; c < GEMVT_CG; ++c) acc[c][k] = fma(mv[c][i].y, vv[k].y, fma(mv[c][i].x, vv[k].x, acc[c][k]));
       }
     }
     if ((nrows & 1) && lane == 31) {   // odd tail row (only at the very end of an odd-length matrix)
       const int64_t r = r0 + nrows - 1;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        const double vv = ldg_nc1(a.v[k] + r);
+        const double vv = ldg_nc1((NV > 3 ? a.vbase + (int64_t)k * a.vstride : a.v[k < 3 ? k : 0]) + r);
 #pragma unroll
         for (int c = 0; c < GEMVT_CG; ++c)
           if (c < ncols) acc[c][k] = fma(ldg_stream1(a.M + (c0 + c) * a.ld + r), vv, acc[c][k]);
@@ -112,7 +118,7 @@ __global__ void __launch_bounds__(GEMVT_THREADS, 1) gemvt_kernel(GemvtArgs a) {
   }
   flush();
   __syncthreads();
-  for (int i = tid; i < nu * GEMVT_CG * NV; i += GEMVT_THREADS) {
+  for (int i = tid; i < nu * GEMVT_CG * NV; i += THREADS) {
     const int k = i % NV, c = (i / NV) % GEMVT_CG, ul = i / (NV * GEMVT_CG);
     const int64_t unit = u0 + ul;
     const int64_t p = unit / a.ngroups, g = unit - p * a.ngroups;
@@ -122,7 +128,7 @@ __global__ void __launch_bounds__(GEMVT_THREADS, 1) gemvt_kernel(GemvtArgs a) {
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < GEMVT_WARPS; ++w) s += sl[w];
-    double* o = (k == 0) ? a.out[0] : (k == 1 ? a.out[1] : a.out[2]);
+    double* o = (NV > 3) ? a.obase + (int64_t)k * a.ostride : ((k == 0) ? a.out[0] : (k == 1 ? a.out[1] : a.out[2]));
     if (a.P == 1) {
       s *= a.scale;
       if (a.addend) s += a.addscale * a.addend[col];

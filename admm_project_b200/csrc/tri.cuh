@@ -216,4 +216,15 @@ __global__ void panel_reduce_kernel(PanelReduceArgs a) {
   }
 }
 
+// strided variant for class batches: out[k*ostride + j] = scale * sum_p ws[(k*panels + p)*cols + j]
+__global__ void panel_reduce_strided_kernel(const double* ws, double* out, int64_t ostride, int nv, int panels, int64_t cols,
+                                            double scale) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (j >= cols || k >= nv) return;
+  double s = 0.0;
+  for (int p = 0; p < panels; ++p) s += ws[((int64_t)k * panels + p) * cols + j];
+  out[(int64_t)k * ostride + j] = scale * s;
+}
+
 }  // namespace admmb200

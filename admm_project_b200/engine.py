@@ -196,6 +196,34 @@ class Engine:
             out.update(pnorm=hist[0], dnorm=hist[1], perr=hist[2], derr=hist[3])
         return out
 
+    def solve_unwrapped_batch(self, opts, aux, X0=None, Z0=None, U0=None, want_history=True):
+        """nb A = D problems sharing the D of the last setup_unwrapped (one-vs-all SVM); aux is
+        m_local x nb (or a device pointer with ld = m_local)."""
+        n, _, m = self.dims()
+        if isinstance(aux, tuple):               # (device pointer, nb)
+            aux_p, nb, keep = C.c_void_p(int(aux[0])), int(aux[1]), None
+        else:
+            keep = L.fmat(aux)
+            nb = keep.shape[1]
+            aux_p = L.ptr(keep)
+        mats = []
+        for a, rows in ((X0, n), (Z0, m), (U0, m)):
+            mats.append(None if a is None else L.fmat(np.asarray(a, dtype=np.float64).reshape(rows, nb, order="F")))
+        N = int(opts.maxiters) if opts.maxiters > 0 else 1000
+        steps = np.zeros(nb, dtype=np.int64)
+        status = np.zeros(nb, dtype=np.int32)
+        X = np.zeros((n, nb), order="F")
+        Z, U = (np.zeros((m, nb), order="F") for _ in range(2)) if want_history else (None, None)
+        hist = [np.full((N, nb), np.nan, order="F") for _ in range(3)] if want_history else [None] * 3
+        ms = C.c_double()
+        L.check(self._lib.admm_b200_solve_unwrapped_batch(self._h, C.byref(opts), nb, aux_p, m, *(L.ptr(a) for a in mats),
+                                                          L.ptr(steps), L.ptr(status), L.ptr(X), L.ptr(Z), L.ptr(U),
+                                                          *(L.ptr(a) for a in hist), C.byref(ms)))
+        out = dict(steps=steps, status=status, xopt=X, loop_ms=ms.value)
+        if want_history:
+            out.update(zopt=Z, uopt=U, pnorm=hist[0], perr=hist[1], objevals=hist[2])
+        return out
+
     def iterate_raw(self, opts, which=0, reps=1):
         L.check(self._lib.admm_b200_iterate_raw(self._h, C.byref(opts), int(which), int(reps)))
 

@@ -2,7 +2,7 @@
 device (Gram / Cholesky / inverse factor), then ``admm``."""
 from .lasso import lasso                       # noqa: F401
 from .unwrappedadmm import unwrappedadmm       # noqa: F401
-from .linearsvm import linearsvm               # noqa: F401
+from .linearsvm import linearsvm, linearsvm_onevsall   # noqa: F401
 from .robustfit import huberfit, lad           # noqa: F401
 from .basispursuit import basispursuit        # noqa: F401
 from .totalvariation import totalvariation    # noqa: F401

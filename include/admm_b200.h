@@ -200,6 +200,18 @@ int admm_b200_solve_lasso_batch(admm_b200_handle* h, const admm_b200_options* op
                                 int64_t* steps, int32_t* status, double* xopt, double* zopt, double* uopt,
                                 double* pnorm, double* dnorm, double* perr, double* derr, double* loop_ms);
 
+/* nb (<= 16) A = D problems that share the D of the last admm_b200_setup_unwrapped -- the one-vs-all
+ * classifiers of examples/mnistsvm.m:121-156 (BASELINE.json configs[2]) -- advanced together: D is
+ * swept twice per iteration for ALL classes.  aux: m_local x nb labels / targets (this rank's rows),
+ * X0 / Z0 / U0: n x nb, m_local x nb, m_local x nb initial iterates (NULL = zeros; unwrappedadmm.m:87-89
+ * draws them with rand).  Options as forced by unwrappedadmm.m:90-92 (nodualerror = 1, relax = 1).
+ * Each class runs admm.m's loop with its own stop test; a stopped class is frozen.  Row-sharded runs
+ * exchange ONE allreduce of nb x [D'r ; scalars] per iteration.  pnorm / perr / objevals: maxiters x nb. */
+int admm_b200_solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options* opts, int64_t nb, const double* aux,
+                                    int64_t ldaux, const double* X0, const double* Z0, const double* U0, int64_t* steps,
+                                    int32_t* status, double* xopt, double* zopt, double* uopt, double* pnorm, double* perr,
+                                    double* objevals, double* loop_ms);
+
 /* Sizes of the current problem: nA (x), nB (z), m (u) -- admm.m:74-76. */
 int admm_b200_get_dims(admm_b200_handle* h, int64_t* nA, int64_t* nB, int64_t* m);
 /* Lower Cholesky factor of the current setup (k x k, column-major, ldL >= k) for setup parity

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--cols", type=int, default=0)
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--dual", type=int, default=-1, help="1: with dual residual (3-vector pass), 0: nodualerror")
+    ap.add_argument("--batch", type=int, default=0, help="one-vs-all class batch of this many label columns (svm)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -76,6 +77,32 @@ def main():
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             out[name + "_us"] = float(t.item())
+    if a.batch:
+        nbc = a.batch
+        lab = torch.where(torch.rand(nbc, ld, dtype=torch.float64, device=dev, generator=g) < 0.1, 1.0, -1.0).to(torch.float64)
+        ob = eng.default_options()
+        ob.nodualerror, ob.domaxiters, ob.maxiters, ob.check_every, ob.stopcond = 1, 1, 100, 100, 2
+        # column k of the m_local x nb label matrix = row k of `lab` (column stride ld)
+        import ctypes as C
+        res_keep = []
+        def run_batch():
+            n_, _, m_ = eng.dims()
+            steps = np.zeros(nbc, dtype=np.int64); status = np.zeros(nbc, dtype=np.int32); X = np.zeros((n_, nbc), order="F")
+            ms = C.c_double()
+            L.check(eng._lib.admm_b200_solve_unwrapped_batch(eng._h, C.byref(ob), nbc, C.c_void_p(lab.data_ptr()), ld, None, None, None,
+                                                             L.ptr(steps), L.ptr(status), L.ptr(X), None, None, None, None, None, C.byref(ms)))
+            return ms.value
+        with torch.cuda.stream(stream):
+            run_batch()
+            if world > 1:
+                dist.barrier()
+            tb = run_batch()
+        t = torch.tensor([tb / 100 * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["batch"] = {"classes": nbc, "us_per_iter_all_classes": float(t.item()),
+                        "class_iters_per_s": nbc * 1e6 / float(t.item()),
+                        "speedup_vs_sequential": nbc * out["iter_us"] / float(t.item())}
     passes = 2
     out["bytes_per_iter_total"] = passes * m * n * 8
     out["GBs_total"] = out["bytes_per_iter_total"] / (out["iter_us"] * 1e-6) / 1e9
