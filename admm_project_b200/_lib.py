@@ -35,7 +35,8 @@ class Options(C.Structure):
                 ("maxiters", C.c_int64), ("domaxiters", C.c_int32), ("stopcond", C.c_int32),
                 ("nodualerror", C.c_int32), ("convtest", C.c_int32), ("objevals", C.c_int32),
                 ("history", C.c_int32), ("xsolve", C.c_int32), ("check_every", C.c_int32),
-                ("fast", C.c_int32), ("fasttype", C.c_int32), ("restart", C.c_double), ("dvaltol", C.c_double)]
+                ("fast", C.c_int32), ("fasttype", C.c_int32), ("restart", C.c_double), ("dvaltol", C.c_double),
+                ("graph", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -82,6 +83,7 @@ SYMBOLS = {
     "admm_b200_factor_solve": (_int, [_vp, _vp, _vp, _i32]),
     "admm_b200_iterate_raw": (_int, [_vp, C.POINTER(Options), _int, _int]),
     "admm_b200_launch_count": (_i64, [_vp]),
+    "admm_b200_graph_replays": (_i64, [_vp]),
     "admm_b200_get_setup_phases": (_int, [_vp, C.POINTER(C.c_double)]),
     "admm_b200_slicemaker": (_int, [_i64, _i64, C.POINTER(_i64)]),
 }

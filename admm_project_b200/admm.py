@@ -70,6 +70,7 @@ def admm(xminf, zming, options):
     o.history = int(bool(setopt(options, "history", 1)))                    # extension
     o.xsolve = int(setopt(options, "xsolve", L.XSOLVE_INVFACTOR))
     o.check_every = int(setopt(options, "check_every", 8))
+    o.graph = int(bool(setopt(options, "graph", 1)))                        # extension: CUDA-graph bursts
     o.fast = int(bool(setopt(options, "fast", 0)))                          # admm.m:59-60, 267-298
     o.fasttype = int(setopt(options, "fasttype", "weak") == "weak")
     alg = (2 if o.fasttype else 1) if o.fast else 0

@@ -71,7 +71,8 @@ struct admm_b200_handle {
   cudaEvent_t ev_la[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[4] = {nullptr, nullptr, nullptr, nullptr};
   double phase_ms[4] = {0, 0, 0, 0};  // gram (+Dts), cholesky, inverse factor (+transpose), total
-  int64_t launches = 0;
+  int64_t launches = 0;       // kernels launched (a graph replay counts the kernels it holds)
+  int64_t graph_replays = 0;  // CUDA graph launches of the iteration loop
 
   // problem
   int kind = 0;
@@ -1365,6 +1366,67 @@ static void prepare_loop(admm_b200_handle* h, const admm_b200_options& o, int64_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Burst runner.  The host enqueues check_every iterations, then reads the device stop flag.  The
+// kernels of an iteration have identical arguments every time (iteration counters, history slots
+// and stop state live on the device), so from the second full burst on the burst is ONE CUDA graph
+// launch: small problems (C1 lasso, the L2-resident shards of C3) are launch-bound otherwise
+// (~3 us of host work per kernel against 6-12 us kernels).  The first burst always runs eagerly: it
+// performs every lazy allocation, plan upload and cudaFuncSetAttribute, none of which may happen
+// inside a stream capture.  `period`: a graph may only hold a multiple of `period` iterations (the
+// total-variation loop alternates two buffer halves on the host side).
+// ---------------------------------------------------------------------------------------------
+template <class EnqueueOne, class Finished>
+static void run_bursts(admm_b200_handle* h, const admm_b200_options& o, int64_t N, int period, EnqueueOne&& enqueue_one,
+                       Finished&& finished) {
+  const int check = std::max(1, o.check_every);
+  const bool graph_ok = o.graph && check % period == 0 && !getenv("ADMM_B200_DEBUG") && !getenv("ADMM_B200_NO_GRAPH");
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int64_t graph_launches = 0;
+  auto drop = [&]() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    exec = nullptr; graph = nullptr;
+  };
+  try {
+    int64_t enq = 0, bursts = 0;
+    while (true) {
+      const int64_t burst = std::min<int64_t>(check, N - enq);
+      if (graph_ok && bursts >= 1 && burst == check) {
+        if (!exec) {
+          const int64_t before = h->launches;
+          ADMM_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+          try {
+            for (int64_t c = 0; c < burst; ++c) enqueue_one();
+          } catch (...) {
+            cudaGraph_t dead = nullptr;
+            cudaStreamEndCapture(h->stream, &dead);
+            if (dead) cudaGraphDestroy(dead);
+            throw;
+          }
+          ADMM_CUDA(cudaStreamEndCapture(h->stream, &graph));
+          ADMM_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+          graph_launches = h->launches - before;
+          h->launches = before;
+        }
+        ADMM_CUDA(cudaGraphLaunch(exec, h->stream));
+        h->launches += graph_launches;
+        h->graph_replays++;
+      } else {
+        for (int64_t c = 0; c < burst; ++c) enqueue_one();
+      }
+      enq += burst;
+      ++bursts;
+      if (finished() || enq >= N) break;
+    }
+  } catch (...) {
+    drop();
+    throw;
+  }
+  drop();
+}
+
 static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_result* res) {
   validate_options(h, o);
   int64_t N = o.maxiters > 0 ? o.maxiters : 1000;  // admm.m:334-339
@@ -1374,16 +1436,13 @@ static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_res
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
   load_init(h);
   enqueue_first_rhs(h, o);
-  const int check = std::max(1, o.check_every);
-  int64_t enq = 0;
-  while (true) {
-    int64_t burst = std::min<int64_t>(check, N - enq);
-    for (int64_t c = 0; c < burst; ++c) enqueue_iteration(h, o, lp, 0, history);
-    enq += burst;
-    ADMM_CUDA(cudaMemcpyAsync(h->h_ctl, h->ctl, sizeof(LoopCtl), cudaMemcpyDeviceToHost, h->stream));
-    ADMM_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->h_ctl->done || enq >= N) break;
-  }
+  run_bursts(
+      h, o, N, h->kind == ADMM_B200_TOTALVARIATION ? 2 : 1, [&]() { enqueue_iteration(h, o, lp, 0, history); },
+      [&]() {
+        ADMM_CUDA(cudaMemcpyAsync(h->h_ctl, h->ctl, sizeof(LoopCtl), cudaMemcpyDeviceToHost, h->stream));
+        ADMM_CUDA(cudaStreamSynchronize(h->stream));
+        return h->h_ctl->done != 0;
+      });
   ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
   ADMM_CUDA(cudaEventSynchronize(h->ev1));
   float ms = 0;
@@ -1489,12 +1548,10 @@ static void solve_lasso_batch(admm_b200_handle* h, const admm_b200_options& o, i
     lp.hn = hist.p + 4 * N * nb; lp.obj = hist.p + 5 * N * nb;
     lp.dvals = hist.p + 6 * N * nb; lp.avals = hist.p + 7 * N * nb; lp.rst = hist.p + 8 * N * nb;
     ADMM_REQUIRE(lp.alg == 0, ADMM_B200_ERR_UNSUPPORTED, "lasso batch: options.fast is not built for a batch");
-    const int check = std::max(1, o.check_every);
-    int64_t enq = 0;
     int hdone = 0;
-    while (true) {
-      const int64_t burst = std::min<int64_t>(check, N - enq);
-      for (int64_t c = 0; c < burst; ++c) {
+    run_bursts(
+        h, o, N, 1,
+        [&]() {
         GemmOpt g1;           // T = W * Y, W lower triangular
         g1.a_lower = 1;
         gemm(h, 0, 0, n, nb, n, 1.0, h->W.p, h->ldf, Y.p, ld, 0.0, T.p, ld, g1);
@@ -1513,12 +1570,12 @@ static void solve_lasso_batch(admm_b200_handle* h, const admm_b200_options& o, i
         prox_ident_kernel<<<dim3(pg, (unsigned)nb), PROX_THREADS, 0, h->stream>>>(a);
         ADMM_CUDA(cudaGetLastError());
         h->launches++;
-      }
-      enq += burst;
-      ADMM_CUDA(cudaMemcpyAsync(&hdone, done_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      ADMM_CUDA(cudaStreamSynchronize(h->stream));
-      if (hdone >= nb || enq >= N) break;
-    }
+        },
+        [&]() {
+          ADMM_CUDA(cudaMemcpyAsync(&hdone, done_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+          ADMM_CUDA(cudaStreamSynchronize(h->stream));
+          return hdone >= nb;
+        });
     ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
     ADMM_CUDA(cudaEventSynchronize(h->ev1));
     float ms = 0;
@@ -1684,12 +1741,10 @@ static void solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options& 
     ADMM_CUDA(cudaGetLastError());
     gemvt_strided(h, h->dD, h->ldD, m, n, nbt, R.p, mpad, CB.p, cbs);
     allreduce_sum(h, CB.p, cbs * nbt);
-    const int check = std::max(1, o.check_every);
-    int64_t enq = 0;
     int hdone = 0;
-    while (true) {
-      const int64_t burst = std::min<int64_t>(check, N - enq);
-      for (int64_t c = 0; c < burst; ++c) {
+    run_bursts(
+        h, o, N, 1,
+        [&]() {
         GemmOpt g1; g1.a_lower = 1;      // T = W * [d_1 .. d_nb]
         gemm(h, 0, 0, n, nb, n, 1.0, h->W.p, h->ldf, CB.p, cbs, 0.0, T.p, npad, g1);
         GemmOpt g2; g2.a_upper = 1;      // X = W' * T
@@ -1709,12 +1764,12 @@ static void solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options& 
         uwb_epilogue_kernel<<<(unsigned)nb, 256, 0, st>>>(e);
         ADMM_CUDA(cudaGetLastError());
         h->launches++;
-      }
-      enq += burst;
-      ADMM_CUDA(cudaMemcpyAsync(&hdone, done_count, sizeof(int), cudaMemcpyDeviceToHost, st));
-      ADMM_CUDA(cudaStreamSynchronize(st));
-      if (hdone >= nb || enq >= N) break;
-    }
+        },
+        [&]() {
+          ADMM_CUDA(cudaMemcpyAsync(&hdone, done_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+          ADMM_CUDA(cudaStreamSynchronize(st));
+          return hdone >= nb;
+        });
     ADMM_CUDA(cudaEventRecord(h->ev1, st));
     ADMM_CUDA(cudaEventSynchronize(h->ev1));
     float ms = 0;
@@ -1771,6 +1826,7 @@ void admm_b200_default_options(admm_b200_options* o) {
   o->maxiters = 1000; o->domaxiters = 0; o->stopcond = ADMM_B200_STOP_STANDARD; o->nodualerror = 0;
   o->convtest = 0; o->objevals = 0; o->history = 1; o->xsolve = ADMM_B200_XSOLVE_INVFACTOR; o->check_every = 8;
   o->fast = 0; o->fasttype = 1; o->restart = 0.999; o->dvaltol = 1e-8;
+  o->graph = 1; o->reserved = 0;
 }
 
 int admm_b200_create(int device, admm_b200_handle** out) {
@@ -2152,6 +2208,7 @@ int admm_b200_iterate_raw(admm_b200_handle* h, const admm_b200_options* opts, in
 }
 
 int64_t admm_b200_launch_count(admm_b200_handle* h) { return h ? h->launches : 0; }
+int64_t admm_b200_graph_replays(admm_b200_handle* h) { return h ? h->graph_replays : 0; }
 
 int admm_b200_get_setup_phases(admm_b200_handle* h, double* out4) {
   ADMM_API_BEGIN

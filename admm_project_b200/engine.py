@@ -50,6 +50,9 @@ class Engine:
     def launch_count(self):
         return int(self._lib.admm_b200_launch_count(self._h))
 
+    def graph_replays(self):
+        return int(self._lib.admm_b200_graph_replays(self._h))
+
     def setup_phases(self):
         out = (C.c_double * 4)()
         L.check(self._lib.admm_b200_get_setup_phases(self._h, out))

@@ -103,6 +103,9 @@ typedef struct admm_b200_options {
   int32_t fasttype;   /* admm.m:60  1 = 'weak' (default): accelerated ADMM with restart (alg 2); 0 = fast ADMM (alg 1) */
   double restart;     /* admm.m:287 options.restart, default 0.999 (values outside (0,1) become 0.999) */
   double dvaltol;     /* admm.m:291 options.dvaltol, default 1e-8 */
+  int32_t graph;      /* extension, default 1: after the first burst of check_every iterations, replay each
+                         further burst as one CUDA graph launch (same kernels, same arguments, same results) */
+  int32_t reserved;
 } admm_b200_options;
 
 /* What admm.m returns in `results` (admm.m:603-610, 618-658, 682, 746-767).  Every pointer is
@@ -240,6 +243,8 @@ int admm_b200_factor_solve(admm_b200_handle* h, const double* b, double* x, int3
 int admm_b200_iterate_raw(admm_b200_handle* h, const admm_b200_options* opts, int which, int reps);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int64_t admm_b200_launch_count(admm_b200_handle* h);
+/* Number of CUDA graph launches the iteration loops of this handle have issued (options.graph). */
+int64_t admm_b200_graph_replays(admm_b200_handle* h);
 
 /* Device time (ms) of the last setup by phase: [0] Gram (+ D's), [1] Cholesky, [2] inverse factor,
  * [3] total.  (The reference only has tic/toc: results.solverruntime, lasso.m:117,243.) */

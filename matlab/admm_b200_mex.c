@@ -69,6 +69,7 @@ static void read_options(const mxArray* s, admm_b200_options* o) {
   o->fasttype = (int32_t)field(s, "fasttype", 1);   /* 1 = 'weak' (accelerated, restart), 0 = fast ADMM */
   o->restart = field(s, "restart", 0.999);
   o->dvaltol = field(s, "dvaltol", 1e-8);
+  o->graph = (int32_t)field(s, "graph", 1);
 }
 
 static mxArray* put(mxArray* s, const char* name, mwSize m, mwSize n) {

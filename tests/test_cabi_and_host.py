@@ -32,14 +32,15 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     from admm_project_b200 import _lib
-    # options: 6 doubles + int64 + 10 int32 + 2 doubles; result: see header
-    assert ctypes.sizeof(_lib.Options) == 6 * 8 + 8 + 10 * 4 + 2 * 8
+    # options: 6 doubles + int64 + 10 int32 + 2 doubles + 2 int32; result: see header
+    assert ctypes.sizeof(_lib.Options) == 6 * 8 + 8 + 10 * 4 + 2 * 8 + 2 * 4
     assert ctypes.sizeof(_lib.Result) == 8 + 4 + 4 + 3 * 8 + 15 * 8
     o = _lib.Options()
     _lib.load().admm_b200_default_options(ctypes.byref(o))          # admm.m:51-76
     assert (o.rho, o.relax, o.abstol, o.reltol, o.convtol, o.hnormtol) == (1.0, 1.0, 1e-5, 1e-3, 1e-10, 1e-6)
     assert (o.maxiters, o.domaxiters, o.stopcond, o.nodualerror, o.convtest, o.objevals) == (1000, 0, 0, 0, 0, 0)
     assert (o.fast, o.fasttype, o.restart, o.dvaltol) == (0, 1, 0.999, 1e-8)              # admm.m:59-60, 287, 291
+    assert (o.check_every, o.graph) == (8, 1)
 
 
 def test_slicemaker_through_cabi_matches_oracle():
