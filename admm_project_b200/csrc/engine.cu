@@ -33,6 +33,7 @@ void set_error(const char* fmt, ...) {
 }
 
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+static inline int64_t tv_stride(int64_t n);
 
 // a device buffer the handle owns
 struct DBuf {
@@ -914,8 +915,8 @@ static void setup_tv(admm_b200_handle* h, int64_t n, const double* s, double lam
 
 static void tv_prepare(admm_b200_handle* h, double rho) {
   const int64_t n = h->n;
-  h->zz.ensure(2 * round_up(n, 2));   // two halves at an even stride (16-byte loads)
-  h->uu.ensure(2 * round_up(n, 2));
+  h->zz.ensure(2 * tv_stride(n));   // two halves at a 32-byte stride (256-bit loads)
+  h->uu.ensure(2 * tv_stride(n));
   if (h->tv_rho == rho) return;
   // pivots of I + rho*D'D: delta_0 = 1 + rho, delta_i = 1 + 2 rho - rho^2/delta_{i-1}; contraction
   std::vector<double> inv;
@@ -1114,6 +1115,36 @@ static void load_init(admm_b200_handle* h) {
   h->iter_ready = true;
 }
 
+// total variation: the two z/u halves sit 32-byte aligned (256-bit loads of the fused kernel)
+static inline int64_t tv_stride(int64_t n) { return round_up(n, 4); }
+static bool tv_fused_ok(const admm_b200_handle* h) {
+  return 8 * h->tv_halo <= TVF_SEG && !getenv("ADMM_B200_TV_UNFUSED");
+}
+// One fused TV iteration reading half `par` (xonly: only materialise x from that half).
+static void tv_fused_launch(admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, int par, bool xonly,
+                            bool history) {
+  const int64_t n = h->n, st = tv_stride(n);
+  TvFusedArgs a;
+  a.n = n;
+  a.hl = h->tv_halo + 4; a.hr = h->tv_halo + 4;          // >= halo + 1 / halo + 2, multiples of 4 (halo is one of 16)
+  a.S = TVF_SEG - a.hl - a.hr;
+  a.nseg = (n + a.S - 1) / a.S;
+  a.s = h->s.p; a.z = h->zz.p + (int64_t)par * st; a.u = h->uu.p + (int64_t)par * st;
+  a.znew = h->zz.p + (int64_t)(1 - par) * st; a.unew = h->uu.p + (int64_t)(1 - par) * st;
+  a.x = h->x.p;
+  a.rho = o.rho; a.lambda = h->lambda; a.invdelta = h->tvtab.p; a.inv_star = h->tv_inv_star; a.ntab = h->tv_ntab;
+  a.xonly = xonly ? 1 : 0;
+  const int grid = (int)std::min<int64_t>(2 * kNumSM, a.nseg);
+  h->partials.ensure((int64_t)grid * 8);
+  a.partials = h->partials.p; a.ctl = h->ctl; a.lp = lp;
+  a.xvals = history ? h->xvals.p : nullptr;
+  a.zvals = history ? h->zvals.p : nullptr;
+  a.uvals = history ? h->uvals.p : nullptr;
+  tv_fused_kernel<<<grid, TVF_T, 0, h->stream>>>(a);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+}
+
 // which: 0 whole iteration, 1 x-update only, 2 fused pass only
 static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, int which,
                               bool history) {
@@ -1126,7 +1157,12 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
       ADMM_CUDA(cudaFuncSetAttribute(tv_solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TvCfg<16>::SMEM_BYTES));
       configured = true;
     }
-    const int64_t npad = round_up(n, 2);
+    if (which == 0 && tv_fused_ok(h)) {          // small halo: the whole iteration is one kernel (tv.cuh)
+      tv_fused_launch(h, o, lp, h->tv_par, false, history);
+      h->tv_par ^= 1;
+      return;
+    }
+    const int64_t npad = tv_stride(n);
     const double* zc = h->zz.p + (int64_t)h->tv_par * npad;
     const double* uc = h->uu.p + (int64_t)h->tv_par * npad;
     if (which != 2) {
@@ -1449,9 +1485,12 @@ static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_res
   ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   if (h->kind == ADMM_B200_TOTALVARIATION) {   // the last iteration that ran wrote half (steps mod 2)
     const int64_t half = h->h_ctl->it % 2, n = h->n;
-    ADMM_CUDA(cudaMemcpyAsync(h->z.p, h->zz.p + half * round_up(n, 2), (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
-    ADMM_CUDA(cudaMemcpyAsync(h->u.p, h->uu.p + half * round_up(n, 2), (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(h->z.p, h->zz.p + half * tv_stride(n), (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(h->u.p, h->uu.p + half * tv_stride(n), (size_t)n * 8, cudaMemcpyDeviceToDevice, h->stream));
     h->tv_par = (int)half;
+    // the fused iteration keeps x in registers: materialise the x of the last iteration from the
+    // half it read (untouched since: later launches exit on ctl->done)
+    if (tv_fused_ok(h) && h->h_ctl->it >= 1) tv_fused_launch(h, o, lp, (int)(1 - half), true, false);
   }
   if (!res) return;
   const int64_t steps = h->h_ctl->it;

@@ -298,4 +298,267 @@ __global__ void __launch_bounds__(TVP_THREADS, 2) tv_prox_kernel(TvProxArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused iteration (small halos): x-update + z/u pass in ONE kernel, everything register-resident.
+// A thread owns TVF_E consecutive elements for every phase: 256-bit loads of z, u, s -> forward
+// affine scan (y) -> reversed affine scan (x) -> neighbour x's through 3 shared-memory slots per
+// thread -> relaxed soft threshold, u-update, all norms -> 256-bit stores of z, u.  x never goes to
+// memory inside the loop (the next x-update reads only s, z, u): 5 vector passes per iteration
+// instead of 10; the host materialises x once after the loop (xonly = 1 on the half the last
+// iteration read) or the kernel writes it into the history when options.history asks for it.
+// Outputs of a segment: local [hl, SEG - hr) with hl >= halo + 1, hr >= halo + 2 (the prox stencil
+// reads x_{i-1} .. x_{i+2}), both multiples of 4 so every thread chunk is 32-byte aligned.
+// ---------------------------------------------------------------------------------------------
+constexpr int TVF_T = 256;
+constexpr int TVF_E = 8;
+constexpr int TVF_SEG = TVF_T * TVF_E;
+
+struct TvFusedArgs {
+  int64_t n, S, nseg;
+  const double *s, *z, *u;
+  double *znew, *unew;
+  double* x;                // written only when xonly
+  double rho, lambda;
+  const double* invdelta;
+  double inv_star;
+  int ntab, hl, hr, xonly;
+  double* partials;         // [gridDim.x][8]
+  LoopCtl* ctl;
+  LoopParams lp;
+  double *xvals, *zvals, *uvals;
+};
+
+__device__ __forceinline__ void ld256(const double* p, double* v) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st256(double* p, const double* v) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+// Carry-in of this thread for an affine scan over the CTA in thread order (REV = false) or in
+// reversed thread order (REV = true); the carry into the first thread in scan order is 0.
+template <int T, bool REV>
+__device__ __forceinline__ double block_affine_carry_t(Affine mine, double* shA, double* shB) {
+  constexpr int W = T / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Affine inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double pa = REV ? __shfl_down_sync(0xffffffffu, inc.A, d) : __shfl_up_sync(0xffffffffu, inc.A, d);
+    const double pb = REV ? __shfl_down_sync(0xffffffffu, inc.B, d) : __shfl_up_sync(0xffffffffu, inc.B, d);
+    if (REV ? (lane + d < 32) : (lane >= d)) inc = compose(inc, Affine{pa, pb});
+  }
+  if (lane == (REV ? 0 : 31)) { shA[warp] = inc.A; shB[warp] = inc.B; }
+  __syncthreads();
+  if (warp == 0) {
+    const int src = REV ? (W - 1 - lane) : lane;          // warps in scan order
+    Affine w = (lane < W) ? Affine{shA[src], shB[src]} : Affine{1.0, 0.0};
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double pa = __shfl_up_sync(0xffffffffu, w.A, d);
+      const double pb = __shfl_up_sync(0xffffffffu, w.B, d);
+      if (lane >= d) w = compose(w, Affine{pa, pb});
+    }
+    if (lane < W) { shA[32 + src] = w.A; shB[32 + src] = w.B; }
+  }
+  __syncthreads();
+  const double pa = REV ? __shfl_down_sync(0xffffffffu, inc.A, 1) : __shfl_up_sync(0xffffffffu, inc.A, 1);
+  const double pb = REV ? __shfl_down_sync(0xffffffffu, inc.B, 1) : __shfl_up_sync(0xffffffffu, inc.B, 1);
+  Affine excl = (REV ? (lane < 31) : (lane > 0)) ? Affine{pa, pb} : Affine{1.0, 0.0};
+  const int prevw = REV ? warp + 1 : warp - 1;            // the warp before this one in scan order
+  if (prevw >= 0 && prevw < W) excl = compose(excl, Affine{shA[32 + prevw], shB[32 + prevw]});
+  __syncthreads();
+  return excl.B;
+}
+
+__global__ void __launch_bounds__(TVF_T, 2) tv_fused_kernel(TvFusedArgs a) {
+  LoopCtl* ctl = a.ctl;
+  if (!a.xonly && ctl->done) return;
+  constexpr int E = TVF_E;
+  __shared__ double shA[64], shB[64];
+  __shared__ double xe[3][TVF_T];                          // first, second and last x of every thread
+  __shared__ double red_sh[(TVF_T / 32) * 8];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x;
+  const int it = ctl->it;
+  const double rho = a.rho, relax = a.lp.relax, thr = a.lambda / rho;
+  const int64_t n = a.n;
+  double racc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) racc[k] = 0.0;
+
+  for (int64_t seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
+    const int j0 = tid * E;
+    const int64_t i0 = seg * a.S - a.hl + j0;              // global index of the chunk's first element
+    // z[i0-1 .. i0+E], u[i0-1 .. i0+E-1], s[i0 .. i0+E-1]; zero outside [0, n)
+    double zr[E + 2], ur[E + 1], sr[E];
+    const bool interior = (i0 >= 1 && i0 + E + 1 <= n);
+    if (interior) {
+      ld256(a.z + i0, zr + 1); ld256(a.z + i0 + 4, zr + 5);
+      ld256(a.u + i0, ur + 1); ld256(a.u + i0 + 4, ur + 5);
+      ld256(a.s + i0, sr); ld256(a.s + i0 + 4, sr + 4);
+      zr[0] = a.z[i0 - 1]; ur[0] = a.u[i0 - 1]; zr[E + 1] = a.z[i0 + E];
+    } else {
+#pragma unroll
+      for (int k = 0; k < E + 2; ++k) { const int64_t i = i0 - 1 + k; zr[k] = (i >= 0 && i < n) ? a.z[i] : 0.0; }
+#pragma unroll
+      for (int k = 0; k < E + 1; ++k) { const int64_t i = i0 - 1 + k; ur[k] = (i >= 0 && i < n) ? a.u[i] : 0.0; }
+#pragma unroll
+      for (int k = 0; k < E; ++k) { const int64_t i = i0 + k; sr[k] = (i >= 0 && i < n) ? a.s[i] : 0.0; }
+    }
+    // 1/delta_i for i = i0-1 .. i0+E-1 (the table ends at the fixed point of the pivot sequence)
+    double idv[E + 1];
+    if (i0 - 1 >= a.ntab) {
+#pragma unroll
+      for (int k = 0; k < E + 1; ++k) idv[k] = a.inv_star;
+    } else {
+#pragma unroll
+      for (int k = 0; k < E + 1; ++k) {
+        const int64_t i = i0 - 1 + k;
+        idv[k] = (i >= 0 && i < a.ntab) ? a.invdelta[i] : a.inv_star;
+      }
+    }
+
+    // ---- forward: y_i = r_i + fa_i*y_{i-1}; r = s + rho*D'(z-u), fa_i = rho/delta_{i-1}
+    double r[E], fa[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int64_t i = i0 + e;
+      const bool in = (i >= 0 && i < n);
+      const double w = zr[e + 1] - ur[e + 1], wl = zr[e] - ur[e];
+      r[e] = in ? fma(rho, w - wl, sr[e]) : 0.0;
+      fa[e] = (in && i > 0) ? rho * idv[e] : 0.0;
+    }
+    Affine m{1.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < E; ++e) m = Affine{fa[e] * m.A, fma(fa[e], m.B, r[e])};
+    double carry = block_affine_carry_t<TVF_T, false>(m, shA, shB);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      carry = fma(fa[e], carry, r[e]);
+      r[e] = carry;                                        // y_i
+    }
+    // ---- backward: x_i = y_i/delta_i + (rho/delta_i)*x_{i+1}, scanned from the right
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int64_t i = i0 + e;
+      const bool in = (i >= 0 && i < n);
+      const double id = in ? idv[e + 1] : 0.0;
+      r[e] = id * r[e];
+      fa[e] = (in && i < n - 1) ? rho * id : 0.0;
+    }
+    Affine mb{1.0, 0.0};
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e) mb = Affine{fa[e] * mb.A, fma(fa[e], mb.B, r[e])};
+    carry = block_affine_carry_t<TVF_T, true>(mb, shA, shB);
+    double xx[E + 3];                                      // x[i0-1 .. i0+E+1]
+#pragma unroll
+    for (int e = E - 1; e >= 0; --e) {
+      carry = fma(fa[e], carry, r[e]);
+      xx[e + 1] = carry;
+    }
+    const int jlo = a.hl - j0, jhi = TVF_SEG - a.hr - j0;  // outputs of this chunk: e in [jlo, jhi)
+    if (a.xonly) {
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (e >= jlo && e < jhi && i0 + e < n) a.x[i0 + e] = xx[e + 1];
+      continue;
+    }
+    xe[0][tid] = xx[1]; xe[1][tid] = xx[2]; xe[2][tid] = xx[E];
+    __syncthreads();
+    xx[0] = tid > 0 ? xe[2][tid - 1] : 0.0;
+    xx[E + 1] = tid < TVF_T - 1 ? xe[0][tid + 1] : 0.0;
+    xx[E + 2] = tid < TVF_T - 1 ? xe[1][tid + 1] : 0.0;
+
+    // ---- z/u pass on elements i0-1+k; k = 0 is the left neighbour, recomputed only for the D'
+    // stencils of the dual residual (same arithmetic as tv_prox_kernel)
+    double zn_o[E], un_o[E];
+    double ul = 0.0, dzl = 0.0;
+#pragma unroll
+    for (int k = 0; k < E + 1; ++k) {
+      const int64_t i = i0 - 1 + k;
+      const double x0 = xx[k], x1 = xx[k + 1], x2 = xx[k + 2];
+      const double Dx = (i < n - 1) ? (x0 - x1) : x0;
+      const double zp = zr[k], up = ur[k];
+      double Axh = Dx, w;
+      if (relax != 1.0) {
+        // admm.m:517 / :521 with getProxOps.m:199 applying D to the vector in x's slot
+        Axh = relax * Dx - (1.0 - relax) * (-zp - 0.0);
+        const double Dx1 = (i + 1 < n - 1) ? (x1 - x2) : x1;
+        const double Axh1 = relax * Dx1 - (1.0 - relax) * (-zr[k + 1] - 0.0);
+        w = up + ((i < n - 1) ? (Axh - Axh1) : Axh);
+      } else {
+        w = up + Dx;
+      }
+      const double zn = soft_threshold(w, thr);
+      const double un = up + (Axh + (-zn) - 0.0);
+      const double dz = zn - zp;
+      if (k >= 1) {
+        const int e = k - 1;
+        zn_o[e] = zn; un_o[e] = un;
+        if (e >= jlo && e < jhi && i < n) {
+          const double du = un - up;
+          const double pr = Dx + (-zn) - 0.0;
+          const double dtdz = rho * ((i > 0) ? (dz - dzl) : dz);
+          const double dtu = rho * ((i > 0) ? (un - ul) : un);
+          const double xs = x0 - sr[e];
+          racc[0] = fma(pr, pr, racc[0]);
+          racc[1] = fma(Dx, Dx, racc[1]);
+          racc[2] = fma(zn, zn, racc[2]);
+          racc[3] = fma(dtdz, dtdz, racc[3]);
+          racc[4] = fma(dtu, dtu, racc[4]);
+          racc[5] = fma(dz, dz, racc[5]);
+          racc[6] = fma(du, du, racc[6]);
+          racc[7] += 0.5 * xs * xs + ((i < n - 1) ? a.lambda * fabs(Dx) : 0.0);
+        }
+      }
+      ul = un; dzl = dz;
+    }
+    // stores: whole 4-element groups with one 256-bit store when they are entirely outputs
+#pragma unroll
+    for (int g = 0; g < E / 4; ++g) {
+      const int e0 = 4 * g;
+      if (e0 >= jlo && e0 + 4 <= jhi && i0 + e0 + 4 <= n) {
+        st256(a.znew + i0 + e0, zn_o + e0);
+        st256(a.unew + i0 + e0, un_o + e0);
+      } else {
+#pragma unroll
+        for (int e = e0; e < e0 + 4; ++e)
+          if (e >= jlo && e < jhi && i0 + e < n) { a.znew[i0 + e] = zn_o[e]; a.unew[i0 + e] = un_o[e]; }
+      }
+    }
+    if (a.xvals) {
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if (e >= jlo && e < jhi && i0 + e < n) {
+          a.xvals[(int64_t)it * n + i0 + e] = xx[e + 1];
+          a.zvals[(int64_t)it * n + i0 + e] = zn_o[e];
+          a.uvals[(int64_t)it * n + i0 + e] = un_o[e];
+        }
+    }
+  }
+  if (a.xonly) return;
+  block_reduce_store<8>(racc, a.partials + (int64_t)blockIdx.x * 8, red_sh);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(&ctl->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < 8) {
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(a.partials + (int64_t)b * 8 + threadIdx.x);
+    red_sh[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double red[8] = {red_sh[0], red_sh[1], red_sh[2], 0.0, red_sh[3], red_sh[4], red_sh[5], red_sh[6]};
+    ctl->ticket = 0;
+    loop_epilogue(ctl, a.lp, red, (double)n, (double)n, red_sh[7]);
+  }
+}
+
 }  // namespace admmb200
