@@ -1126,21 +1126,33 @@ static void tv_fused_launch(admm_b200_handle* h, const admm_b200_options& o, con
   const int64_t n = h->n, st = tv_stride(n);
   TvFusedArgs a;
   a.n = n;
-  a.hl = h->tv_halo + 4; a.hr = h->tv_halo + 4;          // >= halo + 1 / halo + 2, multiples of 4 (halo is one of 16)
+  a.hl = h->tv_halo + TVF_E; a.hr = h->tv_halo + TVF_E;   // >= halo + 1 / halo + 2, multiples of E (halo is one of 16)
   a.S = TVF_SEG - a.hl - a.hr;
   a.nseg = (n + a.S - 1) / a.S;
   a.s = h->s.p; a.z = h->zz.p + (int64_t)par * st; a.u = h->uu.p + (int64_t)par * st;
   a.znew = h->zz.p + (int64_t)(1 - par) * st; a.unew = h->uu.p + (int64_t)(1 - par) * st;
   a.x = h->x.p;
   a.rho = o.rho; a.lambda = h->lambda; a.invdelta = h->tvtab.p; a.inv_star = h->tv_inv_star; a.ntab = h->tv_ntab;
+  a.c = o.rho * h->tv_inv_star;
+  a.cp[0] = 1.0;
+  for (int e = 1; e <= TVF_E; ++e) a.cp[e] = a.cp[e - 1] * a.c;
+  a.pw[0] = a.cp[TVF_E];
+  // fast segments: window [g, g + SEG) with g = seg*S - hl,  g - 1 >= ntab,  g >= 1,  g + SEG + 2 <= n
+  a.seg_lo = (std::max<int64_t>(h->tv_ntab + 1, 1) + a.hl + a.S - 1) / a.S;
+  a.seg_hi = (n - TVF_SEG - 2 + a.hl >= 0) ? std::min<int64_t>(a.nseg, (n - TVF_SEG - 2 + a.hl) / a.S + 1) : 0;
+  if (a.seg_hi < a.seg_lo) a.seg_hi = a.seg_lo;
+  for (int k = 1; k < 5; ++k) a.pw[k] = a.pw[k - 1] * a.pw[k - 1];
+  a.aw = a.pw[4] * a.pw[4];
   a.xonly = xonly ? 1 : 0;
-  const int grid = (int)std::min<int64_t>(2 * kNumSM, a.nseg);
-  h->partials.ensure((int64_t)grid * 8);
-  a.partials = h->partials.p; a.ctl = h->ctl; a.lp = lp;
+  a.ctl = h->ctl; a.lp = lp;
   a.xvals = history ? h->xvals.p : nullptr;
   a.zvals = history ? h->zvals.p : nullptr;
   a.uvals = history ? h->uvals.p : nullptr;
-  tv_fused_kernel<<<grid, TVF_T, 0, h->stream>>>(a);
+  const int grid = (int)std::min<int64_t>(2 * kNumSM, a.nseg);
+  h->partials.ensure((int64_t)grid * 8);
+  a.partials = h->partials.p;
+  if (o.relax == 1.0) tv_fused_kernel<true><<<grid, TVF_T, 0, h->stream>>>(a);
+  else tv_fused_kernel<false><<<grid, TVF_T, 0, h->stream>>>(a);
   ADMM_CUDA(cudaGetLastError());
   h->launches++;
 }

@@ -307,11 +307,18 @@ __global__ void __launch_bounds__(TVP_THREADS, 2) tv_prox_kernel(TvProxArgs a) {
 // instead of 10; the host materialises x once after the loop (xonly = 1 on the half the last
 // iteration read) or the kernel writes it into the history when options.history asks for it.
 // Outputs of a segment: local [hl, SEG - hr) with hl >= halo + 1, hr >= halo + 2 (the prox stencil
-// reads x_{i-1} .. x_{i+2}), both multiples of 4 so every thread chunk is 32-byte aligned.
+// reads x_{i-1} .. x_{i+2}), both multiples of TVF_E so a thread is all output or all halo.
+//
+// Two bodies per kernel.  FAST (every segment whose whole window lies in 1 .. n-3 and past the
+// pivot table): no predicates, the recurrence multiplier is the constant c = rho/delta*, so a
+// thread's affine map is (c^E, B) and the block scans carry only B with powers of c precomputed on
+// the host -- 3 barriers per segment.  SLOW (the first and last one or two segments, and every
+// segment of a small problem): the general predicated code in rolled loops on local arrays.
 // ---------------------------------------------------------------------------------------------
 constexpr int TVF_T = 256;
 constexpr int TVF_E = 8;
 constexpr int TVF_SEG = TVF_T * TVF_E;
+constexpr int TVF_W = TVF_T / 32;
 
 struct TvFusedArgs {
   int64_t n, S, nseg;
@@ -321,6 +328,11 @@ struct TvFusedArgs {
   double rho, lambda;
   const double* invdelta;
   double inv_star;
+  double c;                 // rho*inv_star
+  double cp[TVF_E + 1];     // c^k, k = 0 .. E
+  double pw[5];             // c^(E*2^k): the map of 2^k consecutive fast threads
+  double aw;                // c^(E*32): a whole warp
+  int64_t seg_lo, seg_hi;   // segments [seg_lo, seg_hi) take the predicate-free body
   int ntab, hl, hr, xonly;
   double* partials;         // [gridDim.x][8]
   LoopCtl* ctl;
@@ -371,170 +383,292 @@ __device__ __forceinline__ double block_affine_carry_t(Affine mine, double* shA,
   return excl.B;
 }
 
+// The same carry when every thread's map is (c^E, B): only B travels.  lanepow[k] = c^(E*k).  shW
+// holds the TVF_W warp totals of THIS scan (the two scans of a segment use different arrays, so no
+// trailing barrier is needed: the next write comes two barriers later).
+template <bool REV>
+__device__ __forceinline__ double tvf_carry(double B, const TvFusedArgs& a, const double* lanepow, double* shW) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double inc = B;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int d = 1 << k;
+    const double p = REV ? __shfl_down_sync(0xffffffffu, inc, d) : __shfl_up_sync(0xffffffffu, inc, d);
+    if (REV ? (lane + d < 32) : (lane >= d)) inc = fma(a.pw[k], p, inc);
+  }
+  if (lane == (REV ? 0 : 31)) shW[warp] = inc;
+  __syncthreads();
+  // carry into this warp: Horner over the warps before it in scan order (at most 7 broadcast loads)
+  double wc = 0.0;
+  if (REV) {
+    for (int v = TVF_W - 1; v > warp; --v) wc = fma(a.aw, wc, shW[v]);
+  } else {
+    for (int v = 0; v < warp; ++v) wc = fma(a.aw, wc, shW[v]);
+  }
+  const double pB = REV ? __shfl_down_sync(0xffffffffu, inc, 1) : __shfl_up_sync(0xffffffffu, inc, 1);
+  const double exB = (REV ? (lane < 31) : (lane > 0)) ? pB : 0.0;
+  return fma(lanepow[REV ? 31 - lane : lane], wc, exB);
+}
+
+// ---- FAST body: every element the thread touches is interior and past the pivot table
+template <bool RELAX1>
+__device__ __forceinline__ void tvf_fast_segment(const TvFusedArgs& a, int64_t i0, bool is_out, int it, double* racc,
+                                                 const double* lanepow, double* shW, double (*xe)[TVF_T]) {
+  constexpr int E = TVF_E;
+  const int tid = threadIdx.x;
+  const double rho = a.rho, c = a.c, ids = a.inv_star;
+  double zr[E + 2], ur[E + 1], sr[E];                      // z[i0-1 .. i0+E], u[i0-1 .. i0+E-1], s[i0 .. i0+E-1]
+  ld256(a.z + i0, zr + 1); ld256(a.z + i0 + 4, zr + 5);
+  ld256(a.u + i0, ur + 1); ld256(a.u + i0 + 4, ur + 5);
+  ld256(a.s + i0, sr); ld256(a.s + i0 + 4, sr + 4);
+  zr[0] = a.z[i0 - 1]; ur[0] = a.u[i0 - 1]; zr[E + 1] = a.z[i0 + E];
+  // forward: y_i = r_i + c*y_{i-1}, r = s + rho*D'(z - u)
+  double r[E];
+  {
+    double wl = zr[0] - ur[0];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const double w = zr[e + 1] - ur[e + 1];
+      r[e] = fma(rho, w - wl, sr[e]);
+      wl = w;
+    }
+  }
+  // local prefixes first (y with a zero carry-in), so that after the block scan every element is ONE
+  // independent fma away: y_e = c^(e+1)*carry + prefix_e -- the dependent chain is walked once, not twice
+#pragma unroll
+  for (int e = 1; e < E; ++e) r[e] = fma(c, r[e - 1], r[e]);
+  double carry = tvf_carry<false>(r[E - 1], a, lanepow, shW);
+  const double ym1 = carry;                                // y_{i0-1}
+#pragma unroll
+  for (int e = 0; e < E; ++e) r[e] = ids * fma(a.cp[e + 1], carry, r[e]);   // y_i / delta_i
+  // backward: x_i = y_i/delta + c*x_{i+1}, prefixes from the right
+#pragma unroll
+  for (int e = E - 2; e >= 0; --e) r[e] = fma(c, r[e + 1], r[e]);
+  carry = tvf_carry<true>(r[0], a, lanepow, shW + TVF_W);
+  double xx[E + 3];                                        // x[i0-1 .. i0+E+1]
+#pragma unroll
+  for (int e = 0; e < E; ++e) xx[e + 1] = fma(a.cp[E - e], carry, r[e]);
+  if (a.xonly) {
+    if (is_out) { st256(a.x + i0, xx + 1); st256(a.x + i0 + 4, xx + 5); }
+    return;
+  }
+  if (RELAX1) {
+    // the neighbours' x the stencil needs come out of the recurrences themselves: the carry of the
+    // reversed scan IS x_{i0+E}, and x_{i0-1} = y_{i0-1}/delta + c*x_{i0} -- no exchange, no barrier
+    if (!is_out) return;                                   // halo threads: nothing to produce
+    xx[E + 1] = carry;
+    xx[0] = fma(c, xx[1], ids * ym1);
+    xx[E + 2] = 0.0;
+  } else {
+    xe[0][tid] = xx[1]; xe[1][tid] = xx[2]; xe[2][tid] = xx[E];
+    __syncthreads();
+    if (!is_out) return;
+    xx[0] = xe[2][tid - 1];                                // outputs never sit in the first / last thread
+    xx[E + 1] = xe[0][tid + 1];
+    xx[E + 2] = xe[1][tid + 1];
+  }
+  const double relax = a.lp.relax, thr = a.lambda / rho, lambda = a.lambda;
+  double zn_o[E], un_o[E];
+  double ul = 0.0, dzl = 0.0;
+#pragma unroll
+  for (int k = 0; k < E + 1; ++k) {                        // element i0-1+k; k = 0 only feeds the D' stencils
+    const double x0 = xx[k], x1 = xx[k + 1];
+    const double Dx = x0 - x1;
+    const double zp = zr[k], up = ur[k];
+    double Axh = Dx, w;
+    if (!RELAX1) {
+      // admm.m:517 / :521 with getProxOps.m:199 applying D to the vector in x's slot
+      Axh = relax * Dx - (1.0 - relax) * (-zp - 0.0);
+      const double Dx1 = x1 - xx[k + 2];
+      const double Axh1 = relax * Dx1 - (1.0 - relax) * (-zr[k + 1] - 0.0);
+      w = up + (Axh - Axh1);
+    } else {
+      w = up + Dx;
+    }
+    const double zn = soft_threshold(w, thr);
+    const double un = up + (Axh + (-zn) - 0.0);
+    const double dz = zn - zp;
+    if (k >= 1) {
+      const int e = k - 1;
+      zn_o[e] = zn; un_o[e] = un;
+      const double du = un - up;
+      const double pr = Dx + (-zn) - 0.0;
+      const double dtdz = rho * (dz - dzl);
+      const double dtu = rho * (un - ul);
+      const double xs = x0 - sr[e];
+      racc[0] = fma(pr, pr, racc[0]);
+      racc[1] = fma(Dx, Dx, racc[1]);
+      racc[2] = fma(zn, zn, racc[2]);
+      racc[3] = fma(dtdz, dtdz, racc[3]);
+      racc[4] = fma(dtu, dtu, racc[4]);
+      racc[5] = fma(dz, dz, racc[5]);
+      racc[6] = fma(du, du, racc[6]);
+      racc[7] += 0.5 * xs * xs + lambda * fabs(Dx);
+    }
+    ul = un; dzl = dz;
+  }
+  st256(a.znew + i0, zn_o); st256(a.znew + i0 + 4, zn_o + 4);
+  st256(a.unew + i0, un_o); st256(a.unew + i0 + 4, un_o + 4);
+  if (a.xvals) {
+    const int64_t o = (int64_t)it * a.n + i0;              // column `it` of the history: not 32-byte aligned in general
+#pragma unroll
+    for (int e = 0; e < E; ++e) { a.xvals[o + e] = xx[e + 1]; a.zvals[o + e] = zn_o[e]; a.uvals[o + e] = un_o[e]; }
+  }
+}
+
+// ---- SLOW body: the general predicated iteration on local arrays (edge segments, small problems)
+__device__ __noinline__ void tvf_slow_segment(const TvFusedArgs& a, int64_t i0, int jlo, int jhi, int it, double* red,
+                                              double* shA, double* shB, double (*xe)[TVF_T]) {
+  constexpr int E = TVF_E;
+  const int tid = threadIdx.x;
+  const double rho = a.rho, relax = a.lp.relax, thr = a.lambda / rho;
+  const int64_t n = a.n;
+  double zr[E + 2], ur[E + 1], sr[E], idv[E + 1], r[E], fa[E], xx[E + 3];
+#pragma unroll 1
+  for (int k = 0; k < E + 2; ++k) { const int64_t i = i0 - 1 + k; zr[k] = (i >= 0 && i < n) ? a.z[i] : 0.0; }
+#pragma unroll 1
+  for (int k = 0; k < E + 1; ++k) {
+    const int64_t i = i0 - 1 + k;
+    ur[k] = (i >= 0 && i < n) ? a.u[i] : 0.0;
+    idv[k] = (i >= 0 && i < a.ntab) ? a.invdelta[i] : a.inv_star;     // 1/delta_i
+  }
+#pragma unroll 1
+  for (int k = 0; k < E; ++k) { const int64_t i = i0 + k; sr[k] = (i >= 0 && i < n) ? a.s[i] : 0.0; }
+  // forward: y_i = r_i + fa_i*y_{i-1}; r = s + rho*D'(z-u), fa_i = rho/delta_{i-1}
+  Affine m{1.0, 0.0};
+#pragma unroll 1
+  for (int e = 0; e < E; ++e) {
+    const int64_t i = i0 + e;
+    const bool in = (i >= 0 && i < n);
+    const double w = zr[e + 1] - ur[e + 1], wl = zr[e] - ur[e];
+    r[e] = in ? fma(rho, w - wl, sr[e]) : 0.0;
+    fa[e] = (in && i > 0) ? rho * idv[e] : 0.0;
+    m = Affine{fa[e] * m.A, fma(fa[e], m.B, r[e])};
+  }
+  double carry = block_affine_carry_t<TVF_T, false>(m, shA, shB);
+  Affine mb{1.0, 0.0};
+#pragma unroll 1
+  for (int e = 0; e < E; ++e) {
+    carry = fma(fa[e], carry, r[e]);
+    r[e] = carry;                                          // y_i
+  }
+  // backward: x_i = y_i/delta_i + (rho/delta_i)*x_{i+1}, scanned from the right
+#pragma unroll 1
+  for (int e = E - 1; e >= 0; --e) {
+    const int64_t i = i0 + e;
+    const bool in = (i >= 0 && i < n);
+    const double id = in ? idv[e + 1] : 0.0;
+    r[e] = id * r[e];
+    fa[e] = (in && i < n - 1) ? rho * id : 0.0;
+    mb = Affine{fa[e] * mb.A, fma(fa[e], mb.B, r[e])};
+  }
+  carry = block_affine_carry_t<TVF_T, true>(mb, shA, shB);
+#pragma unroll 1
+  for (int e = E - 1; e >= 0; --e) {
+    carry = fma(fa[e], carry, r[e]);
+    xx[e + 1] = carry;
+  }
+  if (a.xonly) {
+#pragma unroll 1
+    for (int e = 0; e < E; ++e)
+      if (e >= jlo && e < jhi && i0 + e < n) a.x[i0 + e] = xx[e + 1];
+    return;
+  }
+  xe[0][tid] = xx[1]; xe[1][tid] = xx[2]; xe[2][tid] = xx[E];
+  __syncthreads();
+  xx[0] = tid > 0 ? xe[2][tid - 1] : 0.0;
+  xx[E + 1] = tid < TVF_T - 1 ? xe[0][tid + 1] : 0.0;
+  xx[E + 2] = tid < TVF_T - 1 ? xe[1][tid + 1] : 0.0;
+  // z/u pass on elements i0-1+k; k = 0 is the left neighbour, recomputed only for the D' stencils of
+  // the dual residual (same arithmetic as tv_prox_kernel)
+  double ul = 0.0, dzl = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < E + 1; ++k) {
+    const int64_t i = i0 - 1 + k;
+    const double x0 = xx[k], x1 = xx[k + 1], x2 = xx[k + 2];
+    const double Dx = (i < n - 1) ? (x0 - x1) : x0;
+    const double zp = zr[k], up = ur[k];
+    double Axh = Dx, w;
+    if (relax != 1.0) {
+      // admm.m:517 / :521 with getProxOps.m:199 applying D to the vector in x's slot
+      Axh = relax * Dx - (1.0 - relax) * (-zp - 0.0);
+      const double Dx1 = (i + 1 < n - 1) ? (x1 - x2) : x1;
+      const double Axh1 = relax * Dx1 - (1.0 - relax) * (-zr[k + 1] - 0.0);
+      w = up + ((i < n - 1) ? (Axh - Axh1) : Axh);
+    } else {
+      w = up + Dx;
+    }
+    const double zn = soft_threshold(w, thr);
+    const double un = up + (Axh + (-zn) - 0.0);
+    const double dz = zn - zp;
+    const int e = k - 1;
+    if (k >= 1 && e >= jlo && e < jhi && i < n) {
+      const double du = un - up;
+      const double pr = Dx + (-zn) - 0.0;
+      const double dtdz = rho * ((i > 0) ? (dz - dzl) : dz);
+      const double dtu = rho * ((i > 0) ? (un - ul) : un);
+      const double xs = x0 - sr[e];
+      red[0] = fma(pr, pr, red[0]);
+      red[1] = fma(Dx, Dx, red[1]);
+      red[2] = fma(zn, zn, red[2]);
+      red[3] = fma(dtdz, dtdz, red[3]);
+      red[4] = fma(dtu, dtu, red[4]);
+      red[5] = fma(dz, dz, red[5]);
+      red[6] = fma(du, du, red[6]);
+      red[7] += 0.5 * xs * xs + ((i < n - 1) ? a.lambda * fabs(Dx) : 0.0);
+      a.znew[i] = zn;
+      a.unew[i] = un;
+      if (a.xvals) {
+        a.xvals[(int64_t)it * n + i] = x0;
+        a.zvals[(int64_t)it * n + i] = zn;
+        a.uvals[(int64_t)it * n + i] = un;
+      }
+    }
+    ul = un; dzl = dz;
+  }
+}
+
+template <bool RELAX1>
 __global__ void __launch_bounds__(TVF_T, 2) tv_fused_kernel(TvFusedArgs a) {
   LoopCtl* ctl = a.ctl;
   if (!a.xonly && ctl->done) return;
-  constexpr int E = TVF_E;
-  __shared__ double shA[64], shB[64];
+  __shared__ double shA[64], shB[64];                      // slow-body scans
+  __shared__ double shW[2 * TVF_W];                        // fast-body scans: warp totals, forward / reversed
+  __shared__ double lanepow[32];                           // c^(E*k)
   __shared__ double xe[3][TVF_T];                          // first, second and last x of every thread
   __shared__ double red_sh[(TVF_T / 32) * 8];
   __shared__ bool is_last;
   const int tid = threadIdx.x;
   const int it = ctl->it;
-  const double rho = a.rho, relax = a.lp.relax, thr = a.lambda / rho;
   const int64_t n = a.n;
+  if (tid < 32) {
+    double p = 1.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if ((tid >> k) & 1) p *= a.pw[k];
+    lanepow[tid] = p;
+  }
+  __syncthreads();
   double racc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) racc[k] = 0.0;
-
+  const int j0 = tid * TVF_E;
+  const int jlo = a.hl - j0, jhi = TVF_SEG - a.hr - j0;    // outputs of this thread's chunk: e in [jlo, jhi)
+  const bool is_out = (jlo <= 0 && jhi >= TVF_E);          // hl, hr are multiples of E: all or nothing
+  // CTA-uniform: the segment's window lies inside 1 .. n-3 and past the pivot table (host-computed range)
   for (int64_t seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
-    const int j0 = tid * E;
-    const int64_t i0 = seg * a.S - a.hl + j0;              // global index of the chunk's first element
-    // z[i0-1 .. i0+E], u[i0-1 .. i0+E-1], s[i0 .. i0+E-1]; zero outside [0, n)
-    double zr[E + 2], ur[E + 1], sr[E];
-    const bool interior = (i0 >= 1 && i0 + E + 1 <= n);
-    if (interior) {
-      ld256(a.z + i0, zr + 1); ld256(a.z + i0 + 4, zr + 5);
-      ld256(a.u + i0, ur + 1); ld256(a.u + i0 + 4, ur + 5);
-      ld256(a.s + i0, sr); ld256(a.s + i0 + 4, sr + 4);
-      zr[0] = a.z[i0 - 1]; ur[0] = a.u[i0 - 1]; zr[E + 1] = a.z[i0 + E];
+    const int64_t i0 = seg * a.S - a.hl + j0;              // global index of this thread's first element
+    if (seg >= a.seg_lo && seg < a.seg_hi) {
+      tvf_fast_segment<RELAX1>(a, i0, is_out, it, racc, lanepow, shW, xe);
     } else {
+      // the callee's sums come back through memory; racc itself must stay in registers
+      // (and the callee gets its own copy of the arguments: handing it a reference to the kernel
+      // parameters makes the compiler read them from a stack copy everywhere, fast body included)
+      double red[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      const TvFusedArgs la = a;
+      tvf_slow_segment(la, i0, jlo, jhi, it, red, shA, shB, xe);
 #pragma unroll
-      for (int k = 0; k < E + 2; ++k) { const int64_t i = i0 - 1 + k; zr[k] = (i >= 0 && i < n) ? a.z[i] : 0.0; }
-#pragma unroll
-      for (int k = 0; k < E + 1; ++k) { const int64_t i = i0 - 1 + k; ur[k] = (i >= 0 && i < n) ? a.u[i] : 0.0; }
-#pragma unroll
-      for (int k = 0; k < E; ++k) { const int64_t i = i0 + k; sr[k] = (i >= 0 && i < n) ? a.s[i] : 0.0; }
-    }
-    // 1/delta_i for i = i0-1 .. i0+E-1 (the table ends at the fixed point of the pivot sequence)
-    double idv[E + 1];
-    if (i0 - 1 >= a.ntab) {
-#pragma unroll
-      for (int k = 0; k < E + 1; ++k) idv[k] = a.inv_star;
-    } else {
-#pragma unroll
-      for (int k = 0; k < E + 1; ++k) {
-        const int64_t i = i0 - 1 + k;
-        idv[k] = (i >= 0 && i < a.ntab) ? a.invdelta[i] : a.inv_star;
-      }
-    }
-
-    // ---- forward: y_i = r_i + fa_i*y_{i-1}; r = s + rho*D'(z-u), fa_i = rho/delta_{i-1}
-    double r[E], fa[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int64_t i = i0 + e;
-      const bool in = (i >= 0 && i < n);
-      const double w = zr[e + 1] - ur[e + 1], wl = zr[e] - ur[e];
-      r[e] = in ? fma(rho, w - wl, sr[e]) : 0.0;
-      fa[e] = (in && i > 0) ? rho * idv[e] : 0.0;
-    }
-    Affine m{1.0, 0.0};
-#pragma unroll
-    for (int e = 0; e < E; ++e) m = Affine{fa[e] * m.A, fma(fa[e], m.B, r[e])};
-    double carry = block_affine_carry_t<TVF_T, false>(m, shA, shB);
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      carry = fma(fa[e], carry, r[e]);
-      r[e] = carry;                                        // y_i
-    }
-    // ---- backward: x_i = y_i/delta_i + (rho/delta_i)*x_{i+1}, scanned from the right
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-      const int64_t i = i0 + e;
-      const bool in = (i >= 0 && i < n);
-      const double id = in ? idv[e + 1] : 0.0;
-      r[e] = id * r[e];
-      fa[e] = (in && i < n - 1) ? rho * id : 0.0;
-    }
-    Affine mb{1.0, 0.0};
-#pragma unroll
-    for (int e = E - 1; e >= 0; --e) mb = Affine{fa[e] * mb.A, fma(fa[e], mb.B, r[e])};
-    carry = block_affine_carry_t<TVF_T, true>(mb, shA, shB);
-    double xx[E + 3];                                      // x[i0-1 .. i0+E+1]
-#pragma unroll
-    for (int e = E - 1; e >= 0; --e) {
-      carry = fma(fa[e], carry, r[e]);
-      xx[e + 1] = carry;
-    }
-    const int jlo = a.hl - j0, jhi = TVF_SEG - a.hr - j0;  // outputs of this chunk: e in [jlo, jhi)
-    if (a.xonly) {
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-        if (e >= jlo && e < jhi && i0 + e < n) a.x[i0 + e] = xx[e + 1];
-      continue;
-    }
-    xe[0][tid] = xx[1]; xe[1][tid] = xx[2]; xe[2][tid] = xx[E];
-    __syncthreads();
-    xx[0] = tid > 0 ? xe[2][tid - 1] : 0.0;
-    xx[E + 1] = tid < TVF_T - 1 ? xe[0][tid + 1] : 0.0;
-    xx[E + 2] = tid < TVF_T - 1 ? xe[1][tid + 1] : 0.0;
-
-    // ---- z/u pass on elements i0-1+k; k = 0 is the left neighbour, recomputed only for the D'
-    // stencils of the dual residual (same arithmetic as tv_prox_kernel)
-    double zn_o[E], un_o[E];
-    double ul = 0.0, dzl = 0.0;
-#pragma unroll
-    for (int k = 0; k < E + 1; ++k) {
-      const int64_t i = i0 - 1 + k;
-      const double x0 = xx[k], x1 = xx[k + 1], x2 = xx[k + 2];
-      const double Dx = (i < n - 1) ? (x0 - x1) : x0;
-      const double zp = zr[k], up = ur[k];
-      double Axh = Dx, w;
-      if (relax != 1.0) {
-        // admm.m:517 / :521 with getProxOps.m:199 applying D to the vector in x's slot
-        Axh = relax * Dx - (1.0 - relax) * (-zp - 0.0);
-        const double Dx1 = (i + 1 < n - 1) ? (x1 - x2) : x1;
-        const double Axh1 = relax * Dx1 - (1.0 - relax) * (-zr[k + 1] - 0.0);
-        w = up + ((i < n - 1) ? (Axh - Axh1) : Axh);
-      } else {
-        w = up + Dx;
-      }
-      const double zn = soft_threshold(w, thr);
-      const double un = up + (Axh + (-zn) - 0.0);
-      const double dz = zn - zp;
-      if (k >= 1) {
-        const int e = k - 1;
-        zn_o[e] = zn; un_o[e] = un;
-        if (e >= jlo && e < jhi && i < n) {
-          const double du = un - up;
-          const double pr = Dx + (-zn) - 0.0;
-          const double dtdz = rho * ((i > 0) ? (dz - dzl) : dz);
-          const double dtu = rho * ((i > 0) ? (un - ul) : un);
-          const double xs = x0 - sr[e];
-          racc[0] = fma(pr, pr, racc[0]);
-          racc[1] = fma(Dx, Dx, racc[1]);
-          racc[2] = fma(zn, zn, racc[2]);
-          racc[3] = fma(dtdz, dtdz, racc[3]);
-          racc[4] = fma(dtu, dtu, racc[4]);
-          racc[5] = fma(dz, dz, racc[5]);
-          racc[6] = fma(du, du, racc[6]);
-          racc[7] += 0.5 * xs * xs + ((i < n - 1) ? a.lambda * fabs(Dx) : 0.0);
-        }
-      }
-      ul = un; dzl = dz;
-    }
-    // stores: whole 4-element groups with one 256-bit store when they are entirely outputs
-#pragma unroll
-    for (int g = 0; g < E / 4; ++g) {
-      const int e0 = 4 * g;
-      if (e0 >= jlo && e0 + 4 <= jhi && i0 + e0 + 4 <= n) {
-        st256(a.znew + i0 + e0, zn_o + e0);
-        st256(a.unew + i0 + e0, un_o + e0);
-      } else {
-#pragma unroll
-        for (int e = e0; e < e0 + 4; ++e)
-          if (e >= jlo && e < jhi && i0 + e < n) { a.znew[i0 + e] = zn_o[e]; a.unew[i0 + e] = un_o[e]; }
-      }
-    }
-    if (a.xvals) {
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-        if (e >= jlo && e < jhi && i0 + e < n) {
-          a.xvals[(int64_t)it * n + i0 + e] = xx[e + 1];
-          a.zvals[(int64_t)it * n + i0 + e] = zn_o[e];
-          a.uvals[(int64_t)it * n + i0 + e] = un_o[e];
-        }
+      for (int k = 0; k < 8; ++k) racc[k] += red[k];
     }
   }
   if (a.xonly) return;

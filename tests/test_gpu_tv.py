@@ -37,6 +37,19 @@ def test_totalvariation_matches_oracle(engine, n, rho, relax, lam):
         assert (obj(res["xopt"]) < obj(truth)) == (obj(ref["xopt"]) < obj(truth))    # totalvariationtest.m:151-155
 
 
+@pytest.mark.parametrize("n,relax", [(9001, 1.0), (6000, 1.3)])
+def test_totalvariation_history_through_the_fused_kernel(engine, n, relax):
+    # n > 2 windows of the fused kernel: interior segments take its predicate-free body, the first and
+    # last its general body; the x history is written by the kernel itself (x never reaches h->x)
+    s, _ = gen.tv_problem(3, n)
+    opts = {"objevals": 1, "maxiters": 25, "domaxiters": 1, "relax": relax, "history": 1}
+    ref = oracle.totalvariation(s, 2.0, opts)
+    res = totalvariation(s, 2.0, opts, engine=engine)
+    assert res["steps"] == ref["steps"] == 25
+    for k in ("xopt", "zopt", "uopt", "pnorm", "dnorm", "perr", "derr", "objevals", "xvals", "zvals", "uvals"):
+        assert rel(res[k], ref[k]) < 1e-9, (k, rel(res[k], ref[k]))
+
+
 def test_totalvariation_x_update_is_the_tridiagonal_solve(engine):
     # one iteration from random (z0, u0): x must solve (I + rho D'D) x = s + rho D'(z0 - u0)
     n, rho = 40000, 3.0
