@@ -1117,13 +1117,21 @@ static void load_init(admm_b200_handle* h) {
 
 // total variation: the two z/u halves sit 32-byte aligned (256-bit loads of the fused kernel)
 static inline int64_t tv_stride(int64_t n) { return round_up(n, 4); }
-static bool tv_fused_ok(const admm_b200_handle* h) {
-  return 8 * h->tv_halo <= TVF_SEG && !getenv("ADMM_B200_TV_UNFUSED");
+// CTA size of the fused iteration kernel, 0 when the halo is too wide for it (overhead > 25 %)
+static int tv_fused_threads(const admm_b200_handle* h) {
+  if (getenv("ADMM_B200_TV_UNFUSED")) return 0;
+  static const int pref = getenv("ADMM_B200_TVF_T") ? atoi(getenv("ADMM_B200_TVF_T")) : 128;
+  if (pref == 128 && 8 * h->tv_halo <= 128 * TVF_E) return 128;
+  if (8 * h->tv_halo <= 256 * TVF_E) return 256;
+  return 0;
 }
+static bool tv_fused_ok(const admm_b200_handle* h) { return tv_fused_threads(h) != 0; }
 // One fused TV iteration reading half `par` (xonly: only materialise x from that half).
 static void tv_fused_launch(admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, int par, bool xonly,
                             bool history) {
   const int64_t n = h->n, st = tv_stride(n);
+  const int T = tv_fused_threads(h);
+  const int64_t TVF_SEG = (int64_t)T * TVF_E;
   TvFusedArgs a;
   a.n = n;
   a.hl = h->tv_halo + TVF_E; a.hr = h->tv_halo + TVF_E;   // >= halo + 1 / halo + 2, multiples of E (halo is one of 16)
@@ -1148,11 +1156,16 @@ static void tv_fused_launch(admm_b200_handle* h, const admm_b200_options& o, con
   a.xvals = history ? h->xvals.p : nullptr;
   a.zvals = history ? h->zvals.p : nullptr;
   a.uvals = history ? h->uvals.p : nullptr;
-  const int grid = (int)std::min<int64_t>(2 * kNumSM, a.nseg);
+  const int grid = (int)std::min<int64_t>((512 / T) * kNumSM, a.nseg);
   h->partials.ensure((int64_t)grid * 8);
   a.partials = h->partials.p;
-  if (o.relax == 1.0) tv_fused_kernel<true><<<grid, TVF_T, 0, h->stream>>>(a);
-  else tv_fused_kernel<false><<<grid, TVF_T, 0, h->stream>>>(a);
+  if (T == 128) {
+    if (o.relax == 1.0) tv_fused_kernel<128, true><<<grid, 128, 0, h->stream>>>(a);
+    else tv_fused_kernel<128, false><<<grid, 128, 0, h->stream>>>(a);
+  } else {
+    if (o.relax == 1.0) tv_fused_kernel<256, true><<<grid, 256, 0, h->stream>>>(a);
+    else tv_fused_kernel<256, false><<<grid, 256, 0, h->stream>>>(a);
+  }
   ADMM_CUDA(cudaGetLastError());
   h->launches++;
 }

@@ -315,10 +315,8 @@ __global__ void __launch_bounds__(TVP_THREADS, 2) tv_prox_kernel(TvProxArgs a) {
 // the host -- 3 barriers per segment.  SLOW (the first and last one or two segments, and every
 // segment of a small problem): the general predicated code in rolled loops on local arrays.
 // ---------------------------------------------------------------------------------------------
-constexpr int TVF_T = 256;
 constexpr int TVF_E = 8;
-constexpr int TVF_SEG = TVF_T * TVF_E;
-constexpr int TVF_W = TVF_T / 32;
+constexpr int TVF_TMAX = 256;                              // CTA sizes built: 128 (4 CTAs / SM) and 256 (2 CTAs / SM)
 
 struct TvFusedArgs {
   int64_t n, S, nseg;
@@ -386,8 +384,9 @@ __device__ __forceinline__ double block_affine_carry_t(Affine mine, double* shA,
 // The same carry when every thread's map is (c^E, B): only B travels.  lanepow[k] = c^(E*k).  shW
 // holds the TVF_W warp totals of THIS scan (the two scans of a segment use different arrays, so no
 // trailing barrier is needed: the next write comes two barriers later).
-template <bool REV>
+template <int T, bool REV>
 __device__ __forceinline__ double tvf_carry(double B, const TvFusedArgs& a, const double* lanepow, double* shW) {
+  constexpr int TVF_W = T / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double inc = B;
 #pragma unroll
@@ -411,9 +410,10 @@ __device__ __forceinline__ double tvf_carry(double B, const TvFusedArgs& a, cons
 }
 
 // ---- FAST body: every element the thread touches is interior and past the pivot table
-template <bool RELAX1>
+template <int T, bool RELAX1>
 __device__ __forceinline__ void tvf_fast_segment(const TvFusedArgs& a, int64_t i0, bool is_out, int it, double* racc,
-                                                 const double* lanepow, double* shW, double (*xe)[TVF_T]) {
+                                                 const double* lanepow, double* shW, double (*xe)[TVF_TMAX]) {
+  constexpr int TVF_W = T / 32;
   constexpr int E = TVF_E;
   const int tid = threadIdx.x;
   const double rho = a.rho, c = a.c, ids = a.inv_star;
@@ -437,14 +437,14 @@ __device__ __forceinline__ void tvf_fast_segment(const TvFusedArgs& a, int64_t i
   // independent fma away: y_e = c^(e+1)*carry + prefix_e -- the dependent chain is walked once, not twice
 #pragma unroll
   for (int e = 1; e < E; ++e) r[e] = fma(c, r[e - 1], r[e]);
-  double carry = tvf_carry<false>(r[E - 1], a, lanepow, shW);
+  double carry = tvf_carry<T, false>(r[E - 1], a, lanepow, shW);
   const double ym1 = carry;                                // y_{i0-1}
 #pragma unroll
   for (int e = 0; e < E; ++e) r[e] = ids * fma(a.cp[e + 1], carry, r[e]);   // y_i / delta_i
   // backward: x_i = y_i/delta + c*x_{i+1}, prefixes from the right
 #pragma unroll
   for (int e = E - 2; e >= 0; --e) r[e] = fma(c, r[e + 1], r[e]);
-  carry = tvf_carry<true>(r[0], a, lanepow, shW + TVF_W);
+  carry = tvf_carry<T, true>(r[0], a, lanepow, shW + TVF_W);
   double xx[E + 3];                                        // x[i0-1 .. i0+E+1]
 #pragma unroll
   for (int e = 0; e < E; ++e) xx[e + 1] = fma(a.cp[E - e], carry, r[e]);
@@ -517,8 +517,9 @@ __device__ __forceinline__ void tvf_fast_segment(const TvFusedArgs& a, int64_t i
 }
 
 // ---- SLOW body: the general predicated iteration on local arrays (edge segments, small problems)
+template <int T>
 __device__ __noinline__ void tvf_slow_segment(const TvFusedArgs& a, int64_t i0, int jlo, int jhi, int it, double* red,
-                                              double* shA, double* shB, double (*xe)[TVF_T]) {
+                                              double* shA, double* shB, double (*xe)[TVF_TMAX]) {
   constexpr int E = TVF_E;
   const int tid = threadIdx.x;
   const double rho = a.rho, relax = a.lp.relax, thr = a.lambda / rho;
@@ -545,7 +546,7 @@ __device__ __noinline__ void tvf_slow_segment(const TvFusedArgs& a, int64_t i0, 
     fa[e] = (in && i > 0) ? rho * idv[e] : 0.0;
     m = Affine{fa[e] * m.A, fma(fa[e], m.B, r[e])};
   }
-  double carry = block_affine_carry_t<TVF_T, false>(m, shA, shB);
+  double carry = block_affine_carry_t<T, false>(m, shA, shB);
   Affine mb{1.0, 0.0};
 #pragma unroll 1
   for (int e = 0; e < E; ++e) {
@@ -562,7 +563,7 @@ __device__ __noinline__ void tvf_slow_segment(const TvFusedArgs& a, int64_t i0, 
     fa[e] = (in && i < n - 1) ? rho * id : 0.0;
     mb = Affine{fa[e] * mb.A, fma(fa[e], mb.B, r[e])};
   }
-  carry = block_affine_carry_t<TVF_T, true>(mb, shA, shB);
+  carry = block_affine_carry_t<T, true>(mb, shA, shB);
 #pragma unroll 1
   for (int e = E - 1; e >= 0; --e) {
     carry = fma(fa[e], carry, r[e]);
@@ -577,8 +578,8 @@ __device__ __noinline__ void tvf_slow_segment(const TvFusedArgs& a, int64_t i0, 
   xe[0][tid] = xx[1]; xe[1][tid] = xx[2]; xe[2][tid] = xx[E];
   __syncthreads();
   xx[0] = tid > 0 ? xe[2][tid - 1] : 0.0;
-  xx[E + 1] = tid < TVF_T - 1 ? xe[0][tid + 1] : 0.0;
-  xx[E + 2] = tid < TVF_T - 1 ? xe[1][tid + 1] : 0.0;
+  xx[E + 1] = tid < T - 1 ? xe[0][tid + 1] : 0.0;
+  xx[E + 2] = tid < T - 1 ? xe[1][tid + 1] : 0.0;
   // z/u pass on elements i0-1+k; k = 0 is the left neighbour, recomputed only for the D' stencils of
   // the dual residual (same arithmetic as tv_prox_kernel)
   double ul = 0.0, dzl = 0.0;
@@ -628,15 +629,16 @@ __device__ __noinline__ void tvf_slow_segment(const TvFusedArgs& a, int64_t i0, 
   }
 }
 
-template <bool RELAX1>
-__global__ void __launch_bounds__(TVF_T, 2) tv_fused_kernel(TvFusedArgs a) {
+template <int T, bool RELAX1>
+__global__ void __launch_bounds__(T, 512 / T) tv_fused_kernel(TvFusedArgs a) {
+  constexpr int TVF_W = T / 32;
   LoopCtl* ctl = a.ctl;
   if (!a.xonly && ctl->done) return;
   __shared__ double shA[64], shB[64];                      // slow-body scans
   __shared__ double shW[2 * TVF_W];                        // fast-body scans: warp totals, forward / reversed
   __shared__ double lanepow[32];                           // c^(E*k)
-  __shared__ double xe[3][TVF_T];                          // first, second and last x of every thread
-  __shared__ double red_sh[(TVF_T / 32) * 8];
+  __shared__ double xe[3][TVF_TMAX];                          // first, second and last x of every thread
+  __shared__ double red_sh[(T / 32) * 8];
   __shared__ bool is_last;
   const int tid = threadIdx.x;
   const int it = ctl->it;
@@ -653,20 +655,20 @@ __global__ void __launch_bounds__(TVF_T, 2) tv_fused_kernel(TvFusedArgs a) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) racc[k] = 0.0;
   const int j0 = tid * TVF_E;
-  const int jlo = a.hl - j0, jhi = TVF_SEG - a.hr - j0;    // outputs of this thread's chunk: e in [jlo, jhi)
+  const int jlo = a.hl - j0, jhi = T * TVF_E - a.hr - j0;    // outputs of this thread's chunk: e in [jlo, jhi)
   const bool is_out = (jlo <= 0 && jhi >= TVF_E);          // hl, hr are multiples of E: all or nothing
   // CTA-uniform: the segment's window lies inside 1 .. n-3 and past the pivot table (host-computed range)
   for (int64_t seg = blockIdx.x; seg < a.nseg; seg += gridDim.x) {
     const int64_t i0 = seg * a.S - a.hl + j0;              // global index of this thread's first element
     if (seg >= a.seg_lo && seg < a.seg_hi) {
-      tvf_fast_segment<RELAX1>(a, i0, is_out, it, racc, lanepow, shW, xe);
+      tvf_fast_segment<T, RELAX1>(a, i0, is_out, it, racc, lanepow, shW, xe);
     } else {
       // the callee's sums come back through memory; racc itself must stay in registers
       // (and the callee gets its own copy of the arguments: handing it a reference to the kernel
       // parameters makes the compiler read them from a stack copy everywhere, fast body included)
       double red[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
       const TvFusedArgs la = a;
-      tvf_slow_segment(la, i0, jlo, jhi, it, red, shA, shB, xe);
+      tvf_slow_segment<T>(la, i0, jlo, jhi, it, red, shA, shB, xe);
 #pragma unroll
       for (int k = 0; k < 8; ++k) racc[k] += red[k];
     }

@@ -15,7 +15,7 @@ def rel(a, b):
 
 @pytest.mark.parametrize("n,rho,relax,lam", [(128, 1.0, 1.0, 5.0), (1000, 1.0, 1.5, 2.0), (50000, 1.0, 1.0, 3.0),
                                              (20001, 50.0, 1.0, 3.0), (30000, 7.0, 1.7, 1.0), (2, 2.0, 1.3, 0.5),
-                                             (17, 1.0, 1.0, 0.5)])
+                                             (17, 1.0, 1.0, 0.5), (30011, 20.0, 1.0, 2.0), (12345, 20.0, 1.2, 2.0)])
 def test_totalvariation_matches_oracle(engine, n, rho, relax, lam):
     s, truth = gen.tv_problem(0, n)
     opts = {"objevals": 1, "maxiters": 3000, "rho": rho, "relax": relax, "history": int(n <= 1000)}
