@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libadmm_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOTPOSDEF, ERR_COMM, ERR_UNSUPPORTED = range(7)
-LASSO, BASISPURSUIT, TOTALVARIATION, SVM_HINGE, SVM_01, HUBERFIT, LAD, PROX_NONNEG, PROX_BOX = range(1, 10)
+LASSO, BASISPURSUIT, TOTALVARIATION, SVM_HINGE, SVM_01, HUBERFIT, LAD, PROX_NONNEG, PROX_BOX, MODEL = range(1, 11)
 STOP_STANDARD, STOP_HNORM, STOP_BOTH = 0, 1, 2
 RUNNING, CONVERGED_STD, CONVERGED_HNORM, MAXITERS, DIVERGED_RETURN, CONVERGED_DVAL = range(6)
 XSOLVE_INVFACTOR, XSOLVE_SUBST = 0, 1
@@ -64,6 +64,7 @@ SYMBOLS = {
     "admm_b200_setup_basispursuit": (_int, [_vp, _i64, _i64, _vp, _i64, _vp]),
     "admm_b200_setup_totalvariation": (_int, [_vp, _i64, _vp, _d]),
     "admm_b200_setup_quadratic": (_int, [_vp, _i32, _i64, _vp, _i64, _vp, _d, _d, _vp, _vp]),
+    "admm_b200_setup_model": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _d]),
     "admm_b200_get_unique_id": (_int, [_vp]),
     "admm_b200_comm_init": (_int, [_vp, _int, _int, _vp]),
     "admm_b200_comm_destroy": (_int, [_vp]),

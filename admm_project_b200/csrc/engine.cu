@@ -116,6 +116,8 @@ struct admm_b200_handle {
   // quadratic objective with box / nonneg prox: P (full, for the objective), bounds, constant r
   DBuf Pfull, lb, ub;
   double qp_r = 0.0;
+  // model problem: second matrix / vector, both Gram matrices (kept for rho changes), second factor
+  DBuf Q2, s2, dts2, G1, G2, L2, W2, WT2, zsol;
   // total variation: double-buffered z/u, pivot table of the constant tridiagonal
   DBuf zz, uu, tvtab;
   int tv_par = 0, tv_ntab = 0, tv_halo = 0;
@@ -655,9 +657,17 @@ static void gemvn(admm_b200_handle* h, const double* D, int64_t ld, int64_t m, i
   h->launches++;
 }
 
-// x = L' \ (L \ b) with the cached factor (size k)
-static void factor_solve(admm_b200_handle* h, const double* b, double* tmp, double* x, int xsolve, const int* done) {
+// x = L' \ (L \ b) with the cached factor (size k); second = the z-update factor of the model problem
+static void factor_solve(admm_b200_handle* h, const double* b, double* tmp, double* x, int xsolve, const int* done,
+                         bool second = false) {
   ADMM_REQUIRE(h->have_factor, ADMM_B200_ERR_STATE, "no cached factor: call a setup function first");
+  if (second) {
+    ADMM_REQUIRE(xsolve == ADMM_B200_XSOLVE_INVFACTOR && h->W2.p && h->WT2.p, ADMM_B200_ERR_UNSUPPORTED,
+                 "the model problem's z-update is built for xsolve = INVFACTOR");
+    coldot(h, COLDOT_UPPER, h->WT2.p, h->ldf, h->k, h->k, b, tmp, 1.0, nullptr, 0.0, done);
+    coldot(h, COLDOT_LOWER, h->W2.p, h->ldf, h->k, h->k, tmp, x, 1.0, nullptr, 0.0, done);
+    return;
+  }
   if (xsolve == ADMM_B200_XSOLVE_INVFACTOR) {
     ADMM_REQUIRE(h->have_inverse, ADMM_B200_ERR_STATE,
                  "xsolve = INVFACTOR but the setup was done with xsolve = SUBST (no inverse factor was built)");
@@ -894,6 +904,67 @@ static void setup_quadratic(admm_b200_handle* h, int kind, int64_t n, const doub
   h->iter_ready = false;
 }
 
+// Model problem (solvers/model.m:119-146, getProxOps.m:55-110, 952-1012):
+//   x = (PtP + rho I) \ (Ptr + rho (z - u)),   z = (QtQ + rho I) \ (Qts + rho (xhat + u)).
+// Both Gram matrices stay on the device; (re)factoring for a rho is n^3/3 flop per matrix, no pass
+// over P or Q.
+static void model_factor(admm_b200_handle* h, double rho) {
+  const int64_t n = h->n;
+  ADMM_CUDA(cudaEventRecord(h->evp[1], h->stream));
+  for (int which = 1; which >= 0; --which) {              // Q first, then P (which ends up in L / W / WT)
+    const DBuf& G = which ? h->G2 : h->G1;
+    h->L.ensure(h->ldf * n);
+    ADMM_CUDA(cudaMemcpyAsync(h->L.p, G.p, (size_t)h->ldf * n * 8, cudaMemcpyDeviceToDevice, h->stream));
+    add_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->L.p, h->ldf, n, rho);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+    factor_current(h, n, true);
+    if (which) { std::swap(h->L, h->L2); std::swap(h->W, h->W2); std::swap(h->WT, h->WT2); }
+  }
+  h->rho_setup = rho;
+}
+
+static void setup_model(admm_b200_handle* h, int64_t m, int64_t n, const double* P, int64_t ldP, const double* Q,
+                        int64_t ldQ, const double* r, const double* s, double rho) {
+  ADMM_REQUIRE(m > 0 && n > 0 && P && Q && r && s && ldP >= m && ldQ >= m, ADMM_B200_ERR_INVALID,
+               "model: bad dimensions or null input");
+  ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
+  ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
+  h->have_factor = false;
+  h->kind = ADMM_B200_MODEL;
+  h->tall = true;
+  h->xsolve = ADMM_B200_XSOLVE_INVFACTOR;
+  h->nA = h->nB = h->mc = n;
+  h->lambda = 0.0;
+  stage_matrix(h, m, n, P, ldP);                          // h->dD (P), used in place when it is a device pointer
+  const int64_t ldq = round_up(m, 2);
+  h->Q2.ensure(ldq * n);
+  ADMM_CUDA(cudaMemcpy2DAsync(h->Q2.p, (size_t)ldq * 8, Q, (size_t)ldQ * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDefault,
+                              h->stream));
+  h->s.ensure(round_up(m, 2)); h->s2.ensure(round_up(m, 2));
+  copy_in(h, h->s.p, r, m);
+  copy_in(h, h->s2.p, s, m);
+  h->dts.ensure(round_up(n, 2)); h->dts2.ensure(round_up(n, 2));
+  coldot(h, COLDOT_FULL, h->dD, h->ldD, m, n, h->s.p, h->dts.p);        // Ptr = P'*r   (model.m:124)
+  coldot(h, COLDOT_FULL, h->Q2.p, ldq, m, n, h->s2.p, h->dts2.p);       // Qts = Q'*s   (model.m:126)
+  h->ldf = round_up(n, 16);
+  h->G1.ensure(h->ldf * n); h->G2.ensure(h->ldf * n);
+  GemmOpt o;
+  o.lower_only = 1;
+  gemm(h, 1, 0, n, n, m, 1.0, h->dD, h->ldD, h->dD, h->ldD, 0.0, h->G1.p, h->ldf, o);   // PtP (model.m:123)
+  gemm(h, 1, 0, n, n, m, 1.0, h->Q2.p, ldq, h->Q2.p, ldq, 0.0, h->G2.p, h->ldf, o);     // QtQ (model.m:125)
+  model_factor(h, rho);
+  ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
+  ADMM_CUDA(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->setup_ms = h->phase_ms[3] = ms;
+  ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->evp[1]));
+  h->phase_ms[0] = ms;
+  h->have_init = false;
+  h->iter_ready = false;
+}
+
 // Total variation (solvers/totalvariation.m:122-164): only s and lambda are data; the operator D
 // is implicit.  The pivot table depends on rho and is (re)built when the loop starts.
 static void setup_tv(admm_b200_handle* h, int64_t n, const double* s, double lambda) {
@@ -1083,6 +1154,7 @@ static void alloc_iterates(admm_b200_handle* h) {
   h->t1.ensure(big);
   h->t2.ensure(big);
   h->partials.ensure(2 * kNumSM * 16);
+  if (h->kind == ADMM_B200_MODEL) h->zsol.ensure(round_up(h->nB, 2));
   h->fv.ensure(round_up(h->nB, 2)); h->fuhat.ensure(round_up(h->mc, 2));
   h->fzprev.ensure(round_up(h->nB, 2)); h->fuprev.ensure(round_up(h->mc, 2));
   if (is_unwrapped(h->kind)) {
@@ -1231,7 +1303,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     if (which == 1) return;
     ProxIdentArgs a;
     a.n = n; a.x = h->x.p; a.z = h->z.p; a.u = h->u.p; a.dts = nullptr; a.y = h->y.p;
-    a.lb = a.ub = nullptr;
+    a.lb = a.ub = nullptr; a.zin = nullptr;
     a.thresh = 1.0 / o.rho;                      // getProxOps.m:142
     a.objscale = 1.0;                            // obj = norm(x,1), basispursuit.m:140
     a.kind = PROX_SOFT; a.next = NEXT_DIFF; a.obj_l1_of_x = 1;
@@ -1278,7 +1350,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     }
     ProxIdentArgs a;
     a.n = n; a.x = h->x.p; a.z = h->z.p; a.u = h->u.p; a.dts = h->dts.p; a.y = h->y.p;
-    a.lb = qp ? h->lb.p : nullptr;
+    a.lb = qp ? h->lb.p : nullptr; a.zin = nullptr;
     a.ub = qp ? h->ub.p : nullptr;
     a.thresh = h->lambda / o.rho;
     a.objscale = qp ? 0.0 : h->lambda;
@@ -1294,6 +1366,50 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
     if (lp.alg != 0) {   // acceleration pass (admm.m:562-600) + scalar epilogue
+      AccelIdentArgs b;
+      b.n = n; b.z = h->z.p; b.u = h->u.p; b.zprev = h->fzprev.p; b.uprev = h->fuprev.p; b.dts = a.dts;
+      b.v = h->fv.p; b.uhat = h->fuhat.p; b.y = h->y.p; b.next = a.next;
+      b.partials = h->partials.p; b.ctl = h->ctl; b.lp = lp;
+      accel_ident_kernel<<<prox_grid(n), PROX_THREADS, 0, h->stream>>>(b);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+    }
+  } else if (h->kind == ADMM_B200_MODEL) {
+    const int64_t n = h->n, m = h->m;
+    const bool fastmode = lp.alg != 0;
+    if (which != 2) factor_solve(h, h->y.p, h->t1.p, h->x.p, o.xsolve, done);       // xminModel, getProxOps.m:973
+    if (which == 1) return;
+    // zminModel (getProxOps.m:1011): z = (QtQ + rho I) \ (Qts + rho*(x + u)); x is Axhat when relaxed
+    // (admm.m:521), u is uhat for the fast variants (admm.m:508)
+    model_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, h->x.p, h->z.p, fastmode ? h->fuhat.p : h->u.p,
+                                                                         h->dts2.p, o.rho, o.relax, h->t2.p, h->ctl);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+    factor_solve(h, h->t2.p, h->t1.p, h->zsol.p, o.xsolve, done, true);
+    if (o.objevals && which == 0) {
+      // obj = 1/2*norm(P*x - r)^2 + 1/2*norm(Q*z - s)^2   (model.m:139-140)
+      gemvn(h, h->dD, h->ldD, m, n, h->x.p, h->t2.p, 1.0, 0.0, nullptr, done);
+      half_sqdist_kernel<<<1, 1024, 0, h->stream>>>(h->t2.p, h->s.p, m, h->ctl, 0);
+      gemvn(h, h->Q2.p, round_up(m, 2), m, n, h->zsol.p, h->t2.p, 1.0, 0.0, nullptr, done);
+      half_sqdist_kernel<<<1, 1024, 0, h->stream>>>(h->t2.p, h->s2.p, m, h->ctl, 1);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches += 2;
+    }
+    ProxIdentArgs a;
+    a.n = n; a.x = h->x.p; a.z = h->z.p; a.u = h->u.p; a.dts = h->dts.p; a.y = h->y.p;
+    a.lb = a.ub = nullptr; a.zin = h->zsol.p;
+    a.thresh = 0.0; a.objscale = 0.0;
+    a.kind = PROX_GIVEN; a.next = NEXT_LASSO; a.obj_l1_of_x = 0;
+    a.partials = h->partials.p; a.ctl = h->ctl; a.lp = lp;
+    a.ld = 0; a.thresh_v = a.objscale_v = nullptr; a.hist_stride = 0; a.done_count = nullptr; a.xkeep = nullptr;
+    a.xvals = history ? h->xvals.p : nullptr;
+    a.zvals = history ? h->zvals.p : nullptr;
+    a.uvals = history ? h->uvals.p : nullptr;
+    a.v = h->fv.p; a.uhat = h->fuhat.p; a.zprev = h->fzprev.p; a.uprev = h->fuprev.p;
+    prox_ident_kernel<<<prox_grid(n), PROX_THREADS, 0, h->stream>>>(a);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+    if (fastmode) {   // acceleration pass (admm.m:562-600) + scalar epilogue
       AccelIdentArgs b;
       b.n = n; b.z = h->z.p; b.u = h->u.p; b.zprev = h->fzprev.p; b.uprev = h->fuprev.p; b.dts = a.dts;
       b.v = h->fv.p; b.uhat = h->fuhat.p; b.y = h->y.p; b.next = a.next;
@@ -1368,7 +1484,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
 
 static void enqueue_first_rhs(admm_b200_handle* h, const admm_b200_options& o) {
   if (h->kind == ADMM_B200_LASSO || h->kind == ADMM_B200_BASISPURSUIT || h->kind == ADMM_B200_PROX_BOX ||
-      h->kind == ADMM_B200_PROX_NONNEG) {
+      h->kind == ADMM_B200_PROX_NONNEG || h->kind == ADMM_B200_MODEL) {
     const int64_t n = h->n;
     const bool bp = h->kind == ADMM_B200_BASISPURSUIT;
     first_rhs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(n, h->z.p, h->u.p, bp ? nullptr : h->dts.p, o.rho,
@@ -1403,6 +1519,7 @@ static void validate_options(admm_b200_handle* h, const admm_b200_options& o) {
     ADMM_REQUIRE(o.relax == 1.0, ADMM_B200_ERR_INVALID,
                  "Inner matrix dimensions must agree. (linearsvm with relax ~= 1: the reference's zminLinearSVM "
                  "multiplies D (m x n) by the relaxed m-vector, getProxOps.m:1088, admm.m:521)");
+  if (h->kind == ADMM_B200_MODEL && o.rho != h->rho_setup) model_factor(h, o.rho);   // getProxOps.m:967-970
   if (h->kind == ADMM_B200_LASSO || h->kind == ADMM_B200_PROX_BOX || h->kind == ADMM_B200_PROX_NONNEG)
     ADMM_REQUIRE(o.rho == h->rho_setup, ADMM_B200_ERR_INVALID,
                  "options.rho (%g) differs from the rho the factor was built with (%g); redo the setup", o.rho,
@@ -1624,7 +1741,7 @@ static void solve_lasso_batch(admm_b200_handle* h, const admm_b200_options& o, i
         gemm(h, 1, 0, n, nb, n, 1.0, h->W.p, h->ldf, T.p, ld, 0.0, X.p, ld, g2);
         ProxIdentArgs a;
         a.n = n; a.x = X.p; a.z = Z.p; a.u = U.p; a.dts = h->dts.p; a.y = Y.p;
-        a.lb = a.ub = nullptr;
+        a.lb = a.ub = nullptr; a.zin = nullptr;
         a.thresh = 0.0; a.objscale = 0.0;
         a.kind = PROX_SOFT; a.next = NEXT_LASSO; a.obj_l1_of_x = 0;
         a.partials = part.p; a.ctl = ctl; a.lp = lp;
@@ -1939,7 +2056,8 @@ int admm_b200_destroy(admm_b200_handle* h) {
   cudaStreamSynchronize(h->stream);
   DBuf* bufs[] = {&h->ownD, &h->s, &h->dts, &h->L, &h->W, &h->WT, &h->x, &h->z, &h->u, &h->y, &h->t1, &h->t2,
                   &h->x0, &h->z0, &h->u0, &h->partials, &h->hist, &h->xvals, &h->zvals, &h->uvals, &h->gemm_ws,
-                  &h->gemv_ws, &h->scratch, &h->cd_ws, &h->aux, &h->rvec, &h->dzvec, &h->cb, &h->uw_partials, &h->zz, &h->uu, &h->tvtab, &h->Pfull, &h->lb, &h->ub, &h->fv, &h->fuhat, &h->fzprev, &h->fuprev};
+                  &h->gemv_ws, &h->scratch, &h->cd_ws, &h->aux, &h->rvec, &h->dzvec, &h->cb, &h->uw_partials, &h->zz, &h->uu, &h->tvtab, &h->Pfull, &h->lb, &h->ub, &h->fv, &h->fuhat, &h->fzprev, &h->fuprev,
+                  &h->Q2, &h->s2, &h->dts2, &h->G1, &h->G2, &h->L2, &h->W2, &h->WT2, &h->zsol};
   for (DBuf* b : bufs) b->release();
   for (ColdotPlan* p : h->plans) {
     cudaFree(p->d_cta_pos); cudaFree(p->d_pos_item); cudaFree(p->d_order); cudaFree(p->d_items);
@@ -2012,6 +2130,14 @@ int admm_b200_setup_quadratic(admm_b200_handle* h, int32_t kind, int64_t n, cons
   ADMM_API_BEGIN
   check_handle(h);
   setup_quadratic(h, kind, n, P, ldP, q, r, rho, lb, ub);
+  ADMM_API_END
+}
+
+int admm_b200_setup_model(admm_b200_handle* h, int64_t m, int64_t n, const double* P, int64_t ldP, const double* Q,
+                          int64_t ldQ, const double* r, const double* s, double rho) {
+  ADMM_API_BEGIN
+  admmb200::check_handle(h);
+  admmb200::setup_model(h, m, n, P, ldP, Q, ldQ, r, s, rho);
   ADMM_API_END
 }
 

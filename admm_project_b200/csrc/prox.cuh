@@ -40,7 +40,7 @@ struct LoopParams {
   double *dvals, *avals, *rst;
 };
 
-enum { PROX_SOFT = 0, PROX_NONNEG = 1, PROX_BOX = 2 };
+enum { PROX_SOFT = 0, PROX_NONNEG = 1, PROX_BOX = 2, PROX_GIVEN = 3 };   // GIVEN: z was computed by a solve (model problem)
 enum { NEXT_LASSO = 0, NEXT_DIFF = 1 };
 constexpr int PROX_NRED = 10;
 constexpr int PROX_THREADS = 256;
@@ -52,6 +52,7 @@ struct ProxIdentArgs {
   const double* dts;      // Dts (lasso) or NULL
   double* y;              // rhs of the next x-update
   const double *lb, *ub;  // box bounds (length n) or NULL
+  const double* zin;      // PROX_GIVEN: the z-update result (getProxOps.m:1011)
   double thresh;          // lambda/rho (lasso), 1/rho (bp)
   double objscale;        // objective = objpart + objscale * sum|z| (lasso: lambda) / sum|x| (bp)
   int kind, next, obj_l1_of_x;
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(PROX_THREADS) prox_ident_kernel(ProxIdentArgs 
     double z;
     if (a.kind == PROX_SOFT) z = soft_threshold(v, a.thresh);
     else if (a.kind == PROX_NONNEG) z = fmax(v, 0.0);
+    else if (a.kind == PROX_GIVEN) z = a.zin[i];
     else z = fmin(a.ub[i], fmax(a.lb[i], v));
     const double u = up + (xh + (-z) - 0.0);
     a.z[i] = z;
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(PROX_THREADS) accel_ident_kernel(AccelIdentArg
 
 // objective term 0.5*||D x - s||^2 from r = D*x computed by the GEMV kernel (lasso.m:227)
 __global__ void half_sqdist_kernel(const double* __restrict__ r, const double* __restrict__ s, int64_t m,
-                                   LoopCtl* ctl) {
+                                   LoopCtl* ctl, int accumulate = 0) {
   if (ctl->done) return;
   __shared__ double sh[32];
   double acc = 0.0;
@@ -350,8 +352,21 @@ __global__ void half_sqdist_kernel(const double* __restrict__ r, const double* _
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w];
-    ctl->objpart = 0.5 * t;
+    ctl->objpart = accumulate ? ctl->objpart + 0.5 * t : 0.5 * t;
   }
+}
+
+// Model problem (getProxOps.m:1011): right-hand side of the z-update, Qts + rho*(xhat + u), with the
+// relaxed xhat of admm.m:517 (A = 1, B = -1, c = 0) and uhat in place of u for the fast variants.
+__global__ void model_rhs_kernel(int64_t n, const double* __restrict__ x, const double* __restrict__ z,
+                                 const double* __restrict__ u, const double* __restrict__ qts, double rho, double relax,
+                                 double* __restrict__ t, const LoopCtl* ctl) {
+  if (ctl->done) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double xh = x[i];
+  if (relax != 1.0) xh = relax * xh - (1.0 - relax) * (-z[i] - 0.0);
+  t[i] = qts[i] + rho * (xh + u[i]);
 }
 
 // objective 1/2*x'*P*x + q'*x + r from t = P*x (quadraticprogram.m: options.obj)
@@ -372,6 +387,11 @@ __global__ void quad_obj_kernel(const double* __restrict__ x, const double* __re
 }
 
 // A[i][i] += shift;  v = -v
+__global__ void add_diag_kernel(double* A, int64_t lda, int64_t n, double shift) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) A[i + i * lda] += shift;
+}
+
 __global__ void add_diag_negate_kernel(double* A, int64_t lda, int64_t n, double shift, double* v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {

@@ -112,6 +112,16 @@ class Engine:
                                                     L.ptr(lb), L.ptr(ub)))
         return n
 
+    def setup_model(self, P, Q, r, s, rho):
+        """admm_b200_setup_model: PtP, QtQ, Ptr, Qts and both Cholesky factors on the device."""
+        pp, m, n, ldp, keepP = self._matrix(P)
+        qp, mq, nq, ldq, keepQ = self._matrix(Q)
+        rv, sv = L.fvec(r, m, "r"), L.fvec(s, m, "s")
+        self._keep = [keepP, keepQ, rv, sv]
+        L.check(self._lib.admm_b200_setup_model(self._h, m, n, C.c_void_p(pp), ldp, C.c_void_p(qp), ldq, L.ptr(rv),
+                                                L.ptr(sv), float(rho)))
+        return m, n
+
     # -- row-sharded runs (one process per GPU) ---------------------------------------------------
     def comm_init(self, rank, nranks, unique_id):
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))

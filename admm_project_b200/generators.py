@@ -91,3 +91,14 @@ def bp_problem(seed, rows, cols, density=0.1):
     testx = rs.randn(cols) * (rs.rand(cols) < density)
     s = D @ testx
     return D, s, testx
+
+
+def model_problem(seed, rows, cols):
+    """testers/modeltest.m:112-120: P, Q ~ N(0,1) (rows x cols), r, s ~ N(0,1); the true minimiser of
+    1/2||Px-r||^2 + 1/2||Qx-s||^2 is (P'P + Q'Q) \\ (P'r + Q's)."""
+    rs = np.random.RandomState(seed)
+    P = np.asfortranarray(rs.randn(rows, cols))
+    Q = np.asfortranarray(rs.randn(rows, cols))
+    r, s = rs.randn(rows), rs.randn(rows)
+    truex = np.linalg.solve(P.T @ P + Q.T @ Q, P.T @ r + Q.T @ s)
+    return P, Q, r, s, truex

@@ -53,7 +53,7 @@ def _setup_rows(eng, kind, D, aux, C):
     eng.row_range = (lo, hi)
 
 
-_OUT = ("model", "linearprogram", "quadraticprogram", "covarianceselection")
+_OUT = ("linearprogram", "quadraticprogram", "covarianceselection")
 
 
 def getproxops(problem, args):
@@ -107,6 +107,18 @@ def getproxops(problem, args):
         eng.setup_quadratic(PROX_BOX, args["P"], args["q"], args.get("r", 0.0), args["rho"], args["lb"], args["ub"])
         minx = EngineProx("xminf", "quadraticprogram", "xminQuadraticProgramBounded", eng, {})
         minz = EngineProx("zming", "quadraticprogram", "zminQuadraticProgramBounded", eng, {})
+    elif problem == "model":                                                # getProxOps.m:55-110
+        eng = _need_engine(eng, problem)
+        # The reference hands over PtP, Ptr, QtQ, Qts (model.m:123-128); the engine forms them on the device
+        # from P, Q, r, s (DMMA Gram), keeps both Gram matrices and caches chol(. + rho*I) -- the reference
+        # re-adds rho and re-solves the dense systems in every iteration (:967-973, :1004-1011).
+        for key in ("P", "Q", "r", "s"):
+            if key not in args:
+                raise EngineError(ERR_UNSUPPORTED, "getproxops('model'): pass args.P, args.Q, args.r, args.s -- the "
+                                  "Gram matrices are formed on the device")
+        eng.setup_model(args["P"], args["Q"], args["r"], args["s"], args.get("rho", 1.0))
+        minx = EngineProx("xminf", "model", "xminModel", eng, {})
+        minz = EngineProx("zming", "model", "zminModel", eng, {})
     elif problem in _OUT:
         raise EngineError(ERR_UNSUPPORTED, "problem '%s' is outside the engine's hot path (SURVEY.md section 2)" % problem)
     else:

@@ -7,3 +7,4 @@ from .robustfit import huberfit, lad           # noqa: F401
 from .basispursuit import basispursuit        # noqa: F401
 from .totalvariation import totalvariation    # noqa: F401
 from .quadraticprogram import quadraticprogram  # noqa: F401
+from .model import model                        # noqa: F401

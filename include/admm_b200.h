@@ -55,7 +55,8 @@ enum {
   ADMM_B200_HUBERFIT = 6,       /* getProxOps.m:890-912, zminHuberSoftThresholding :1529-1539 */
   ADMM_B200_LAD = 7,            /* getProxOps.m:780-810, xminLAD :1511-1515 */
   ADMM_B200_PROX_NONNEG = 8,    /* z-prox of linearprogram / quadraticprogram: pos(x+u) :1378-1382 */
-  ADMM_B200_PROX_BOX = 9        /* z-prox of bounded QP: min(ub,max(lb,x+u)) :1470-1474 */
+  ADMM_B200_PROX_BOX = 9,       /* z-prox of bounded QP: min(ub,max(lb,x+u)) :1470-1474 */
+  ADMM_B200_MODEL = 10          /* getProxOps.m:55-110, xminModel :952-974, zminModel :989-1012 */
 };
 
 /* ---- stop conditions (admm.m:706-722) ------------------------------------------------------ */
@@ -173,6 +174,15 @@ int admm_b200_setup_totalvariation(admm_b200_handle* h, int64_t n, const double*
  *                                lb / ub may be NULL. */
 int admm_b200_setup_quadratic(admm_b200_handle* h, int32_t kind, int64_t n, const double* P, int64_t ldP, const double* q,
                               double r, double rho, const double* lb, const double* ub);
+
+/* solvers/model.m:119-146 -- minimise 1/2||P x - r||^2 + 1/2||Q x - s||^2 (P, Q are m x n) as f(x) + g(z),
+ * x - z = 0.  PtP = P'P, QtQ = Q'Q, Ptr = P'r, Qts = Q's are formed on the device (model.m:123-128);
+ * the reference's prox operators re-add rho to the diagonals and re-solve the dense systems with `\`
+ * in EVERY iteration (getProxOps.m:967-973, 1004-1011: `rhoprev` is never updated).  The engine keeps
+ * both Gram matrices and caches chol(PtP + rho I), chol(QtQ + rho I); a later solve with a different
+ * options.rho only re-adds the diagonal and refactors (examples/stepsizetesting.m sweeps rho). */
+int admm_b200_setup_model(admm_b200_handle* h, int64_t m, int64_t n, const double* P, int64_t ldP, const double* Q,
+                          int64_t ldQ, const double* r, const double* s, double rho);
 
 /* Row-sharded runs, one process per GPU.  Rank 0 calls admm_b200_get_unique_id (128 bytes, an
  * ncclUniqueId), the host side broadcasts it (torch.distributed / MPI / a file), every rank calls

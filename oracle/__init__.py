@@ -1,6 +1,6 @@
 """ORACLE -- CPU (NumPy/SciPy, FP64) restatement of the hot path of PeterSutor/ADMM-Project:
 admm.m, the in-scope getProxOps.m operators, errorcheck.m's slicemaker and the one-time setup
-of solvers/{lasso,unwrappedadmm,linearsvm,huberfit,lad,totalvariation,basispursuit}.m.
+of solvers/{lasso,unwrappedadmm,linearsvm,huberfit,lad,totalvariation,basispursuit,model}.m.
 
 THIS IS TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs may import it.  PARITY UNPINNED: the reference is MATLAB,
@@ -13,4 +13,4 @@ from .errorcheck import errorcheck, slicemaker                     # noqa: F401
 from .getproxops import (getproxops, zminSoftThresholding, minz01, zminNonNegative,   # noqa: F401
                          make_zminBox, subplus, pos, huber)
 from .solvers import (lasso, unwrappedadmm, linearsvm, huberfit, lad,                 # noqa: F401
-                      totalvariation, basispursuit, quadraticprogram)
+                      totalvariation, basispursuit, quadraticprogram, model)

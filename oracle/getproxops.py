@@ -169,7 +169,17 @@ def getproxops(problem, args):
             R = state["R"]
             return _tri_upper_solve(R, _tri_lower_solve(R.T, rho * (z - u) - q))
         minz = make_zminBox(lb, ub)
-    elif problem in ("model", "linearprogram", "quadraticprogram", "covarianceselection"):
+    elif problem == "model":                                                # :55-110
+        PtP, Ptr, QtQ, Qts, n = args["PtP"], args["Ptr"], args["QtQ"], args["Qts"], args["n"]
+
+        # `rhoprev = 0` is never updated (:64), so rho is re-added to the diagonal of a fresh copy and
+        # the dense system is re-solved with `\` (SPD -> Cholesky) in every iteration (:967-973, :1004-1011)
+        def minx(_x, z, u, rho):                                            # xminModel
+            return sla.solve(PtP + rho * np.eye(n), Ptr + rho * (z - u), assume_a="pos", check_finite=False)
+
+        def minz(x, _z, u, rho):                                            # zminModel
+            return sla.solve(QtQ + rho * np.eye(n), Qts + rho * (x + u), assume_a="pos", check_finite=False)
+    elif problem in ("linearprogram", "quadraticprogram", "covarianceselection"):
         raise MatlabError("oracle: problem '%s' is out of scope (SURVEY.md section 2)" % problem)
     else:
         raise MatlabError("Invalid input for problem - given string is not a solver!")

@@ -260,3 +260,39 @@ def quadraticprogram(P, q, r, cons1, cons2, options):
     results = admm(minx, minz, options)
     results["solverruntime"] = time.perf_counter() - t0
     return results
+
+
+def model(P, Q, r, s, options):
+    """solvers/model.m:99-146 (error checks :158-218): minimise 1/2||Px - r||^2 + 1/2||Qz - s||^2, x - z = 0."""
+    t0 = time.perf_counter()
+    P, Q = np.asarray(P, dtype=np.float64), np.asarray(Q, dtype=np.float64)
+    if P.ndim != 2:
+        raise MatlabError("Argument P is not a matrix!")
+    if Q.ndim != 2:
+        raise MatlabError("Argument Q is not a matrix!")
+    r, s = np.asarray(r, dtype=np.float64), np.asarray(s, dtype=np.float64)
+    isvec = lambda a: a.ndim <= 1 or (a.ndim == 2 and 1 in a.shape)
+    if not isvec(r):
+        raise MatlabError("Argument r is not a vector!")
+    if not isvec(s):
+        raise MatlabError("Argument s is not a vector!")
+    r, s = _col(r), _col(s)
+    if P.shape[0] != Q.shape[0]:
+        raise MatlabError("Number of rows in P do not match number of rows in Q!")
+    if P.shape[1] != Q.shape[1]:
+        raise MatlabError("Number of columns in P do not match number of columns in Q!")
+    if P.shape[0] != r.shape[0]:
+        raise MatlabError("Number of rows in P does not match length of vector r!")
+    if Q.shape[0] != s.shape[0]:
+        raise MatlabError("Number of rows in Q does not match length of vector s!")
+    if not isinstance(options, dict):
+        raise MatlabError("Given options argument is not a struct! Please check your arguments and try again.")
+    options = dict(options)
+    n = P.shape[1]
+    args = dict(PtP=P.T @ P, Ptr=P.T @ r, QtQ=Q.T @ Q, Qts=Q.T @ s, n=n)    # :123-128
+    minx, minz, _ = getproxops("Model", args)
+    options.update(A=1, B=-1, c=0, m=n, nA=n, nB=n)                         # :133-138
+    options["obj"] = lambda x, z: 0.5 * float(np.sum((P @ x - r) ** 2)) + 0.5 * float(np.sum((Q @ z - s) ** 2))
+    results = admm(minx, minz, options)
+    results["solverruntime"] = time.perf_counter() - t0
+    return results

@@ -39,6 +39,8 @@ def cases():
     yield "tv_300", pack(oracle.totalvariation(s, 2.0, {"objevals": 1, "maxiters": 2000}), s=s, lam=2.0)
     D, s, _ = gen.bp_problem(0, 24, 60, density=0.08)
     yield "bp_24x60", pack(oracle.basispursuit(D, s, {"objevals": 1, "maxiters": 5000}), D=D, s=s)
+    P, Q, r, s, _ = gen.model_problem(0, 60, 24)
+    yield "model_60x24", pack(oracle.model(P, Q, r, s, {"objevals": 1, "relax": 1.3}), P=P, Q=Q, r=r, s=s, relax=1.3)
 
 
 if __name__ == "__main__":

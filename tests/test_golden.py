@@ -32,11 +32,13 @@ def run(name, g, mod, **kw):
         return mod.totalvariation(g["in_s"], float(g["in_lam"]), dict(o, maxiters=2000), **kw)
     if name.startswith("bp"):
         return mod.basispursuit(g["in_D"], g["in_s"], dict(o, maxiters=5000), **kw)
+    if name.startswith("model"):
+        return mod.model(g["in_P"], g["in_Q"], g["in_r"], g["in_s"], dict(o, relax=float(g["in_relax"])), **kw)
     raise AssertionError(name)
 
 
 def test_fixtures_exist():
-    assert len(FILES) == 7
+    assert len(FILES) == 8
 
 
 @pytest.mark.parametrize("path", FILES, ids=[os.path.basename(f)[:-4] for f in FILES])

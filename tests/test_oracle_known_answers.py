@@ -193,3 +193,23 @@ def test_unwrapped_forced_options():                         # unwrappedadmm.m:8
     o = r["options"]
     assert o["maxiters"] == 1000 and o["stopcond"] == "both" and o["nodualerror"] == 1
     assert np.all(np.isnan(r["dnorm"])) and np.all(np.isnan(r["derr"]))
+
+
+def test_model_converges_to_the_least_squares_solution_and_passes_modeltest():
+    # the minimiser of 1/2||Px-r||^2 + 1/2||Qx-s||^2 is (P'P + Q'Q) \\ (P'r + Q's) (modeltest.m:117);
+    # pass criterion modeltest.m:133-141 with errtol = 1e-3 and the tester's options (:124-129)
+    from admm_project_b200.generators import model_problem
+    P, Q, r, s, truex = model_problem(0, 128, 128)
+    res = oracle.model(P, Q, r, s, {"objevals": 1, "maxiters": 10000, "convtest": 1, "stopcond": "both"})
+    obj = lambda x: 0.5 * np.sum((P @ x - r) ** 2) + 0.5 * np.sum((Q @ x - s) ** 2)
+    assert abs(1 - obj(res["xopt"]) / obj(truex)) <= 1e-3 and np.linalg.norm(truex - res["xopt"]) <= 1e-3
+    assert abs(res["objopt"] - (0.5 * np.sum((P @ res["xopt"] - r) ** 2) + 0.5 * np.sum((Q @ res["zopt"] - s) ** 2))) < 1e-9
+    # a fixed point of both prox operators is the optimum: one iteration started there stays there
+    rho = 2.0
+    u = -(P.T @ (P @ truex - r)) / rho                     # stationarity of the x-update at (truex, truex, u)
+    minx, minz, _ = oracle.getproxops("Model", dict(PtP=P.T @ P, Ptr=P.T @ r, QtQ=Q.T @ Q, Qts=Q.T @ s, n=128))
+    assert np.allclose(minx(None, truex, u, rho), truex, atol=1e-9)
+    assert np.allclose(minz(truex, None, u, rho), truex, atol=1e-9)
+    # the accelerated variant reaches the optimum to rounding (examples/fasteradmmcomparison.m)
+    acc = oracle.model(P, Q, r, s, {"fast": 1, "maxiters": 2000})
+    assert np.linalg.norm(acc["xopt"] - truex) < 1e-10
