@@ -172,6 +172,11 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
   } else if (!strcmp(cmd, "setup_totalvariation")) {     /* (h, s, lambda) */
     check(admm_b200_setup_totalvariation(get_handle(prhs[1]), (int64_t)mxGetNumberOfElements(prhs[2]),
                                          dense(prhs[2], "s"), mxGetScalar(prhs[3])));
+  } else if (!strcmp(cmd, "setup_model")) {              /* (h, P, Q, r, s, rho) */
+    int64_t m = (int64_t)mxGetM(prhs[2]);
+    check(admm_b200_setup_model(get_handle(prhs[1]), m, (int64_t)mxGetN(prhs[2]), dense(prhs[2], "P"), m,
+                                dense(prhs[3], "Q"), (int64_t)mxGetM(prhs[3]), dense(prhs[4], "r"), dense(prhs[5], "s"),
+                                nrhs > 6 ? mxGetScalar(prhs[6]) : 1.0));
   } else if (!strcmp(cmd, "set_lambda")) {
     check(admm_b200_set_lambda(get_handle(prhs[1]), mxGetScalar(prhs[2])));
   } else if (!strcmp(cmd, "set_init")) {                 /* (h, x0, z0, u0), [] = zeros */

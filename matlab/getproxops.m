@@ -25,7 +25,10 @@ switch problem
         admm_b200_mex('setup_unwrapped', args.h, 6, args.D, args.s, 0);
     case 'lad'
         admm_b200_mex('setup_unwrapped', args.h, 7, args.D, args.s, 0);
-    case {'model', 'linearprogram', 'quadraticprogram', 'covarianceselection'}
+    case 'model'                                           % P, Q, r, s instead of PtP .. Qts (model.m:123-128): Grams on the device
+        rho = 1; if isfield(args, 'rho'), rho = args.rho; end
+        admm_b200_mex('setup_model', args.h, args.P, args.Q, args.r, args.s, rho);
+    case {'linearprogram', 'quadraticprogram', 'covarianceselection'}
         error('admm_b200: problem ''%s'' is outside the engine''s hot path.', problem);
     otherwise
         error('Invalid input for problem - given string is not a solver!');
