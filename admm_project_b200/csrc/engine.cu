@@ -1558,7 +1558,10 @@ template <class EnqueueOne, class Finished>
 static void run_bursts(admm_b200_handle* h, const admm_b200_options& o, int64_t N, int period, EnqueueOne&& enqueue_one,
                        Finished&& finished) {
   const int check = std::max(1, o.check_every);
-  const bool graph_ok = o.graph && check % period == 0 && !getenv("ADMM_B200_DEBUG") && !getenv("ADMM_B200_NO_GRAPH");
+  // Row-sharded handles stay eager: with the per-iteration ncclAllReduce inside the graph the 2-GPU SVM loop
+  // measured SLOWER (133 vs 115 us per iteration, profiles/r01_notes.md); ADMM_B200_GRAPH_NCCL=1 overrides.
+  const bool graph_ok = o.graph && check % period == 0 && !getenv("ADMM_B200_DEBUG") && !getenv("ADMM_B200_NO_GRAPH") &&
+                        (h->nranks == 1 || getenv("ADMM_B200_GRAPH_NCCL"));
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   int64_t graph_launches = 0;
