@@ -19,6 +19,7 @@
 #include "gemvt.cuh"
 #include "unwrapped.cuh"
 #include "uwbatch.cuh"
+#include "onepass.cuh"
 #include "tv.cuh"
 #include <dlfcn.h>
 
@@ -109,7 +110,7 @@ struct admm_b200_handle {
   bool iter_ready = false;
   DBuf fv, fuhat, fzprev, fuprev;   // fast / accelerated ADMM state
   // A = D family (svm / huber / lad)
-  DBuf aux, rvec, dzvec, cb, uw_partials;
+  DBuf aux, rvec, dzvec, cb, uw_partials, op_dpart;
   unsigned* grid_ticket = nullptr;
   int64_t m_total = 0;
   double svmC = 0.0;
@@ -1242,6 +1243,33 @@ static void tv_fused_launch(admm_b200_handle* h, const admm_b200_options& o, con
   h->launches++;
 }
 
+// Tile height of the single-pass A = D iteration (onepass.cuh), 0 when the two-pass kernels are used:
+// wide matrices (the n-column tile does not fit shared memory at >= 16 rows), the fast variants (their
+// restart decision sits between the two products), unaligned D, or problems too small to matter.
+static int onepass_rows(const admm_b200_handle* h, const LoopParams& lp) {
+  if (lp.alg != 0 || getenv("ADMM_B200_NO_ONEPASS")) return 0;
+  const int64_t n = h->n, npad = round_up(n, 2);
+  if (n > (int64_t)OP_MAXCOLS * OP_THREADS) return 0;
+  if ((((uintptr_t)h->dD) & 15) != 0 || (h->ldD % 2) != 0) return 0;
+  if (!getenv("ADMM_B200_FORCE_ONEPASS") && (n < 128 || h->m * n < ((int64_t)1 << 21))) return 0;
+  const size_t budget = 227 * 1024;
+  if (OnepassCfg<32>::smem_bytes(n, npad) <= budget) return 32;
+  if (OnepassCfg<24>::smem_bytes(n, npad) <= budget) return 24;
+  if (OnepassCfg<16>::smem_bytes(n, npad) <= budget) return 16;
+  return 0;
+}
+
+template <int R>
+static void onepass_launch_t(admm_b200_handle* h, const OnepassArgs& a, int grid) {
+  static size_t conf = 0;
+  const size_t smem = OnepassCfg<R>::smem_bytes(a.uw.n, a.npad);
+  if (smem > conf) {
+    ADMM_CUDA(cudaFuncSetAttribute(uw_onepass_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  uw_onepass_kernel<R><<<grid, OP_THREADS, smem, h->stream>>>(a);
+}
+
 // which: 0 whole iteration, 1 x-update only, 2 fused pass only
 static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, int which,
                               bool history) {
@@ -1447,6 +1475,33 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     a.zvals = history ? h->zvals.p : nullptr;
     a.uvals = history ? h->uvals.p : nullptr;
     a.alg = lp.alg; a.v = h->fv.p; a.uhat = h->fuhat.p; a.zprev = h->fzprev.p; a.uprev = h->fuprev.p;
+    if (const int R = onepass_rows(h, lp)) {
+      // D read once: D_g*x, the prox and D_g'*[rhs, dz, u] from one shared-memory tile (onepass.cuh)
+      OnepassArgs op;
+      op.uw = a; op.nv = nv; op.npad = npad;
+      op.ntiles = (m + R - 1) / R;
+      const int grid1 = (int)std::min<int64_t>(kNumSM, op.ntiles);
+      h->op_dpart.ensure((int64_t)grid1 * nv * npad);
+      h->uw_partials.ensure((int64_t)grid1 * UW_NRED);
+      op.dpart = h->op_dpart.p; op.partials = h->uw_partials.p;
+      if (R == 32) onepass_launch_t<32>(h, op, grid1);
+      else if (R == 24) onepass_launch_t<24>(h, op, grid1);
+      else onepass_launch_t<16>(h, op, grid1);
+      ADMM_CUDA(cudaGetLastError());
+      uw_onepass_finish_kernel<<<(unsigned)((nv * n + 255) / 256), 256, 0, h->stream>>>(h->op_dpart.p, grid1, nv, n, npad, d,
+                                                                                        h->uw_partials.p, scal, h->ctl);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches += 2;
+      allreduce_sum(h, d, (int64_t)nv * npad + UW_NRED);
+      UwEpiArgs e;
+      e.n = n; e.x = h->x.p; e.dzv = (nv == 3) ? d + npad : nullptr; e.duv = (nv == 3) ? d + 2 * npad : nullptr;
+      e.scalars = scal; e.m_total = (double)h->m_total; e.kind = a.kind; e.C = h->svmC; e.ctl = h->ctl; e.lp = lp;
+      e.xvals = history ? h->xvals.p : nullptr;
+      uw_epilogue_kernel<<<1, 256, 0, h->stream>>>(e);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+      return;
+    }
     dim3 grid((unsigned)rb, (unsigned)chunks);
     const bool vec_ok = (((uintptr_t)h->dD & 15) == 0) && (h->ldD % 2 == 0);
     if (vec_ok) uw_gemv_prox_kernel<2><<<grid, UW_THREADS, 0, h->stream>>>(a);
@@ -2060,7 +2115,7 @@ int admm_b200_destroy(admm_b200_handle* h) {
   DBuf* bufs[] = {&h->ownD, &h->s, &h->dts, &h->L, &h->W, &h->WT, &h->x, &h->z, &h->u, &h->y, &h->t1, &h->t2,
                   &h->x0, &h->z0, &h->u0, &h->partials, &h->hist, &h->xvals, &h->zvals, &h->uvals, &h->gemm_ws,
                   &h->gemv_ws, &h->scratch, &h->cd_ws, &h->aux, &h->rvec, &h->dzvec, &h->cb, &h->uw_partials, &h->zz, &h->uu, &h->tvtab, &h->Pfull, &h->lb, &h->ub, &h->fv, &h->fuhat, &h->fzprev, &h->fuprev,
-                  &h->Q2, &h->s2, &h->dts2, &h->G1, &h->G2, &h->L2, &h->W2, &h->WT2, &h->zsol};
+                  &h->op_dpart, &h->Q2, &h->s2, &h->dts2, &h->G1, &h->G2, &h->L2, &h->W2, &h->WT2, &h->zsol};
   for (DBuf* b : bufs) b->release();
   for (ColdotPlan* p : h->plans) {
     cudaFree(p->d_cta_pos); cudaFree(p->d_pos_item); cudaFree(p->d_order); cudaFree(p->d_items);

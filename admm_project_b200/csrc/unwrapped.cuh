@@ -50,10 +50,12 @@ __device__ __forceinline__ double huber1(double v) {  // CVX huber(v, 1)
   return a <= 1.0 ? a * a : 2.0 * a - 1.0;
 }
 
-// z-prox, u-update and norm terms of one row (admm.m:515-548 with A = D, B = -1)
-__device__ __forceinline__ void uw_row(const UwArgs& a, int64_t i, double Ax, int it, double (&r)[UW_NRED]) {
-  const double zp = a.z[i], uold = a.u[i], aux = a.aux[i];
-  const double up = a.alg ? a.uhat[i] : uold;
+// z-prox, u-update and norm terms of one row (admm.m:515-548 with A = D, B = -1) -- arithmetic only:
+// zp / uold are the row's current z / u, up the u the prox uses (uhat for the fast variants), vprev the
+// predictor v (fast variants).  Returns z, u; the sums go to r[].
+struct UwRowOut { double z, u, dz, c; };
+__device__ __forceinline__ UwRowOut uw_row_core(const UwArgs& a, double zp, double uold, double up, double aux,
+                                                double vprev, double Ax, double (&r)[UW_NRED]) {
   const double c = (a.kind >= UW_HUBER) ? aux : 0.0;
   double xh = Ax;
   if (a.relax != 1.0) xh = a.relax * Ax - (1.0 - a.relax) * (-zp - c);   // admm.m:517
@@ -76,22 +78,11 @@ __device__ __forceinline__ void uw_row(const UwArgs& a, int64_t i, double Ax, in
     obj = fabs(z);                         // lad.m:148
   }
   const double u = up + (xh + (-z) - c);   // admm.m:542/548
-  a.z[i] = z;
-  a.u[i] = u;
   const double dz = z - zp, du = u - uold, pr = Ax + (-z) - c;
-  if (a.alg == 0) {
-    a.rvec[i] = (a.kind >= UW_HUBER) ? (aux + z - u) : (z - u);
-    if (a.dzvec) a.dzvec[i] = dz;
-  } else {
-    a.zprev[i] = zp;
-    a.uprev[i] = uold;
-    const double e1 = u - up, e2 = z - a.v[i];
+  if (a.alg != 0) {
+    const double e1 = u - up, e2 = z - vprev;
     r[7] = fma(e1, e1, r[7]);      // ||u - uhat||^2
     r[8] = fma(e2, e2, r[8]);      // ||B(z - v)||^2
-  }
-  if (a.zvals) {
-    a.zvals[(int64_t)it * a.m + i] = z;
-    a.uvals[(int64_t)it * a.m + i] = u;
   }
   r[0] = fma(pr, pr, r[0]);
   r[1] = fma(Ax, Ax, r[1]);
@@ -100,6 +91,26 @@ __device__ __forceinline__ void uw_row(const UwArgs& a, int64_t i, double Ax, in
   r[4] = fma(dz, dz, r[4]);
   r[5] = fma(du, du, r[5]);
   r[6] += obj;
+  return UwRowOut{z, u, dz, c};
+}
+
+__device__ __forceinline__ void uw_row(const UwArgs& a, int64_t i, double Ax, int it, double (&r)[UW_NRED]) {
+  const double zp = a.z[i], uold = a.u[i], aux = a.aux[i];
+  const double up = a.alg ? a.uhat[i] : uold;
+  const UwRowOut o = uw_row_core(a, zp, uold, up, aux, a.alg ? a.v[i] : 0.0, Ax, r);
+  a.z[i] = o.z;
+  a.u[i] = o.u;
+  if (a.alg == 0) {
+    a.rvec[i] = (a.kind >= UW_HUBER) ? (aux + o.z - o.u) : (o.z - o.u);
+    if (a.dzvec) a.dzvec[i] = o.dz;
+  } else {
+    a.zprev[i] = zp;
+    a.uprev[i] = uold;
+  }
+  if (a.zvals) {
+    a.zvals[(int64_t)it * a.m + i] = o.z;
+    a.uvals[(int64_t)it * a.m + i] = o.u;
+  }
 }
 
 template <int VEC>
