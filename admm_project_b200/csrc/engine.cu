@@ -1249,7 +1249,7 @@ static void tv_fused_launch(admm_b200_handle* h, const admm_b200_options& o, con
 static int onepass_rows(const admm_b200_handle* h, const LoopParams& lp) {
   if (lp.alg != 0 || getenv("ADMM_B200_NO_ONEPASS")) return 0;
   const int64_t n = h->n, npad = round_up(n, 2);
-  if (n > (int64_t)OP_MAXCOLS * OP_THREADS) return 0;
+  if (n > (int64_t)OP_MAXCOLS * OP_SLOTS) return 0;
   if ((((uintptr_t)h->dD) & 15) != 0 || (h->ldD % 2) != 0) return 0;
   if (!getenv("ADMM_B200_FORCE_ONEPASS") && (n < 128 || h->m * n < ((int64_t)1 << 21))) return 0;
   const size_t budget = 227 * 1024;
@@ -1259,15 +1259,21 @@ static int onepass_rows(const admm_b200_handle* h, const LoopParams& lp) {
   return 0;
 }
 
-template <int R>
+template <int R, int NCH>
 static void onepass_launch_t(admm_b200_handle* h, const OnepassArgs& a, int grid) {
   static size_t conf = 0;
   const size_t smem = OnepassCfg<R>::smem_bytes(a.uw.n, a.npad);
   if (smem > conf) {
-    ADMM_CUDA(cudaFuncSetAttribute(uw_onepass_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ADMM_CUDA(cudaFuncSetAttribute(uw_onepass_kernel<R, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conf = smem;
   }
-  uw_onepass_kernel<R><<<grid, OP_THREADS, smem, h->stream>>>(a);
+  uw_onepass_kernel<R, NCH><<<grid, OP_THREADS, smem, h->stream>>>(a);
+}
+template <int R>
+static void onepass_launch(admm_b200_handle* h, const OnepassArgs& a, int grid) {
+  // 2 column chunks: measured on B200 against 1 (no overlap inside a tile) and 4 (more barriers):
+  // C3 128 / 138 / 137 us per iteration, C4 8.60 / 9.92 / 9.83 ms (profiles/r01_notes.md)
+  onepass_launch_t<R, 2>(h, a, grid);
 }
 
 // which: 0 whole iteration, 1 x-update only, 2 fused pass only
@@ -1481,14 +1487,14 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
       op.uw = a; op.nv = nv; op.npad = npad;
       op.ntiles = (m + R - 1) / R;
       const int grid1 = (int)std::min<int64_t>(kNumSM, op.ntiles);
-      h->op_dpart.ensure((int64_t)grid1 * nv * npad);
+      h->op_dpart.ensure((int64_t)grid1 * 2 * nv * npad);
       h->uw_partials.ensure((int64_t)grid1 * UW_NRED);
       op.dpart = h->op_dpart.p; op.partials = h->uw_partials.p;
-      if (R == 32) onepass_launch_t<32>(h, op, grid1);
-      else if (R == 24) onepass_launch_t<24>(h, op, grid1);
-      else onepass_launch_t<16>(h, op, grid1);
+      if (R == 32) onepass_launch<32>(h, op, grid1);
+      else if (R == 24) onepass_launch<24>(h, op, grid1);
+      else onepass_launch<16>(h, op, grid1);
       ADMM_CUDA(cudaGetLastError());
-      uw_onepass_finish_kernel<<<(unsigned)((nv * n + 255) / 256), 256, 0, h->stream>>>(h->op_dpart.p, grid1, nv, n, npad, d,
+      uw_onepass_finish_kernel<<<(unsigned)((nv * n + UW_NRED + 7) / 8), 256, 0, h->stream>>>(h->op_dpart.p, 2 * grid1, grid1, nv, n, npad, d,
                                                                                         h->uw_partials.p, scal, h->ctl);
       ADMM_CUDA(cudaGetLastError());
       h->launches += 2;

@@ -9,31 +9,36 @@
 // height is 32 (n <= ~800), 24 (n <= ~1030) or 16 rows, bounded by 227 KB of shared memory, and the
 // two-pass kernels stay for wider matrices.
 //
-// Pipeline inside the single CTA per SM (512 threads): the tile is loaded with cp.async in 4 column
-// chunks.  The D*x phase starts on chunk 0 while chunks 1..3 are still in flight; the D' phase releases
-// chunk c as soon as it has been used, and the NEXT tile's chunk c is issued into it immediately, so
-// loads are in flight during both compute phases.  Column j of the tile sits at T[j*(R+2) + i].
+// Pipeline inside the single CTA per SM (512 threads): the tile is loaded with cp.async in NCH column
+// chunks.  The D*x phase starts on chunk 0 while the later chunks are still in flight; the D' phase
+// releases chunk c as soon as it has been used, and the NEXT tile's chunk c is issued into it
+// immediately, so loads are in flight during both compute phases.  Column j of the tile sits at
+// T[j*(R+2) + i]: 16-byte aligned columns, and both access patterns (row pairs of one column in the D*x
+// phase, one column per lane in the D' phase) are free of bank conflicts with LDS.128.
 #pragma once
 #include "unwrapped.cuh"
 
 namespace admmb200 {
 
 constexpr int OP_THREADS = 512;
-constexpr int OP_NCH = 4;
-constexpr int OP_MAXCOLS = 3;          // columns per thread in the D' phase: n <= 1536
+constexpr int OP_SLOTS = 256;          // D' phase: thread = (column slot, row half)
+constexpr int OP_MAXCOLS = 6;          // columns per slot: n <= 1536
 
 struct OnepassArgs {
   UwArgs uw;                           // alg == 0 only
   int nv;                              // 1 (nodualerror) or 3
   int64_t ntiles, npad;
-  double* dpart;                       // [gridDim.x][nv][npad] per-CTA partial D'[.]
+  double* dpart;                       // [gridDim.x][2 row halves][nv][npad] per-CTA partial D'[.]
   double* partials;                    // [gridDim.x][UW_NRED]
 };
 
 template <int R> struct OnepassCfg {
-  static constexpr int RS = R + 2, G = OP_THREADS / R;
+  static constexpr int RS = R + 2;                      // column stride of the tile: 16-byte aligned, conflict-free LDS.128
+  static constexpr int RP = R / 2;                      // row pairs
+  static constexpr int JSTEP = OP_THREADS / RP;         // column groups of the load / D*x mapping
+  static constexpr int ACTIVE = JSTEP * RP;             // threads that take part in it (504 of 512 for R = 24)
   static size_t smem_bytes(int64_t n, int64_t npad) {
-    return (size_t)(n * RS + npad + G * R + 3 * R + (OP_THREADS / 32) * UW_NRED) * 8;
+    return (size_t)(n * RS + npad + JSTEP * R + 3 * R + (OP_THREADS / 32) * UW_NRED) * 8;
   }
 };
 
@@ -43,31 +48,37 @@ __device__ __forceinline__ void cp_async16_zfill(double* smem_dst, const double*
                : "memory");
 }
 
-template <int R>
+template <int R, int OP_NCH>
 __global__ void __launch_bounds__(OP_THREADS, 1) uw_onepass_kernel(OnepassArgs a) {
   const UwArgs& u = a.uw;
   if (u.ctl->done) return;
-  constexpr int RS = OnepassCfg<R>::RS, RP = R / 2, G = OnepassCfg<R>::G;
+  using Cfg = OnepassCfg<R>;
+  constexpr int RS = Cfg::RS, RP = Cfg::RP, JSTEP = Cfg::JSTEP, ACTIVE = Cfg::ACTIVE, RH = R / 2;
   extern __shared__ __align__(16) double sm[];
   const int64_t n = u.n, m = u.m;
   double* T = sm;
   double* xs = T + n * RS;
-  double* wpart = xs + a.npad;
-  double* rs = wpart + G * R;
+  double* wpart = xs + a.npad;          // [JSTEP][R]
+  double* rs = wpart + JSTEP * R;       // [3][R]: rhs, dz, u of the tile's rows
   double* redsh = rs + 3 * R;
   const int tid = threadIdx.x, it = u.ctl->it;
   const int64_t CW = (n + OP_NCH - 1) / OP_NCH;
   for (int64_t j = tid; j < n; j += OP_THREADS) xs[j] = u.x[j];
+  // load / D*x mapping: thread = (row pair q, column group j0); D' mapping: thread = (column slot sc, row half hh)
+  const int q = tid % RP, j0 = tid / RP;
+  const int sc = tid % OP_SLOTS, hh = tid / OP_SLOTS;
 
   auto issue = [&](int64_t tile, int c) {               // column chunk c of `tile` -> shared memory
-    const int64_t cbeg = c * CW, cend = min(n, cbeg + CW), row0 = tile * R;
-    const int64_t units = (cend - cbeg) * RP;
-    for (int64_t idx = tid; idx < units; idx += OP_THREADS) {
-      const int64_t j = cbeg + idx / RP;
-      const int q = (int)(idx % RP);
-      const int64_t row = row0 + 2 * q;
+    if (tid < ACTIVE) {
+      const int64_t cbeg = c * CW, cend = min(n, cbeg + CW), row = tile * R + 2 * q;
       const int bytes = (int)min((int64_t)16, max((int64_t)0, (m - row) * 8));   // rows past m read as zero
-      cp_async16_zfill(T + j * RS + 2 * q, u.D + (bytes > 0 ? row : 0) + j * u.ld, bytes);
+      const double* src = u.D + (bytes > 0 ? row : 0) + (cbeg + j0) * u.ld;      // a valid address even when bytes == 0
+      double* dst = T + (cbeg + j0) * RS + 2 * q;
+      for (int64_t j = cbeg + j0; j < cend; j += JSTEP) {
+        cp_async16_zfill(dst, src, bytes);
+        src += (int64_t)JSTEP * u.ld;
+        dst += JSTEP * RS;
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -83,72 +94,95 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uw_onepass_kernel(OnepassArgs a
   double racc[UW_NRED];
 #pragma unroll
   for (int k = 0; k < UW_NRED; ++k) racc[k] = 0.0;
-  const int ri = tid % R, rg = tid / R;
+  const bool rowthread = (tid < 8 * R) && ((tid & 7) == 0);   // one of 8 lanes that sum a row's partial dots
+  const int myrow = tid >> 3;
 
   for (; tile < a.ntiles; tile += gridDim.x) {
-    // the R row threads fetch their z, u, aux now; the values are needed after the D*x phase
-    const int64_t row = tile * R + tid;
+    // the row threads fetch their z, u, aux now; the values are needed after the D*x phase
+    const int64_t row = tile * R + myrow;
     double zp = 0.0, uold = 0.0, aux = 0.0;
-    if (tid < R && row < m) { zp = u.z[row]; uold = u.u[row]; aux = u.aux[row]; }
-    // ---- w = T x, chunk by chunk as the loads land
-    double s = 0.0;
+    if (rowthread && row < m) { zp = u.z[row]; uold = u.u[row]; aux = u.aux[row]; }
+    // ---- w = T x, chunk by chunk as the loads land: a row PAIR per thread (one LDS.128 per column)
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int c = 0; c < OP_NCH; ++c) {
-      if (c == 0) cp_async_wait<OP_NCH - 1>();
-      else if (c == 1) cp_async_wait<OP_NCH - 2>();
-      else if (c == 2) cp_async_wait<OP_NCH - 3>();
+      if (OP_NCH - 1 - c == 3) cp_async_wait<3>();
+      else if (OP_NCH - 1 - c == 2) cp_async_wait<2>();
+      else if (OP_NCH - 1 - c == 1) cp_async_wait<1>();
       else cp_async_wait<0>();
       __syncthreads();
-      const int64_t cbeg = c * CW, cend = min(n, cbeg + CW);
-      if (rg < G)
-        for (int64_t j = cbeg + rg; j < cend; j += G) s = fma(T[j * RS + ri], xs[j], s);
-    }
-    if (rg < G) wpart[rg * R + ri] = s;
-    __syncthreads();
-    if (tid < R) {
-      double w = 0.0;
+      if (tid < ACTIVE) {
+        const int64_t cbeg = c * CW, cend = min(n, cbeg + CW);
+        const double* tp = T + (cbeg + j0) * RS + 2 * q;
 #pragma unroll 4
-      for (int g = 0; g < G; ++g) w += wpart[g * R + tid];          // fixed order
-      double rv = 0.0, dzv = 0.0, uv = 0.0;
-      if (row < m) {
-        const UwRowOut o = uw_row_core(u, zp, uold, uold, aux, 0.0, w, racc);
-        u.z[row] = o.z;
-        u.u[row] = o.u;
-        if (u.zvals) {
-          u.zvals[(int64_t)it * m + row] = o.z;
-          u.uvals[(int64_t)it * m + row] = o.u;
+        for (int64_t j = cbeg + j0; j < cend; j += JSTEP) {
+          const double2 t = *reinterpret_cast<const double2*>(tp);
+          const double xj = xs[j];
+          s0 = fma(t.x, xj, s0);
+          s1 = fma(t.y, xj, s1);
+          tp += JSTEP * RS;
         }
-        rv = (u.kind >= UW_HUBER) ? (aux + o.z - o.u) : (o.z - o.u);
-        dzv = o.dz;
-        uv = o.u;
       }
-      rs[tid] = rv; rs[R + tid] = dzv; rs[2 * R + tid] = uv;
+    }
+    if (tid < ACTIVE) *reinterpret_cast<double2*>(wpart + j0 * R + 2 * q) = make_double2(s0, s1);
+    __syncthreads();
+    if (tid < 8 * R) {                                   // whole warps: 8 lanes per row, fixed summation order
+      double w = 0.0;
+      for (int g = tid & 7; g < JSTEP; g += 8) w += wpart[g * R + myrow];
+      w += __shfl_xor_sync(0xffffffffu, w, 4);
+      w += __shfl_xor_sync(0xffffffffu, w, 2);
+      w += __shfl_xor_sync(0xffffffffu, w, 1);
+      if ((tid & 7) == 0) {
+        double rv = 0.0, dzv = 0.0, uv = 0.0;
+        if (row < m) {
+          const UwRowOut o = uw_row_core(u, zp, uold, uold, aux, 0.0, w, racc);
+          u.z[row] = o.z;
+          u.u[row] = o.u;
+          if (u.zvals) {
+            u.zvals[(int64_t)it * m + row] = o.z;
+            u.uvals[(int64_t)it * m + row] = o.u;
+          }
+          rv = (u.kind >= UW_HUBER) ? (aux + o.z - o.u) : (o.z - o.u);
+          dzv = o.dz;
+          uv = o.u;
+        }
+        rs[myrow] = rv; rs[R + myrow] = dzv; rs[2 * R + myrow] = uv;
+      }
     }
     __syncthreads();
-    // ---- d += T'[rhs, dz, u]; chunk c is released -- and refilled with the next tile -- as soon as it is used
+    // ---- d += T'[rhs, dz, u] on this thread's half of the rows; chunk c is released -- and refilled with the
+    // next tile -- as soon as it has been used
     const int64_t next = tile + gridDim.x;
 #pragma unroll
     for (int c = 0; c < OP_NCH; ++c) {
       const int64_t cbeg = c * CW, cend = min(n, cbeg + CW);
 #pragma unroll
       for (int k = 0; k < OP_MAXCOLS; ++k) {
-        const int64_t j = tid + (int64_t)k * OP_THREADS;
+        const int64_t j = sc + (int64_t)k * OP_SLOTS;
         if (j >= cbeg && j < cend) {
-          const double* col = T + j * RS;
+          const double* col = T + j * RS + hh * RH;
+          const double* rr = rs + hh * RH;
           if (a.nv == 3) {
             double a0 = acc[0][k], a1 = acc[1][k], a2 = acc[2][k];
-#pragma unroll 8
-            for (int i = 0; i < R; ++i) {
-              const double t = col[i];
-              a0 = fma(t, rs[i], a0);
-              a1 = fma(t, rs[R + i], a1);
-              a2 = fma(t, rs[2 * R + i], a2);
+#pragma unroll
+            for (int i = 0; i < RH; i += 2) {
+              const double2 t = *reinterpret_cast<const double2*>(col + i);
+              const double2 r0 = *reinterpret_cast<const double2*>(rr + i);
+              const double2 r1 = *reinterpret_cast<const double2*>(rr + R + i);
+              const double2 r2 = *reinterpret_cast<const double2*>(rr + 2 * R + i);
+              a0 = fma(t.x, r0.x, a0); a0 = fma(t.y, r0.y, a0);
+              a1 = fma(t.x, r1.x, a1); a1 = fma(t.y, r1.y, a1);
+              a2 = fma(t.x, r2.x, a2); a2 = fma(t.y, r2.y, a2);
             }
             acc[0][k] = a0; acc[1][k] = a1; acc[2][k] = a2;
           } else {
             double a0 = acc[0][k];
-#pragma unroll 8
-            for (int i = 0; i < R; ++i) a0 = fma(col[i], rs[i], a0);
+#pragma unroll
+            for (int i = 0; i < RH; i += 2) {
+              const double2 t = *reinterpret_cast<const double2*>(col + i);
+              const double2 r0 = *reinterpret_cast<const double2*>(rr + i);
+              a0 = fma(t.x, r0.x, a0); a0 = fma(t.y, r0.y, a0);
+            }
             acc[0][k] = a0;
           }
         }
@@ -157,11 +191,11 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uw_onepass_kernel(OnepassArgs a
       if (next < a.ntiles) issue(next, c);
     }
   }
-  // per-CTA partials; uw_onepass_finish_kernel sums them in CTA order
-  double* dp = a.dpart + (int64_t)blockIdx.x * a.nv * a.npad;
+  // per-CTA, per-row-half partials; uw_onepass_finish_kernel sums them in a fixed order
+  double* dp = a.dpart + ((int64_t)blockIdx.x * 2 + hh) * a.nv * a.npad;
 #pragma unroll
   for (int k = 0; k < OP_MAXCOLS; ++k) {
-    const int64_t j = tid + (int64_t)k * OP_THREADS;
+    const int64_t j = sc + (int64_t)k * OP_SLOTS;
     if (j < n) {
       dp[j] = acc[0][k];
       if (a.nv == 3) { dp[a.npad + j] = acc[1][k]; dp[2 * a.npad + j] = acc[2][k]; }
@@ -170,21 +204,29 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uw_onepass_kernel(OnepassArgs a
   block_reduce_store<UW_NRED>(racc, a.partials + (int64_t)blockIdx.x * UW_NRED, redsh);
 }
 
-// d_k = sum over CTAs of their partials (fixed order), scalars likewise
-__global__ void uw_onepass_finish_kernel(const double* dpart, int nparts, int nv, int64_t n, int64_t npad, double* d,
-                                         const double* partials, double* scalars, const LoopCtl* ctl) {
+// d_k = sum over the CTAs' partials, scalars likewise.  One WARP per output: lane l adds parts l, l+32, ...
+// in order, then a fixed xor tree -- a thread per output would walk ~300 dependent L2 loads (20+ us).
+__global__ void __launch_bounds__(256) uw_onepass_finish_kernel(const double* dpart, int ndparts, int nparts, int nv, int64_t n,
+                                                                int64_t npad, double* d, const double* partials,
+                                                                double* scalars, const LoopCtl* ctl) {
   if (ctl->done) return;
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < (int64_t)nv * n) {
-    const int64_t k = t / n, j = t % n;
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // output index
+  const int64_t nout = (int64_t)nv * n;
+  if (w < nout + UW_NRED) {
     double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += dpart[((int64_t)p * nv + k) * npad + j];
-    d[k * npad + j] = s;
-  }
-  if (blockIdx.x == 0 && threadIdx.x < UW_NRED) {
-    double s = 0.0;
-    for (int p = 0; p < nparts; ++p) s += partials[(int64_t)p * UW_NRED + threadIdx.x];
-    scalars[threadIdx.x] = s;
+    if (w < nout) {
+      const int64_t k = w / n, j = w % n;
+      for (int p = lane; p < ndparts; p += 32) s += dpart[((int64_t)p * nv + k) * npad + j];
+    } else {
+      for (int p = lane; p < nparts; p += 32) s += partials[(int64_t)p * UW_NRED + (w - nout)];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      if (w < nout) d[(w / n) * npad + (w % n)] = s;
+      else scalars[w - nout] = s;
+    }
   }
 }
 

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("problem,fast", [("svm", ""), ("huber", ""), ("lad", ""), ("huber", "weak"), ("lad", "strong")])
+@pytest.mark.parametrize("problem,fast", [("svm", ""), ("huber", ""), ("lad", ""), ("huber", "weak"), ("lad", "strong"),
+                                          ("huber", "onepass"), ("svm", "onepass")])
 def test_two_rank_run_matches_serial_oracle(problem, fast):
     import torch
     if torch.cuda.device_count() < 2:
@@ -19,7 +20,11 @@ def test_two_rank_run_matches_serial_oracle(problem, fast):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "run_sharded.py"), "--check",
            "--problem", problem, "--rows", "5001", "--cols", "64"] + (["--fast", fast] if fast else [])
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ)
+    if fast == "onepass":          # the single-pass tile kernel (csrc/onepass.cuh) on every rank's row block
+        cmd = cmd[:-2]
+        env["ADMM_B200_FORCE_ONEPASS"] = "1"
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("SHARDED ")]
     assert line, p.stdout[-2000:] + p.stderr[-2000:]
     out = json.loads(line[-1][8:])
