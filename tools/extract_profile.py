@@ -16,7 +16,10 @@ WANT = [r"^gpu__time_duration\.sum$", r"^dram__bytes_read\.sum$", r"^dram__bytes
         r"^sm__inst_executed_pipe_tensor_subpipe_dmma\.avg\.pct_of_peak_sustained_active$",
         r"^l1tex__data_bank_conflicts_pipe_lsu_mem_shared\.sum$", r"^lts__t_sector_hit_rate\.pct$",
         r"^sm__cycles_active\.(avg|max|min)$", r"^sm__throughput\.avg\.pct_of_peak_sustained_elapsed$",
-        r"^smsp__average_warps_issue_stalled_(wait|math_pipe_throttle|long_scoreboard|barrier|short_scoreboard)_per_issue_active\.ratio$"]
+        r"^smsp__average_warps_issue_stalled_(wait|math_pipe_throttle|long_scoreboard|barrier|short_scoreboard)_per_issue_active\.ratio$",
+        r"^smsp__inst_executed\.sum$", r"^smsp__issue_active\.avg\.pct_of_peak_sustained_active$",
+        r"^sm__pipe_fp64_cycles_active\.avg\.pct_of_peak_sustained_active$",
+        r"^l1tex__data_pipe_lsu_wavefronts\.avg\.pct_of_peak_sustained_elapsed$"]
 
 
 def rows_of(rep):
@@ -34,7 +37,8 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     traffic = {}
     lines = []
-    for name, key in (("prof_gram", "gram_dram_bytes"), ("prof_coldot", "xupdate_dram_bytes")):
+    for name, key in (("prof_gram", "gram_dram_bytes"), ("prof_coldot", "xupdate_dram_bytes"),
+                      ("prof_tvfused", "tv_fused_dram_bytes"), ("prof_onepass", "onepass_dram_bytes")):
         rep = os.path.join(ROOT, "gpurun_out", name + ".ncu-rep")
         if not os.path.exists(rep):
             continue
