@@ -1608,9 +1608,9 @@ static void prepare_loop(admm_b200_handle* h, const admm_b200_options& o, int64_
 // ---------------------------------------------------------------------------------------------
 // Burst runner.  The host enqueues check_every iterations, then reads the device stop flag.  The
 // kernels of an iteration have identical arguments every time (iteration counters, history slots
-// and stop state live on the device), so from the second full burst on the burst is ONE CUDA graph
+// and stop state live on the device), so from the third full burst on the burst is ONE CUDA graph
 // launch: small problems (C1 lasso, the L2-resident shards of C3) are launch-bound otherwise
-// (~3 us of host work per kernel against 6-12 us kernels).  The first burst always runs eagerly: it
+// (~3 us of host work per kernel against 6-12 us kernels).  The first bursts always run eagerly: the first
 // performs every lazy allocation, plan upload and cudaFuncSetAttribute, none of which may happen
 // inside a stream capture.  `period`: a graph may only hold a multiple of `period` iterations (the
 // total-variation loop alternates two buffer halves on the host side).
@@ -1635,7 +1635,7 @@ static void run_bursts(admm_b200_handle* h, const admm_b200_options& o, int64_t 
     int64_t enq = 0, bursts = 0;
     while (true) {
       const int64_t burst = std::min<int64_t>(check, N - enq);
-      if (graph_ok && bursts >= 1 && burst == check) {
+      if (graph_ok && bursts >= 2 && burst == check) {   // capture + instantiate (~0.3 ms) only pays for long loops
         if (!exec) {
           const int64_t before = h->launches;
           ADMM_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));

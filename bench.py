@@ -183,10 +183,13 @@ def run_ours(args):
 
         # ---- time to tolerance (reltol 1e-4) from resident D ----------------------------------
         tol_opts = dict(opts, domaxiters=0, maxiters=(3 if args.light else 1000), check_every=8)
-        t0 = time.perf_counter()
-        rt = lasso(Ddev, s.data_ptr(), lam, tol_opts, engine=eng)
-        torch.cuda.synchronize()
-        tol_wall = (time.perf_counter() - t0) * 1e3
+        tol_wall = []
+        for _ in range(1 if args.light else 2):     # the first call with a new maxiters re-allocates the histories
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rt = lasso(Ddev, s.data_ptr(), lam, tol_opts, engine=eng)
+            torch.cuda.synchronize()
+            tol_wall.append((time.perf_counter() - t0) * 1e3)
 
         # ---- the 64-lambda batch of configs[1]: x-update as two triangular DMMA GEMMs ---------------
         batch = None
@@ -285,7 +288,7 @@ def run_ours(args):
         "setup_ms": phases,
         "lambda_batch": batch,
         "time_to_tol": {"reltol": RELTOL, "steps": int(rt["steps"]), "setup_ms": rt["engine"]["setup_ms"],
-                        "loop_ms": rt["engine"]["loop_ms"], "wall_ms": tol_wall},
+                        "loop_ms": rt["engine"]["loop_ms"], "wall_ms": tol_wall[-1], "first_call_wall_ms": tol_wall[0]},
         "roofline": {"kernel": "gemm_f64_dmma_kernel<T,N> (Gram D'D + rho*I, lower tiles)", "bound": "tensor",
                      "achieved": gram_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": gram_tflops / fp64_peak,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",

@@ -104,8 +104,9 @@ typedef struct admm_b200_options {
   int32_t fasttype;   /* admm.m:60  1 = 'weak' (default): accelerated ADMM with restart (alg 2); 0 = fast ADMM (alg 1) */
   double restart;     /* admm.m:287 options.restart, default 0.999 (values outside (0,1) become 0.999) */
   double dvaltol;     /* admm.m:291 options.dvaltol, default 1e-8 */
-  int32_t graph;      /* extension, default 1: after the first burst of check_every iterations, replay each
-                         further burst as one CUDA graph launch (same kernels, same arguments, same results) */
+  int32_t graph;      /* extension, default 1: after the first two bursts of check_every iterations, replay each
+                         further burst as one CUDA graph launch (same kernels, same arguments, same results);
+                         single-rank handles only (row-sharded loops stay eager) */
   int32_t reserved;
 } admm_b200_options;
 
