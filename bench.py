@@ -217,9 +217,12 @@ def run_ours(args):
     # ---- e2e: host buffers through the public API -------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        Dh = torch.empty((N_COLS, M), dtype=torch.float64, pin_memory=True)
+        try:
+            Dh = torch.empty((N_COLS, M), dtype=torch.float64, pin_memory=True)
+        except RuntimeError:            # N replicas x 4.3 GB of pinned host memory may not be available
+            Dh = torch.empty((N_COLS, M), dtype=torch.float64)
         Dh.copy_(Dt)
-        sh = torch.empty(M, dtype=torch.float64, pin_memory=True)
+        sh = torch.empty(M, dtype=torch.float64, pin_memory=Dh.is_pinned())
         sh.copy_(s)
         D_np = Dh.numpy().T                 # (M, N_COLS) Fortran-ordered view of the pinned buffer
         s_np = sh.numpy()
@@ -240,7 +243,7 @@ def run_ours(args):
                "h2d_bytes_per_step": int(M * N_COLS * 8 + M * 8),
                "d2h_bytes_per_step": int(3 * N_COLS * 8 + 4 * ITERS * 8),
                "steps": e2e_steps, "ms_per_step": float(wmax.item()) / e2e_steps * 1e3,
-               "api": "admm_project_b200.lasso(D_host, s_host, lambda, options)"}
+               "api": "admm_project_b200.lasso(D_host, s_host, lambda, options)", "host_memory": "pinned" if Dh.is_pinned() else "pageable"}
         assert re["steps"] == ITERS
 
     if rank != 0:
