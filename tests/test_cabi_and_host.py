@@ -84,6 +84,26 @@ def test_host_mirror_argument_checks():
     assert setopt({"Hnormtol": 1, "Hreltol": 2.0}, "Hnormtol", 1e-6) == 2.0
 
 
+def test_model_mirror_argument_checks_run_before_any_device_work():
+    # solvers/model.m:158-218 -- the reference's errorcheck texts, raised by the mirror without a GPU
+    from admm_project_b200 import EngineError, MatlabError, getproxops, model
+    P, Q, r, s = np.ones((6, 3)), np.ones((6, 3)), np.ones(6), np.ones(6)
+    with pytest.raises(MatlabError, match="rows in P do not match number of rows in Q"):
+        model(P, Q[:4], r, s, {})
+    with pytest.raises(MatlabError, match="columns in P do not match number of columns in Q"):
+        model(P, Q[:, :2], r, s, {})
+    with pytest.raises(MatlabError, match="does not match length of vector r"):
+        model(P, Q, r[:5], s, {})
+    with pytest.raises(MatlabError, match="does not match length of vector s"):
+        model(P, Q, r, s[:5], {})
+    with pytest.raises(MatlabError, match="Argument r is not a vector"):
+        model(P, Q, np.ones((6, 2)), s, {})
+    with pytest.raises(MatlabError, match="not a struct"):
+        model(P, Q, r, s, 3)
+    with pytest.raises(EngineError, match="device-resident"):
+        getproxops("Model", {"PtP": P.T @ P})                   # no engine: there is no CPU path
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "admm_project_b200")
     for dirpath, _, files in os.walk(pkg):
