@@ -302,7 +302,7 @@ def run_ours(args):
                           "frac_of_8TBs_nominal": xupd_gbs / 8000.0, "peak_source": peak_src,
                           "algorithmic_bytes": tri_bytes, "traffic": (traffic or {}).get("xupdate_dram_bytes")},
     }
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:          # rank 0 at N = 1 only
         out["cpu_baseline"] = cpu_baseline(CPU_SAMPLE_ROWS, CPU_SAMPLE_ITERS)
     print(json.dumps(out))
     if world > 1:
@@ -344,12 +344,26 @@ def cpu_baseline(rows, iters):
             "extrapolated_full_workload_iters_per_s": ITERS / ((dt - r["runtime"]) * M / rows + r["runtime"] / iters * ITERS)}
 
 
+def use_all_cores():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use every host thread it can.
+    Must run before NumPy / OpenBLAS are loaded (env) and again afterwards (threadpoolctl) to be sure."""
+    cores = len(os.sched_getaffinity(0))
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(cores)
+    return cores
+
+
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
     world = env_int("WORLD_SIZE", 1)
-    cores = len(os.sched_getaffinity(0))
+    cores = use_all_cores()
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     rows, iters = CPU_SAMPLE_ROWS, CPU_SAMPLE_ITERS
     D, s, lam = cpu_problem(rows, N_COLS)
     for _ in range(min(args.warmup, 1)):
