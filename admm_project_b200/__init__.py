@@ -15,5 +15,6 @@ from .getproxops import getproxops, EngineProx                   # noqa: F401
 from .errorcheck import errorcheck                               # noqa: F401
 from . import solvers                                            # noqa: F401
 from . import mnist                                              # noqa: F401
+from . import testers                                            # noqa: F401
 from .solvers import linearsvm_onevsall                       # noqa: F401
 from .solvers import lasso, unwrappedadmm, linearsvm, huberfit, lad, basispursuit, totalvariation, quadraticprogram, model   # noqa: F401
