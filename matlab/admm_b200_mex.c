@@ -8,6 +8,8 @@
  *         admm_b200_mex('setup_unwrapped', h, kind, D, aux, C)     unwrappedadmm.m:96-123, huberfit.m:166, lad.m:134
  *         admm_b200_mex('setup_basispursuit', h, D, s)             basispursuit.m:116-120
  *         admm_b200_mex('setup_totalvariation', h, s, lambda)      totalvariation.m:127-131
+ *         admm_b200_mex('setup_model', h, P, Q, r, s, rho)         model.m:119-146
+ *         admm_b200_mex('setup_quadratic', h, kind, P, q, r, rho, lb, ub)   quadraticprogram.m:210-216 (kind 9 = box, 8 = nonneg)
  *         admm_b200_mex('set_lambda', h, lambda)                   getProxOps.m:455
  *         admm_b200_mex('set_init', h, x0, z0, u0)                 admm.m:252-254 ([] = zeros)
  *   res = admm_b200_mex('solve', h, opts)                          admm.m:496-767
@@ -177,6 +179,12 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     check(admm_b200_setup_model(get_handle(prhs[1]), m, (int64_t)mxGetN(prhs[2]), dense(prhs[2], "P"), m,
                                 dense(prhs[3], "Q"), (int64_t)mxGetM(prhs[3]), dense(prhs[4], "r"), dense(prhs[5], "s"),
                                 nrhs > 6 ? mxGetScalar(prhs[6]) : 1.0));
+  } else if (!strcmp(cmd, "setup_quadratic")) {          /* (h, kind, P, q, r, rho, lb, ub) */
+    int64_t n = (int64_t)mxGetM(prhs[3]);
+    const double* lb = (nrhs > 7 && !mxIsEmpty(prhs[7])) ? dense(prhs[7], "lb") : NULL;
+    const double* ub = (nrhs > 8 && !mxIsEmpty(prhs[8])) ? dense(prhs[8], "ub") : NULL;
+    check(admm_b200_setup_quadratic(get_handle(prhs[1]), (int32_t)mxGetScalar(prhs[2]), n, dense(prhs[3], "P"), n,
+                                    dense(prhs[4], "q"), mxGetScalar(prhs[5]), mxGetScalar(prhs[6]), lb, ub));
   } else if (!strcmp(cmd, "set_lambda")) {
     check(admm_b200_set_lambda(get_handle(prhs[1]), mxGetScalar(prhs[2])));
   } else if (!strcmp(cmd, "set_init")) {                 /* (h, x0, z0, u0), [] = zeros */

@@ -28,7 +28,13 @@ switch problem
     case 'model'                                           % P, Q, r, s instead of PtP .. Qts (model.m:123-128): Grams on the device
         rho = 1; if isfield(args, 'rho'), rho = args.rho; end
         admm_b200_mex('setup_model', args.h, args.P, args.Q, args.r, args.s, rho);
-    case {'linearprogram', 'quadraticprogram', 'covarianceselection'}
+    case 'quadraticprogram'                                % only the 'bounded' form (getProxOps.m:1441-1474) is on the device
+        if ~isfield(args, 'constraint') || ~strcmp(args.constraint, 'bounded')
+            error('admm_b200: quadraticprogram ''standard'' (dense KKT solve every iteration) is outside the engine''s hot path.');
+        end
+        r = 0; if isfield(args, 'r'), r = args.r; end
+        admm_b200_mex('setup_quadratic', args.h, 9, args.P, args.q, r, args.rho, args.lb, args.ub);
+    case {'linearprogram', 'covarianceselection'}
         error('admm_b200: problem ''%s'' is outside the engine''s hot path.', problem);
     otherwise
         error('Invalid input for problem - given string is not a solver!');
