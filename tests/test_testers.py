@@ -40,6 +40,16 @@ def test_solvertester_sweeps_sizes_with_the_oracle():
         testers.solvertester("covarianceselection", solvers=oracle)
 
 
+@pytest.mark.parametrize("solver", ["huberfit", "basispursuit", "totalvariation", "model", "linearsvm"])
+def test_solvertester_every_in_scope_solver_with_the_oracle(solver):
+    import oracle
+    np.random.seed(3)
+    lo = 7 if solver == "linearsvm" else 4             # 2^5 + 2^5 jittered points do not pin the 45-degree line to 5 %
+    out = testers.solvertester(solver, lo, lo + 1, trials=1, seed=1, solvers=oracle)
+    assert len(out["trials"]) == 2
+    assert out["failures"] == 0, out
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", DEMOS)
 def test_engine_passes_the_reference_testers_and_agrees_with_the_oracle(engine, name):
