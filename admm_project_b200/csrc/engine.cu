@@ -35,6 +35,12 @@ void set_error(const char* fmt, ...) {
 
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 static inline int64_t tv_stride(int64_t n);
+// cudaFuncSetAttribute state is per DEVICE: a process that drives several GPUs (one handle each) must
+// configure every kernel once per device, so the 'already configured' marks are kept per device.
+struct PerDevice {
+  size_t v[64] = {};
+  size_t& operator()(int dev) { return v[dev & 63]; }
+};
 
 // a device buffer the handle owns
 struct DBuf {
@@ -173,11 +179,12 @@ static void ensure_tickets(admm_b200_handle* h, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 template <bool AK, bool BK, int VEC, int BN>
 static void gemm_launch_t(admm_b200_handle* h, const GemmArgs& g, dim3 grid) {
-  static bool configured = false;
+  static PerDevice configured_pd;
+  size_t& configured = configured_pd(h->device);
   if (!configured) {
     ADMM_CUDA(cudaFuncSetAttribute(gemm_f64_dmma_kernel<AK, BK, VEC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    GEMM_SMEM_BYTES));
-    configured = true;
+    configured = 1;
   }
   gemm_f64_dmma_kernel<AK, BK, VEC, BN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(g);
   ADMM_CUDA(cudaGetLastError());
@@ -285,10 +292,11 @@ static void transpose(admm_b200_handle* h, const double* in, int64_t rows, int64
 // want_inverse, otherwise only its diagonal blocks are valid.
 static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda, double* W, int64_t ldw,
                           bool want_inverse) {
-  static bool configured = false;
+  static PerDevice configured_pd;
+  size_t& configured = configured_pd(h->device);
   if (!configured) {
     ADMM_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_DIAG_SMEM));
-    configured = true;
+    configured = 1;
   }
   ADMM_CUDA(cudaMemsetAsync(h->fail, 0, sizeof(int), h->stream));
   ADMM_CUDA(cudaMemset2DAsync(W, (size_t)ldw * 8, 0, (size_t)k * 8, (size_t)k, h->stream));
@@ -521,8 +529,8 @@ static void gemvt_multi(admm_b200_handle* h, const double* M, int64_t ld, int64_
   a.units_per_cta = (nunits + grid - 1) / grid;
   const size_t smem = (size_t)a.units_per_cta * GEMVT_CG * nv * GEMVT_WARPS * 8;
   ADMM_REQUIRE(smem <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED, "gemvt: too many column groups per CTA");
-  static size_t configured[2] = {0, 0};
-  size_t& conf = configured[nv == 3];
+  static PerDevice configured_pd[2];
+  size_t& conf = configured_pd[nv == 3](h->device);
   if (smem > conf && smem > 48 * 1024) {
     if (nv == 1) ADMM_CUDA(cudaFuncSetAttribute(gemvt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else ADMM_CUDA(cudaFuncSetAttribute(gemvt_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -566,8 +574,8 @@ static void coldot_multi(admm_b200_handle* h, int mode, const double* M, int64_t
   const ColdotPlan* plan = coldot_plan(h, mode, rows, cols);
   const size_t smem = (size_t)plan->max_pos * nv * COLDOT_WARPS * 8;
   ADMM_REQUIRE(smem <= 200 * 1024, ADMM_B200_ERR_UNSUPPORTED, "coldot: too many columns per CTA (%d)", plan->max_pos);
-  static size_t configured[2] = {0, 0};
-  size_t& conf = configured[nv == 3];
+  static PerDevice configured_pd[2];
+  size_t& conf = configured_pd[nv == 3](h->device);
   if (smem > conf && smem > 48 * 1024) {
     if (nv == 1) ADMM_CUDA(cudaFuncSetAttribute(coldot_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else ADMM_CUDA(cudaFuncSetAttribute(coldot_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1270,7 +1278,8 @@ static int onepass2_rows(int64_t n) {
 }
 template <int R>
 static void onepass2_launch(admm_b200_handle* h, const OnepassArgs& a, int grid) {
-  static size_t conf = 0;
+  static PerDevice conf_pd;
+  size_t& conf = conf_pd(h->device);
   const int64_t n = a.uw.n, nh = (n + 1) / 2 + (((n + 1) / 2) & 1);
   const size_t smem = Onepass2Cfg<R>::smem_bytes(nh);
   if (smem > conf) {
@@ -1282,7 +1291,8 @@ static void onepass2_launch(admm_b200_handle* h, const OnepassArgs& a, int grid)
 
 template <int R, int NCH>
 static void onepass_launch_t(admm_b200_handle* h, const OnepassArgs& a, int grid) {
-  static size_t conf = 0;
+  static PerDevice conf_pd;
+  size_t& conf = conf_pd(h->device);
   const size_t smem = OnepassCfg<R>::smem_bytes(a.uw.n, a.npad);
   if (smem > conf) {
     ADMM_CUDA(cudaFuncSetAttribute(uw_onepass_kernel<R, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1303,11 +1313,12 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
   const int* done = &h->ctl->done;
   if (h->kind == ADMM_B200_TOTALVARIATION) {
     const int64_t n = h->n;
-    static bool configured = false;
+    static PerDevice configured_pd;
+    size_t& configured = configured_pd(h->device);
     if (!configured) {
       ADMM_CUDA(cudaFuncSetAttribute(tv_solve_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TvCfg<8>::SMEM_BYTES));
       ADMM_CUDA(cudaFuncSetAttribute(tv_solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TvCfg<16>::SMEM_BYTES));
-      configured = true;
+      configured = 1;
     }
     if (which == 0 && tv_fused_ok(h)) {          // small halo: the whole iteration is one kernel (tv.cuh)
       tv_fused_launch(h, o, lp, h->tv_par, false, history);
@@ -1892,7 +1903,8 @@ static void solve_lasso_batch(admm_b200_handle* h, const admm_b200_options& o, i
 // ---------------------------------------------------------------------------------------------
 template <int NV>
 static void gemvt_strided_t(admm_b200_handle* h, GemvtArgs& a, int grid, size_t smem) {
-  static size_t conf = 0;
+  static PerDevice conf_pd;
+  size_t& conf = conf_pd(h->device);
   if (smem > conf && smem > 48 * 1024) {
     ADMM_CUDA(cudaFuncSetAttribute(gemvt_kernel<NV, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conf = smem;
@@ -1947,10 +1959,11 @@ struct UwBatchOut {
 
 template <int NB>
 static void uwb_pass1_t(admm_b200_handle* h, const UwbArgs& a, dim3 grid, size_t smem) {
-  static bool configured = false;
+  static PerDevice configured_pd;
+  size_t& configured = configured_pd(h->device);
   if (!configured) {
     ADMM_CUDA(cudaFuncSetAttribute(uwb_gemm_prox_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
+    configured = 1;
   }
   uwb_gemm_prox_kernel<NB><<<grid, UW_THREADS, smem, h->stream>>>(a);
 }
