@@ -182,6 +182,8 @@ def totalvariation(s, lam, options):
     options = dict(options)
     if not (np.isscalar(lam) and np.real(lam) >= 0):                        # :190-194
         raise MatlabError("Given lambda parameter is not a nonnegative number!")
+    if np.ndim(s) > 1 and 1 not in np.shape(s):                             # :197-199
+        raise MatlabError("Argument s is not a vector!")
     s = _col(s)
     n = s.shape[0]
     # D = spdiags([ones(n,1) -ones(n,1)], 0:1, n, n)  (:127): D(i,i)=1, D(i,i+1)=-1
