@@ -49,6 +49,11 @@ class Result(C.Structure):
                 ("dvals", _dp), ("avals", _dp), ("restarted", _dp)]
 
 
+class Info(C.Structure):
+    _fields_ = [("generation", C.c_int64), ("zero_cols", C.c_int64), ("diag_ratio", C.c_double),
+                ("xsolve_effective", C.c_int32), ("p2p_ready", C.c_int32), ("nranks", C.c_int32), ("rank", C.c_int32)]
+
+
 # every symbol include/admm_b200.h declares: name -> (restype, argtypes)
 _i64, _i32, _d, _vp, _int = C.c_int64, C.c_int32, C.c_double, C.c_void_p, C.c_int
 SYMBOLS = {
@@ -60,6 +65,7 @@ SYMBOLS = {
     "admm_b200_set_stream": (_int, [_vp, _vp]),
     "admm_b200_synchronize": (_int, [_vp]),
     "admm_b200_setup_lasso": (_int, [_vp, _i64, _i64, _vp, _i64, _vp, _d, _i32]),
+    "admm_b200_setup_lasso_sharded": (_int, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _d, _i32]),
     "admm_b200_setup_unwrapped": (_int, [_vp, _i32, _i64, _i64, _i64, _vp, _i64, _vp, _d]),
     "admm_b200_setup_basispursuit": (_int, [_vp, _i64, _i64, _vp, _i64, _vp]),
     "admm_b200_setup_totalvariation": (_int, [_vp, _i64, _vp, _d]),
@@ -86,6 +92,7 @@ SYMBOLS = {
     "admm_b200_launch_count": (_i64, [_vp]),
     "admm_b200_graph_replays": (_i64, [_vp]),
     "admm_b200_get_setup_phases": (_int, [_vp, C.POINTER(C.c_double)]),
+    "admm_b200_get_info": (_int, [_vp, C.POINTER(Info)]),
     "admm_b200_slicemaker": (_int, [_i64, _i64, C.POINTER(_i64)]),
 }
 

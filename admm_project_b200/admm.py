@@ -40,6 +40,10 @@ def admm(xminf, zming, options):
     if xminf.engine is not zming.engine or xminf.problem != zming.problem:
         raise L.EngineError(L.ERR_INVALID, "admm: xminf and zming belong to different problems/engines")
     eng = xminf.engine
+    gen = getattr(eng, "generation", None)
+    if gen is not None and (xminf.generation != gen or zming.generation != gen):
+        raise L.EngineError(L.ERR_STATE, "admm: these proximal operators were made for an earlier setup of this engine "
+                            "(an Engine holds one problem; call getproxops / the solver again)")
 
     # admm.m:51-76
     if setopt(options, "adaptive", 0):
@@ -103,7 +107,11 @@ def admm(xminf, zming, options):
         results["Hnormtol"] = o.hnormtol
 
     start = time.perf_counter()
-    r = eng.solve(o, want_history=bool(o.history))
+    try:
+        r = eng.solve(o, want_history=bool(o.history))
+    finally:
+        if getattr(eng, "_owned", False):       # made by the solver for this one call (engine.acquire_engine)
+            eng.close()
     if sharded:                                     # results carry full-length z / u like the reference's
         for key in ("zopt", "uopt", "zvals", "uvals"):
             if key in r:

@@ -21,6 +21,7 @@
 #include "uwbatch.cuh"
 #include "onepass.cuh"
 #include "tv.cuh"
+#include "p2p.cuh"
 #include <dlfcn.h>
 
 namespace admmb200 {
@@ -133,12 +134,29 @@ struct admm_b200_handle {
   // row-sharded runs: one NCCL communicator per handle (one process per GPU)
   void* comm = nullptr;
   int rank = 0, nranks = 1;
+  // one-shot peer-memory allreduce over NVLink (p2p.cuh): this rank's mailbox + the peers' mapped mailboxes
+  P2PState p2p;
+  bool lasso_sharded = false;    // lasso set up from row shards (Gram allreduced, iterations replicated)
+  int64_t generation = 0;        // bumped by every setup_*: stale (minx, minz) pairs are rejected by the host mirror
+  double diag_ratio = 1.0;       // (max L_ii / min L_ii)^2 of the last factor: cheap lower bound of cond(A)
+  int xsolve_eff = ADMM_B200_XSOLVE_INVFACTOR;   // x-update realisation actually used (SUBST when the guard fired)
+  int64_t zero_cols = 0;         // A = D problems: all-zero columns of D handled as pinv does (x_j = 0)
   std::vector<ColdotPlan*> plans;
   unsigned* tickets = nullptr;
   int64_t tickets_cap = 0;
 };
 
 namespace admmb200 {
+
+// run a scope's launches on another stream of the handle; the handle's stream is restored when the scope ends
+struct StreamSwap {
+  admm_b200_handle* h;
+  cudaStream_t saved;
+  StreamSwap(admm_b200_handle* hh, cudaStream_t s) : h(hh), saved(hh->stream) { hh->stream = s; }
+  ~StreamSwap() { h->stream = saved; }
+};
+
+static void allreduce_sum(admm_b200_handle* h, double* buf, int64_t count, const int* done = nullptr);
 
 static void check_handle(admm_b200_handle* h) {
   ADMM_REQUIRE(h != nullptr, ADMM_B200_ERR_INVALID, "null handle");
@@ -342,14 +360,15 @@ static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda
       to.allow_splitk = 0;
       ADMM_CUDA(cudaEventRecord(h->ev_la[0], sA));
       ADMM_CUDA(cudaStreamWaitEvent(sB, h->ev_la[0], 0));
-      h->stream = sB;
-      gemm(h, 0, 1, rem2, n1, wb, -1.0, P, lda, P, lda, 1.0, A + K1 + K1 * lda, lda, to);
-      ADMM_CUDA(cudaEventRecord(h->ev_la[1], sB));
-      if (rem2 > n1) {
-        double* P2 = P + n1;   // rows K1+n1.. of the panel
-        gemm(h, 0, 1, rem2 - n1, rem2 - n1, wb, -1.0, P2, lda, P2, lda, 1.0, A + (K1 + n1) + (K1 + n1) * lda, lda, to);
+      {
+        StreamSwap on_b(h, sB);   // restores h->stream on every exit path (a throwing gemm must not leave the handle on stream2)
+        gemm(h, 0, 1, rem2, n1, wb, -1.0, P, lda, P, lda, 1.0, A + K1 + K1 * lda, lda, to);
+        ADMM_CUDA(cudaEventRecord(h->ev_la[1], sB));
+        if (rem2 > n1) {
+          double* P2 = P + n1;   // rows K1+n1.. of the panel
+          gemm(h, 0, 1, rem2 - n1, rem2 - n1, wb, -1.0, P2, lda, P2, lda, 1.0, A + (K1 + n1) + (K1 + n1) * lda, lda, to);
+        }
       }
-      h->stream = sA;
       ADMM_CUDA(cudaStreamWaitEvent(sA, h->ev_la[1], 0));
     }
   }
@@ -741,27 +760,81 @@ static void stage_matrix(admm_b200_handle* h, int64_t m, int64_t n, const double
   h->n = n;
 }
 
+// (max L_ii / min L_ii)^2 <= cond_2(A): a free lower bound of the condition number of the factored matrix
+__global__ void diag_minmax_kernel(const double* __restrict__ L, int64_t ld, int64_t k, double* out2) {
+  __shared__ double smin[32], smax[32];
+  double lo = __longlong_as_double(0x7ff0000000000000LL), hi = 0.0;
+  for (int64_t i = threadIdx.x; i < k; i += blockDim.x) {
+    const double v = fabs(L[i + i * ld]);
+    lo = fmin(lo, v); hi = fmax(hi, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fmin(lo, smin[w]); hi = fmax(hi, smax[w]); }
+    out2[0] = lo; out2[1] = hi;
+  }
+}
+
+// The inverse-factor x-update (x = W'(W y), W = inv(L)) and the two substitutions the reference runs
+// (getProxOps.m:1200) agree to ~1e-15 relative up to cond(A) ~ 1e8 (tests/test_gpu_conditioning.py; both are
+// bounded by the error of the Cholesky factor itself).  Beyond the guard the factor is so ill-conditioned that
+// no two implementations agree to 1e-9 any more; the engine then runs the reference's own formulation.
+static double cond_guard() {
+  static const double g = getenv("ADMM_B200_COND_GUARD") ? atof(getenv("ADMM_B200_COND_GUARD")) : 1e9;
+  return g;
+}
+
 static void factor_current(admm_b200_handle* h, int64_t k, bool want_inverse) {
   // h->L holds the lower triangle of the SPD matrix
   h->W.ensure(h->ldf * k);
   potrf_blocked(h, k, h->L.p, h->ldf, h->W.p, h->ldf, want_inverse);
   if (want_inverse) {
     h->WT.ensure(h->ldf * k);
+    ADMM_CUDA(cudaMemsetAsync(h->WT.p, 0, (size_t)h->ldf * k * 8, h->stream));   // rows k..ldf-1 are read as padding
     transpose(h, h->W.p, k, k, h->ldf, h->WT.p, h->ldf);
   }
+  h->t2.ensure(2);
+  diag_minmax_kernel<<<1, 1024, 0, h->stream>>>(h->L.p, h->ldf, k, h->t2.p);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+  double mm[2] = {1.0, 1.0};
+  ADMM_CUDA(cudaMemcpyAsync(mm, h->t2.p, 16, cudaMemcpyDeviceToHost, h->stream));
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  h->diag_ratio = (mm[0] > 0.0) ? (mm[1] / mm[0]) * (mm[1] / mm[0]) : __builtin_inf();
+  h->xsolve_eff = (want_inverse && h->diag_ratio <= cond_guard()) ? ADMM_B200_XSOLVE_INVFACTOR : ADMM_B200_XSOLVE_SUBST;
   h->k = k;
   h->have_factor = true;
   h->have_inverse = want_inverse;
 }
 
-static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD, const double* s,
-                        double rho, int xsolve) {
-  ADMM_REQUIRE(m > 0 && n > 0 && D && s && ldD >= m, ADMM_B200_ERR_INVALID, "lasso: bad dimensions or null input");
+// the x-update realisation a solve uses: the caller's choice, except that INVFACTOR gives way to SUBST when the
+// conditioning guard fired at setup
+static int eff_xsolve(const admm_b200_handle* h, const admm_b200_options& o) {
+  return (o.xsolve == ADMM_B200_XSOLVE_INVFACTOR && h->xsolve_eff == ADMM_B200_XSOLVE_SUBST) ? ADMM_B200_XSOLVE_SUBST : o.xsolve;
+}
+
+// m = THIS rank's rows, m_total = rows of the whole problem.  m_total > m (row shards, one process per GPU):
+// every rank forms D_g'D_g and D_g's_g on its rows, ONE allreduce sums the n x n Gram (+ D's), and every rank
+// factors the same matrix -- the transpose reduction of unwrappedadmm.m:114-122 applied to lasso.m:160,168.
+static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t m_total, int64_t n, const double* D, int64_t ldD,
+                        const double* s, double rho, int xsolve) {
+  ADMM_REQUIRE(m > 0 && n > 0 && D && s && ldD >= m && m_total >= m, ADMM_B200_ERR_INVALID, "lasso: bad dimensions or null input");
   ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
+  const bool sharded = h->nranks > 1 && m_total > m;
+  ADMM_REQUIRE(m_total == m || h->nranks > 1, ADMM_B200_ERR_STATE, "lasso: row shards need a communicator (admm_b200_comm_init)");
+  ADMM_REQUIRE(!sharded || m_total >= n, ADMM_B200_ERR_UNSUPPORTED,
+               "lasso: only the tall problem (rows >= columns) is row-sharded; the fat one factors D*D', which couples all rows");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
   h->kind = ADMM_B200_LASSO;
-  h->tall = (m >= n);
+  h->lasso_sharded = sharded;
+  h->m_total = m_total;
+  h->tall = (m_total >= n);
   h->rho_setup = rho;
   h->xsolve = xsolve;
   h->nA = h->nB = h->mc = n;
@@ -771,6 +844,10 @@ static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double*
   const int64_t k = h->tall ? n : m;
   h->ldf = round_up(k, 16);
   h->L.ensure(h->ldf * k);
+  if (sharded) {   // the whole buffer is summed over ranks: no uninitialised words (NaN patterns) in the padding
+    ADMM_CUDA(cudaMemsetAsync(h->L.p, 0, (size_t)h->ldf * k * 8, h->stream));
+    ADMM_CUDA(cudaMemsetAsync(h->dts.p, 0, (size_t)round_up(n, 2) * 8, h->stream));
+  }
   GemmOpt o;
   o.lower_only = 1;
   constexpr int64_t kPanelRows = 16384;
@@ -791,7 +868,7 @@ static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double*
                                   cudaMemcpyHostToDevice, sX));
       ADMM_CUDA(cudaEventRecord(h->ev_la[p & 1], sX));
       ADMM_CUDA(cudaStreamWaitEvent(sC, h->ev_la[p & 1], 0));
-      o.diag_add = (p == npanels - 1) ? rho : 0.0;
+      o.diag_add = (p == npanels - 1 && !sharded) ? rho : 0.0;
       gemm(h, 1, 0, n, n, rows, 1.0, h->ownD.p + r0, ld, h->ownD.p + r0, ld, p ? 1.0 : 0.0, h->L.p, h->ldf, o);
       coldot(h, COLDOT_FULL, h->ownD.p + r0, ld, rows, n, h->s.p + r0, h->dts.p, 1.0, p ? h->dts.p : nullptr, 1.0);
     }
@@ -800,12 +877,21 @@ static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double*
   // Dts = D'*s  (lasso.m:160)
   coldot(h, COLDOT_FULL, h->dD, h->ldD, m, n, h->s.p, h->dts.p);
   if (h->tall) {  // chol(D'*D + rho*I)  (lasso.m:168)
-    o.diag_add = rho;
+    o.diag_add = sharded ? 0.0 : rho;
     gemm(h, 1, 0, n, n, m, 1.0, h->dD, h->ldD, h->dD, h->ldD, 0.0, h->L.p, h->ldf, o);
   } else {        // chol(1/rho*(D*D') + I)  (lasso.m:172)
     o.diag_add = 1.0;
     gemm(h, 0, 1, m, m, n, 1.0 / rho, h->dD, h->ldD, h->dD, h->ldD, 0.0, h->L.p, h->ldf, o);
   }
+  }
+  if (sharded) {
+    // W = sum_g D_g'D_g, Dts = sum_g D_g's_g (unwrappedadmm.m:114-122), then + rho*I once.  The strict upper
+    // tiles of L are never read, but the buffer travels whole: one NCCL ring/NVLS allreduce of ldf*n doubles.
+    allreduce_sum(h, h->L.p, h->ldf * n);
+    allreduce_sum(h, h->dts.p, round_up(n, 2));
+    add_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->L.p, h->ldf, n, rho);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
   }
   ADMM_CUDA(cudaEventRecord(h->evp[1], h->stream));
   factor_current(h, k, xsolve == ADMM_B200_XSOLVE_INVFACTOR);
@@ -823,6 +909,7 @@ static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double*
   h->phase_ms[2] = ms;
   h->have_init = false;
   h->iter_ready = false;
+  h->generation++;
 }
 
 // Basis pursuit (solvers/basispursuit.m:116-120): the reference caches the dense n x n projector
@@ -832,7 +919,7 @@ static void setup_bp(admm_b200_handle* h, int64_t m, int64_t n, const double* D,
   ADMM_REQUIRE(m > 0 && n > 0 && D && s && ldD >= m, ADMM_B200_ERR_INVALID, "basispursuit: bad dimensions or null input");
   ADMM_REQUIRE(m < n, ADMM_B200_ERR_INVALID, "basispursuit: D must have fewer rows than columns");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
   stage_matrix(h, m, n, D, ldD);
   h->s.ensure(round_up(m, 2));
   copy_in(h, h->s.p, s, m);
@@ -859,6 +946,7 @@ static void setup_bp(admm_b200_handle* h, int64_t m, int64_t n, const double* D,
   h->phase_ms[2] = ms;
   h->have_init = false;
   h->iter_ready = false;
+  h->generation++;
 }
 
 // Quadratic objective 1/2 x'Px + q'x + r with a projection as z-prox (quadraticprogram.m 'bounded'
@@ -873,7 +961,7 @@ static void setup_quadratic(admm_b200_handle* h, int kind, int64_t n, const doub
   ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
   ADMM_REQUIRE(kind != ADMM_B200_PROX_BOX || (lb && ub), ADMM_B200_ERR_INVALID, "setup_quadratic: box bounds missing");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
   h->kind = kind;
   h->tall = true;
   h->m = h->n = n;
@@ -911,6 +999,7 @@ static void setup_quadratic(admm_b200_handle* h, int kind, int64_t n, const doub
   h->setup_ms = h->phase_ms[3] = ms;
   h->have_init = false;
   h->iter_ready = false;
+  h->generation++;
 }
 
 // Model problem (solvers/model.m:119-146, getProxOps.m:55-110, 952-1012):
@@ -939,7 +1028,7 @@ static void setup_model(admm_b200_handle* h, int64_t m, int64_t n, const double*
                "model: bad dimensions or null input");
   ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
   h->kind = ADMM_B200_MODEL;
   h->tall = true;
   h->xsolve = ADMM_B200_XSOLVE_INVFACTOR;
@@ -972,6 +1061,7 @@ static void setup_model(admm_b200_handle* h, int64_t m, int64_t n, const double*
   h->phase_ms[0] = ms;
   h->have_init = false;
   h->iter_ready = false;
+  h->generation++;
 }
 
 // Total variation (solvers/totalvariation.m:122-164): only s and lambda are data; the operator D
@@ -979,7 +1069,7 @@ static void setup_model(admm_b200_handle* h, int64_t m, int64_t n, const double*
 static void setup_tv(admm_b200_handle* h, int64_t n, const double* s, double lambda) {
   ADMM_REQUIRE(n > 0 && s, ADMM_B200_ERR_INVALID, "totalvariation: bad dimensions or null input");
   ADMM_REQUIRE(lambda >= 0, ADMM_B200_ERR_INVALID, "Given lambda parameter is not a nonnegative number!");
-  h->have_factor = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
   h->kind = ADMM_B200_TOTALVARIATION;
   h->m = h->n = n;
   h->nA = h->nB = h->mc = n;
@@ -991,6 +1081,7 @@ static void setup_tv(admm_b200_handle* h, int64_t n, const double* s, double lam
   h->tv_rho = -1.0;
   h->have_init = false;
   h->iter_ready = false;
+  h->generation++;
 }
 
 static void tv_prepare(admm_b200_handle* h, double rho) {
@@ -1033,6 +1124,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclId*) = nullptr;
   int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -1049,9 +1141,10 @@ static void nccl_load() {
   g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(g_nccl.lib, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
-  ADMM_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy, ADMM_B200_ERR_COMM,
+  ADMM_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.AllGather && g_nccl.CommDestroy, ADMM_B200_ERR_COMM,
                "libnccl is missing a required symbol");
 }
 #define ADMM_NCCL(call)                                                                          \
@@ -1061,17 +1154,117 @@ static void nccl_load() {
                  g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?");                       \
   } while (0)
 
+// ---- peer-memory mailboxes (p2p.cuh) ---------------------------------------------------------------
+static void p2p_teardown(admm_b200_handle* h) {
+  P2PState& P = h->p2p;
+  for (int r = 0; r < P2P_MAXRANKS; ++r)
+    if (P.opened[r]) { cudaIpcCloseMemHandle(P.opened[r]); P.opened[r] = nullptr; }
+  if (P.local) cudaFree(P.local);
+  if (P.dev.seq) cudaFree(P.dev.seq);
+  P = P2PState();
+}
+
+// Called by every rank right after the NCCL communicator exists.  Allocates and zeroes this rank's mailbox,
+// exchanges the CUDA IPC handles through ncclAllGather and maps every peer's mailbox.  When the peers cannot
+// be mapped (no peer access between the devices, IPC disabled in the container, ADMM_B200_NO_P2P=1) the small
+// allreduces stay on NCCL; admm_b200_comm_info reports which transport is in use.
+static void p2p_setup(admm_b200_handle* h) {
+  P2PState& P = h->p2p;
+  const int R = h->nranks;
+  if (R < 2 || R > P2P_MAXRANKS) return;
+  const bool want = !getenv("ADMM_B200_NO_P2P");
+  P.bytes = (size_t)P2P_FLAG_BYTES + (size_t)2 * R * P2P_CAP * 8;
+  ADMM_CUDA(cudaMalloc(&P.local, P.bytes));
+  ADMM_CUDA(cudaMemsetAsync(P.local, 0, P.bytes, h->stream));
+  void* ctr = nullptr;                       // seq (8) | ticket (4) | ticket2 (4) | err (4)
+  ADMM_CUDA(cudaMalloc(&ctr, 64));
+  ADMM_CUDA(cudaMemsetAsync(ctr, 0, 64, h->stream));
+  P.dev.seq = (unsigned long long*)ctr;
+  P.dev.ticket = (unsigned*)((char*)ctr + 8);
+  P.dev.err = (int*)((char*)ctr + 16);
+  P.dev.rank = h->rank; P.dev.nranks = R; P.dev.cap = P2P_CAP;
+  // handle exchange: [R][64 bytes + 1 flag byte]
+  struct Slot { cudaIpcMemHandle_t hd; int ok; int pad[3]; };
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  Slot mine{};
+  mine.ok = 0;
+  if (want && cudaIpcGetMemHandle(&mine.hd, P.local) == cudaSuccess) mine.ok = 1;
+  else cudaGetLastError();
+  Slot* dall = nullptr;
+  ADMM_CUDA(cudaMalloc(&dall, sizeof(Slot) * (R + 1)));
+  std::vector<Slot> all(R);
+  try {
+    ADMM_CUDA(cudaMemcpyAsync(dall + R, &mine, sizeof(Slot), cudaMemcpyHostToDevice, h->stream));
+    ADMM_NCCL(g_nccl.AllGather(dall + R, dall, sizeof(Slot), /*ncclInt8*/ 0, h->comm, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(all.data(), dall, sizeof(Slot) * R, cudaMemcpyDeviceToHost, h->stream));
+    ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  } catch (...) {
+    cudaFree(dall);
+    throw;
+  }
+  int ok = 1;
+  for (int r = 0; r < R; ++r) ok &= all[r].ok;
+  for (int r = 0; r < R && ok; ++r) {
+    if (r == h->rank) { P.dev.mail[r] = (unsigned char*)P.local; continue; }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[r].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      break;
+    }
+    P.opened[r] = ptr;
+    P.dev.mail[r] = (unsigned char*)ptr;
+  }
+  // every rank must agree on the transport: min over ranks of `ok` (1 double through NCCL)
+  double* dok = (double*)dall;
+  double hok = ok;
+  try {
+    ADMM_CUDA(cudaMemcpyAsync(dok, &hok, 8, cudaMemcpyHostToDevice, h->stream));
+    ADMM_NCCL(g_nccl.AllReduce(dok, dok, 1, /*ncclDouble*/ 8, /*ncclMin*/ 3, h->comm, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(&hok, dok, 8, cudaMemcpyDeviceToHost, h->stream));
+    ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  } catch (...) {
+    cudaFree(dall);
+    throw;
+  }
+  cudaFree(dall);
+  P.ready = hok > 0.5;
+  if (!P.ready && want && h->rank == 0)
+    fprintf(stderr, "libadmm_b200: peer mailboxes could not be mapped (CUDA IPC); small allreduces stay on NCCL\n");
+}
+
 static void comm_destroy(admm_b200_handle* h) {
+  p2p_teardown(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   h->comm = nullptr;
   h->rank = 0;
   h->nranks = 1;
 }
 
-// in-place sum over ranks of `count` doubles on the handle's stream (no-op for a single rank)
-static void allreduce_sum(admm_b200_handle* h, double* buf, int64_t count) {
+// in-place sum over ranks of `count` doubles on the handle's stream (no-op for a single rank).  Small
+// messages go through the peer mailboxes (two tiny kernels, graph-capturable, bitwise identical result on
+// every rank); large ones (the n x n Gram) through ncclAllReduce.
+static void allreduce_sum(admm_b200_handle* h, double* buf, int64_t count, const int* done) {
   if (h->nranks <= 1) return;
+  if (h->p2p.ready && count <= P2P_CAP) {
+    const int grid = (int)std::max<int64_t>(1, (count + 255) / 256);
+    p2p_push_kernel<<<std::min(grid, 32), 256, 0, h->stream>>>(h->p2p.dev, buf, count, done);
+    ADMM_CUDA(cudaGetLastError());
+    p2p_wait_sum_kernel<<<grid, 256, 0, h->stream>>>(h->p2p.dev, buf, count, done, h->p2p.dev.ticket + 1);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches += 2;
+    return;
+  }
   ADMM_NCCL(g_nccl.AllReduce(buf, buf, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->comm, h->stream));
+}
+
+// after a loop: a mailbox wait that timed out means a peer died or fell out of step
+static void p2p_check(admm_b200_handle* h) {
+  if (!h->p2p.ready) return;
+  int err = 0;
+  ADMM_CUDA(cudaMemcpyAsync(&err, h->p2p.dev.err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  ADMM_REQUIRE(err == 0, ADMM_B200_ERR_COMM, "peer-memory allreduce timed out: a rank stopped taking part in the exchange");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1087,7 +1280,7 @@ static void setup_unwrapped(admm_b200_handle* h, int kind, int64_t m_local, int6
   if (kind == ADMM_B200_SVM_HINGE || kind == ADMM_B200_SVM_01)
     ADMM_REQUIRE(C >= 0, ADMM_B200_ERR_INVALID, "Given regularization parameter C is not a nonnegative number!");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
   stage_matrix(h, m_local, n, D, ldD);
   h->aux.ensure(round_up(m_local, 2));
   copy_in(h, h->aux.p, aux, m_local);
@@ -1103,8 +1296,34 @@ static void setup_unwrapped(admm_b200_handle* h, int kind, int64_t m_local, int6
   o.lower_only = 1;
   gemm(h, 1, 0, n, n, m_local, 1.0, h->dD, h->ldD, h->dD, h->ldD, 0.0, h->L.p, h->ldf, o);
   allreduce_sum(h, h->L.p, h->ldf * n);
+  // An all-zero column j of D (constant-zero pixels of MNIST, examples/mnistsvm.m) makes W = D'D singular: row and
+  // column j of W vanish.  The reference's serial x-update is pinv(D)*(z-u) (unwrappedadmm.m:76-78,
+  // linearsvm.m:185), whose minimum-norm solution has x_j = 0 exactly; putting W_jj = 1 gives the same x
+  // (d_j = D(:,j)'(z-u) = 0), so the cached Cholesky reproduces pinv for this rank deficiency.
+  {
+    int* cnt = h->fail;
+    ADMM_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), h->stream));
+    fix_zero_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->L.p, h->ldf, n, cnt);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+    int zc = 0;
+    ADMM_CUDA(cudaMemcpyAsync(&zc, cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    ADMM_CUDA(cudaStreamSynchronize(h->stream));
+    h->zero_cols = zc;
+  }
   ADMM_CUDA(cudaEventRecord(h->evp[1], h->stream));
-  factor_current(h, n, true);
+  try {
+    factor_current(h, n, true);
+  } catch (const ArgFail& f) {
+    if (f.code != ADMM_B200_ERR_NOTPOSDEF) throw;
+    // any other rank deficiency (collinear columns, fewer rows than columns): the reference's parfor path warns
+    // "Matrix is singular to working precision" at W\d (unwrappedadmm.m:139) and its serial path takes pinv(D)
+    std::string first = g_err;
+    set_error("D'*D is singular beyond all-zero columns (%s): the x-update of unwrappedadmm.m needs pinv(D) "
+              "(unwrappedadmm.m:76) for such a D; the engine reproduces pinv for all-zero columns only",
+              first.c_str());
+    throw;
+  }
   ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
   ADMM_CUDA(cudaEventSynchronize(h->ev1));
   float ms = 0;
@@ -1118,6 +1337,7 @@ static void setup_unwrapped(admm_b200_handle* h, int kind, int64_t m_local, int6
   h->phase_ms[2] = ms;
   h->have_init = false;
   h->iter_ready = false;
+  h->generation++;
 }
 
 static bool is_unwrapped(int kind) {
@@ -1363,7 +1583,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     if (which != 2) {
       // x = P(z-u) + q (getProxOps.m:1031) as v - D'((DD') \ (D v - s)), v = z - u in h->y
       gemvn(h, h->dD, h->ldD, m, n, h->y.p, h->t1.p, 1.0, -1.0, h->s.p, done);
-      factor_solve(h, h->t1.p, h->t2.p, h->t1.p, o.xsolve, done);
+      factor_solve(h, h->t1.p, h->t2.p, h->t1.p, eff_xsolve(h, o), done);
       coldot(h, COLDOT_FULL, h->dD, h->ldD, m, n, h->t1.p, h->x.p, -1.0, h->y.p, 1.0, done);
     }
     if (which == 1) return;
@@ -1397,11 +1617,11 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     if (which != 2) {
       if (h->tall) {
         // x = U \ (L \ y)   (getProxOps.m:1200)
-        factor_solve(h, h->y.p, h->t1.p, h->x.p, o.xsolve, done);
+        factor_solve(h, h->y.p, h->t1.p, h->x.p, eff_xsolve(h, o), done);
       } else {
         // x = y/rho - D'*(U \ (L \ (D*y)))/rho^2   (getProxOps.m:1204)
         gemvn(h, h->dD, h->ldD, m, n, h->y.p, h->t1.p, 1.0, 0.0, nullptr, done);
-        factor_solve(h, h->t1.p, h->t2.p, h->t1.p, o.xsolve, done);
+        factor_solve(h, h->t1.p, h->t2.p, h->t1.p, eff_xsolve(h, o), done);
         coldot(h, COLDOT_FULL, h->dD, h->ldD, m, n, h->t1.p, h->x.p, -1.0 / (o.rho * o.rho), h->y.p, 1.0 / o.rho, done);
       }
     }
@@ -1413,6 +1633,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
       else half_sqdist_kernel<<<1, 1024, 0, h->stream>>>(h->t2.p, h->s.p, m, h->ctl);
       ADMM_CUDA(cudaGetLastError());
       h->launches++;
+      if (h->lasso_sharded) allreduce_sum(h, &h->ctl->objpart, 1, done);   // 1/2*||D x - s||^2 over all row shards
     }
     ProxIdentArgs a;
     a.n = n; a.x = h->x.p; a.z = h->z.p; a.u = h->u.p; a.dts = h->dts.p; a.y = h->y.p;
@@ -1443,7 +1664,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
   } else if (h->kind == ADMM_B200_MODEL) {
     const int64_t n = h->n, m = h->m;
     const bool fastmode = lp.alg != 0;
-    if (which != 2) factor_solve(h, h->y.p, h->t1.p, h->x.p, o.xsolve, done);       // xminModel, getProxOps.m:973
+    if (which != 2) factor_solve(h, h->y.p, h->t1.p, h->x.p, ADMM_B200_XSOLVE_INVFACTOR, done);       // xminModel, getProxOps.m:973
     if (which == 1) return;
     // zminModel (getProxOps.m:1011): z = (QtQ + rho I) \ (Qts + rho*(x + u)); x is Axhat when relaxed
     // (admm.m:521), u is uhat for the fast variants (admm.m:508)
@@ -1451,7 +1672,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
                                                                          h->dts2.p, o.rho, o.relax, h->t2.p, h->ctl);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
-    factor_solve(h, h->t2.p, h->t1.p, h->zsol.p, o.xsolve, done, true);
+    factor_solve(h, h->t2.p, h->t1.p, h->zsol.p, ADMM_B200_XSOLVE_INVFACTOR, done, true);
     if (o.objevals && which == 0) {
       // obj = 1/2*norm(P*x - r)^2 + 1/2*norm(Q*z - s)^2   (model.m:139-140)
       gemvn(h, h->dD, h->ldD, m, n, h->x.p, h->t2.p, 1.0, 0.0, nullptr, done);
@@ -1491,7 +1712,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     double* scal = h->cb.p + (int64_t)nv * npad;
     if (which != 2) {
       // x = W \ d (unwrappedadmm.m:139) / Rt \ (R \ d) (getProxOps.m:1514), d summed over ranks
-      factor_solve(h, d, h->t1.p, h->x.p, o.xsolve, done);
+      factor_solve(h, d, h->t1.p, h->x.p, eff_xsolve(h, o), done);
     }
     if (which == 1) return;
     UwArgs a;
@@ -1547,7 +1768,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
                                                                                         h->uw_partials.p, scal, h->ctl);
       ADMM_CUDA(cudaGetLastError());
       h->launches += 2;
-      allreduce_sum(h, d, (int64_t)nv * npad + UW_NRED);
+      allreduce_sum(h, d, (int64_t)nv * npad + UW_NRED, done);
       UwEpiArgs e;
       e.n = n; e.x = h->x.p; e.dzv = (nv == 3) ? d + npad : nullptr; e.duv = (nv == 3) ? d + 2 * npad : nullptr;
       e.scalars = scal; e.m_total = (double)h->m_total; e.kind = a.kind; e.C = h->svmC; e.ctl = h->ctl; e.lp = lp;
@@ -1566,7 +1787,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     if (lp.alg != 0) {
       // fast variants: the restart decision needs the rank-summed ||u-uhat||^2, ||z-v||^2 BEFORE the
       // acceleration pass, so the scalars travel in their own (tiny) allreduce
-      allreduce_sum(h, scal, UW_NRED);
+      allreduce_sum(h, scal, UW_NRED, done);
       uw_accel_decide_kernel<<<1, 1, 0, h->stream>>>(h->ctl, lp, scal);
       ADMM_CUDA(cudaGetLastError());
       uw_accel_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, h->z.p, h->u.p, h->fzprev.p, h->fuprev.p,
@@ -1579,7 +1800,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     const double* vs[3] = {h->rvec.p, h->dzvec.p, h->u.p};
     double* os[3] = {d, d + npad, d + 2 * npad};
     coldot_multi(h, COLDOT_FULL, h->dD, h->ldD, m, n, nv, vs, os, 1.0, nullptr, 0.0, done);
-    allreduce_sum(h, d, (int64_t)nv * npad + (lp.alg == 0 ? UW_NRED : 0));
+    allreduce_sum(h, d, (int64_t)nv * npad + (lp.alg == 0 ? UW_NRED : 0), done);
     UwEpiArgs e;
     e.n = n; e.x = h->x.p; e.dzv = (nv == 3) ? d + npad : nullptr; e.duv = (nv == 3) ? d + 2 * npad : nullptr;
     e.scalars = scal; e.m_total = (double)h->m_total; e.kind = a.kind; e.C = h->svmC; e.ctl = h->ctl; e.lp = lp;
@@ -1671,7 +1892,7 @@ static void run_bursts(admm_b200_handle* h, const admm_b200_options& o, int64_t 
   // Row-sharded handles stay eager: with the per-iteration ncclAllReduce inside the graph the 2-GPU SVM loop
   // measured SLOWER (133 vs 115 us per iteration, profiles/r01_notes.md); ADMM_B200_GRAPH_NCCL=1 overrides.
   const bool graph_ok = o.graph && check % period == 0 && !getenv("ADMM_B200_DEBUG") && !getenv("ADMM_B200_NO_GRAPH") &&
-                        (h->nranks == 1 || getenv("ADMM_B200_GRAPH_NCCL"));
+                        (h->nranks == 1 || h->p2p.ready || getenv("ADMM_B200_GRAPH_NCCL"));
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   int64_t graph_launches = 0;
@@ -1736,6 +1957,7 @@ static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_res
       });
   ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
   ADMM_CUDA(cudaEventSynchronize(h->ev1));
+  p2p_check(h);
   float ms = 0;
   ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   if (h->kind == ADMM_B200_TOTALVARIATION) {   // the last iteration that ran wrote half (steps mod 2)
@@ -2068,6 +2290,7 @@ static void solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options& 
         });
     ADMM_CUDA(cudaEventRecord(h->ev1, st));
     ADMM_CUDA(cudaEventSynchronize(h->ev1));
+    p2p_check(h);
     float ms = 0;
     ADMM_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     if (out.loop_ms) *out.loop_ms = ms;
@@ -2213,7 +2436,15 @@ int admm_b200_setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const doubl
                           double rho, int32_t xsolve) {
   ADMM_API_BEGIN
   check_handle(h);
-  setup_lasso(h, m, n, D, ldD, s, rho, xsolve);
+  setup_lasso(h, m, m, n, D, ldD, s, rho, xsolve);
+  ADMM_API_END
+}
+
+int admm_b200_setup_lasso_sharded(admm_b200_handle* h, int64_t m_local, int64_t m_total, int64_t n, const double* D,
+                                  int64_t ldD, const double* s, double rho, int32_t xsolve) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  setup_lasso(h, m_local, m_total, n, D, ldD, s, rho, xsolve);
   ADMM_API_END
 }
 
@@ -2280,6 +2511,7 @@ int admm_b200_comm_init(admm_b200_handle* h, int rank, int nranks, const void* u
   h->comm = comm;
   h->rank = rank;
   h->nranks = nranks;
+  p2p_setup(h);     // also performs the first collectives, so NCCL's lazy channel setup is not inside a timed setup
   ADMM_API_END
 }
 
@@ -2520,6 +2752,20 @@ int admm_b200_get_setup_phases(admm_b200_handle* h, double* out4) {
   check_handle(h);
   ADMM_REQUIRE(out4 != nullptr, ADMM_B200_ERR_INVALID, "null output");
   for (int i = 0; i < 4; ++i) out4[i] = h->phase_ms[i];
+  ADMM_API_END
+}
+
+int admm_b200_get_info(admm_b200_handle* h, admm_b200_info* out) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(out != nullptr, ADMM_B200_ERR_INVALID, "null output");
+  out->generation = h->generation;
+  out->zero_cols = h->zero_cols;
+  out->diag_ratio = h->diag_ratio;
+  out->xsolve_effective = h->xsolve_eff;
+  out->p2p_ready = h->p2p.ready ? 1 : 0;
+  out->nranks = h->nranks;
+  out->rank = h->rank;
   ADMM_API_END
 }
 

@@ -1,0 +1,148 @@
+// p2p.cuh -- one-shot allreduce of a SMALL message over NVLink peer memory (one process per GPU).
+//
+// The row-sharded solvers exchange ONE message per iteration: [D_g'r ; D_g'dz ; D_g'u ; scalars], 6-100 KB
+// (unwrappedadmm.m:127-139 sums the same vectors over parfor slices on the client).  At that size a
+// collective is pure latency, and a library allreduce between two small kernels costs more than the
+// kernels (profiles/r01_scaling_unwrapped.txt: 8-GPU SVM at 19 % efficiency).  Here every rank owns a
+// MAILBOX in its HBM, mapped into every peer with CUDA IPC:
+//
+//     mailbox = flags[2][R] (uint64)  +  slots[2][R][cap] (double)          R = ranks, 2 = parity
+//
+// Exchange number s (a device-resident counter, identical on every rank):
+//   push : rank r stores its `count` doubles into slot[s&1][r] of EVERY rank's mailbox (remote stores over
+//          NVLink; the own copy is a local store), fences at system scope, and the last CTA to finish
+//          sets flag[s&1][r] = s+1 in every mailbox (st.release.sys);
+//   wait : each rank spins on its OWN mailbox until all R flags read s+1 (ld.acquire.sys, local HBM/L2),
+//          then sums the R slots in RANK ORDER -- every rank adds the same numbers in the same order, so
+//          the result is bitwise identical everywhere and the replicated stop decision stays replicated.
+// Parity double-buffering is enough: a rank can only start exchange s+2 after every rank has finished
+// reading exchange s (stream order on each rank + the flags of exchange s+1).
+// No host involvement, fixed kernel arguments: the exchange can sit inside a CUDA graph.
+// A spin that sees no progress for ~2 s sets *err and gives up (a dead peer must not hang the GPU).
+#pragma once
+#include "common.cuh"
+
+namespace admmb200 {
+
+constexpr int P2P_MAXRANKS = 8;
+constexpr int64_t P2P_CAP = 16384;          // doubles per slot (128 KB): n-vector of C2, 16-class batch of C3
+constexpr int P2P_FLAG_BYTES = 256;         // flags[2][8] uint64 = 128 B, padded
+
+struct P2PDev {
+  int rank, nranks;
+  int64_t cap;
+  unsigned char* mail[P2P_MAXRANKS];        // base of every rank's mailbox as mapped in THIS process
+  unsigned long long* seq;                  // exchanges completed (device memory of this rank)
+  unsigned* ticket;                         // last-CTA election of the push
+  int* err;                                 // set when a wait timed out
+  __device__ __forceinline__ unsigned long long* flags(int r, int par) const {
+    return reinterpret_cast<unsigned long long*>(mail[r]) + par * P2P_MAXRANKS;
+  }
+  __device__ __forceinline__ double* slot(int r, int par, int src) const {
+    return reinterpret_cast<double*>(mail[r] + P2P_FLAG_BYTES) + ((int64_t)par * nranks + src) * cap;
+  }
+};
+
+struct P2PState {
+  bool ready = false;
+  P2PDev dev{};
+  void* local = nullptr;                    // this rank's mailbox (cudaMalloc)
+  void* opened[P2P_MAXRANKS] = {};          // cudaIpcOpenMemHandle results (nullptr for the own rank)
+  size_t bytes = 0;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// store one value of this rank's contribution into every mailbox
+__device__ __forceinline__ void p2p_store(const P2PDev& p, int par, int64_t idx, double v) {
+#pragma unroll
+  for (int r = 0; r < P2P_MAXRANKS; ++r)
+    if (r < p.nranks) p.slot(r, par, p.rank)[idx] = v;
+}
+
+// Called by ALL threads of the CTA after their p2p_store calls; `nctas` CTAs take part.  The last CTA to
+// arrive publishes the flags.  (Every CTA's stores are fenced at system scope before its ticket.)
+__device__ __forceinline__ void p2p_signal(const P2PDev& p, int par, unsigned long long s, unsigned nctas) {
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool p2p_last;
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(p.ticket, 1u);
+    p2p_last = (t == nctas - 1);
+    if (p2p_last) *p.ticket = 0;
+  }
+  __syncthreads();
+  if (!p2p_last) return;
+  __threadfence_system();
+  if (threadIdx.x < p.nranks) st_release_sys(p.flags(threadIdx.x, par) + p.rank, s + 1);
+}
+
+// Spin (whole CTA; thread r watches rank r) until every rank's flag of this exchange is up.  Returns false
+// on a timeout (and sets *err).
+__device__ __forceinline__ bool p2p_wait(const P2PDev& p, int par, unsigned long long s) {
+  __shared__ int p2p_bad;
+  if (threadIdx.x == 0) p2p_bad = 0;
+  __syncthreads();
+  if (threadIdx.x < p.nranks) {
+    const unsigned long long* f = p.flags(p.rank, par) + threadIdx.x;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) < s + 1) {
+      if (clock64() - t0 > 4000000000LL) {   // ~2 s at 1.9 GHz
+        p2p_bad = 1;
+        *p.err = 1;
+        break;
+      }
+      __nanosleep(20);
+    }
+  }
+  __syncthreads();
+  return p2p_bad == 0;
+}
+
+// ---- generic two-kernel form: buf (count doubles, this rank's device memory) <- sum over ranks ----------
+__global__ void __launch_bounds__(256) p2p_push_kernel(P2PDev p, const double* __restrict__ buf, int64_t count, const int* done) {
+  if ((done && *done) || *p.err) return;
+  const unsigned long long s = *p.seq;
+  const int par = (int)(s & 1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    p2p_store(p, par, i, buf[i]);
+  p2p_signal(p, par, s, gridDim.x);
+}
+
+// one CTA per 256 outputs; CTA 0 bumps the counter after a grid-wide ticket
+__global__ void __launch_bounds__(256) p2p_wait_sum_kernel(P2PDev p, double* __restrict__ buf, int64_t count, const int* done,
+                                                           unsigned* ticket2) {
+  if ((done && *done) || *p.err) return;
+  const unsigned long long s = *p.seq;
+  const int par = (int)(s & 1);
+  const bool ok = p2p_wait(p, par, s);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ok && i < count) {
+    double acc = 0.0;
+    for (int r = 0; r < p.nranks; ++r) acc += ld_relaxed_sys(p.slot(p.rank, par, r) + i);   // rank order: same sum everywhere
+    buf[i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(ticket2, 1u);
+    if (t == gridDim.x - 1) {       // every CTA has read *p.seq and its slots
+      *ticket2 = 0;
+      *p.seq = s + 1;
+    }
+  }
+}
+
+}  // namespace admmb200

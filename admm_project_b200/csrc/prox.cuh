@@ -392,6 +392,15 @@ __global__ void add_diag_kernel(double* A, int64_t lda, int64_t n, double shift)
   if (i < n) A[i + i * lda] += shift;
 }
 
+// W_jj = 1 where the Gram matrix has an exactly zero diagonal entry (an all-zero column of D); counts them
+__global__ void fix_zero_diag_kernel(double* A, int64_t lda, int64_t n, int* count) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && A[i + i * lda] == 0.0) {
+    A[i + i * lda] = 1.0;
+    atomicAdd(count, 1);
+  }
+}
+
 __global__ void add_diag_negate_kernel(double* A, int64_t lda, int64_t n, double shift, double* v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {

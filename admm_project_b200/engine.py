@@ -75,8 +75,29 @@ class Engine:
         p, m, n, ld, keep = self._matrix(D)
         sv = s if isinstance(s, (int, np.integer)) else L.fvec(s, m, "s")
         self._keep = [keep, sv]
+        self.m_total = self.row_range = None
         L.check(self._lib.admm_b200_setup_lasso(self._h, m, n, C.c_void_p(p), ld, L.ptr(sv), float(rho), int(xsolve)))
         return m, n
+
+    def setup_lasso_sharded(self, D_local, s_local, rho, m_total, xsolve=L.XSOLVE_INVFACTOR):
+        """admm_b200_setup_lasso_sharded: D_local / s_local are THIS rank's rows of the tall problem."""
+        p, m, n, ld, keep = self._matrix(D_local)
+        sv = s_local if isinstance(s_local, (int, np.integer)) else L.fvec(s_local, m, "s")
+        self._keep = [keep, sv]
+        self.m_total, self.row_range = int(m_total), None
+        L.check(self._lib.admm_b200_setup_lasso_sharded(self._h, m, int(m_total), n, C.c_void_p(p), ld, L.ptr(sv),
+                                                        float(rho), int(xsolve)))
+        return m, n
+
+    def info(self):
+        """admm_b200_get_info as a dict (generation, zero_cols, diag_ratio, xsolve_effective, p2p_ready, ...)."""
+        out = L.Info()
+        L.check(self._lib.admm_b200_get_info(self._h, C.byref(out)))
+        return {k: getattr(out, k) for k, _ in L.Info._fields_}
+
+    @property
+    def generation(self):
+        return self.info()["generation"]
 
     def setup_unwrapped(self, kind, D_local, aux_local, Cval=0.0, m_total=None):
         """admm_b200_setup_unwrapped: D_local / aux_local are THIS rank's rows."""
@@ -84,6 +105,7 @@ class Engine:
         av = aux_local if isinstance(aux_local, (int, np.integer)) else L.fvec(aux_local, m, "ell / s")
         self._keep = [keep, av]
         self.m_total = int(m_total) if m_total is not None else m
+        self.row_range = None            # set by the caller that knows which rows these are
         L.check(self._lib.admm_b200_setup_unwrapped(self._h, int(kind), m, self.m_total, n, C.c_void_p(p), ld,
                                                     L.ptr(av), float(Cval)))
         return m, n
@@ -92,12 +114,14 @@ class Engine:
         p, m, n, ld, keep = self._matrix(D)
         sv = s if isinstance(s, (int, np.integer)) else L.fvec(s, m, "s")
         self._keep = [keep, sv]
+        self.m_total = self.row_range = None
         L.check(self._lib.admm_b200_setup_basispursuit(self._h, m, n, C.c_void_p(p), ld, L.ptr(sv)))
         return m, n
 
     def setup_totalvariation(self, s, lam):
         sv = L.fvec(s)
         self._keep = [sv]
+        self.m_total = self.row_range = None
         L.check(self._lib.admm_b200_setup_totalvariation(self._h, sv.size, L.ptr(sv), float(lam)))
         return sv.size
 
@@ -108,6 +132,7 @@ class Engine:
         lb = None if lb is None else L.fvec(lb, n, "lb")
         ub = None if ub is None else L.fvec(ub, n, "ub")
         self._keep = [P, q, lb, ub]
+        self.m_total = self.row_range = None
         L.check(self._lib.admm_b200_setup_quadratic(self._h, int(kind), n, L.ptr(P), n, L.ptr(q), float(r), float(rho),
                                                     L.ptr(lb), L.ptr(ub)))
         return n
@@ -118,6 +143,7 @@ class Engine:
         qp, mq, nq, ldq, keepQ = self._matrix(Q)
         rv, sv = L.fvec(r, m, "r"), L.fvec(s, m, "s")
         self._keep = [keepP, keepQ, rv, sv]
+        self.m_total = self.row_range = None
         L.check(self._lib.admm_b200_setup_model(self._h, m, n, C.c_void_p(pp), ldp, C.c_void_p(qp), ldq, L.ptr(rv),
                                                 L.ptr(sv), float(rho)))
         return m, n
@@ -275,6 +301,18 @@ class Engine:
         x = np.zeros_like(b)
         L.check(self._lib.admm_b200_factor_solve(self._h, L.ptr(b), L.ptr(x), int(xsolve)))
         return x
+
+
+def acquire_engine(engine, options):
+    """The engine a solver call runs on: the caller's (argument or options['engine']) or a fresh one on
+    options['device'].  A fresh one is marked `_owned`; admm() closes it when the loop has returned, so a
+    solver call without an explicit engine does not hold GPU buffers until garbage collection."""
+    eng = engine or options.get("engine")
+    if eng is not None:
+        return eng
+    eng = Engine(int(options.get("device", 0)))
+    eng._owned = True
+    return eng
 
 
 def slicemaker(length, workers):

@@ -19,6 +19,9 @@ class EngineProx:
 
     def __init__(self, role, problem, name, engine, params):
         self.role, self.problem, self.name, self.engine, self.params = role, problem, name, engine, params
+        # An Engine holds ONE problem: the pair is valid only for the setup it was made for.  admm() compares this
+        # stamp with the engine's current one and refuses a stale pair (a later setup on the same engine).
+        self.generation = engine.generation if engine is not None and hasattr(engine, "generation") else None
 
     def __call__(self, *a, **k):
         raise EngineError(ERR_UNSUPPORTED, "%s is a device-resident proximal operator; it is evaluated inside "
@@ -123,4 +126,5 @@ def getproxops(problem, args):
         raise EngineError(ERR_UNSUPPORTED, "problem '%s' is outside the engine's hot path (SURVEY.md section 2)" % problem)
     else:
         raise MatlabError("Invalid input for problem - given string is not a solver!")
+    minx.generation = minz.generation = getattr(eng, "generation", None)      # stamp AFTER the setup this call ran
     return minx, minz, extra

@@ -57,3 +57,15 @@ def gather_rows(local, m_total):
     out = np.concatenate(parts, axis=0)
     assert out.shape[0] == m_total, (out.shape, m_total)
     return out
+
+
+def shared_draw(draw):
+    """Run `draw()` (a function that consumes the NumPy global RNG) on rank 0 and hand its result to every rank:
+    a random init drawn per rank would make the global z0 / u0 a patchwork of unrelated streams."""
+    rank, world = dist_info()
+    if world == 1:
+        return draw()
+    import torch.distributed as dist
+    payload = [draw() if rank == 0 else None]
+    dist.broadcast_object_list(payload, src=0)
+    return payload[0]

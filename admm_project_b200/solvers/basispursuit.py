@@ -6,7 +6,7 @@ import time
 import numpy as np
 
 from ..admm import admm
-from ..engine import DeviceMatrix, Engine
+from ..engine import DeviceMatrix, Engine, acquire_engine
 from ..errorcheck import MatlabError
 from ..getproxops import getproxops
 
@@ -33,7 +33,7 @@ def basispursuit(D, s, options, engine=None):
         raise MatlabError("Given options is not a struct! At least pass empty struct!")
     options = dict(options)
     n = nD
-    eng = engine or options.get("engine") or Engine(int(options.get("device", 0)))
+    eng = acquire_engine(engine, options)
     # basispursuit.m:116-120 builds P = I - D'((DD')\D), q = D'((DD')\s); the engine factors D*D' instead
     minx, minz, _ = getproxops("BasisPursuit", {"engine": eng, "D": D, "s": s})    # :127
     options.update(A=1, B=-1, c=0, m=n, nA=n, nB=n, solver="basispursuit")  # :130-137

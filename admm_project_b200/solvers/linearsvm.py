@@ -5,10 +5,11 @@ import time
 
 import numpy as np
 
-from ..engine import DeviceMatrix, Engine
+from ..engine import DeviceMatrix, Engine, acquire_engine
 from ..errorcheck import MatlabError, errorcheck
 from ..getproxops import getproxops
 from .unwrappedadmm import unwrappedadmm
+from ..parallel import attach_comm, gather_rows, row_range, shared_draw
 
 
 def linearsvm(D, ell, C, options, engine=None):
@@ -27,7 +28,7 @@ def linearsvm(D, ell, C, options, engine=None):
     else:
         m = int(getattr(D, "m_total", D.shape[0]))
     loss = options.get("lossfunction", "hinge")                             # :154-158
-    eng = engine or options.get("engine") or Engine(int(options.get("device", 0)))
+    eng = acquire_engine(engine, options)
     args = {"engine": eng, "D": D, "ell": ell, "C": float(C), "lossfunction": loss}   # :210-214
     if options.get("parallel") in ("both", "zming", "xminf"):               # :170-205
         options["parallel"] = "both"
@@ -64,21 +65,33 @@ def linearsvm_onevsall(D, ELL, C, options, engine=None):
         raise L.EngineError(L.ERR_UNSUPPORTED, "linearsvm_onevsall: the class batch is built for the hinge loss")
     m, n = D.shape
     K = ELL.shape[1]
-    eng = engine or options.get("engine") or Engine(int(options.get("device", 0)))
-    if eng.nranks > 1:
-        raise L.EngineError(L.ERR_UNSUPPORTED, "linearsvm_onevsall: use Engine.solve_unwrapped_batch directly for "
-                            "row-sharded runs (every rank passes its own rows)")
-    X0, Z0, U0 = np.zeros((n, K), order="F"), np.zeros((m, K), order="F"), np.zeros((m, K), order="F")
-    for k in range(K):                       # same draw order as K successive unwrappedadmm calls
-        X0[:, k], Z0[:, k], U0[:, k] = np.random.rand(n), np.random.rand(m), np.random.rand(m)
-    eng.setup_unwrapped(L.SVM_HINGE, D, ELL[:, 0], float(C))
+    eng = acquire_engine(engine, options)
+    # Under torch.distributed every rank keeps its row block of D / ELL (errorcheck.m:249-259) and the batch
+    # exchanges ONE allreduce of K x [D'r ; scalars] per iteration.  Rank 0 draws the initial iterates for all.
+    rank, world = attach_comm(eng)
+    lo, hi = row_range(m, rank, world)
+
+    def draw():
+        X0, Z0, U0 = np.zeros((n, K), order="F"), np.zeros((m, K), order="F"), np.zeros((m, K), order="F")
+        for k in range(K):                   # same draw order as K successive unwrappedadmm calls (:87-89)
+            X0[:, k], Z0[:, k], U0[:, k] = np.random.rand(n), np.random.rand(m), np.random.rand(m)
+        return X0, Z0, U0
+    X0, Z0, U0 = shared_draw(draw)
+    eng.setup_unwrapped(L.SVM_HINGE, D[lo:hi, :], ELL[lo:hi, 0], float(C), m_total=m)
+    eng.row_range = (lo, hi)
     o = eng.default_options()
     o.rho = float(options.get("rho", 1.0))
     o.abstol, o.reltol = float(options.get("abstol", 1e-5)), float(options.get("reltol", 1e-3))
     o.hnormtol = float(options["Hreltol"]) if "Hnormtol" in options else 1e-6
     o.objevals = int(bool(options.get("objevals", 0)))
     o.maxiters, o.stopcond, o.nodualerror = 1000, L.STOP_BOTH, 1          # unwrappedadmm.m:90-92
-    r = eng.solve_unwrapped_batch(o, ELL, X0, Z0, U0)
+    try:
+        r = eng.solve_unwrapped_batch(o, ELL[lo:hi, :], X0, Z0[lo:hi, :], U0[lo:hi, :])
+    finally:
+        if getattr(eng, "_owned", False):
+            eng.close()
+    if world > 1:                               # results carry full-length z / u like the reference's
+        r["zopt"], r["uopt"] = gather_rows(r["zopt"], m), gather_rows(r["uopt"], m)
     out = []
     for k in range(K):
         s = int(r["steps"][k])

@@ -8,7 +8,7 @@ import time
 import numpy as np
 
 from ..admm import admm
-from ..engine import DeviceMatrix, Engine
+from ..engine import DeviceMatrix, Engine, acquire_engine
 from ..errorcheck import MatlabError
 from ..getproxops import getproxops
 
@@ -42,7 +42,7 @@ def model(P, Q, r, s, options, engine=None):
         raise MatlabError("Given options argument is not a struct! Please check your arguments and try again.")
     options = dict(options)
     n = P.shape[1]
-    eng = engine or options.get("engine") or Engine(int(options.get("device", 0)))
+    eng = acquire_engine(engine, options)
     rho = float(options["rho"]) if "rho" in options else 1.0
     args = {"engine": eng, "P": P, "Q": Q, "r": r, "s": s, "n": n, "rho": rho}      # model.m:123-128
     minx, minz, _ = getproxops("Model", args)

@@ -9,7 +9,7 @@ import numpy as np
 
 from .. import _lib as L
 from ..admm import admm
-from ..engine import Engine
+from ..engine import Engine, acquire_engine
 from ..errorcheck import MatlabError
 from ..getproxops import getproxops
 
@@ -40,7 +40,7 @@ def quadraticprogram(P, q, r, cons1, cons2, options, engine=None):
         raise MatlabError("Given constraint variables do not specify an upper and lower bound on solution x!")
     n = nP
     rho = float(options["rho"]) if "rho" in options else 1.0                # :171-175
-    eng = engine or options.get("engine") or Engine(int(options.get("device", 0)))
+    eng = acquire_engine(engine, options)
     args = {"engine": eng, "P": P, "q": q, "r": float(r), "lb": c1, "ub": c2, "rho": rho, "n": n,
             "constraint": "bounded"}                                        # :210-216
     minx, minz, _ = getproxops("quadraticprogram", args)

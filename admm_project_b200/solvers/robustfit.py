@@ -7,7 +7,7 @@ import time
 import numpy as np
 
 from ..admm import admm
-from ..engine import DeviceMatrix, Engine
+from ..engine import DeviceMatrix, Engine, acquire_engine
 from ..errorcheck import MatlabError
 from ..getproxops import getproxops
 
@@ -27,7 +27,7 @@ def _robustfit(problem, D, s, options, engine):
         m, n = D.shape
     else:
         m, n = int(getattr(D, "m_total", D.shape[0])), D.shape[1]
-    eng = engine or options.get("engine") or Engine(int(options.get("device", 0)))
+    eng = acquire_engine(engine, options)
     args = {"engine": eng, "D": D, "s": s}
     if "relax" in options and options["relax"] != 1:                        # huberfit.m:156-158, lad.m:124-126
         args["userelax"] = 1

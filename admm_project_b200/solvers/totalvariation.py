@@ -6,7 +6,7 @@ import time
 import numpy as np
 
 from ..admm import admm
-from ..engine import Engine
+from ..engine import Engine, acquire_engine
 from ..errorcheck import MatlabError
 from ..getproxops import getproxops
 
@@ -23,7 +23,7 @@ def totalvariation(s, lam, options, engine=None):
         raise MatlabError("Given options is not a struct! At least pass empty struct!")
     options = dict(options)
     n = s.shape[0]
-    eng = engine or options.get("engine") or Engine(int(options.get("device", 0)))
+    eng = acquire_engine(engine, options)
     # :127-131 build D = spdiags([1 -1],0:1,n,n), Dt, DtD, Id; the engine keeps them implicit
     xmin, zmin, _ = getproxops("TotalVariation", {"engine": eng, "s": s, "lambda": float(lam)})   # :148
     options.update(A="D", At="D'", B=-1, mB=n, nB=n, c=0, m=n)              # :151-161

@@ -15,6 +15,7 @@ from ..admm import admm
 from ..engine import DeviceMatrix
 from ..errorcheck import MatlabError, errorcheck
 from ..getproxops import EngineProx
+from ..parallel import shared_draw
 
 
 def unwrappedadmm(zming, D, options):
@@ -43,9 +44,11 @@ def unwrappedadmm(zming, D, options):
     options["nB"] = m
     options["c"] = 0
     options["m"] = m
-    options["x0"] = np.random.rand(n)        # same draw order as the reference: x0, z0, u0
-    options["z0"] = np.random.rand(m)
-    options["u0"] = np.random.rand(m)
+    # same draw order as the reference: x0, z0, u0 (:87-89).  Under torch.distributed rank 0 draws and everybody
+    # receives the same vectors, so every rank cuts its rows out of ONE global init and results['x0'|'z0'|'u0']
+    # describe the init that was actually used.
+    options["x0"], options["z0"], options["u0"] = shared_draw(lambda: (np.random.rand(n), np.random.rand(m),
+                                                                       np.random.rand(m)))
     options["maxiters"] = 1000
     options["stopcond"] = "both"
     options["nodualerror"] = 1

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define ADMM_B200_VERSION 100 /* 0.1.0 */
+#define ADMM_B200_VERSION 200 /* 0.2.0 */
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -146,13 +146,23 @@ int admm_b200_synchronize(admm_b200_handle* h);
  * chol(DD'/rho + I,'lower') (m < n).  D is m x n, leading dimension ldD. */
 int admm_b200_setup_lasso(admm_b200_handle* h, int64_t m, int64_t n, const double* D, int64_t ldD,
                           const double* s, double rho, int32_t xsolve);
+/* The same setup from ROW SHARDS, one process per GPU (admm_b200_comm_init first): D / s hold THIS rank's
+ * m_local rows (errorcheck.m:249-259 partition), m_total is the global row count (m_total >= n).  Every rank
+ * forms D_g'D_g and D_g's_g, ONE allreduce sums them -- the transpose reduction of unwrappedadmm.m:114-122
+ * applied to lasso.m:160,168 -- and every rank factors the same n x n matrix; the iterations then run
+ * replicated (x, z, u are n-vectors), the objective 1/2*||D x - s||^2 is summed over the shards. */
+int admm_b200_setup_lasso_sharded(admm_b200_handle* h, int64_t m_local, int64_t m_total, int64_t n, const double* D,
+                                  int64_t ldD, const double* s, double rho, int32_t xsolve);
 /* The A = D problems (constraint D*x - z = c): linear SVM by unwrapped ADMM / transpose reduction
  * (solvers/unwrappedadmm.m:43-141, linearsvm.m:154-243; c = 0, aux = labels ell, C = regularisation),
  * Huber fitting and least absolute deviations (huberfit.m:155-183, lad.m:123-151; c = aux = s).
  * kind is ADMM_B200_SVM_HINGE / SVM_01 / HUBERFIT / LAD.  D holds THIS rank's m_local rows
  * (errorcheck.m:249-259 partition, admm_b200_slicemaker); m_total is the global row count.
  * W = sum over ranks of D_g'*D_g (unwrappedadmm.m:114-122) is allreduced when a communicator is
- * attached, then R = chol(W,'lower') is cached on every rank (huberfit.m:166, lad.m:134). */
+ * attached, then R = chol(W,'lower') is cached on every rank (huberfit.m:166, lad.m:134).
+ * All-zero columns of D (constant-zero MNIST pixels, examples/mnistsvm.m) get x_j = 0, which is what the
+ * reference's serial x-update pinv(D)*(z-u) (unwrappedadmm.m:76-78, linearsvm.m:185) returns; any other rank
+ * deficiency fails with ADMM_B200_ERR_NOTPOSDEF and a text that says so. */
 int admm_b200_setup_unwrapped(admm_b200_handle* h, int32_t kind, int64_t m_local, int64_t m_total, int64_t n,
                               const double* D, int64_t ldD, const double* aux, double C);
 
@@ -192,7 +202,10 @@ int admm_b200_setup_model(admm_b200_handle* h, int64_t m, int64_t n, const doubl
 int admm_b200_get_unique_id(void* out128);
 int admm_b200_comm_init(admm_b200_handle* h, int rank, int nranks, const void* unique_id128);
 int admm_b200_comm_destroy(admm_b200_handle* h);
-/* In-place sum over ranks of `count` doubles (host or device pointer); no-op for a single rank. */
+/* comm_init also maps every peer's MAILBOX (CUDA IPC over NVLink): messages of up to 32768 doubles -- the one
+ * exchange per iteration of the row-sharded loops -- are summed by a one-shot peer-memory allreduce inside the
+ * engine's own kernels (p2p.cuh) instead of a library collective; larger ones (the n x n Gram) use ncclAllReduce.
+ * In-place sum over ranks of `count` doubles (host or device pointer); no-op for a single rank. */
 int admm_b200_allreduce(admm_b200_handle* h, double* buf, int64_t count);
 
 /* getProxOps.m:455 -- lambda of the soft threshold; may be changed between solves without
@@ -260,6 +273,17 @@ int64_t admm_b200_graph_replays(admm_b200_handle* h);
 /* Device time (ms) of the last setup by phase: [0] Gram (+ D's), [1] Cholesky, [2] inverse factor,
  * [3] total.  (The reference only has tic/toc: results.solverruntime, lasso.m:117,243.) */
 int admm_b200_get_setup_phases(admm_b200_handle* h, double* out4);
+
+/* State of the last setup and of the communicator (host mirror, tests). */
+typedef struct admm_b200_info {
+  int64_t generation;       /* bumped by every successful setup: a (minx, minz) pair made for an older setup is stale */
+  int64_t zero_cols;        /* A = D problems: all-zero columns of D handled as pinv does (x_j = 0) */
+  double diag_ratio;        /* (max L_ii / min L_ii)^2 of the cached factor, a lower bound of cond_2 */
+  int32_t xsolve_effective; /* ADMM_B200_XSOLVE_*: SUBST when diag_ratio exceeded the guard (1e9, env ADMM_B200_COND_GUARD) */
+  int32_t p2p_ready;        /* 1: small allreduces run over the peer mailboxes, 0: over NCCL */
+  int32_t nranks, rank;
+} admm_b200_info;
+int admm_b200_get_info(admm_b200_handle* h, admm_b200_info* out);
 
 /* errorcheck.m:216-267 slicemaker, balanced case (slices == 0, :249-259): out[w] = rows of
  * worker w; this is the row partition of the multi-GPU solvers. */

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), "libadmm_b200.so does not export " + n
         assert n in _lib.SYMBOLS, "ctypes binding missing for " + n
     assert sorted(_lib.SYMBOLS) == names
-    assert lib.admm_b200_version() == 100
+    assert lib.admm_b200_version() == 200
 
 
 def test_struct_layouts_match_header():
