@@ -18,6 +18,16 @@ class DeviceMatrix:
         self.keepalive = keepalive
 
 
+class RowShard:
+    """THIS rank's rows of a row-sharded data matrix held in HOST memory (one process per GPU):
+    ``RowShard(D_local, m_total)``.  The solvers accept it wherever the reference takes D; a DeviceMatrix with an
+    ``m_total`` attribute is the device-resident equivalent."""
+
+    def __init__(self, array, m_total, row_range=None):
+        self.array, self.m_total, self.row_range = array, int(m_total), row_range
+        self.shape = (int(array.shape[0]), int(array.shape[1]))
+
+
 class Engine:
     def __init__(self, device=0):
         lib = L.load()
@@ -67,8 +77,16 @@ class Engine:
     def _matrix(D):
         if isinstance(D, DeviceMatrix):
             return D.ptr, D.shape[0], D.shape[1], D.ld, D
+        if isinstance(D, RowShard):
+            D = D.array
+        a = np.asarray(D)
+        # a column-major matrix or a ROW SLICE of one (strides (8, 8*ld)) is used in place with its leading
+        # dimension: slicing the rows of a rank out of a pinned host matrix must not copy it
+        if a.ndim == 2 and a.dtype == np.float64 and a.shape[0] > 0 and a.shape[1] > 0 and a.strides[0] == 8 and \
+                a.strides[1] % 8 == 0 and a.strides[1] >= 8 * a.shape[0]:
+            return a.ctypes.data, a.shape[0], a.shape[1], a.strides[1] // 8, a
         a = L.fmat(D)
-        return a.ctypes.data, a.shape[0], a.shape[1], a.shape[0], a
+        return a.ctypes.data, a.shape[0], a.shape[1], max(a.shape[0], 1), a
 
     # -- setup -----------------------------------------------------------------------------
     def setup_lasso(self, D, s, rho, xsolve=L.XSOLVE_INVFACTOR):

@@ -102,3 +102,47 @@ def model_problem(seed, rows, cols):
     r, s = rs.randn(rows), rs.randn(rows)
     truex = np.linalg.solve(P.T @ P + Q.T @ Q, P.T @ r + Q.T @ s)
     return P, Q, r, s, truex
+
+
+def lasso_problem_big(seed, rows, cols):
+    """testers/lassotest.m:109-122 at BASELINE sizes (65536 x 8192 is 4.3 GB): the same recipe as lasso_problem,
+    drawn in column blocks by independent PCG64 streams on a thread pool so it takes seconds."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    nblk = (cols + 255) // 256
+    kids = np.random.SeedSequence(seed).spawn(nblk + 1)
+    rs = np.random.default_rng(kids[-1])
+    testx = rs.standard_normal(cols) * (rs.random(cols) < 0.6)
+    D = np.empty((rows, cols), order="F")
+
+    def fill(b):
+        j0 = b * 256
+        w = min(256, cols - j0)
+        blk = np.random.default_rng(kids[b]).standard_normal((w, rows))
+        blk /= np.sqrt(np.einsum("ij,ij->i", blk, blk))[:, None]
+        D[:, j0:j0 + w] = blk.T
+    with ThreadPoolExecutor(max_workers=len(os.sched_getaffinity(0))) as ex:
+        list(ex.map(fill, range(nblk)))
+    s = D @ testx + math.sqrt(0.001) * rs.standard_normal(rows)
+    lam = 0.1 * float(np.max(np.abs(D.T @ s)))
+    return D, s, lam, testx
+
+
+def randn_big(seed, rows, cols, colnorm=False):
+    """rows x cols N(0,1) in Fortran order, drawn in parallel column blocks (huber / lad / bp at BASELINE sizes)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    nblk = (cols + 127) // 128
+    kids = np.random.SeedSequence(seed).spawn(nblk)
+    D = np.empty((rows, cols), order="F")
+
+    def fill(b):
+        j0 = b * 128
+        w = min(128, cols - j0)
+        blk = np.random.default_rng(kids[b]).standard_normal((w, rows))
+        if colnorm:
+            blk /= np.sqrt(np.einsum("ij,ij->i", blk, blk))[:, None]
+        D[:, j0:j0 + w] = blk.T
+    with ThreadPoolExecutor(max_workers=len(os.sched_getaffinity(0))) as ex:
+        list(ex.map(fill, range(nblk)))
+    return D

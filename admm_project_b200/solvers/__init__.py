@@ -1,6 +1,6 @@
 """Host-side mirrors of solvers/<name>.m: argument checks as in the reference, one-time setup on the
 device (Gram / Cholesky / inverse factor), then ``admm``."""
-from .lasso import lasso                       # noqa: F401
+from .lasso import lasso, lasso_path           # noqa: F401
 from .unwrappedadmm import unwrappedadmm       # noqa: F401
 from .linearsvm import linearsvm, linearsvm_onevsall   # noqa: F401
 from .robustfit import huberfit, lad           # noqa: F401

@@ -7,7 +7,7 @@ import numpy as np
 
 from .. import _lib as L
 from ..admm import admm
-from ..engine import DeviceMatrix, Engine, acquire_engine
+from ..engine import DeviceMatrix, Engine, RowShard, acquire_engine
 from ..errorcheck import MatlabError
 from ..getproxops import getproxops
 from ..parallel import attach_comm, row_range, dist_info
@@ -18,7 +18,7 @@ def lasso(D, s, lam, options, engine=None):
     if not isinstance(options, dict):
         raise MatlabError("Given options is not a struct! At least pass empty struct!")
     options = dict(options)
-    if not isinstance(D, DeviceMatrix):
+    if not isinstance(D, (DeviceMatrix, RowShard)):
         D = np.asarray(D, dtype=np.float64)
         if D.ndim != 2:                                                     # lasso.m:132-136 (errorcheck ismatrix)
             raise MatlabError("Argument D is not a matrix!")
@@ -42,8 +42,8 @@ def lasso(D, s, lam, options, engine=None):
     # unwrappedadmm.m:114-122) and every rank factors the same n x n matrix; the n-sized iterations run replicated.
     xs = int(options.get("xsolve", L.XSOLVE_INVFACTOR))
     rank, world = attach_comm(eng)
-    if isinstance(D, DeviceMatrix) and getattr(D, "m_total", None) and world > 1:
-        eng.setup_lasso_sharded(D, s, rho, int(D.m_total), xs)      # the DeviceMatrix holds THIS rank's rows
+    if isinstance(D, (DeviceMatrix, RowShard)) and getattr(D, "m_total", None) and world > 1:
+        eng.setup_lasso_sharded(D, s, rho, int(D.m_total), xs)      # D / s hold THIS rank's rows
         m = int(D.m_total)
     elif world > 1 and m >= n and not isinstance(D, DeviceMatrix):
         lo, hi = row_range(m, rank, world)

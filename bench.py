@@ -9,15 +9,17 @@ bookkeeping; domaxiters = 1 so exactly ITERS run).
   value : ITERS * steps / device time, D and s already resident in HBM.
   e2e   : the same call through the public API admm_project_b200.lasso(D, s, lambda, options) with D
           and s in pinned HOST memory -- H2D of D and s, setup, loop, D2H of the results struct -- all
-          inside the timed region.
+          inside the timed region; e2e_pageable is the same from ordinary (pageable) host memory.
 Extra keys: loop_iters_per_s (steady-state loop only), time_to_tol (reltol 1e-4 from resident D),
-setup phases in TFLOP/s, roofline of the dominant kernel (the DMMA Gram) and of the per-iteration
-x-update (HBM), and a CPU baseline (oracle restatement of the reference, bounded sample).
+setup phases, roofline of the dominant kernel (the DMMA Gram) and of the per-iteration x-update (HBM), the
+64-lambda batch, the row-sharded linear SVM of configs[2] (svm_c3) and a CPU baseline (oracle restatement of
+the reference on the SAME workload).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
-N > 1 (torchrun): the single lasso problem does not shard ("replicas only"): every rank
-runs an independent replica (its own lambda of the regularisation path), no data-path collective;
-value is the sum over ranks (weak scaling), time is the max over ranks.
+N > 1 (torchrun): STRONG scaling of the same problem.  D is sharded by rows (errorcheck.m:249-259), every rank
+forms D_g'D_g and D_g's_g, ONE allreduce sums the 8192 x 8192 Gram (the transpose reduction of
+unwrappedadmm.m:114-122), every rank factors it and runs the n-sized iterations; the 64 lambda columns are
+split over the ranks; svm_c3 is the row-sharded SVM iteration with its one peer-memory allreduce per iteration.
 """
 from __future__ import annotations
 
@@ -36,7 +38,17 @@ sys.path.insert(0, ROOT)
 M, N_COLS = 65536, 8192          # BASELINE.json configs[1]
 ITERS = 200                      # "iters/s also with domaxiters=1, maxiters=200"
 RELTOL = 1e-4                    # north_star: "reaching reltol 1e-4"
-CPU_SAMPLE_ROWS, CPU_SAMPLE_ITERS = 32768, 50   # ~10 s of CPU work on the box's 16 cores
+REF_MAX_STEPS = 2                # CPU arm: full workload per step (~10-15 s on 16 cores), at most this many timed steps
+SVM_M, SVM_N, SVM_CLASSES = 60000, 784, 10       # BASELINE.json configs[2]
+
+
+def workload_config():
+    """The `config` object of BOTH arms (identical, so the driver's ratio compares like with like)."""
+    return {"workload": "lasso_65536x8192_fp64 (BASELINE.json configs[1]); step = setup (D's, Gram+rho*I, "
+                        "Cholesky) + %d ADMM iterations" % ITERS,
+            "rows": M, "cols": N_COLS, "iters_per_step": ITERS, "rho": 1.0, "relax": 1.0,
+            "lambda": "0.1*max|D's|", "reltol": RELTOL,
+            "l2": "inputs larger than L2 (D 4.3 GB, factor 0.27-0.54 GB per iteration)"}
 
 
 def env_int(name, default):
@@ -115,8 +127,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from admm_project_b200 import DeviceMatrix, Engine, lasso
+    from admm_project_b200 import DeviceMatrix, Engine, RowShard, lasso
     from admm_project_b200 import _lib as L
+    from admm_project_b200.parallel import attach_comm, row_range
 
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
@@ -132,17 +145,39 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    Dt, s, lam_max = make_problem_device(torch, dev, M, N_COLS, seed=0)
-    lam = lam_max * 10.0 ** (-(rank % 64) / 21.0)        # replica r solves lambda_r of the path
+    def max_over_ranks(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # The SAME problem at every N (same seed on every rank); rank r keeps rows [lo, hi) of it.
+    Dt, s, lam = make_problem_device(torch, dev, M, N_COLS, seed=0)
+    lam_max = lam / 0.1
+    lo, hi = row_range(M, rank, world)
+    ml = hi - lo
+    if world > 1:
+        ld = ml + (ml & 1)
+        Dsh = torch.zeros(N_COLS, ld, dtype=torch.float64, device=dev)
+        Dsh[:, :ml] = Dt[:, lo:hi]
+        ssh = s[lo:hi].contiguous()
+        del Dt, s
+        torch.cuda.empty_cache()
+    else:
+        ld, Dsh, ssh = M, Dt, s
     eng = Engine(local)
     torch.cuda.synchronize()
     eng.set_stream(stream.cuda_stream)
-    Ddev = DeviceMatrix(Dt.data_ptr(), M, N_COLS, M, keepalive=Dt)
+    if world > 1:
+        attach_comm(eng)           # NCCL communicator + peer mailboxes; its first collectives run here, not in a timed setup
+    Ddev = DeviceMatrix(Dsh.data_ptr(), ml, N_COLS, ld, keepalive=Dsh)
+    if world > 1:
+        Ddev.m_total, Ddev.row_range = M, (lo, hi)
     opts = {"rho": 1.0, "relax": 1.0, "abstol": 1e-5, "reltol": RELTOL, "history": 0,
             "domaxiters": 1, "maxiters": ITERS, "check_every": 50}
 
     def step_resident():
-        return lasso(Ddev, s.data_ptr(), lam, opts, engine=eng)
+        return lasso(Ddev, ssh.data_ptr(), lam, opts, engine=eng)
 
     # ---- value: D resident -------------------------------------------------------------------
     with torch.cuda.stream(stream):
@@ -161,7 +196,7 @@ def run_ours(args):
         launches = eng.launch_count() - l0          # kernels executed (a CUDA-graph replay counts the kernels it holds)
         graph_replays = eng.graph_replays() - g0
         phases = eng.setup_phases()
-        loop_ms = r["engine"]["loop_ms"]
+        assert r["steps"] == ITERS
 
         # ---- per-kernel timing inside the same process (CUDA events on the launching stream) ---
         o = eng.default_options()
@@ -177,76 +212,88 @@ def run_ours(args):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / reps * 1e3       # us
         reps = 2 if args.light else 200
-        xupd_us = timed_raw(1, reps)
-        prox_us = timed_raw(2, reps)
-        iter_us = timed_raw(0, reps)
+        xupd_us = max_over_ranks(timed_raw(1, reps))
+        prox_us = max_over_ranks(timed_raw(2, reps))
+        iter_us = max_over_ranks(timed_raw(0, reps))
 
         # ---- time to tolerance (reltol 1e-4) from resident D ----------------------------------
         tol_opts = dict(opts, domaxiters=0, maxiters=(3 if args.light else 1000), check_every=8)
         tol_wall = []
         for _ in range(1 if args.light else 2):     # the first call with a new maxiters re-allocates the histories
-            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
-            rt = lasso(Ddev, s.data_ptr(), lam, tol_opts, engine=eng)
+            rt = lasso(Ddev, ssh.data_ptr(), lam, tol_opts, engine=eng)
             torch.cuda.synchronize()
-            tol_wall.append((time.perf_counter() - t0) * 1e3)
+            tol_wall.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
 
-        # ---- the 64-lambda batch of configs[1]: x-update as two triangular DMMA GEMMs ---------------
+        # ---- the 64-lambda batch of configs[1]: x-update as two triangular DMMA GEMMs; the lambda columns are
+        # split over the ranks (no communication) -------------------------------------------------------------
         batch = None
         if not args.light:
             ob = eng.default_options()
             ob.reltol = RELTOL
             ob.domaxiters, ob.maxiters, ob.check_every = 1, 40, 40
-            lams = (10.0 * lam_max) * 10.0 ** (-np.arange(64) / 21.0)   # lambda_max = max|D's| down to 1e-3 of it
-            eng.solve_lasso_batch(ob, lams, want_history=False)               # warm-up
-            rb = eng.solve_lasso_batch(ob, lams, want_history=False)
-            us = rb["loop_ms"] / 40 * 1e3
+            lams = lam_max * 10.0 ** (-np.arange(64) / 21.0)              # lambda_max = max|D's| down to 1e-3 of it
+            clo, chi = row_range(64, rank, world)
+            mine = lams[clo:chi]
+            eng.solve_lasso_batch(ob, mine, want_history=False)               # warm-up
+            barrier()
+            rb = eng.solve_lasso_batch(ob, mine, want_history=False)
+            us = max_over_ranks(rb["loop_ms"] / 40 * 1e3)
             ob.domaxiters, ob.maxiters, ob.check_every = 0, 1000, 8
-            rt64 = eng.solve_lasso_batch(ob, lams, want_history=False)
-            batch = {"nb": 64, "us_per_iter": us, "rhs_iters_per_s": 64 * 1e6 / us,
+            rt64 = eng.solve_lasso_batch(ob, mine, want_history=False)
+            batch = {"nb": 64, "columns_per_rank": int(chi - clo), "us_per_iter": us, "rhs_iters_per_s": 64 * 1e6 / us,
                      "tflops_triangular": 2.0 * N_COLS * N_COLS * 64 / (us * 1e-6) / 1e12,
-                     "to_tol_ms": rt64["loop_ms"], "steps_min": int(rt64["steps"].min()), "steps_max": int(rt64["steps"].max())}
+                     "to_tol_ms": max_over_ranks(rt64["loop_ms"]), "steps_min_rank0": int(rt64["steps"].min()),
+                     "steps_max_rank0": int(rt64["steps"].max())}
 
-    # max over ranks
-    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_max = float(tmax.item())
-    value = ITERS * args.steps * world / (ms_max / 1e3)
+    ms_max = max_over_ranks(ms)
+    value = ITERS * args.steps / (ms_max / 1e3)          # the ONE problem, however many GPUs share it (strong scaling)
 
     # ---- e2e: host buffers through the public API -------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        try:
-            Dh = torch.empty((N_COLS, M), dtype=torch.float64, pin_memory=True)
-        except RuntimeError:            # N replicas x 4.3 GB of pinned host memory may not be available
-            Dh = torch.empty((N_COLS, M), dtype=torch.float64)
-        Dh.copy_(Dt)
-        sh = torch.empty(M, dtype=torch.float64, pin_memory=Dh.is_pinned())
-        sh.copy_(s)
-        D_np = Dh.numpy().T                 # (M, N_COLS) Fortran-ordered view of the pinned buffer
+    def e2e_leg(pinned):
+        Dh = torch.empty((N_COLS, ml), dtype=torch.float64, pin_memory=pinned)
+        Dh.copy_(Dsh[:, :ml])
+        sh = torch.empty(ml, dtype=torch.float64, pin_memory=pinned)
+        sh.copy_(ssh)
+        D_np = Dh.numpy().T                 # (ml, N_COLS) column-major view of the host buffer
         s_np = sh.numpy()
+        D_arg = RowShard(D_np, M, (lo, hi)) if world > 1 else D_np
         eng.set_stream(None)
-        lasso(D_np, s_np, lam, opts, engine=eng)          # warm-up (allocations)
+        lasso(D_arg, s_np, lam, opts, engine=eng)          # warm-up (allocations)
         barrier()
         e2e_steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            re = lasso(D_np, s_np, lam, opts, engine=eng)
+            re = lasso(D_arg, s_np, lam, opts, engine=eng)
         eng.synchronize()
         barrier()
-        wall = time.perf_counter() - t0
-        wmax = torch.tensor([wall], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
-        e2e = {"value": ITERS * e2e_steps * world / float(wmax.item()), "unit": "iters/s",
-               "h2d_bytes_per_step": int(M * N_COLS * 8 + M * 8),
-               "d2h_bytes_per_step": int(3 * N_COLS * 8 + 4 * ITERS * 8),
-               "steps": e2e_steps, "ms_per_step": float(wmax.item()) / e2e_steps * 1e3,
-               "api": "admm_project_b200.lasso(D_host, s_host, lambda, options)", "host_memory": "pinned" if Dh.is_pinned() else "pageable"}
+        wall = max_over_ranks(time.perf_counter() - t0)
         assert re["steps"] == ITERS
+        return {"value": ITERS * e2e_steps / wall, "unit": "iters/s",
+                "h2d_bytes_per_step": int(M * N_COLS * 8 + M * 8),            # all ranks together
+                "d2h_bytes_per_step": int(world * (3 * N_COLS * 8 + 4 * ITERS * 8)),
+                "steps": e2e_steps, "ms_per_step": wall / e2e_steps * 1e3,
+                "api": "admm_project_b200.lasso(D_host, s_host, lambda, options)" if world == 1 else
+                       "admm_project_b200.lasso(RowShard(D_host_rows, m_total), s_host_rows, lambda, options) on every rank",
+                "host_memory": "pinned" if pinned else "pageable"}
+    e2e = e2e_pageable = None
+    if not args.no_e2e:
+        try:
+            e2e = e2e_leg(True)
+        except RuntimeError as ex:          # pinned host memory may not be available
+            e2e = {"unavailable": "pinned host allocation failed: %s" % str(ex)[:80]}
+        if not args.light:
+            e2e_pageable = e2e_leg(False)
+        eng.set_stream(stream.cuda_stream)
+
+    # ---- configs[2]: linear SVM by transpose reduction, 60000 x 784, rows sharded over the ranks ------------------
+    svm = None
+    if not args.light and not args.no_svm:
+        svm = svm_leg(torch, dist, np, eng, stream, dev, world, rank, barrier, max_over_ranks)
 
     if rank != 0:
+        eng.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -267,58 +314,132 @@ def run_ours(args):
     fp64_peak = 2 * 8192 ** 3 * (1 if args.light else 5) / (c0.elapsed_time(c1) / 1e3) / 1e12
     del a, b
 
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp))
-    gram_flops = M * N_COLS * (N_COLS + 1)               # symmetric half, SURVEY.md section 8d
+    gram_flops = ml * N_COLS * (N_COLS + 1)              # symmetric half of this rank's rows, SURVEY.md section 8d
     gram_tflops = gram_flops / (phases["gram_ms"] / 1e3) / 1e12
     tri_bytes = N_COLS * (N_COLS + 1) * 8                # two reads of one triangle per iteration
     xupd_gbs = tri_bytes / (xupd_us * 1e-6) / 1e9
+    info = eng.info()
     out = {
         "metric": "admm_iters_per_s", "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "lasso_65536x8192_fp64 (BASELINE.json configs[1]); step = setup (D's, Gram+rho*I, "
-                               "Cholesky, inverse factor) + %d ADMM iterations" % ITERS,
-                   "rows": M, "cols": N_COLS, "iters_per_step": ITERS, "rho": 1.0, "relax": 1.0,
-                   "lambda": "0.1*max|D's|", "l2": "inputs larger than L2 (D 4.3 GB, factor 2 x 0.27 GB per iteration)",
-                   "parallelism": "replicas only" if world > 1 else "single GPU"},
-        "e2e": e2e, "gpu_launches": int(launches), "graph_replays": int(graph_replays),
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(),
+        "parallelism": "single GPU" if world == 1 else
+                       "rows of D sharded over %d ranks; one ncclAllReduce of the 8192x8192 Gram + D's per step; Cholesky and "
+                       "the n-sized iterations replicated; lambda batch split by columns" % world,
+        "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": int(launches), "graph_replays": int(graph_replays),
         "clocks": clk.summary(),
         "loop_iters_per_s": 1e6 / iter_us,
         "loop_us_per_iter": {"iteration": iter_us, "x_update": xupd_us, "fused_prox": prox_us},
         "setup_ms": phases,
         "lambda_batch": batch,
+        "svm_c3": svm,
         "time_to_tol": {"reltol": RELTOL, "steps": int(rt["steps"]), "setup_ms": rt["engine"]["setup_ms"],
                         "loop_ms": rt["engine"]["loop_ms"], "wall_ms": tol_wall[-1], "first_call_wall_ms": tol_wall[0]},
-        "roofline": {"kernel": "gemm_f64_dmma_kernel<T,N> (Gram D'D + rho*I, lower tiles)", "bound": "tensor",
-                     "achieved": gram_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": gram_tflops / fp64_peak,
+        "roofline": {"kernel": "gemm_f64_dmma_kernel<T,N> (Gram D_g'D_g, lower tiles, this rank's %d rows)" % ml,
+                     "bound": "tensor", "achieved": gram_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": gram_tflops / fp64_peak,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                      "algorithmic_flops": gram_flops,
-                     "traffic": (traffic or {}).get("gram_dram_bytes")},
-        "roofline_iter": {"kernel": "coldot_kernel<1> x2 (x = W'(W y): L\\ and L'\\ as products with the cached inverse factor)", "bound": "hbm",
+                     "traffic": None},          # no in-run DRAM counter; the ncu figure of this round is in profiles/
+        "roofline_iter": {"kernel": "x-update x = W'(W y) on the cached inverse factor", "bound": "hbm",
                           "achieved": xupd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": xupd_gbs / hbm_peak,
                           "frac_of_8TBs_nominal": xupd_gbs / 8000.0, "peak_source": peak_src,
-                          "algorithmic_bytes": tri_bytes, "traffic": (traffic or {}).get("xupdate_dram_bytes")},
+                          "algorithmic_bytes": tri_bytes, "traffic": None},
+        "comm": {"p2p_mailboxes": bool(info["p2p_ready"])} if world > 1 else None,
     }
-    if not args.no_cpu and world == 1:          # rank 0 at N = 1 only
-        out["cpu_baseline"] = cpu_baseline(CPU_SAMPLE_ROWS, CPU_SAMPLE_ITERS)
+    if not args.no_cpu and world == 1 and not args.light:          # rank 0 at N = 1 only
+        out["cpu_baseline"] = cpu_baseline()
     print(json.dumps(out))
+    eng.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def svm_leg(torch, dist, np, eng, stream, dev, world, rank, barrier, max_over_ranks):
+    """BASELINE.json configs[2]: hinge-loss linear SVM via unwrapped ADMM / transpose reduction on synthetic
+    MNIST-shaped data (60000 x 784, U(0,1) with 81 % zeros, ten one-vs-all label columns), rows sharded over the
+    ranks.  Reports the per-iteration time of one classifier and of the ten-class batch (device time, max over
+    ranks); the driver's per-N runs give the strong-scaling efficiency."""
+    from admm_project_b200 import DeviceMatrix
+    from admm_project_b200 import _lib as L
+    from admm_project_b200.parallel import row_range
+    import ctypes as C
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234)                                   # same stream on every rank: ONE global problem
+    Dt = torch.rand(SVM_N, SVM_M, dtype=torch.float64, device=dev, generator=g) * \
+        (torch.rand(SVM_N, SVM_M, dtype=torch.float64, device=dev, generator=g) < 0.19)
+    digit = torch.randint(0, SVM_CLASSES, (SVM_M,), device=dev, generator=g)
+    lo, hi = row_range(SVM_M, rank, world)
+    ml = hi - lo
+    ld = ml + (ml & 1)
+    Dsh = torch.zeros(SVM_N, ld, dtype=torch.float64, device=dev)
+    Dsh[:, :ml] = Dt[:, lo:hi]
+    lab = -torch.ones(SVM_CLASSES, ld, dtype=torch.float64, device=dev)      # column k of the ml x 10 label matrix = row k
+    lab[digit[lo:hi], torch.arange(ml, device=dev)] = 1.0
+    del Dt
+    torch.cuda.synchronize()
+    D = DeviceMatrix(Dsh.data_ptr(), ml, SVM_N, ld, keepalive=Dsh)
+    out = {"rows": SVM_M, "cols": SVM_N, "classes": SVM_CLASSES, "rows_per_rank": ml}
+    with torch.cuda.stream(stream):
+        eng.setup_unwrapped(L.SVM_HINGE, D, lab.data_ptr(), 0.5, m_total=SVM_M)
+        out["setup_ms"] = eng.setup_phases()["total_ms"]
+        og = eng.default_options()
+        og.nodualerror, og.history, og.domaxiters, og.maxiters, og.check_every, og.stopcond = 1, 0, 1, 400, 50, 2
+        best = 1e30
+        for _ in range(3):
+            barrier()
+            r = eng.solve(og, want_history=False)
+            best = min(best, max_over_ranks(r["loop_ms"] * 1e3 / max(r["steps"], 1)))
+        out["single_us_per_iter"] = best
+        out["single_hbm_gbs_algorithmic"] = 2.0 * SVM_M * SVM_N * 8 / (best * 1e-6) / 1e9      # 2 passes over D (SURVEY 8d)
+        ob = eng.default_options()
+        ob.nodualerror, ob.domaxiters, ob.maxiters, ob.check_every, ob.stopcond = 1, 1, 200, 50, 2
+        n_, _, m_ = eng.dims()
+
+        def run_batch():
+            steps = np.zeros(SVM_CLASSES, dtype=np.int64)
+            status = np.zeros(SVM_CLASSES, dtype=np.int32)
+            X = np.zeros((n_, SVM_CLASSES), order="F")
+            msb = C.c_double()
+            L.check(eng._lib.admm_b200_solve_unwrapped_batch(eng._h, C.byref(ob), SVM_CLASSES, C.c_void_p(lab.data_ptr()), ld,
+                                                             None, None, None, L.ptr(steps), L.ptr(status), L.ptr(X), None,
+                                                             None, None, None, None, C.byref(msb)))
+            return msb.value
+        run_batch()
+        bestb = 1e30
+        for _ in range(2):
+            barrier()
+            bestb = min(bestb, max_over_ranks(run_batch() / 200 * 1e3))
+        out["batch10_us_per_iter"] = bestb
+        out["batch10_class_iters_per_s"] = SVM_CLASSES * 1e6 / bestb
+    return out
+
+
 # --------------------------------------------------------------------------------------------
-# CPU legs: the oracle (NumPy/SciPy restatement of admm.m / lasso.m; no MATLAB/Octave in the image)
+# CPU legs: the oracle (NumPy/SciPy restatement of admm.m / lasso.m; no MATLAB/Octave in the image) on the SAME
+# workload as the GPU arm -- all 65536 rows, ITERS iterations per step
 # --------------------------------------------------------------------------------------------
 def cpu_problem(rows, cols, seed=0):
+    """testers/lassotest.m:109-122 at rows x cols; column blocks are drawn by independent PCG64 streams on a
+    thread pool (NumPy releases the GIL while it fills), so the 4.3 GB matrix takes seconds, not half a minute."""
     import numpy as np
-    rs = np.random.RandomState(seed)
-    testx = rs.randn(cols) * (rs.rand(cols) < 0.6)
-    D = np.asfortranarray(rs.randn(rows, cols))
-    D /= np.sqrt(np.einsum("ij,ij->j", D, D))[None, :]
-    s = D @ testx + math.sqrt(0.001) * rs.randn(rows)
+    from concurrent.futures import ThreadPoolExecutor
+    ss = np.random.SeedSequence(seed)
+    kids = ss.spawn((cols + 255) // 256 + 1)
+    rs = np.random.default_rng(kids[-1])
+    testx = rs.standard_normal(cols) * (rs.random(cols) < 0.6)
+    D = np.empty((rows, cols), order="F")
+
+    def fill(b):
+        j0 = b * 256
+        w = min(256, cols - j0)
+        blk = np.random.default_rng(kids[b]).standard_normal((w, rows))
+        blk /= np.sqrt(np.einsum("ij,ij->i", blk, blk))[:, None]      # unit-norm columns of D
+        D[:, j0:j0 + w] = blk.T
+    with ThreadPoolExecutor(max_workers=len(os.sched_getaffinity(0))) as ex:
+        list(ex.map(fill, range((cols + 255) // 256)))
+    s = D @ testx + math.sqrt(0.001) * rs.standard_normal(rows)
     lam = 0.1 * float(np.max(np.abs(D.T @ s)))
     return D, s, lam
 
@@ -332,24 +453,30 @@ def cpu_call(D, s, lam, iters):
     return dt, r
 
 
-def cpu_baseline(rows, iters):
-    cores = len(os.sched_getaffinity(0))
-    D, s, lam = cpu_problem(rows, N_COLS)
-    dt, r = cpu_call(D, s, lam, iters)
-    return {"value": iters / dt, "unit": "iters/s", "cores": cores, "kind": "port",
-            "sample": "oracle.lasso (NumPy/SciPy restatement of lasso.m + admm.m, OpenBLAS) on %d of %d rows x %d "
-                      "cols, setup + %d iterations, one call" % (rows, M, N_COLS, iters),
-            "seconds": dt, "loop_s_per_iter": r["runtime"] / iters, "setup_s": dt - r["runtime"],
-            # the same call at the full workload (setup scales with the rows, the loop does not), for orientation
-            "extrapolated_full_workload_iters_per_s": ITERS / ((dt - r["runtime"]) * M / rows + r["runtime"] / iters * ITERS)}
+CPU_KIND = ("oracle.lasso: NumPy/SciPy (OpenBLAS) restatement of solvers/lasso.m + admm.m; the reference is MATLAB "
+            "and neither MATLAB nor Octave exists in the image")
+
+
+def cpu_baseline():
+    cores = use_all_cores()
+    D, s, lam = cpu_problem(M, N_COLS)
+    dt, r = cpu_call(D, s, lam, ITERS)
+    return {"value": ITERS / dt, "unit": "iters/s", "cores": cores, "kind": "port",
+            "sample": "%s; the full workload once: %d x %d, setup + %d iterations" % (CPU_KIND, M, N_COLS, ITERS),
+            "seconds": dt, "loop_s_per_iter": r["runtime"] / ITERS, "setup_s": dt - r["runtime"], "same_config": True}
 
 
 def use_all_cores():
     """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use every host thread it can.
-    Must run before NumPy / OpenBLAS are loaded (env) and again afterwards (threadpoolctl) to be sure."""
+    Set before NumPy / OpenBLAS are loaded (env) and again afterwards (threadpoolctl) to be sure."""
     cores = len(os.sched_getaffinity(0))
     for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[k] = str(cores)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
     return cores
 
 
@@ -359,29 +486,22 @@ def run_reference(args):
         return
     world = env_int("WORLD_SIZE", 1)
     cores = use_all_cores()
-    try:
-        from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=cores)
-    except Exception:
-        pass
-    rows, iters = CPU_SAMPLE_ROWS, CPU_SAMPLE_ITERS
-    D, s, lam = cpu_problem(rows, N_COLS)
-    for _ in range(min(args.warmup, 1)):
-        cpu_call(D, s, lam, 2)
+    D, s, lam = cpu_problem(M, N_COLS)
+    if args.warmup > 0:
+        cpu_call(D[:4096], s[:4096], lam, 2)            # loads BLAS / SciPy, spins the thread pool up; not the workload
+    steps = max(1, min(args.steps, REF_MAX_STEPS))      # every timed step IS the full workload; fewer of them than the GPU arm
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_call(D, s, lam, iters)
+    for _ in range(steps):
+        cpu_call(D, s, lam, ITERS)
     dt = time.perf_counter() - t0
-    value = iters * args.steps / dt
-    sample = ("oracle.lasso (CPU restatement of lasso.m + admm.m; the reference is MATLAB and neither MATLAB nor "
-              "Octave exists in the image) on %d of %d rows x %d cols, step = setup + %d iterations" %
-              (rows, M, N_COLS, iters))
+    value = ITERS * steps / dt
+    sample = "%s; %d timed steps of the full workload (%d requested): %d x %d, setup + %d iterations each" % (
+        CPU_KIND, steps, args.steps, M, N_COLS, ITERS)
     print(json.dumps({
         "impl": "reference", "metric": "admm_iters_per_s", "value": value, "unit": "iters/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "lasso_65536x8192_fp64 (BASELINE.json configs[1]), bounded sample", "rows": rows,
-                   "cols": N_COLS, "iters_per_step": iters},
+        "steps": steps, "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(), "same_config": True,
         "cpu_baseline": {"value": value, "unit": "iters/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -393,7 +513,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs")
+    ap.add_argument("--no-svm", action="store_true", help="skip the configs[2] SVM leg")
     ap.add_argument("--light", action="store_true", help="timed steps only (the command profiled under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -13,4 +13,4 @@ from .errorcheck import errorcheck, slicemaker                     # noqa: F401
 from .getproxops import (getproxops, zminSoftThresholding, minz01, zminNonNegative,   # noqa: F401
                          make_zminBox, subplus, pos, huber)
 from .solvers import (lasso, unwrappedadmm, linearsvm, huberfit, lad,                 # noqa: F401
-                      totalvariation, basispursuit, quadraticprogram, model)
+                      totalvariation, basispursuit, basispursuit_factored, quadraticprogram, model)

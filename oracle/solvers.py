@@ -230,6 +230,31 @@ def basispursuit(D, s, options):
     return results
 
 
+def basispursuit_factored(D, s, options):
+    """Test aid for n where the reference's dense n x n projector does not fit the host (n = 32768: two 8.6 GB
+    temporaries): the SAME loop as basispursuit() with the x-update P*(z-u) + q (getProxOps.m:1031) applied as
+    v - D'((DD') \\ (D v - s)), which is the algebra of P and q (basispursuit.m:116-120) without forming them.
+    tests/test_oracle_known_answers.py pins it to the explicit-P path (1e-13) at sizes where both fit."""
+    t0 = time.perf_counter()
+    options = dict(options)
+    D = np.asarray(D, dtype=np.float64)
+    s = _col(s)
+    mD, n = D.shape
+    if not (mD < n and mD == s.shape[0]):
+        raise MatlabError("oracle: basispursuit_factored needs an underdetermined system")
+    cho = sla.cho_factor(D @ D.T, lower=True)
+    _, minz, _ = getproxops("BasisPursuit", dict(P=np.zeros((1, 1)), q=np.zeros(1)))
+
+    def minx(x, z, u, rho):
+        v = z - u
+        return v - D.T @ sla.cho_solve(cho, D @ v - s)
+    options.update(A=1, B=-1, c=0, m=n, nA=n, nB=n, solver="basispursuit")
+    options["obj"] = lambda x, z: float(np.sum(np.abs(x)))
+    results = admm(minx, minz, options)
+    results["solverruntime"] = time.perf_counter() - t0
+    return results
+
+
 def quadraticprogram(P, q, r, cons1, cons2, options):
     """solvers/quadraticprogram.m:99-257, 'bounded' constraint branch only (:210-216; error checks
     :259-366).  The 'standard' branch (dense KKT solve per iteration) is out of scope."""

@@ -64,6 +64,24 @@ def _worker(rank, world, port, q):
             assert np.allclose(x, ref["xvals"][:, it], rtol=1e-9, atol=1e-12)
             assert abs(np.sqrt(msg.numpy()[n]) - ref["pnorm"][it]) <= 1e-9 * ref["pnorm"][it] + 1e-10
         assert np.allclose(gather_rows(z, m), ref["zopt"], rtol=1e-9, atol=1e-12)
+        # row-sharded lasso setup (admm_b200_setup_lasso_sharded): ONE allreduce of [D_g'D_g ; D_g's_g], + rho*I once,
+        # every rank factors the same matrix -> the serial oracle's factor and Dts (lasso.m:160,168)
+        Dl, sl, lam, _ = gen.lasso_problem(1, m, n)
+        G = torch.from_numpy(np.concatenate([(Dl[lo:hi].T @ Dl[lo:hi]).reshape(-1), Dl[lo:hi].T @ sl[lo:hi]]))
+        dist.all_reduce(G)
+        Gm = G.numpy()[:n * n].reshape(n, n) + 1.0 * np.eye(n)
+        assert np.allclose(np.linalg.cholesky(Gm), np.linalg.cholesky(Dl.T @ Dl + np.eye(n)), rtol=1e-12, atol=1e-14)
+        assert np.allclose(G.numpy()[n * n:], Dl.T @ sl, rtol=1e-12, atol=1e-14)
+        # the lambda columns of a regularisation path are split by the same balancing rule, no communication
+        clo, chi = row_range(7, rank, world)
+        assert (clo, chi) == ((0, 4) if rank == 0 else (4, 7))
+        # rank 0 draws the random init of unwrappedadmm.m:87-89 for everybody
+        from admm_project_b200.parallel import shared_draw
+        np.random.seed(100 + rank)                                 # different streams on purpose
+        x0 = shared_draw(lambda: np.random.rand(5))
+        both = [None, None]
+        dist.all_gather_object(both, x0)
+        assert np.array_equal(both[0], both[1])
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback

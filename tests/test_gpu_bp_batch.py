@@ -23,12 +23,12 @@ def test_basispursuit_matches_oracle(engine, rows, cols):
     res = basispursuit(D, s, opts, engine=engine)
     assert res["steps"] == ref["steps"]
     for k in ("xopt", "zopt", "uopt", "pnorm", "dnorm", "perr", "derr", "objevals"):
-        assert rel(res[k], ref[k]) < 1e-8, (k, rel(res[k], ref[k]))
+        assert rel(res[k], ref[k]) < TOL, (k, rel(res[k], ref[k]))
     # basispursuittest.m:136-143: the engine's answer passes/fails the tester exactly as the oracle's does
     crit = lambda r: (np.sum(np.abs(r["xopt"])) <= np.sum(np.abs(testx)),
                       np.mean(np.abs(D @ r["xopt"] - s) / np.abs(s)) <= 1e-10)
     assert crit(res) == crit(ref)
-    assert np.linalg.norm(D @ res["xopt"] - s) <= 1e-8 * np.linalg.norm(s)
+    assert np.linalg.norm(D @ res["xopt"] - s) <= 1e-9 * np.linalg.norm(s)
 
 
 def test_basispursuit_reference_errors(engine):

@@ -20,14 +20,14 @@ def compare(res, ref, fasttype):
     for k in ("xopt", "zopt", "uopt", "avals", "objevals"):
         assert rel(res[k], ref[k]) < TOL, (k, rel(res[k], ref[k]))
     if fasttype == "weak":
-        assert rel(res["dvals"], ref["dvals"]) < 1e-7
+        assert rel(res["dvals"], ref["dvals"]) < TOL, rel(res["dvals"], ref["dvals"])
         assert np.array_equal(res["restarted"], ref["restarted"])
         assert res["pnorm"].size == 0 and "perr" not in res and res["dvaltol"] == ref["dvaltol"]
     else:
         for k in ("pnorm", "perr"):
             assert rel(res[k], ref[k]) < TOL, k
         ok = ~np.isnan(ref["dnorm"])
-        assert rel(res["dnorm"][ok], ref["dnorm"][ok]) < 1e-7 and rel(res["derr"][ok], ref["derr"][ok]) < TOL
+        assert rel(res["dnorm"][ok], ref["dnorm"][ok]) < TOL and rel(res["derr"][ok], ref["derr"][ok]) < TOL
 
 
 @pytest.mark.parametrize("fasttype", ["weak", "strong"])
@@ -73,4 +73,4 @@ def test_svm_and_bp_fast(engine):
     res = basispursuit(D, s, opts, engine=engine)
     assert res["steps"] == ref["steps"]
     for k in ("xopt", "zopt", "uopt", "avals", "pnorm", "dnorm"):
-        assert rel(res[k], ref[k]) < 1e-8, k
+        assert rel(res[k], ref[k]) < TOL, (k, rel(res[k], ref[k]))

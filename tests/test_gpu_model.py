@@ -30,6 +30,9 @@ def test_model_matches_oracle_with_the_testers_options(engine, rows, cols):
     ref = oracle.model(P, Q, r, s, opts)
     res = model(P, Q, r, s, opts, engine=engine)
     compare(res, ref)
+    assert rel(res["Hnormsq"], ref["Hnormsq"]) < TOL, rel(res["Hnormsq"], ref["Hnormsq"])
+    # elementwise too; the late entries are squared differences of nearly equal iterates (||dz|| ~ 1e-6 ||z||), so they
+    # carry ~6 fewer digits than the iterates in ANY implementation
     assert np.allclose(res["Hnormsq"], ref["Hnormsq"], rtol=1e-6, atol=1e-22)
     for k in ("xvals", "zvals", "uvals"):
         assert rel(res[k], ref[k]) < TOL, k
@@ -58,7 +61,7 @@ def test_model_fast_variants(engine, fasttype):
         assert rel(res[k], ref[k]) < TOL, (k, rel(res[k], ref[k]))
     if fasttype == "weak":
         assert np.array_equal(res["restarted"], ref["restarted"])
-        assert rel(res["dvals"], ref["dvals"]) < 1e-7
+        assert rel(res["dvals"], ref["dvals"]) < TOL, rel(res["dvals"], ref["dvals"])
     else:
         assert rel(res["pnorm"], ref["pnorm"]) < TOL
 

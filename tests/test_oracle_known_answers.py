@@ -213,3 +213,16 @@ def test_model_converges_to_the_least_squares_solution_and_passes_modeltest():
     # the accelerated variant reaches the optimum to rounding (examples/fasteradmmcomparison.m)
     acc = oracle.model(P, Q, r, s, {"fast": 1, "maxiters": 2000})
     assert np.linalg.norm(acc["xopt"] - truex) < 1e-10
+
+
+def test_basispursuit_factored_form_equals_explicit_projector():
+    """The oracle's test aid for n = 32768 (basispursuit_factored: v - D'((DD')\\(Dv - s))) against the reference's
+    explicit P, q (basispursuit.m:116-120, getProxOps.m:1031): same steps, iterates within 1e-12."""
+    from admm_project_b200 import generators as gen
+    for rows, cols in ((64, 128), (100, 501)):
+        D, s, _ = gen.bp_problem(0, rows, cols, density=0.05)
+        opts = {"objevals": 1, "maxiters": 10000, "convtest": 0}
+        a, b = oracle.basispursuit(D, s, opts), oracle.basispursuit_factored(D, s, opts)
+        assert a["steps"] == b["steps"]
+        for k in ("xopt", "zopt", "uopt", "pnorm", "dnorm", "objevals"):
+            assert np.linalg.norm(a[k] - b[k]) <= 1e-12 * np.linalg.norm(a[k]), k

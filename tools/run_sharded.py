@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from admm_project_b200 import Engine, huberfit, lad, linearsvm  # noqa: E402
+from admm_project_b200 import Engine, huberfit, lad, lasso, lasso_path, linearsvm, linearsvm_onevsall  # noqa: E402
 from admm_project_b200 import generators as gen  # noqa: E402
 
 
@@ -34,7 +34,55 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = Engine(local)
     out = {"problem": args.problem, "world": world, "rows": args.rows, "cols": args.cols}
-    if args.problem == "svm":
+    if args.problem == "lasso":
+        # row-sharded setup (admm_b200_setup_lasso_sharded): every rank hands the FULL host matrix to lasso(), which
+        # keeps its own rows; the result must be the serial oracle's on every rank
+        D, s, lam, _ = gen.lasso_problem(0, args.rows, args.cols)
+        opts = {"objevals": 1, "relax": 1.5, "history": 0}
+        res = lasso(D, s, lam, opts, engine=eng)
+        out["p2p"] = eng.info()["p2p_ready"]
+        if args.check and rank == 0:
+            ref = __import__("oracle").lasso(D, s, lam, opts)
+    elif args.problem == "lassopath":
+        D, s, lam, _ = gen.lasso_problem(0, args.rows, args.cols)
+        lams = (lam / 0.1) * 10.0 ** (-np.arange(7) / 3.0)
+        rb = lasso_path(D, s, lams, {"reltol": 1e-4}, engine=eng)
+        oks = []
+        if args.check and rank == 0:
+            import oracle
+            for j in range(7):
+                ref = oracle.lasso(D, s, lams[j], {"reltol": 1e-4, "history": 0})
+                oks.append(bool(rb["steps"][j] == ref["steps"] and rel(rb["xopt"][:, j], ref["xopt"]) < 1e-9 and
+                                rel(rb["zopt"][:, j], ref["zopt"]) < 1e-9 and
+                                rel(rb["pnorm"][:ref["steps"], j], ref["pnorm"]) < 1e-9))
+        if rank == 0:
+            print("SHARDED " + json.dumps({"problem": "lassopath", "world": world, "ok": bool(oks) and all(oks), "cols_ok": oks,
+                                           "zopt_len": args.rows, "steps": [int(v) for v in rb["steps"]]}))
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    elif args.problem == "svmbatch":
+        D, ELL = gen.svm_mnist_like(0, args.rows, args.cols, nclass=3)
+        D = D + 1e-3 * np.random.RandomState(1).randn(*D.shape)
+        np.random.seed(3)
+        outs = linearsvm_onevsall(D, ELL, 0.5, {"objevals": 1}, engine=eng)
+        oks = []
+        if args.check and rank == 0:
+            import oracle
+            np.random.seed(3)
+            for k in range(3):
+                ref = oracle.linearsvm(D, ELL[:, k], 0.5, {"objevals": 1, "history": 0})
+                oks.append(bool(outs[k]["steps"] == ref["steps"] and rel(outs[k]["xopt"], ref["xopt"]) < 1e-9 and
+                                rel(outs[k]["zopt"], ref["zopt"]) < 1e-9 and rel(outs[k]["uopt"], ref["uopt"]) < 1e-9))
+        if rank == 0:
+            print("SHARDED " + json.dumps({"problem": "svmbatch", "world": world, "ok": bool(oks) and all(oks), "cols_ok": oks,
+                                           "zopt_len": int(outs[0]["zopt"].shape[0]), "p2p": eng.info()["p2p_ready"]}))
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    elif args.problem == "svm":
         D, ell = gen.svm_mnist_like(0, args.rows, args.cols, nclass=3)
         D = D + 1e-3 * np.random.RandomState(1).randn(*D.shape)
         aux = ell[:, 1]
@@ -58,7 +106,7 @@ def main():
             ref = (oracle.huberfit if args.problem == "huber" else oracle.lad)(D, s, opts)
     out["steps"] = res["steps"]
     out["loop_ms"] = res["engine"]["loop_ms"]
-    out["zopt_len"] = int(res["zopt"].shape[0])
+    out["zopt_len"] = int(res["zopt"].shape[0]) if args.problem != "lasso" else args.rows
     if args.check and rank == 0:
         out["ref_steps"] = ref["steps"]
         out["err_x"], out["err_z"], out["err_u"] = rel(res["xopt"], ref["xopt"]), rel(res["zopt"], ref["zopt"]), rel(res["uopt"], ref["uopt"])
