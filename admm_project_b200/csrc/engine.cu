@@ -22,6 +22,7 @@
 #include "onepass.cuh"
 #include "tv.cuh"
 #include "p2p.cuh"
+#include "symtri.cuh"
 #include <dlfcn.h>
 
 namespace admmb200 {
@@ -68,6 +69,14 @@ struct ColdotPlan {
   int grid = 0, panels = 1, max_pos = 1, nitems = 0, npos = 0;
   int *d_cta_pos = nullptr, *d_pos_item = nullptr, *d_order = nullptr;
   ColdotItem* d_items = nullptr;
+};
+
+// round plan of the one-pass x-update (symtri.cuh) for one (k, column range)
+struct SymtriPlan {
+  int64_t k = 0, c_lo = 0, c_hi = 0;
+  int grid = 0;
+  int *d_cta_round = nullptr, *d_round_ent = nullptr;
+  SymtriEnt* d_ents = nullptr;
 };
 
 }  // namespace admmb200
@@ -142,6 +151,9 @@ struct admm_b200_handle {
   int xsolve_eff = ADMM_B200_XSOLVE_INVFACTOR;   // x-update realisation actually used (SUBST when the guard fired)
   int64_t zero_cols = 0;         // A = D problems: all-zero columns of D handled as pinv does (x_j = 0)
   std::vector<ColdotPlan*> plans;
+  std::vector<SymtriPlan*> st_plans;
+  DBuf st_part;                  // per-CTA partial x of the one-pass x-update
+  bool xshard = false;           // lasso from row shards with a large factor: the x-update is split by columns over the ranks
   unsigned* tickets = nullptr;
   int64_t tickets_cap = 0;
 };
@@ -685,6 +697,98 @@ static void gemvn(admm_b200_handle* h, const double* D, int64_t ld, int64_t m, i
   h->launches++;
 }
 
+// ---------------------------------------------------------------------------------------------
+// one-pass x-update (symtri.cuh)
+// ---------------------------------------------------------------------------------------------
+// Columns [c_lo, c_hi) of WT: this rank's share (equal triangle AREA per rank) or all of them.
+static void symtri_range(int64_t k, int rank, int nranks, int64_t& c_lo, int64_t& c_hi) {
+  auto bound = [&](int g) { return (int64_t)llround((double)k * sqrt((double)g / (double)nranks)); };
+  c_lo = (nranks > 1) ? bound(rank) : 0;
+  c_hi = (nranks > 1) ? (rank == nranks - 1 ? k : bound(rank + 1)) : k;
+}
+
+static SymtriPlan* symtri_plan(admm_b200_handle* h, int64_t k, int64_t c_lo, int64_t c_hi) {
+  for (auto& e : h->st_plans)
+    if (e->k == k && e->c_lo == c_lo && e->c_hi == c_hi) return e;
+  SymtriPlan* pl = new SymtriPlan();
+  pl->k = k; pl->c_lo = c_lo; pl->c_hi = c_hi;
+  // visiting order: longest remaining column, shortest remaining column, ... (their lengths sum to c_lo + c_hi + 1)
+  std::vector<int> order;
+  for (int64_t lo = c_lo, hi = c_hi - 1; lo <= hi;) {
+    order.push_back((int)hi--);
+    if (lo <= hi) order.push_back((int)lo++);
+  }
+  std::vector<SymtriEnt> ents;
+  std::vector<int> round_ent;
+  std::vector<int64_t> round_bytes;
+  int used = 0, cnt = 0;
+  for (int c : order) {
+    const int len = c + 1, padded = (len + 1) & ~1;
+    if (cnt == 0 || used + padded > ST_STAGE || cnt == ST_CPR) {
+      round_ent.push_back((int)ents.size());
+      round_bytes.push_back(0);
+      used = 0; cnt = 0;
+    }
+    ents.push_back(SymtriEnt{c, used, len, 0});
+    used += padded; ++cnt;
+    round_bytes.back() += (int64_t)padded * 8;
+  }
+  round_ent.push_back((int)ents.size());
+  const int nrounds = (int)round_bytes.size();
+  // contiguous rounds per CTA, equal cost (bytes + a fixed cost per round for the two barriers)
+  const int grid = std::max(1, std::min(kNumSM, nrounds));
+  std::vector<int64_t> cost(nrounds + 1, 0);
+  for (int r = 0; r < nrounds; ++r) cost[r + 1] = cost[r] + round_bytes[r] + 4096;
+  std::vector<int> cta_round(grid + 1, 0);
+  int c = 0;
+  for (int b = 1; b <= grid; ++b) {
+    const int64_t target = (int64_t)((double)cost[nrounds] * b / grid);
+    while (c < nrounds && (b == grid || cost[c + 1] <= target)) ++c;
+    cta_round[b] = c;
+  }
+  pl->grid = grid;
+  ADMM_CUDA(cudaMalloc(&pl->d_cta_round, cta_round.size() * sizeof(int)));
+  ADMM_CUDA(cudaMalloc(&pl->d_round_ent, round_ent.size() * sizeof(int)));
+  ADMM_CUDA(cudaMalloc(&pl->d_ents, std::max<size_t>(ents.size(), 1) * sizeof(SymtriEnt)));
+  ADMM_CUDA(cudaMemcpyAsync(pl->d_cta_round, cta_round.data(), cta_round.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  ADMM_CUDA(cudaMemcpyAsync(pl->d_round_ent, round_ent.data(), round_ent.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  ADMM_CUDA(cudaMemcpyAsync(pl->d_ents, ents.data(), ents.size() * sizeof(SymtriEnt), cudaMemcpyHostToDevice, h->stream));
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));   // the host vectors die here (same reason as coldot_plan)
+  h->st_plans.push_back(pl);
+  return pl;
+}
+
+static bool symtri_ok(const admm_b200_handle* h, int64_t k, int64_t ld, const double* WT) {
+  static const bool off = getenv("ADMM_B200_NO_SYMTRI") != nullptr;
+  return !off && k <= ST_MAXK && k >= 2 && (ld % 2 == 0) && (((uintptr_t)WT & 15) == 0);
+}
+
+// x = WT * (WT' * b) = W'(W b) in one pass over WT (upper triangular, columns contiguous).  shard: this rank
+// takes an equal-area range of columns and the rank sums are allreduced (row-sharded lasso, large k).
+static void symtri_solve(admm_b200_handle* h, const double* WT, int64_t ld, int64_t k, const double* b, double* x,
+                         const int* done, bool shard) {
+  static PerDevice configured_pd;
+  size_t& configured = configured_pd(h->device);
+  if (!configured) {
+    ADMM_CUDA(cudaFuncSetAttribute(symtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
+    configured = 1;
+  }
+  int64_t c_lo, c_hi;
+  symtri_range(k, shard ? h->rank : 0, shard ? h->nranks : 1, c_lo, c_hi);
+  SymtriPlan* pl = symtri_plan(h, k, c_lo, c_hi);
+  const int kpad = (int)round_up(k, 2);
+  h->st_part.ensure((int64_t)pl->grid * kpad);
+  SymtriArgs a;
+  a.WT = WT; a.ld = ld; a.k = (int)k; a.kpad = kpad; a.y = b; a.xpart = h->st_part.p; a.done = done;
+  a.cta_round = pl->d_cta_round; a.round_ent = pl->d_round_ent; a.ents = pl->d_ents;
+  symtri_kernel<<<pl->grid, ST_THREADS, ST_SMEM, h->stream>>>(a);
+  ADMM_CUDA(cudaGetLastError());
+  symtri_reduce_kernel<<<(unsigned)((k + 31) / 32), 256, 0, h->stream>>>(h->st_part.p, pl->grid, kpad, (int)k, x, 1.0, nullptr, 0.0, done);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches += 2;
+  if (shard) allreduce_sum(h, x, kpad, done);
+}
+
 // x = L' \ (L \ b) with the cached factor (size k); second = the z-update factor of the model problem
 static void factor_solve(admm_b200_handle* h, const double* b, double* tmp, double* x, int xsolve, const int* done,
                          bool second = false) {
@@ -692,6 +796,10 @@ static void factor_solve(admm_b200_handle* h, const double* b, double* tmp, doub
   if (second) {
     ADMM_REQUIRE(xsolve == ADMM_B200_XSOLVE_INVFACTOR && h->W2.p && h->WT2.p, ADMM_B200_ERR_UNSUPPORTED,
                  "the model problem's z-update is built for xsolve = INVFACTOR");
+    if (symtri_ok(h, h->k, h->ldf, h->WT2.p)) {
+      symtri_solve(h, h->WT2.p, h->ldf, h->k, b, x, done, false);
+      return;
+    }
     coldot(h, COLDOT_UPPER, h->WT2.p, h->ldf, h->k, h->k, b, tmp, 1.0, nullptr, 0.0, done);
     coldot(h, COLDOT_LOWER, h->W2.p, h->ldf, h->k, h->k, tmp, x, 1.0, nullptr, 0.0, done);
     return;
@@ -699,6 +807,10 @@ static void factor_solve(admm_b200_handle* h, const double* b, double* tmp, doub
   if (xsolve == ADMM_B200_XSOLVE_INVFACTOR) {
     ADMM_REQUIRE(h->have_inverse, ADMM_B200_ERR_STATE,
                  "xsolve = INVFACTOR but the setup was done with xsolve = SUBST (no inverse factor was built)");
+    if (symtri_ok(h, h->k, h->ldf, h->WT.p)) {       // one pass over the triangle (symtri.cuh)
+      symtri_solve(h, h->WT.p, h->ldf, h->k, b, x, done, h->xshard);
+      return;
+    }
     // t = W b : row i of W is column i of WT (rows 0..i)
     coldot(h, COLDOT_UPPER, h->WT.p, h->ldf, h->k, h->k, b, tmp, 1.0, nullptr, 0.0, done);
     // x = W' t : x_j = column j of W (rows j..k-1) . t
@@ -830,9 +942,12 @@ static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t m_total, int64_t
   ADMM_REQUIRE(!sharded || m_total >= n, ADMM_B200_ERR_UNSUPPORTED,
                "lasso: only the tall problem (rows >= columns) is row-sharded; the fat one factors D*D', which couples all rows");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
   h->kind = ADMM_B200_LASSO;
   h->lasso_sharded = sharded;
+  // a large factor on several GPUs: every rank streams its equal-area share of the inverse factor's columns and one
+  // mailbox allreduce of the n-vector sums them (x = sum_i w_i (w_i . y) splits over i)
+  h->xshard = sharded && h->p2p.ready && n >= 4096 && n <= ST_MAXK && round_up(n, 2) <= P2P_CAP && !getenv("ADMM_B200_NO_XSHARD");
   h->m_total = m_total;
   h->tall = (m_total >= n);
   h->rho_setup = rho;
@@ -919,7 +1034,7 @@ static void setup_bp(admm_b200_handle* h, int64_t m, int64_t n, const double* D,
   ADMM_REQUIRE(m > 0 && n > 0 && D && s && ldD >= m, ADMM_B200_ERR_INVALID, "basispursuit: bad dimensions or null input");
   ADMM_REQUIRE(m < n, ADMM_B200_ERR_INVALID, "basispursuit: D must have fewer rows than columns");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
   stage_matrix(h, m, n, D, ldD);
   h->s.ensure(round_up(m, 2));
   copy_in(h, h->s.p, s, m);
@@ -961,7 +1076,7 @@ static void setup_quadratic(admm_b200_handle* h, int kind, int64_t n, const doub
   ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
   ADMM_REQUIRE(kind != ADMM_B200_PROX_BOX || (lb && ub), ADMM_B200_ERR_INVALID, "setup_quadratic: box bounds missing");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
   h->kind = kind;
   h->tall = true;
   h->m = h->n = n;
@@ -1028,7 +1143,7 @@ static void setup_model(admm_b200_handle* h, int64_t m, int64_t n, const double*
                "model: bad dimensions or null input");
   ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
   h->kind = ADMM_B200_MODEL;
   h->tall = true;
   h->xsolve = ADMM_B200_XSOLVE_INVFACTOR;
@@ -1069,7 +1184,7 @@ static void setup_model(admm_b200_handle* h, int64_t m, int64_t n, const double*
 static void setup_tv(admm_b200_handle* h, int64_t n, const double* s, double lambda) {
   ADMM_REQUIRE(n > 0 && s, ADMM_B200_ERR_INVALID, "totalvariation: bad dimensions or null input");
   ADMM_REQUIRE(lambda >= 0, ADMM_B200_ERR_INVALID, "Given lambda parameter is not a nonnegative number!");
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
   h->kind = ADMM_B200_TOTALVARIATION;
   h->m = h->n = n;
   h->nA = h->nB = h->mc = n;
@@ -1280,7 +1395,7 @@ static void setup_unwrapped(admm_b200_handle* h, int kind, int64_t m_local, int6
   if (kind == ADMM_B200_SVM_HINGE || kind == ADMM_B200_SVM_01)
     ADMM_REQUIRE(C >= 0, ADMM_B200_ERR_INVALID, "Given regularization parameter C is not a nonnegative number!");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
   stage_matrix(h, m_local, n, D, ldD);
   h->aux.ensure(round_up(m_local, 2));
   copy_in(h, h->aux.p, aux, m_local);
@@ -1764,15 +1879,20 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
       else if (R == 24) onepass_launch<24>(h, op, grid1);
       else onepass_launch<16>(h, op, grid1);
       ADMM_CUDA(cudaGetLastError());
+      // row-sharded runs with mapped mailboxes: the finish kernel stores this rank's sums into every peer (NVLink)
+      // and the epilogue adds the ranks up -- no library collective, no extra launches
+      const int64_t msg_count = (int64_t)nv * npad + UW_NRED;
+      const int use_mail = (h->nranks > 1 && h->p2p.ready && msg_count <= P2P_CAP) ? 1 : 0;
       uw_onepass_finish_kernel<<<(unsigned)((nv * n + UW_NRED + 7) / 8), 256, 0, h->stream>>>(h->op_dpart.p, ndparts, grid1, nv, n, npad, d,
-                                                                                        h->uw_partials.p, scal, h->ctl);
+                                                                                        h->uw_partials.p, scal, h->ctl, h->p2p.dev, use_mail);
       ADMM_CUDA(cudaGetLastError());
       h->launches += 2;
-      allreduce_sum(h, d, (int64_t)nv * npad + UW_NRED, done);
+      if (!use_mail) allreduce_sum(h, d, msg_count, done);
       UwEpiArgs e;
       e.n = n; e.x = h->x.p; e.dzv = (nv == 3) ? d + npad : nullptr; e.duv = (nv == 3) ? d + 2 * npad : nullptr;
       e.scalars = scal; e.m_total = (double)h->m_total; e.kind = a.kind; e.C = h->svmC; e.ctl = h->ctl; e.lp = lp;
       e.xvals = history ? h->xvals.p : nullptr;
+      e.mail = h->p2p.dev; e.use_mail = use_mail; e.msg = d; e.msg_count = msg_count;
       uw_epilogue_kernel<<<1, 256, 0, h->stream>>>(e);
       ADMM_CUDA(cudaGetLastError());
       h->launches++;
@@ -1805,6 +1925,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     e.n = n; e.x = h->x.p; e.dzv = (nv == 3) ? d + npad : nullptr; e.duv = (nv == 3) ? d + 2 * npad : nullptr;
     e.scalars = scal; e.m_total = (double)h->m_total; e.kind = a.kind; e.C = h->svmC; e.ctl = h->ctl; e.lp = lp;
     e.xvals = history ? h->xvals.p : nullptr;
+    e.mail = h->p2p.dev; e.use_mail = 0; e.msg = nullptr; e.msg_count = 0;
     uw_epilogue_kernel<<<1, 256, 0, h->stream>>>(e);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
@@ -2401,6 +2522,11 @@ int admm_b200_destroy(admm_b200_handle* h) {
     cudaFree(p->d_cta_pos); cudaFree(p->d_pos_item); cudaFree(p->d_order); cudaFree(p->d_items);
     delete p;
   }
+  for (SymtriPlan* p : h->st_plans) {
+    cudaFree(p->d_cta_round); cudaFree(p->d_round_ent); cudaFree(p->d_ents);
+    delete p;
+  }
+  h->st_part.release();
   if (h->tickets) cudaFree(h->tickets);
   if (h->grid_ticket) cudaFree(h->grid_ticket);
   comm_destroy(h);

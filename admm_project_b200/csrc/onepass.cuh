@@ -17,6 +17,7 @@
 // phase, one column per lane in the D' phase) are free of bank conflicts with LDS.128.
 #pragma once
 #include "unwrapped.cuh"
+#include "p2p.cuh"
 
 namespace admmb200 {
 
@@ -407,8 +408,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OP_THREADS, 1) uw_on
 // in order, then a fixed xor tree -- a thread per output would walk ~300 dependent L2 loads (20+ us).
 __global__ void __launch_bounds__(256) uw_onepass_finish_kernel(const double* dpart, int ndparts, int nparts, int nv, int64_t n,
                                                                 int64_t npad, double* d, const double* partials,
-                                                                double* scalars, const LoopCtl* ctl) {
+                                                                double* scalars, const LoopCtl* ctl, P2PDev mail, int use_mail) {
   if (ctl->done) return;
+  if (use_mail && *mail.err) return;
+  // row-sharded runs: the sums of THIS rank go straight into every rank's mailbox (p2p.cuh) -- message layout
+  // [d (nv x npad) ; scalars] -- and the last CTA raises the flags; uw_epilogue_kernel waits and adds the ranks up
+  const unsigned long long seq = use_mail ? *mail.seq : 0ull;
+  const int par = (int)(seq & 1);
   const int lane = threadIdx.x & 31;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // output index
   const int64_t nout = (int64_t)nv * n;
@@ -423,10 +429,13 @@ __global__ void __launch_bounds__(256) uw_onepass_finish_kernel(const double* dp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) {
-      if (w < nout) d[(w / n) * npad + (w % n)] = s;
+      const int64_t idx = (w < nout) ? (w / n) * npad + (w % n) : (int64_t)nv * npad + (w - nout);
+      if (use_mail) p2p_store(mail, par, idx, s);
+      else if (w < nout) d[idx] = s;
       else scalars[w - nout] = s;
     }
   }
+  if (use_mail) p2p_signal(mail, par, seq, gridDim.x);
 }
 
 }  // namespace admmb200

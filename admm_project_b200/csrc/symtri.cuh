@@ -1,0 +1,195 @@
+// symtri.cuh -- the per-iteration x-update x = U \ (L \ y) (getProxOps.m:1200; Rt \ (R \ .) :1514; W \ d
+// unwrappedadmm.m:139) in ONE pass over the cached inverse factor.
+//
+// With W = inv(L):   x = W'(W y) = sum_i w_i (w_i . y),   w_i = row i of W = column i of WT = W' (rows 0..i,
+// contiguous in memory).  A dot product and an AXPY with the SAME column: once a column sits on chip both are
+// done from it, so the triangle is read from HBM once per x-update instead of twice (coldot x 2, tri.cuh) --
+// n(n+1)/2 * 8 bytes = 268 MB at n = 8192.
+//
+// Data path: columns are fetched with the TMA engine as 1-D bulk copies (cp.async.bulk.shared.global, SASS
+// UBLKCP) into a 3-stage shared-memory ring, completion on mbarriers; one thread issues, nobody executes a
+// load instruction for matrix data.  A ROUND is a group of columns that fills one stage (~64 KB): columns are
+// visited longest-with-shortest (their lengths sum to ~k+1), so every round moves the same number of bytes and
+// the 148 CTAs finish together.  While round r is being worked on, rounds r+1 and r+2 are in flight (~130 KB
+// per SM).
+// Compute: thread t owns rows {2t, 2t+1} + 1024 q for every column; its y values and its slice of the result
+// live in registers for the whole kernel.  Per round: partial dots from shared memory (conflict-free LDS.128)
+// -> warp shuffle -> per-warp partials in shared memory -> barrier -> every thread sums the 16 partials in the
+// same fixed order -> AXPY from shared memory into the register accumulators -> barrier -> refill the stage.
+// Each CTA writes its partial x; the partials are summed in CTA order by symtri_reduce_kernel, so the result is
+// bitwise reproducible.  Row-sharded runs give each rank a contiguous range of columns of equal area; the
+// rank sums then go through the mailbox allreduce.
+#pragma once
+#include "common.cuh"
+
+namespace admmb200 {
+
+constexpr int ST_THREADS = 512;
+constexpr int ST_WARPS = ST_THREADS / 32;
+constexpr int ST_Q = 8;                               // row groups of 1024: k <= 8192
+constexpr int ST_MAXK = ST_Q * 2 * ST_THREADS;        // 8192
+constexpr int ST_STAGE = 8192 + 64;                   // doubles per stage: a (longest, shortest) pair + alignment slack
+constexpr int ST_NSTAGE = 3;
+constexpr int ST_CPR = 16;                            // columns per round at most (small factors pack several pairs)
+constexpr size_t ST_SMEM = (size_t)ST_NSTAGE * ST_STAGE * 8 + (size_t)ST_CPR * ST_WARPS * 8 + 64;
+
+struct SymtriEnt { int col, off, len, pad; };        // column, offset in the stage (doubles, even), rows 0..len-1
+
+struct SymtriArgs {
+  const double* WT; int64_t ld;
+  int k, kpad;
+  const double* y;
+  double* xpart;                   // [gridDim.x][kpad]
+  const int* done;
+  const int* cta_round;            // [grid + 1]
+  const int* round_ent;            // [nrounds + 1]
+  const SymtriEnt* ents;
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
+  if (a.done && *a.done) return;
+  extern __shared__ __align__(128) unsigned char st_raw[];
+  double* stage = reinterpret_cast<double*>(st_raw);                                  // [NSTAGE][ST_STAGE]
+  double* wsum = stage + (size_t)ST_NSTAGE * ST_STAGE;                                // [ST_CPR][ST_WARPS]
+  uint64_t* full = reinterpret_cast<uint64_t*>(wsum + ST_CPR * ST_WARPS);             // [NSTAGE]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = a.cta_round[blockIdx.x], r1 = a.cta_round[blockIdx.x + 1];
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < ST_NSTAGE; ++s) mbar_init(full + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto issue = [&](int round) {            // thread 0: all columns of `round` into stage (round - r0) % NSTAGE
+    const int s = (round - r0) % ST_NSTAGE;
+    const int e0 = a.round_ent[round], e1 = a.round_ent[round + 1];
+    unsigned total = 0;
+    for (int e = e0; e < e1; ++e) total += (unsigned)((a.ents[e].len + 1) & ~1) * 8u;
+    mbar_expect_tx(full + s, total);
+    for (int e = e0; e < e1; ++e) {
+      const SymtriEnt en = a.ents[e];
+      tma_bulk_g2s(stage + (size_t)s * ST_STAGE + en.off, a.WT + (int64_t)en.col * a.ld, (unsigned)((en.len + 1) & ~1) * 8u,
+                   full + s);
+    }
+  };
+  if (tid == 0)
+    for (int r = r0; r < r1 && r < r0 + ST_NSTAGE; ++r) issue(r);
+
+  // this thread's rows: 2*tid + 1024*q (+0, +1)
+  double2 yv[ST_Q], acc[ST_Q];
+#pragma unroll
+  for (int q = 0; q < ST_Q; ++q) {
+    const int row = 2 * tid + 1024 * q;
+    yv[q] = make_double2(row < a.k ? a.y[row] : 0.0, row + 1 < a.k ? a.y[row + 1] : 0.0);
+    acc[q] = make_double2(0.0, 0.0);
+  }
+
+  for (int round = r0; round < r1; ++round) {
+    const int s = (round - r0) % ST_NSTAGE;
+    const unsigned parity = (unsigned)(((round - r0) / ST_NSTAGE) & 1);
+    const double* sb = stage + (size_t)s * ST_STAGE;
+    const int e0 = a.round_ent[round], ne = a.round_ent[round + 1] - e0;
+    mbar_wait(full + s, parity);
+    // ---- partial dots w_i . y
+    for (int j = 0; j < ne; ++j) {
+      const SymtriEnt en = a.ents[e0 + j];
+      const double* col = sb + en.off;
+      double p0 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < ST_Q; ++q) {
+        const int row = 2 * tid + 1024 * q;
+        if (row < en.len) {                       // len is rounded up with a zero: row + 1 is loaded too
+          const double2 v = *reinterpret_cast<const double2*>(col + row);
+          p0 = fma(v.x, yv[q].x, p0);
+          p1 = fma(v.y, yv[q].y, p1);
+        }
+      }
+      const double p = warp_sum(p0 + p1);
+      if (lane == 0) wsum[j * ST_WARPS + warp] = p;
+    }
+    __syncthreads();
+    // ---- x += w_i * t_i
+    for (int j = 0; j < ne; ++j) {
+      const SymtriEnt en = a.ents[e0 + j];
+      const double* col = sb + en.off;
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < ST_WARPS; ++w) t += wsum[j * ST_WARPS + w];      // same order in every thread
+#pragma unroll
+      for (int q = 0; q < ST_Q; ++q) {
+        const int row = 2 * tid + 1024 * q;
+        if (row < en.len) {
+          const double2 v = *reinterpret_cast<const double2*>(col + row);
+          acc[q].x = fma(v.x, t, acc[q].x);
+          acc[q].y = fma(v.y, t, acc[q].y);
+        }
+      }
+    }
+    __syncthreads();                              // everybody is done with stage s and with wsum
+    if (tid == 0 && round + ST_NSTAGE < r1) issue(round + ST_NSTAGE);
+  }
+  double* xp = a.xpart + (size_t)blockIdx.x * a.kpad;
+#pragma unroll
+  for (int q = 0; q < ST_Q; ++q) {
+    const int row = 2 * tid + 1024 * q;
+    if (row < a.kpad) *reinterpret_cast<double2*>(xp + row) = acc[q];
+  }
+}
+
+// x[r] = scale * sum over CTAs (fixed order) of xpart[cta][r] (+ addscale * addend[r]).  32 rows x 8 CTA groups per block.
+__global__ void __launch_bounds__(256) symtri_reduce_kernel(const double* __restrict__ xpart, int nparts, int kpad, int k,
+                                                            double* __restrict__ x, double scale, const double* addend,
+                                                            double addscale, const int* done) {
+  if (done && *done) return;
+  __shared__ double sh[8][33];
+  const int rl = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int row = blockIdx.x * 32 + rl;
+  const int per = (nparts + 7) / 8;
+  double s = 0.0;
+  if (row < k)
+    for (int c = g * per; c < min(nparts, (g + 1) * per); ++c) s += __ldcg(xpart + (size_t)c * kpad + row);
+  sh[g][rl] = s;
+  __syncthreads();
+  if (g == 0 && row < k) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sh[i][rl];
+    t *= scale;
+    if (addend) t += addscale * addend[row];
+    x[row] = t;
+  }
+}
+
+}  // namespace admmb200

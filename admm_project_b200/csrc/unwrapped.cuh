@@ -14,6 +14,7 @@
 #pragma once
 #include "common.cuh"
 #include "prox.cuh"
+#include "p2p.cuh"
 
 namespace admmb200 {
 
@@ -244,12 +245,37 @@ struct UwEpiArgs {
   LoopCtl* ctl;
   LoopParams lp;
   double* xvals;                   // optional history (n x maxiters)
+  // row-sharded runs whose message went straight into the mailboxes (uw_onepass_finish_kernel): wait for every
+  // rank, add the ranks up in rank order into msg[0 .. msg_count) (= [d ; D'dz ; D'u ; scalars]) first
+  P2PDev mail;
+  int use_mail;
+  double* msg;
+  int64_t msg_count;
 };
 
 __global__ void __launch_bounds__(256) uw_epilogue_kernel(UwEpiArgs a) {
   LoopCtl* ctl = a.ctl;
   if (ctl->done) return;
   __shared__ double sh[8 * 3];
+  if (a.use_mail) {
+    if (*a.mail.err) return;
+    const unsigned long long seq = *a.mail.seq;
+    const int par = (int)(seq & 1);
+    const bool ok = p2p_wait(a.mail, par, seq);
+    if (ok) {
+      for (int64_t i = threadIdx.x; i < a.msg_count; i += blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < a.mail.nranks; ++r) acc += ld_relaxed_sys(a.mail.slot(a.mail.rank, par, r) + i);
+        a.msg[i] = acc;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *a.mail.seq = seq + 1;
+    if (!ok) {                       // a peer stopped taking part: end the loop, the host raises (p2p_check)
+      if (threadIdx.x == 0) { ctl->status = 3; __threadfence(); ctl->done = 1; }
+      return;
+    }
+  }
   const int it = ctl->it;
   double r[3] = {0.0, 0.0, 0.0};
   for (int64_t i = threadIdx.x; i < a.n; i += blockDim.x) {
