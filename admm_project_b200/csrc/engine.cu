@@ -23,6 +23,7 @@
 #include "tv.cuh"
 #include "p2p.cuh"
 #include "symtri.cuh"
+#include "persist.cuh"
 #include <dlfcn.h>
 
 namespace admmb200 {
@@ -151,6 +152,9 @@ struct admm_b200_handle {
   int xsolve_eff = ADMM_B200_XSOLVE_INVFACTOR;   // x-update realisation actually used (SUBST when the guard fired)
   int64_t zero_cols = 0;         // A = D problems: all-zero columns of D handled as pinv does (x_j = 0)
   std::vector<ColdotPlan*> plans;
+  DBuf Qm, tcur, tlast;          // persistent A = D iteration (persist.cuh): Q_g = D_g inv(R)', t vectors
+  bool have_Q = false;
+  int64_t ldq = 0;
   std::vector<SymtriPlan*> st_plans;
   DBuf st_part;                  // per-CTA partial x of the one-pass x-update
   bool xshard = false;           // lasso from row shards with a large factor: the x-update is split by columns over the ranks
@@ -942,7 +946,7 @@ static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t m_total, int64_t
   ADMM_REQUIRE(!sharded || m_total >= n, ADMM_B200_ERR_UNSUPPORTED,
                "lasso: only the tall problem (rows >= columns) is row-sharded; the fat one factors D*D', which couples all rows");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false; h->have_Q = false;
   h->kind = ADMM_B200_LASSO;
   h->lasso_sharded = sharded;
   // a large factor on several GPUs: every rank streams its equal-area share of the inverse factor's columns and one
@@ -1034,7 +1038,7 @@ static void setup_bp(admm_b200_handle* h, int64_t m, int64_t n, const double* D,
   ADMM_REQUIRE(m > 0 && n > 0 && D && s && ldD >= m, ADMM_B200_ERR_INVALID, "basispursuit: bad dimensions or null input");
   ADMM_REQUIRE(m < n, ADMM_B200_ERR_INVALID, "basispursuit: D must have fewer rows than columns");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false; h->have_Q = false;
   stage_matrix(h, m, n, D, ldD);
   h->s.ensure(round_up(m, 2));
   copy_in(h, h->s.p, s, m);
@@ -1076,7 +1080,7 @@ static void setup_quadratic(admm_b200_handle* h, int kind, int64_t n, const doub
   ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
   ADMM_REQUIRE(kind != ADMM_B200_PROX_BOX || (lb && ub), ADMM_B200_ERR_INVALID, "setup_quadratic: box bounds missing");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false; h->have_Q = false;
   h->kind = kind;
   h->tall = true;
   h->m = h->n = n;
@@ -1143,7 +1147,7 @@ static void setup_model(admm_b200_handle* h, int64_t m, int64_t n, const double*
                "model: bad dimensions or null input");
   ADMM_REQUIRE(rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false; h->have_Q = false;
   h->kind = ADMM_B200_MODEL;
   h->tall = true;
   h->xsolve = ADMM_B200_XSOLVE_INVFACTOR;
@@ -1184,7 +1188,7 @@ static void setup_model(admm_b200_handle* h, int64_t m, int64_t n, const double*
 static void setup_tv(admm_b200_handle* h, int64_t n, const double* s, double lambda) {
   ADMM_REQUIRE(n > 0 && s, ADMM_B200_ERR_INVALID, "totalvariation: bad dimensions or null input");
   ADMM_REQUIRE(lambda >= 0, ADMM_B200_ERR_INVALID, "Given lambda parameter is not a nonnegative number!");
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false; h->have_Q = false;
   h->kind = ADMM_B200_TOTALVARIATION;
   h->m = h->n = n;
   h->nA = h->nB = h->mc = n;
@@ -1287,6 +1291,7 @@ static void p2p_setup(admm_b200_handle* h) {
   P2PState& P = h->p2p;
   const int R = h->nranks;
   if (R < 2 || R > P2P_MAXRANKS) return;
+  p2p_teardown(h);               // a single-rank local mailbox (ensure_mailbox) gives way to the mapped ones
   const bool want = !getenv("ADMM_B200_NO_P2P");
   P.bytes = (size_t)P2P_FLAG_BYTES + (size_t)2 * R * P2P_CAP * 8;
   ADMM_CUDA(cudaMalloc(&P.local, P.bytes));
@@ -1395,7 +1400,7 @@ static void setup_unwrapped(admm_b200_handle* h, int kind, int64_t m_local, int6
   if (kind == ADMM_B200_SVM_HINGE || kind == ADMM_B200_SVM_01)
     ADMM_REQUIRE(C >= 0, ADMM_B200_ERR_INVALID, "Given regularization parameter C is not a nonnegative number!");
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false;
+  h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false; h->have_Q = false;
   stage_matrix(h, m_local, n, D, ldD);
   h->aux.ensure(round_up(m_local, 2));
   copy_in(h, h->aux.p, aux, m_local);
@@ -2060,6 +2065,101 @@ static void run_bursts(admm_b200_handle* h, const admm_b200_options& o, int64_t 
   drop();
 }
 
+// ---------------------------------------------------------------------------------------------
+// persistent A = D iteration (persist.cuh)
+// ---------------------------------------------------------------------------------------------
+// a single rank runs the same kernel on a LOCAL mailbox (no IPC); p2p_setup replaces it when ranks attach
+static void ensure_mailbox(admm_b200_handle* h) {
+  P2PState& P = h->p2p;
+  if (P.local) return;
+  P.bytes = (size_t)P2P_FLAG_BYTES + (size_t)2 * P2P_CAP * 8;
+  ADMM_CUDA(cudaMalloc(&P.local, P.bytes));
+  ADMM_CUDA(cudaMemsetAsync(P.local, 0, P.bytes, h->stream));
+  void* ctr = nullptr;
+  ADMM_CUDA(cudaMalloc(&ctr, 64));
+  ADMM_CUDA(cudaMemsetAsync(ctr, 0, 64, h->stream));
+  P.dev.seq = (unsigned long long*)ctr;
+  P.dev.ticket = (unsigned*)((char*)ctr + 8);
+  P.dev.err = (int*)((char*)ctr + 16);
+  P.dev.rank = 0; P.dev.nranks = 1; P.dev.cap = P2P_CAP;
+  P.dev.mail[0] = (unsigned char*)P.local;
+  P.ready = false;
+}
+
+static bool persist_ok(const admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, bool history) {
+  if (getenv("ADMM_B200_NO_PERSIST")) return false;
+  if (!is_unwrapped(h->kind) || lp.alg != 0 || !o.nodualerror || o.objevals || history || lp.raw) return false;
+  if (!h->have_inverse || h->xsolve_eff != ADMM_B200_XSOLVE_INVFACTOR || o.xsolve != ADMM_B200_XSOLVE_INVFACTOR) return false;
+  if (h->nranks > 1 && !h->p2p.ready) return false;
+  if (round_up(h->n, 2) + UW_NRED > P2P_CAP) return false;
+  return onepass_rows(h, lp) != 0;
+}
+
+template <int R>
+static void persist_launch(admm_b200_handle* h, PersistArgs& a, int grid) {
+  static PerDevice conf_pd;
+  size_t& conf = conf_pd(h->device);
+  const size_t smem = OnepassCfg<R>::smem_bytes(a.uw.n, a.npad);
+  if (smem > conf) {
+    ADMM_CUDA(cudaFuncSetAttribute(uw_persist_kernel<R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  void* args[] = {&a};
+  ADMM_CUDA(cudaLaunchCooperativeKernel((const void*)uw_persist_kernel<R, 2>, dim3(grid), dim3(OP_THREADS), args, smem, h->stream));
+  h->launches++;
+}
+
+// The whole loop of a persist_ok problem.  On return h->x / z / u hold the final iterates and h->h_ctl the loop state.
+static void run_persist(admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, int64_t N) {
+  const int64_t n = h->n, m = h->m, npad = round_up(n, 2);
+  if (h->nranks == 1) ensure_mailbox(h);
+  if (!h->have_Q) {
+    // Q_g = D_g * inv(R)' on this rank's rows: one DMMA GEMM per setup (m x n x n), kept next to D
+    h->ldq = round_up(m, 2);
+    h->Qm.ensure(h->ldq * n);
+    GemmOpt g;
+    gemm(h, 0, 1, m, n, n, 1.0, h->dD, h->ldD, h->W.p, h->ldf, 0.0, h->Qm.p, h->ldq, g);
+    h->have_Q = true;
+  }
+  h->tcur.ensure(npad + 2); h->tlast.ensure(npad + 2);
+  // t of the first iteration: sum_g Q_g' r0_g, r0 = z0 - u0 (unwrappedadmm.m:133) or s + z0 - u0 (getProxOps.m:1514)
+  uw_first_rhs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, h->z.p, h->u.p, h->aux.p, uw_kind(h->kind), h->rvec.p);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+  ADMM_CUDA(cudaMemsetAsync(h->tcur.p, 0, (size_t)(npad + 2) * 8, h->stream));
+  coldot(h, COLDOT_FULL, h->Qm.p, h->ldq, m, n, h->rvec.p, h->tcur.p);
+  allreduce_sum(h, h->tcur.p, npad);
+  ADMM_CUDA(cudaMemcpyAsync(h->tlast.p, h->tcur.p, (size_t)npad * 8, cudaMemcpyDeviceToDevice, h->stream));
+
+  int R = onepass_rows(h, lp);
+  PersistArgs a;
+  UwArgs& u = a.uw;
+  u.D = h->Qm.p; u.ld = h->ldq; u.m = m; u.n = n; u.x = nullptr; u.z = h->z.p; u.u = h->u.p; u.aux = h->aux.p;
+  u.rvec = nullptr; u.dzvec = nullptr; u.rho = o.rho; u.relax = o.relax; u.C = h->svmC; u.kind = uw_kind(h->kind);
+  u.cols_per_chunk = 0; u.ws = nullptr; u.tickets = nullptr; u.partials = nullptr; u.grid_ticket = nullptr; u.scalars = nullptr;
+  u.ctl = h->ctl; u.zvals = u.uvals = nullptr; u.alg = 0; u.v = u.uhat = nullptr; u.zprev = u.uprev = nullptr;
+  a.ntiles = (m + R - 1) / R; a.npad = npad;
+  const int grid = (int)std::min<int64_t>(kNumSM, a.ntiles);
+  h->op_dpart.ensure((int64_t)2 * grid * npad);
+  h->uw_partials.ensure((int64_t)grid * UW_NRED);
+  a.dpart = h->op_dpart.p; a.partials = h->uw_partials.p; a.tcur = h->tcur.p; a.tlast = h->tlast.p;
+  a.mail = h->p2p.dev; a.ctl = h->ctl; a.lp = lp; a.m_total = (double)h->m_total;
+  const int check = std::max(1, o.check_every);
+  int64_t enq = 0;
+  while (true) {
+    a.burst = (int)std::min<int64_t>(check, N - enq);
+    if (R == 32) persist_launch<32>(h, a, grid);
+    else if (R == 24) persist_launch<24>(h, a, grid);
+    else persist_launch<16>(h, a, grid);
+    enq += a.burst;
+    ADMM_CUDA(cudaMemcpyAsync(h->h_ctl, h->ctl, sizeof(LoopCtl), cudaMemcpyDeviceToHost, h->stream));
+    ADMM_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->h_ctl->done != 0 || enq >= N) break;
+  }
+  // x of the last iteration: x = inv(R)' t = W' t, x_j = column j of W (rows j..n-1) . t
+  coldot(h, COLDOT_LOWER, h->W.p, h->ldf, n, n, h->tlast.p, h->x.p);
+}
+
 static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_result* res) {
   validate_options(h, o);
   int64_t N = o.maxiters > 0 ? o.maxiters : 1000;  // admm.m:334-339
@@ -2068,6 +2168,9 @@ static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_res
   LoopParams lp = make_loop_params(h, o, N, 0);
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
   load_init(h);
+  if (persist_ok(h, o, lp, history)) {
+    run_persist(h, o, lp, N);
+  } else {
   enqueue_first_rhs(h, o);
   run_bursts(
       h, o, N, h->kind == ADMM_B200_TOTALVARIATION ? 2 : 1, [&]() { enqueue_iteration(h, o, lp, 0, history); },
@@ -2076,6 +2179,7 @@ static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_res
         ADMM_CUDA(cudaStreamSynchronize(h->stream));
         return h->h_ctl->done != 0;
       });
+  }
   ADMM_CUDA(cudaEventRecord(h->ev1, h->stream));
   ADMM_CUDA(cudaEventSynchronize(h->ev1));
   p2p_check(h);
@@ -2526,7 +2630,8 @@ int admm_b200_destroy(admm_b200_handle* h) {
     cudaFree(p->d_cta_round); cudaFree(p->d_round_ent); cudaFree(p->d_ents);
     delete p;
   }
-  h->st_part.release();
+  h->st_part.release(); h->Qm.release(); h->tcur.release(); h->tlast.release();
+  p2p_teardown(h);
   if (h->tickets) cudaFree(h->tickets);
   if (h->grid_ticket) cudaFree(h->grid_ticket);
   comm_destroy(h);

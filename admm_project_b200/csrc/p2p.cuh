@@ -25,7 +25,7 @@
 namespace admmb200 {
 
 constexpr int P2P_MAXRANKS = 8;
-constexpr int64_t P2P_CAP = 16384;          // doubles per slot (128 KB): n-vector of C2, 16-class batch of C3
+constexpr int64_t P2P_CAP = 32768;          // doubles per slot (256 KB): n-vector of C2, 16-class batch of C3
 constexpr int P2P_FLAG_BYTES = 256;         // flags[2][8] uint64 = 128 B, padded
 
 struct P2PDev {
@@ -90,8 +90,10 @@ __device__ __forceinline__ void p2p_signal(const P2PDev& p, int par, unsigned lo
 }
 
 // Spin (whole CTA; thread r watches rank r) until every rank's flag of this exchange is up.  Returns false
-// on a timeout (and sets *err).
-__device__ __forceinline__ bool p2p_wait(const P2PDev& p, int par, unsigned long long s) {
+// on a timeout (and sets *err).  trap_on_timeout: inside a cooperative kernel a CTA that gave up would leave the
+// others waiting at the grid barrier for ever, so the whole kernel is aborted instead (the host sees a launch
+// failure -- loud, and the GPU stays usable).
+__device__ __forceinline__ bool p2p_wait(const P2PDev& p, int par, unsigned long long s, bool trap_on_timeout = false) {
   __shared__ int p2p_bad;
   if (threadIdx.x == 0) p2p_bad = 0;
   __syncthreads();
@@ -102,6 +104,7 @@ __device__ __forceinline__ bool p2p_wait(const P2PDev& p, int par, unsigned long
       if (clock64() - t0 > 4000000000LL) {   // ~2 s at 1.9 GHz
         p2p_bad = 1;
         *p.err = 1;
+        if (trap_on_timeout) __trap();
         break;
       }
       __nanosleep(20);

@@ -31,7 +31,10 @@ constexpr int ST_MAXK = ST_Q * 2 * ST_THREADS;        // 8192
 constexpr int ST_STAGE = 8192 + 64;                   // doubles per stage: a (longest, shortest) pair + alignment slack
 constexpr int ST_NSTAGE = 3;
 constexpr int ST_CPR = 16;                            // columns per round at most (small factors pack several pairs)
-constexpr size_t ST_SMEM = (size_t)ST_NSTAGE * ST_STAGE * 8 + (size_t)ST_CPR * ST_WARPS * 8 + 64;
+constexpr int ST_MAXENT = 448;                        // plan entries / rounds of a CTA kept in shared memory
+constexpr int ST_MAXROUND = 127;
+constexpr size_t ST_SMEM = (size_t)ST_NSTAGE * ST_STAGE * 8 + (size_t)ST_CPR * ST_WARPS * 8 + 64 + (size_t)ST_MAXENT * 16 +
+                           (size_t)(ST_MAXROUND + 1) * 4;
 
 struct SymtriEnt { int col, off, len, pad; };        // column, offset in the stage (doubles, even), rows 0..len-1
 
@@ -81,9 +84,22 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
   extern __shared__ __align__(128) unsigned char st_raw[];
   double* stage = reinterpret_cast<double*>(st_raw);                                  // [NSTAGE][ST_STAGE]
   double* wsum = stage + (size_t)ST_NSTAGE * ST_STAGE;                                // [ST_CPR][ST_WARPS]
-  uint64_t* full = reinterpret_cast<uint64_t*>(wsum + ST_CPR * ST_WARPS);             // [NSTAGE]
+  uint64_t* full = reinterpret_cast<uint64_t*>(wsum + ST_CPR * ST_WARPS);             // [NSTAGE] (+ padding to 64 bytes)
+  SymtriEnt* s_ents = reinterpret_cast<SymtriEnt*>(full + 8);                         // [ST_MAXENT]
+  int* s_rent = reinterpret_cast<int*>(s_ents + ST_MAXENT);                           // [ST_MAXROUND + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = a.cta_round[blockIdx.x], r1 = a.cta_round[blockIdx.x + 1];
+  // The CTA's slice of the plan goes to shared memory once: a round must not start with a dependent L2 round trip
+  // for its descriptors (measured: ~40 % of the kernel when they were read from global memory every round).
+  const int eb = a.round_ent[r0];
+  const int ne_cta = a.round_ent[r1] - eb;
+  const bool plan_in_smem = (ne_cta <= ST_MAXENT) && (r1 - r0 <= ST_MAXROUND);
+  if (plan_in_smem) {
+    for (int i = tid; i < ne_cta; i += ST_THREADS) s_ents[i] = a.ents[eb + i];
+    for (int i = tid; i <= r1 - r0; i += ST_THREADS) s_rent[i] = a.round_ent[r0 + i] - eb;
+  }
+  auto rent = [&](int round) { return plan_in_smem ? s_rent[round - r0] : a.round_ent[round] - eb; };
+  auto ent = [&](int e) { return plan_in_smem ? s_ents[e] : a.ents[eb + e]; };
 
   if (tid == 0) {
 #pragma unroll
@@ -94,12 +110,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
 
   auto issue = [&](int round) {            // thread 0: all columns of `round` into stage (round - r0) % NSTAGE
     const int s = (round - r0) % ST_NSTAGE;
-    const int e0 = a.round_ent[round], e1 = a.round_ent[round + 1];
+    const int e0 = rent(round), e1 = rent(round + 1);
     unsigned total = 0;
-    for (int e = e0; e < e1; ++e) total += (unsigned)((a.ents[e].len + 1) & ~1) * 8u;
+    for (int e = e0; e < e1; ++e) total += (unsigned)((ent(e).len + 1) & ~1) * 8u;
     mbar_expect_tx(full + s, total);
     for (int e = e0; e < e1; ++e) {
-      const SymtriEnt en = a.ents[e];
+      const SymtriEnt en = ent(e);
       tma_bulk_g2s(stage + (size_t)s * ST_STAGE + en.off, a.WT + (int64_t)en.col * a.ld, (unsigned)((en.len + 1) & ~1) * 8u,
                    full + s);
     }
@@ -120,11 +136,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
     const int s = (round - r0) % ST_NSTAGE;
     const unsigned parity = (unsigned)(((round - r0) / ST_NSTAGE) & 1);
     const double* sb = stage + (size_t)s * ST_STAGE;
-    const int e0 = a.round_ent[round], ne = a.round_ent[round + 1] - e0;
+    const int e0 = rent(round), ne = rent(round + 1) - e0;
     mbar_wait(full + s, parity);
     // ---- partial dots w_i . y
     for (int j = 0; j < ne; ++j) {
-      const SymtriEnt en = a.ents[e0 + j];
+      const SymtriEnt en = ent(e0 + j);
       const double* col = sb + en.off;
       double p0 = 0.0, p1 = 0.0;
 #pragma unroll
@@ -142,7 +158,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
     __syncthreads();
     // ---- x += w_i * t_i
     for (int j = 0; j < ne; ++j) {
-      const SymtriEnt en = a.ents[e0 + j];
+      const SymtriEnt en = ent(e0 + j);
       const double* col = sb + en.off;
       double t = 0.0;
 #pragma unroll

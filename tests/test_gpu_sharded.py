@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("problem,fast", [("svm", ""), ("huber", ""), ("lad", ""), ("huber", "weak"), ("lad", "strong"),
                                           ("huber", "onepass"), ("svm", "onepass"), ("lasso", ""), ("lassopath", ""),
-                                          ("svmbatch", "")])
+                                          ("svmbatch", ""), ("svm", "persist")])
 def test_two_rank_run_matches_serial_oracle(problem, fast):
     import torch
     if torch.cuda.device_count() < 2:
@@ -25,9 +25,11 @@ def test_two_rank_run_matches_serial_oracle(problem, fast):
     if fast == "onepass":          # the single-pass tile kernel (csrc/onepass.cuh) on every rank's row block
         cmd = cmd[:-2]
         env["ADMM_B200_FORCE_ONEPASS"] = "1"
+    if fast == "persist":          # the persistent kernel with its in-kernel mailbox exchange (csrc/persist.cuh)
+        cmd[cmd.index("--rows") + 1], cmd[cmd.index("--cols") + 1] = "20001", "160"
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("SHARDED ")]
     assert line, p.stdout[-2000:] + p.stderr[-2000:]
     out = json.loads(line[-1][8:])
     assert out["ok"], out
-    assert out["zopt_len"] == 5001
+    assert out["zopt_len"] == (20001 if fast == "persist" else 5001)
