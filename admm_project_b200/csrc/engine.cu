@@ -24,6 +24,7 @@
 #include "p2p.cuh"
 #include "symtri.cuh"
 #include "persist.cuh"
+#include "gemm_tma.cuh"
 #include <dlfcn.h>
 
 namespace admmb200 {
@@ -86,7 +87,9 @@ using namespace admmb200;
 
 struct admm_b200_handle {
   int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr, stream2 = nullptr;   // stream2: Cholesky look-ahead
+  cudaStream_t own_stream = nullptr, stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream_hi = nullptr;   // stream_hi / 2 / 3: Cholesky look-ahead (high / middle / low priority)
+  std::vector<cudaEvent_t> ev_pool;   // events of the look-ahead Cholesky (created on first use)
+  DBuf chol_ws;                       // out-of-place panel solves of the look-ahead Cholesky
   cudaEvent_t ev_la[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[4] = {nullptr, nullptr, nullptr, nullptr};
   double phase_ms[4] = {0, 0, 0, 0};  // gram (+Dts), cholesky, inverse factor (+transpose), total
@@ -211,18 +214,47 @@ static void ensure_tickets(admm_b200_handle* h, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 // GEMM launcher
 // ---------------------------------------------------------------------------------------------
-template <bool AK, bool BK, int VEC, int BN>
+template <bool AK, bool BK, int VEC, int BN, int BM = 128>
 static void gemm_launch_t(admm_b200_handle* h, const GemmArgs& g, dim3 grid) {
   static PerDevice configured_pd;
   size_t& configured = configured_pd(h->device);
+  constexpr int smem = GemmCfg<BM>::SMEM_BYTES;
   if (!configured) {
-    ADMM_CUDA(cudaFuncSetAttribute(gemm_f64_dmma_kernel<AK, BK, VEC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   GEMM_SMEM_BYTES));
+    ADMM_CUDA(cudaFuncSetAttribute(gemm_f64_dmma_kernel<AK, BK, VEC, BN, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = 1;
   }
-  gemm_f64_dmma_kernel<AK, BK, VEC, BN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, h->stream>>>(g);
+  gemm_f64_dmma_kernel<AK, BK, VEC, BN, BM><<<grid, GEMM_THREADS, smem, h->stream>>>(g);
   ADMM_CUDA(cudaGetLastError());
   h->launches++;
+}
+
+// ---- TMA descriptors (driver entry point fetched through the runtime: no -lcuda) ---------------------------------
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encode_fn() {
+  static TmapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (TmapEncodeFn)p;
+    else cudaGetLastError();
+  }
+  return fn;
+}
+// K-major operand tiles of a column-major matrix (rows = K, contiguous): box 16 (k) x 128 (columns), 128-byte swizzle
+static bool make_kmajor_tmap(CUtensorMap* tm, const double* base, int64_t K, int64_t cols, int64_t ld) {
+  TmapEncodeFn enc = tmap_encode_fn();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)cols};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 8};
+  cuuint32_t box[2] = {(cuuint32_t)GT_BK, 128u};
+  cuuint32_t estr[2] = {1u, 1u};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 struct GemmOpt {
@@ -231,7 +263,7 @@ struct GemmOpt {
   int batch = 1;
   int64_t strideA = 0, strideB = 0, strideC = 0;
   int allow_splitk = 1;
-  int a_lower = 0, b_lower = 0, a_upper = 0;
+  int a_lower = 0, b_lower = 0, a_upper = 0, b_upper = 0;
 };
 
 static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
@@ -243,16 +275,26 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
   g.alpha = alpha; g.beta = beta; g.diag_add = o.diag_add;
   g.lower_only = o.lower_only;
-  g.a_lower = o.a_lower; g.b_lower = o.b_lower; g.a_upper = o.a_upper;
+  g.a_lower = o.a_lower; g.b_lower = o.b_lower; g.a_upper = o.a_upper; g.b_upper = o.b_upper;
   g.batch = o.batch; g.strideA = o.strideA; g.strideB = o.strideB; g.strideC = o.strideC;
   g.splits = 1; g.k_per_split = std::max<int64_t>(K, 1); g.ws = nullptr;
+  g.bm = GEMM_BM; g.tri_skip = 0;
   const bool skinny = (N <= 64) && !o.lower_only;   // 128 x 64 tiles for few right-hand sides
+  // tall triangular op(A) x few right-hand sides (the lambda batch on a large factor): 256 x 64 tiles, uniform K chunks
+  static const bool no_tall = getenv("ADMM_B200_NO_TALL_TRI") != nullptr;
+  const bool tall_tri = skinny && !no_tall && o.batch == 1 && M >= 2048 && K >= 2048 && (o.a_lower || o.a_upper) && o.allow_splitk &&
+                        (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) && (lda % 2 == 0) && (ldb % 2 == 0);
   const int64_t bnsz = skinny ? 64 : GEMM_BN;
-  const int64_t tm = (M + GEMM_BM - 1) / GEMM_BM, tn = (N + bnsz - 1) / bnsz;
+  const int64_t bmsz = tall_tri ? 256 : GEMM_BM;
+  const int64_t tm = (M + bmsz - 1) / bmsz, tn = (N + bnsz - 1) / bnsz;
   int64_t tiles = o.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   tiles *= o.batch;
   int64_t want_splits = 1;
-  if (o.allow_splitk && tiles < kNumSM && K >= 4096) {
+  if (tall_tri) {
+    static const int64_t chunk = getenv("ADMM_B200_TRI_CHUNK") ? atoll(getenv("ADMM_B200_TRI_CHUNK")) : 1024;
+    want_splits = (K + chunk - 1) / chunk;
+    g.bm = 256; g.tri_skip = want_splits > 1;
+  } else if (o.allow_splitk && tiles < kNumSM && K >= 4096) {
     // few output tiles (n = 784 / 1024 Gram of a tall D): fill the machine twice over
     want_splits = std::min<int64_t>((2 * kNumSM + tiles - 1) / tiles, K / 1024);
   } else if (o.allow_splitk && tiles * 8 <= kNumSM && K >= 256) {
@@ -279,11 +321,40 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   const bool vec_ok = (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                       (o.strideA % 2 == 0) && (o.strideB % 2 == 0);
   dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)(o.batch * g.splits));
+  // Gram-shaped products (both operands K-major, i.e. A'*B on column-major matrices) go through the TMA-fed kernel
+  static const bool no_tma = getenv("ADMM_B200_NO_TMA") != nullptr;
+  if (!no_tma && transa != 0 && transb == 0 && vec_ok && o.batch == 1 && !skinny && !tall_tri && !o.a_lower && !o.b_lower &&
+      !o.a_upper && !o.b_upper && M >= 128 && N >= 128 && K >= 64 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31)) {
+    CUtensorMap tmA, tmB;
+    if (make_kmajor_tmap(&tmA, A, K, M, lda) && make_kmajor_tmap(&tmB, B, K, N, ldb)) {
+      static PerDevice configured_pd;
+      size_t& configured = configured_pd(h->device);
+      if (!configured) {
+        ADMM_CUDA(cudaFuncSetAttribute(gemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
+        configured = 1;
+      }
+      GemmTmaArgs t;
+      t.M = M; t.N = N; t.K = K; t.C = C; t.ldc = ldc; t.alpha = alpha; t.beta = beta; t.diag_add = o.diag_add;
+      t.lower_only = o.lower_only; t.splits = g.splits; t.k_per_split = g.k_per_split; t.ws = g.ws;
+      gemm_tma_kernel<<<grid, GT_THREADS, GT_SMEM_BYTES, h->stream>>>(tmA, tmB, t);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+      if (g.splits > 1) {
+        int64_t total = M * N;
+        dim3 rg((unsigned)std::min<int64_t>((total + 255) / 256, 4 * kNumSM), 1u);
+        gemm_splitk_reduce_kernel<<<rg, 256, 0, h->stream>>>(g);
+        ADMM_CUDA(cudaGetLastError());
+        h->launches++;
+      }
+      return;
+    }
+  }
   const bool AK = transa != 0;  // 'T': op(A)[i,k] = A[k + i*lda]  (K contiguous)
   const bool BK = transb == 0;  // 'N': op(B)[k,j] = B[k + j*ldb]  (K contiguous)
 #define ADMM_GEMM_CASE(a, b)                                     \
   if (AK == a && BK == b) {                                      \
-    if (skinny) {                                                \
+    if (tall_tri) gemm_launch_t<a, b, 2, 64, 256>(h, g, grid);   \
+    else if (skinny) {                                           \
       if (vec_ok) gemm_launch_t<a, b, 2, 64>(h, g, grid);        \
       else gemm_launch_t<a, b, 1, 64>(h, g, grid);               \
     } else if (vec_ok) gemm_launch_t<a, b, 2, 128>(h, g, grid);  \
@@ -324,7 +395,7 @@ static void transpose(admm_b200_handle* h, const double* in, int64_t rows, int64
 // A: k x k, lower triangle holds the SPD matrix; on exit lower(A) = L, strict upper zero.
 // W (k x k, ldw) zero-filled by the caller's allocation step here; on exit W = inv(L) when
 // want_inverse, otherwise only its diagonal blocks are valid.
-static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda, double* W, int64_t ldw,
+static void potrf_blocked_v1(admm_b200_handle* h, int64_t k, double* A, int64_t lda, double* W, int64_t ldw,
                           bool want_inverse) {
   static PerDevice configured_pd;
   size_t& configured = configured_pd(h->device);
@@ -444,6 +515,205 @@ static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda
            W + (start + b) + start * ldw, ldw, oa);
     }
   }
+}
+
+// inverse of a lower-triangular k x k matrix by recursive doubling, starting from inverted b0 x b0 diagonal
+// blocks already in W: for [[A,0],[B,C]]: inv = [[Ai,0],[-Ci*B*Ai, Ci]] (two batched triangular DMMA GEMMs per level)
+static void tri_inverse_doubling(admm_b200_handle* h, int64_t k, const double* A, int64_t lda, double* W, int64_t ldw,
+                                 int64_t b0, DBuf& T) {
+  for (int64_t b = b0; b < k; b *= 2) {
+    const int64_t npairs_full = k / (2 * b);  // pairs whose second block is a full b
+    if (npairs_full > 0) {
+      GemmOpt o1;
+      o1.batch = (int)npairs_full;
+      o1.strideA = 2 * b * (lda + 1);
+      o1.strideB = 2 * b * (ldw + 1);
+      o1.strideC = b * b;
+      o1.allow_splitk = 0;
+      o1.b_lower = 1;
+      gemm(h, 0, 0, b, b, b, 1.0, A + b, lda, W, ldw, 0.0, T.p, b, o1);           // T_p = B_p * Ai_p
+      GemmOpt o2;
+      o2.batch = (int)npairs_full;
+      o2.strideA = 2 * b * (ldw + 1);
+      o2.strideB = b * b;
+      o2.strideC = 2 * b * (ldw + 1);
+      o2.allow_splitk = 0;
+      o2.a_lower = 1;
+      gemm(h, 0, 0, b, b, b, -1.0, W + b + b * ldw, ldw, T.p, b, 0.0, W + b, ldw, o2);   // W21_p = -Ci_p * T_p
+    }
+    const int64_t start = npairs_full * 2 * b;
+    const int64_t cb = k - start - b;  // ragged last pair: second block has cb rows, 0 < cb < b
+    if (cb > 0) {
+      GemmOpt o, oa;
+      o.allow_splitk = oa.allow_splitk = 0;
+      o.b_lower = 1;
+      oa.a_lower = 1;
+      double* Tl = T.p + npairs_full * b * b;
+      gemm(h, 0, 0, cb, b, b, 1.0, A + (start + b) + start * lda, lda, W + start + start * ldw, ldw, 0.0, Tl, cb, o);
+      gemm(h, 0, 0, cb, b, cb, -1.0, W + (start + b) + (start + b) * ldw, ldw, Tl, cb, 0.0,
+           W + (start + b) + start * ldw, ldw, oa);
+    }
+  }
+}
+static int64_t doubling_scratch(int64_t k, int64_t b0) {
+  int64_t need = 1;
+  for (int64_t b = b0; b < k; b *= 2) need = std::max(need, (k / (2 * b) + 1) * b * b);
+  return need;
+}
+
+static void potrf_diag_launch(admm_b200_handle* h, double* A11, int64_t lda, int nb, double* W11, int64_t ldw, int64_t k0) {
+  static PerDevice configured_pd;
+  size_t& configured = configured_pd(h->device);
+  if (!configured) {
+    ADMM_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_DIAG_SMEM));
+    configured = 1;
+  }
+  potrf_diag_kernel<<<1, CHOL_DIAG_THREADS, CHOL_DIAG_SMEM, h->stream>>>(A11, lda, nb, W11, ldw, h->fail, (int)k0);
+  ADMM_CUDA(cudaGetLastError());
+  h->launches++;
+}
+
+// Cholesky AND full inverse of one wb x wb (<= 512) diagonal block, everything on h->stream, no host sync:
+// 128-wide steps (diag kernel, in-place panel solve, trailing update inside the block), then two doubling levels.
+static void potrf_block512(admm_b200_handle* h, double* A, int64_t lda, int64_t wb, double* W, int64_t ldw, int64_t pivot_base,
+                           DBuf& T) {
+  for (int64_t k0 = 0; k0 < wb; k0 += CHOL_NB) {
+    const int nb = (int)std::min<int64_t>(CHOL_NB, wb - k0);
+    double* A11 = A + k0 + k0 * lda;
+    double* W11 = W + k0 + k0 * ldw;
+    potrf_diag_launch(h, A11, lda, nb, W11, ldw, pivot_base + k0);
+    const int64_t rem = wb - k0 - nb;
+    if (rem <= 0) continue;
+    double* A21 = A + (k0 + nb) + k0 * lda;
+    GemmOpt po;
+    po.allow_splitk = 0;
+    gemm(h, 0, 1, rem, nb, nb, 1.0, A21, lda, W11, ldw, 0.0, A21, lda, po);       // in place: N <= one tile column
+    GemmOpt to;
+    to.lower_only = 1;
+    to.allow_splitk = 0;
+    gemm(h, 0, 1, rem, rem, nb, -1.0, A21, lda, A21, lda, 1.0, A + (k0 + nb) + (k0 + nb) * lda, lda, to);
+  }
+  tri_inverse_doubling(h, wb, A, lda, W, ldw, CHOL_NB, T);
+}
+
+// Look-ahead blocked Cholesky (+ inverse factor).  Outer panels of 512 columns.  Three streams:
+//   A (critical chain)  chol + inverse of the 512 x 512 diagonal block P; the block row right below it:
+//                       L21_top = A21_top * inv(L_PP)', and the NEXT diagonal block -= L21_top * L21_top'
+//   B (panel)           the rest of the panel solve L21 = A21 * inv(L_PP)' as ONE DMMA GEMM (K = 512), then the
+//                       update of the next block column A[., P+1] -= L21 * L21_top'
+//   C (bulk)            the big trailing SYRK A[P+2.., P+2..] -= L21 * L21' (K = 512, near Gram efficiency)
+// so the latency-bound chain of diagonal kernels never waits for bulk flops of its own panel (only for the bulk
+// update of the panel before), and the bulk GEMMs keep the other SMs busy meanwhile.
+static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t lda, double* W, int64_t ldw, bool want_inverse) {
+  ADMM_CUDA(cudaMemsetAsync(h->fail, 0, sizeof(int), h->stream));
+  ADMM_CUDA(cudaMemset2DAsync(W, (size_t)ldw * 8, 0, (size_t)k * 8, (size_t)k, h->stream));
+  constexpr int64_t NBO = CHOL_NBO;
+  const int64_t npan = (k + NBO - 1) / NBO;
+  while ((int64_t)h->ev_pool.size() < 5 * npan + 2) {
+    cudaEvent_t e;
+    ADMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ev_pool.push_back(e);
+  }
+  auto ev = [&](int kind, int64_t P) { return h->ev_pool[(size_t)(kind * npan + P)]; };   // 0 W, 1 top, 2 T, 3 A(col), 4 C(bulk)
+  cudaEvent_t ev_start = h->ev_pool[(size_t)(5 * npan)], ev_end = h->ev_pool[(size_t)(5 * npan + 1)];
+  DBuf& T = h->scratch;
+  T.ensure(std::max(doubling_scratch(k, NBO), doubling_scratch(NBO, CHOL_NB)));
+  const int64_t lds = round_up(k, 2);
+  h->chol_ws.ensure(lds * NBO + NBO * NBO);
+  double* S2 = h->chol_ws.p;                 // bulk panel solve result (rows below the top block) x 512
+  double* S1 = h->chol_ws.p + lds * NBO;     // top block solve result, 512 x 512
+  cudaStream_t user = h->stream, sA = h->stream_hi, sB = h->stream2, sC = h->stream3;
+  ADMM_CUDA(cudaEventRecord(ev_start, user));
+  ADMM_CUDA(cudaStreamWaitEvent(sA, ev_start, 0));
+  ADMM_CUDA(cudaStreamWaitEvent(sB, ev_start, 0));
+  ADMM_CUDA(cudaStreamWaitEvent(sC, ev_start, 0));
+  {
+  StreamSwap on_a(h, sA);                  // the chain: every launch below that does not name a stream goes to sA
+  for (int64_t P = 0; P < npan; ++P) {
+    const int64_t K0 = P * NBO, wb = std::min<int64_t>(NBO, k - K0), K1 = K0 + wb;
+    double* APP = A + K0 + K0 * lda;
+    double* WPP = W + K0 + K0 * ldw;
+    // the diagonal block has received the bulk updates of panels <= P-2 on stream C (panel P-1's came on A itself)
+    if (P >= 2) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(4, P - 2), 0));
+    potrf_block512(h, APP, lda, wb, WPP, ldw, K0, T);
+    ADMM_CUDA(cudaEventRecord(ev(0, P), sA));
+    const int64_t rem = k - K1;
+    if (rem <= 0) break;
+    const int64_t n1 = std::min<int64_t>(NBO, rem), rem2 = rem - n1;
+    GemmOpt ts;                              // panel solve as a GEMM with the inverted diagonal block (upper-triangular op(B))
+    ts.allow_splitk = 0;
+    ts.b_upper = 1;
+    // block row P+1 of block column P: updated by the column update of panel P-1 (stream B) and the bulk of <= P-2 (C)
+    if (P >= 1) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(3, P - 1), 0));
+    gemm(h, 0, 1, n1, wb, wb, 1.0, A + K1 + K0 * lda, lda, WPP, ldw, 0.0, S1, NBO, ts);
+    ADMM_CUDA(cudaMemcpy2DAsync(A + K1 + K0 * lda, (size_t)lda * 8, S1, (size_t)NBO * 8, (size_t)n1 * 8, (size_t)wb,
+                                cudaMemcpyDeviceToDevice, sA));
+    {
+      GemmOpt so;
+      so.lower_only = 1;
+      so.allow_splitk = 0;
+      // next diagonal block: bulk of panels <= P-1 must be in (stream C) before this rank-512 update lands on top
+      if (P >= 1) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(4, P - 1), 0));
+      gemm(h, 0, 1, n1, n1, wb, -1.0, A + K1 + K0 * lda, lda, A + K1 + K0 * lda, lda, 1.0, A + K1 + K1 * lda, lda, so);
+    }
+    ADMM_CUDA(cudaEventRecord(ev(1, P), sA));
+    if (rem2 > 0) {
+      double* A21b = A + (K1 + n1) + K0 * lda;          // rows below the top block, columns of panel P
+      ADMM_CUDA(cudaStreamWaitEvent(sB, ev(0, P), 0));
+      if (P >= 2) ADMM_CUDA(cudaStreamWaitEvent(sB, ev(4, P - 2), 0));
+      {
+        StreamSwap on_b(h, sB);
+        gemm(h, 0, 1, rem2, wb, wb, 1.0, A21b, lda, WPP, ldw, 0.0, S2, lds, ts);
+        ADMM_CUDA(cudaMemcpy2DAsync(A21b, (size_t)lda * 8, S2, (size_t)lds * 8, (size_t)rem2 * 8, (size_t)wb,
+                                    cudaMemcpyDeviceToDevice, sB));
+        ADMM_CUDA(cudaEventRecord(ev(2, P), sB));
+        ADMM_CUDA(cudaStreamWaitEvent(sB, ev(1, P), 0));                 // L21_top
+        if (P >= 1) ADMM_CUDA(cudaStreamWaitEvent(sB, ev(4, P - 1), 0)); // bulk of panel P-1 touched this block column too
+        GemmOpt co;
+        co.allow_splitk = 0;
+        gemm(h, 0, 1, rem2, n1, wb, -1.0, A21b, lda, A + K1 + K0 * lda, lda, 1.0, A + (K1 + n1) + K1 * lda, lda, co);
+        ADMM_CUDA(cudaEventRecord(ev(3, P), sB));
+      }
+      {
+        StreamSwap on_c(h, sC);
+        ADMM_CUDA(cudaStreamWaitEvent(sC, ev(2, P), 0));
+        GemmOpt bo;
+        bo.lower_only = 1;
+        bo.allow_splitk = 0;
+        gemm(h, 0, 1, rem2, rem2, wb, -1.0, A21b, lda, A21b, lda, 1.0, A + (K1 + n1) + (K1 + n1) * lda, lda, bo);
+        ADMM_CUDA(cudaEventRecord(ev(4, P), sC));
+      }
+    } else {
+      ADMM_CUDA(cudaEventRecord(ev(3, P), sA));
+      ADMM_CUDA(cudaEventRecord(ev(4, P), sA));
+    }
+  }
+  }
+  ADMM_CUDA(cudaEventRecord(ev_end, sB));
+  ADMM_CUDA(cudaStreamWaitEvent(user, ev_end, 0));
+  ADMM_CUDA(cudaEventRecord(ev_end, sC));
+  ADMM_CUDA(cudaStreamWaitEvent(user, ev_end, 0));
+  ADMM_CUDA(cudaEventRecord(ev_end, sA));
+  ADMM_CUDA(cudaStreamWaitEvent(user, ev_end, 0));
+  {
+    dim3 grid((unsigned)((k + 255) / 256), (unsigned)k);
+    zero_upper_kernel<<<grid, 256, 0, h->stream>>>(A, k, lda);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+  }
+  int fail = 0;
+  ADMM_CUDA(cudaMemcpyAsync(&fail, h->fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  ADMM_REQUIRE(fail == 0, ADMM_B200_ERR_NOTPOSDEF, "Matrix must be positive definite. (pivot %d is not positive)", fail);
+  ADMM_CUDA(cudaEventRecord(h->evp[2], h->stream));
+  if (!want_inverse) return;
+  tri_inverse_doubling(h, k, A, lda, W, ldw, NBO, T);
+}
+
+static void potrf_blocked(admm_b200_handle* h, int64_t k, double* A, int64_t lda, double* W, int64_t ldw, bool want_inverse) {
+  static const bool old = getenv("ADMM_B200_CHOL_V1") != nullptr;
+  if (!old && k > CHOL_NBO) potrf_lookahead(h, k, A, lda, W, ldw, want_inverse);
+  else potrf_blocked_v1(h, k, A, lda, W, ldw, want_inverse);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2595,7 +2865,16 @@ int admm_b200_create(int device, admm_b200_handle** out) {
   admm_b200_handle* h = new admm_b200_handle();
   h->device = device;
   ADMM_CUDA(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-  ADMM_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  {
+    // The look-ahead Cholesky runs its latency-bound chain of small kernels on a HIGH priority stream and the bulk
+    // trailing updates on a LOW priority one: without priorities the block scheduler dispatches kernels in launch
+    // order, so a small chain kernel would wait behind every queued CTA of a big SYRK and nothing would overlap.
+    int least = 0, greatest = 0;
+    ADMM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    ADMM_CUDA(cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, greatest));
+    ADMM_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, (least + greatest) / 2));
+    ADMM_CUDA(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, least));
+  }
   for (auto& e : h->ev_la) ADMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   h->stream = h->own_stream;
   ADMM_CUDA(cudaEventCreate(&h->ev0));
@@ -2643,6 +2922,10 @@ int admm_b200_destroy(admm_b200_handle* h) {
   for (auto& e : h->evp) if (e) cudaEventDestroy(e);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
+  if (h->stream3) cudaStreamDestroy(h->stream3);
+  if (h->stream_hi) cudaStreamDestroy(h->stream_hi);
+  for (auto& e : h->ev_pool) cudaEventDestroy(e);
+  h->chol_ws.release();
   for (auto& e : h->ev_la) if (e) cudaEventDestroy(e);
   delete h;
   ADMM_API_END

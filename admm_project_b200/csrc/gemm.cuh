@@ -29,8 +29,11 @@ struct GemmArgs {
   int lower_only;
   int a_lower, b_lower;   // op(A) / op(B) is lower triangular: restrict the K range per tile
   int a_upper;            // op(A) is upper triangular
+  int b_upper;            // op(B) is upper triangular: op(B)[k][j] = 0 for k > j
   int batch; int64_t strideA, strideB, strideC;
   int splits; int64_t k_per_split; double* ws;   // ws: [batch][splits][M*N]
+  int bm;                 // CTA tile height (128 or 256)
+  int tri_skip;           // split-K with a triangular op(A): work units whose K range is empty neither run nor get summed
 };
 
 // Loads one ROWS x 16 operand tile (ROWS = 128 or 64).  KMAJOR: element (r,k) at g[k + r*ld]; else at g[r + k*ld].
@@ -59,6 +62,7 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
       }
     }
   } else {
+    constexpr int GEMM_LDM = (ROWS > 128) ? ROWS + 4 : admmb200::GEMM_LDM;   // 260 doubles: row stride 2080 B = 32 mod 128
     constexpr int CH2 = ROWS / 2;            // 16-byte chunks per k-row
     constexpr int KR2 = GEMM_THREADS / CH2;  // k-rows per pass
     if (VEC == 2) {
@@ -87,9 +91,23 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
 
 // BN = 128: 8 warps as 2 (M) x 4 (N), warp tile 64 x 32.  BN = 64 (skinny right-hand sides, e.g. the
 // 64-lambda batch): 8 warps as 4 (M) x 2 (N), warp tile 32 x 32, so no DMMA is spent on padding columns.
-template <bool AK, bool BK, int VEC, int BN>
+// BM = 256, BN = 64 (tall triangular op(A) times a few right-hand sides: the lambda batch on an 8192-wide factor):
+// 8 warps as 4 (M) x 2 (N) with the full 64 x 32 warp tile, 3 stages; K is cut into uniform chunks so the
+// (row tile, K chunk) units of a triangular operand are equal pieces of work for the 148 SMs.
+template <int BM> struct GemmCfg {
+  static constexpr int STAGES = (BM == 256) ? 3 : GEMM_STAGES;
+  static constexpr int LDM = (BM > 128) ? BM + 4 : GEMM_LDM;
+  static constexpr int A_TILE = (BM * GEMM_LDK > GEMM_BK * LDM) ? BM * GEMM_LDK : GEMM_BK * LDM;
+  static constexpr int SMEM_BYTES = STAGES * (A_TILE + GEMM_TILE_DOUBLES) * 8;
+};
+template <bool AK, bool BK, int VEC, int BN, int BM = 128>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs p) {
-  constexpr int MI = (BN == 128) ? 8 : 4;
+  constexpr int WM = (BM == 256) ? 4 : ((BN == 128) ? 2 : 4);    // warps along M
+  constexpr int MI = BM / WM / 8;
+  constexpr int GEMM_BM = BM;
+  constexpr int GEMM_STAGES = GemmCfg<BM>::STAGES;
+  constexpr int A_TILE = GemmCfg<BM>::A_TILE;
+  constexpr int LDM_A = GemmCfg<BM>::LDM;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   // grouped tile order (GROUP x GROUP super-tiles): the ~148 CTAs resident at any time then share
@@ -117,14 +135,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
   if (p.b_lower) kbeg = max(kbeg, n0);                      // op(B)[k][j] = 0 for k < j
   if (p.a_lower) kend = min(kend, m0 + (int64_t)GEMM_BM);   // op(A)[i][k] = 0 for k > i
   if (p.a_upper) kbeg = max(kbeg, m0);                      // op(A)[i][k] = 0 for k < i
+  if (p.b_upper) kend = min(kend, n0 + (int64_t)BN);        // op(B)[k][j] = 0 for k > j
   const int nk = (int)((kend - kbeg + GEMM_BK - 1) / GEMM_BK);
+  if (p.tri_skip && nk <= 0) return;      // empty unit of a triangular operand: the reduce pass skips it too
 
   double* sA = smem;
-  double* sB = smem + GEMM_STAGES * GEMM_TILE_DOUBLES;
+  double* sB = smem + GEMM_STAGES * A_TILE;
 
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int wm = (BN == 128) ? (warp & 1) : (warp & 3), wn = (BN == 128) ? (warp >> 1) : (warp >> 2);
+  const int wm = warp % WM, wn = warp / WM;
   const int wrow = wm * (MI * 8);
 
   double acc[MI][4][2];
@@ -136,7 +156,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
 #pragma unroll
   for (int s = 0; s < GEMM_STAGES - 1; ++s) {
     if (s < nk) {
-      gemm_load_tile<AK, VEC, GEMM_BM>(sA + s * GEMM_TILE_DOUBLES, A, p.lda, m0, p.M, kbeg + (int64_t)s * GEMM_BK, kend, tid);
+      gemm_load_tile<AK, VEC, GEMM_BM>(sA + s * A_TILE, A, p.lda, m0, p.M, kbeg + (int64_t)s * GEMM_BK, kend, tid);
       gemm_load_tile<BK, VEC, BN>(sB + s * GEMM_TILE_DOUBLES, B, p.ldb, n0, p.N, kbeg + (int64_t)s * GEMM_BK, kend, tid);
     }
     cp_async_commit();
@@ -149,12 +169,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
       int kn = kt + GEMM_STAGES - 1;
       if (kn < nk) {
         int slot = kn % GEMM_STAGES;
-        gemm_load_tile<AK, VEC, GEMM_BM>(sA + slot * GEMM_TILE_DOUBLES, A, p.lda, m0, p.M, kbeg + (int64_t)kn * GEMM_BK, kend, tid);
+        gemm_load_tile<AK, VEC, GEMM_BM>(sA + slot * A_TILE, A, p.lda, m0, p.M, kbeg + (int64_t)kn * GEMM_BK, kend, tid);
         gemm_load_tile<BK, VEC, BN>(sB + slot * GEMM_TILE_DOUBLES, B, p.ldb, n0, p.N, kbeg + (int64_t)kn * GEMM_BK, kend, tid);
       }
       cp_async_commit();
     }
-    const double* a_s = sA + (kt % GEMM_STAGES) * GEMM_TILE_DOUBLES;
+    const double* a_s = sA + (kt % GEMM_STAGES) * A_TILE;
     const double* b_s = sB + (kt % GEMM_STAGES) * GEMM_TILE_DOUBLES;
 #pragma unroll
     for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
 #pragma unroll
       for (int mi = 0; mi < MI; ++mi) {
         int r = wrow + mi * 8 + g;
-        a[mi] = AK ? a_s[r * GEMM_LDK + k] : a_s[k * GEMM_LDM + r];
+        a[mi] = AK ? a_s[r * GEMM_LDK + k] : a_s[k * LDM_A + r];
       }
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni) {
@@ -220,7 +240,13 @@ __global__ void gemm_splitk_reduce_kernel(GemmArgs p) {
     int64_t r = idx % p.M, c = idx / p.M;
     if (p.lower_only && (c / GEMM_BM) > (r / GEMM_BM)) continue;   // lower_only is used with BN = 128 only
     double s = 0.0;
-    for (int k = 0; k < p.splits; ++k) s += W[(int64_t)k * total + idx];
+    int k0 = 0, k1 = p.splits;
+    if (p.tri_skip) {            // the same K clamps the GEMM kernel applied to row tile r / bm
+      const int64_t m0 = (r / p.bm) * p.bm;
+      if (p.a_lower) k1 = (int)min((int64_t)k1, (m0 + p.bm + p.k_per_split - 1) / p.k_per_split);
+      if (p.a_upper) k0 = (int)(m0 / p.k_per_split);
+    }
+    for (int k = k0; k < k1; ++k) s += W[(int64_t)k * total + idx];
     double v = p.alpha * s;
     if (p.beta != 0.0) v += p.beta * C[r + c * p.ldc];
     if (r == c) v += p.diag_add;

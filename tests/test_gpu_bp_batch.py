@@ -58,3 +58,21 @@ def test_lasso_lambda_batch_matches_per_lambda_oracle(engine, rows, cols, nb):
         n = ref["steps"]
         assert rel(out["pnorm"][:n, j], ref["pnorm"]) < TOL
         assert rel(out["derr"][:n, j], ref["derr"]) < TOL
+
+
+def test_lasso_batch_on_a_large_factor_uses_the_tall_triangular_gemm(engine):
+    """n >= 2048: the two triangular products of the batch run on 256 x 64 tiles with uniform K chunks whose empty
+    (row tile, chunk) units are skipped; every column must still reproduce the oracle's stand-alone run."""
+    D, s, lam, _ = gen.lasso_problem(3, 5000, 2304)
+    lams = (lam / 0.1) * 10.0 ** (-np.arange(9) / 4.0)
+    engine.setup_lasso(D, s, 1.0)
+    o = engine.default_options()
+    rb = engine.solve_lasso_batch(o, lams)
+    for j in (0, 4, 8):
+        ref = oracle.lasso(D, s, lams[j], {"history": 0})
+        assert rb["steps"][j] == ref["steps"]
+        k = ref["steps"]
+        for key in ("xopt", "zopt", "uopt"):
+            assert rel(rb[key][:, j], ref[key]) < TOL, key
+        for key in ("pnorm", "dnorm", "perr", "derr"):
+            assert rel(rb[key][:k, j], ref[key]) < TOL, key

@@ -46,7 +46,7 @@ def test_gram_both_orientations(engine, m, n):
     assert rel(G, 0.5 * D @ D.T + np.eye(m)) < 1e-13
 
 
-@pytest.mark.parametrize("k", [1, 7, 128, 129, 700, 1024, 1500])
+@pytest.mark.parametrize("k", [1, 7, 128, 129, 512, 513, 700, 1024, 1500, 2048, 2500, 4100])   # > 512: look-ahead driver
 def test_potrf_and_inverse_factor(engine, k):
     rs = np.random.RandomState(k)
     X = rs.randn(k + 50, k)
