@@ -264,6 +264,7 @@ struct GemmOpt {
   int64_t strideA = 0, strideB = 0, strideC = 0;
   int allow_splitk = 1;
   int a_lower = 0, b_lower = 0, a_upper = 0, b_upper = 0;
+  int inplace = 0;        // C aliases A: only tilings whose CTAs read nothing another CTA writes (N <= one 128-wide tile column)
 };
 
 static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
@@ -284,8 +285,16 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   static const bool no_tall = getenv("ADMM_B200_NO_TALL_TRI") != nullptr;
   const bool tall_tri = skinny && !no_tall && o.batch == 1 && M >= 2048 && K >= 2048 && (o.a_lower || o.a_upper) && o.allow_splitk &&
                         (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) && (lda % 2 == 0) && (ldb % 2 == 0);
-  const int64_t bnsz = skinny ? 64 : GEMM_BN;
-  const int64_t bmsz = tall_tri ? 256 : GEMM_BM;
+  // small outputs (the chain of the look-ahead Cholesky, factors of a few hundred columns): 64 x 64 tiles put four times
+  // as many SMs to work on a product that would otherwise keep a handful of them busy for 4x as long
+  static const bool no_small = getenv("ADMM_B200_NO_SMALL_TILES") != nullptr;
+  const int64_t t128 = ((M + 127) / 128) * ((N + 127) / 128) * o.batch;
+  const bool small = !no_small && !skinny && !tall_tri && !o.inplace && t128 <= 40 && M >= 64 && N >= 64 &&
+                     (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
+                     (o.strideA % 2 == 0) && (o.strideB % 2 == 0);
+  const int64_t bnsz = (skinny || small) ? 64 : GEMM_BN;
+  const int64_t bmsz = tall_tri ? 256 : (small ? 64 : GEMM_BM);
+  if (small) g.bm = 64;
   const int64_t tm = (M + bmsz - 1) / bmsz, tn = (N + bnsz - 1) / bnsz;
   int64_t tiles = o.lower_only ? tm * (tm + 1) / 2 : tm * tn;
   tiles *= o.batch;
@@ -323,7 +332,7 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)(o.batch * g.splits));
   // Gram-shaped products (both operands K-major, i.e. A'*B on column-major matrices) go through the TMA-fed kernel
   static const bool no_tma = getenv("ADMM_B200_NO_TMA") != nullptr;
-  if (!no_tma && transa != 0 && transb == 0 && vec_ok && o.batch == 1 && !skinny && !tall_tri && !o.a_lower && !o.b_lower &&
+  if (!no_tma && transa != 0 && transb == 0 && vec_ok && o.batch == 1 && !skinny && !tall_tri && !small && !o.a_lower && !o.b_lower &&
       !o.a_upper && !o.b_upper && M >= 128 && N >= 128 && K >= 64 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31)) {
     CUtensorMap tmA, tmB;
     if (make_kmajor_tmap(&tmA, A, K, M, lda) && make_kmajor_tmap(&tmB, B, K, N, ldb)) {
@@ -354,6 +363,7 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
 #define ADMM_GEMM_CASE(a, b)                                     \
   if (AK == a && BK == b) {                                      \
     if (tall_tri) gemm_launch_t<a, b, 2, 64, 256>(h, g, grid);   \
+    else if (small) gemm_launch_t<a, b, 2, 64, 64>(h, g, grid);  \
     else if (skinny) {                                           \
       if (vec_ok) gemm_launch_t<a, b, 2, 64>(h, g, grid);        \
       else gemm_launch_t<a, b, 1, 64>(h, g, grid);               \
@@ -426,6 +436,7 @@ static void potrf_blocked_v1(admm_b200_handle* h, int64_t k, double* A, int64_t 
       // rows it later writes, after its whole K loop.
       GemmOpt po;
       po.allow_splitk = 0;
+      po.inplace = 1;
       gemm(h, 0, 1, rem, nb, nb, 1.0, A21, lda, W11, ldw, 0.0, A21, lda, po);
       // inner trailing update, remaining columns of this outer panel only
       const int64_t pc = K0 + wb - k0 - nb;
@@ -587,6 +598,7 @@ static void potrf_block512(admm_b200_handle* h, double* A, int64_t lda, int64_t 
     double* A21 = A + (k0 + nb) + k0 * lda;
     GemmOpt po;
     po.allow_splitk = 0;
+    po.inplace = 1;
     gemm(h, 0, 1, rem, nb, nb, 1.0, A21, lda, W11, ldw, 0.0, A21, lda, po);       // in place: N <= one tile column
     GemmOpt to;
     to.lower_only = 1;

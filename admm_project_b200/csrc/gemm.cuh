@@ -102,8 +102,10 @@ template <int BM> struct GemmCfg {
 };
 template <bool AK, bool BK, int VEC, int BN, int BM = 128>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs p) {
-  constexpr int WM = (BM == 256) ? 4 : ((BN == 128) ? 2 : 4);    // warps along M
+  constexpr int WM = (BM == 256) ? 4 : ((BM == 64) ? 2 : ((BN == 128) ? 2 : 4));    // warps along M
+  constexpr int WN = 8 / WM;
   constexpr int MI = BM / WM / 8;
+  constexpr int NI = BN / WN / 8;            // 4, or 2 for the 64 x 64 tile (warp tile 32 x 16)
   constexpr int GEMM_BM = BM;
   constexpr int GEMM_STAGES = GemmCfg<BM>::STAGES;
   constexpr int A_TILE = GemmCfg<BM>::A_TILE;
@@ -147,11 +149,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
   const int wm = warp % WM, wn = warp / WM;
   const int wrow = wm * (MI * 8);
 
-  double acc[MI][4][2];
+  double acc[MI][NI][2];
 #pragma unroll
   for (int i = 0; i < MI; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < GEMM_STAGES - 1; ++s) {
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
     const double* b_s = sB + (kt % GEMM_STAGES) * GEMM_TILE_DOUBLES;
 #pragma unroll
     for (int ks = 0; ks < GEMM_BK / 4; ++ks) {
-      double a[MI], b[4];
+      double a[MI], b[NI];
       const int k = ks * 4 + t;
 #pragma unroll
       for (int mi = 0; mi < MI; ++mi) {
@@ -186,14 +188,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
         a[mi] = AK ? a_s[r * GEMM_LDK + k] : a_s[k * LDM_A + r];
       }
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni) {
-        int c = wn * 32 + ni * 8 + g;
+      for (int ni = 0; ni < NI; ++ni) {
+        int c = wn * (NI * 8) + ni * 8 + g;
         b[ni] = BK ? b_s[c * GEMM_LDK + k] : b_s[k * GEMM_LDM + c];
       }
 #pragma unroll
       for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        for (int ni = 0; ni < NI; ++ni) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
     }
   }
   cp_async_wait<0>();
@@ -204,10 +206,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni)
+      for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          int64_t r = m0 + wrow + mi * 8 + g, c = n0 + wn * 32 + ni * 8 + 2 * t + e;
+          int64_t r = m0 + wrow + mi * 8 + g, c = n0 + wn * (NI * 8) + ni * 8 + 2 * t + e;
           if (r < p.M && c < p.N) W[r + c * p.M] = acc[mi][ni][e];
         }
   } else {
@@ -215,10 +217,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
 #pragma unroll
     for (int mi = 0; mi < MI; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni)
+      for (int ni = 0; ni < NI; ++ni)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          int64_t r = m0 + wrow + mi * 8 + g, c = n0 + wn * 32 + ni * 8 + 2 * t + e;
+          int64_t r = m0 + wrow + mi * 8 + g, c = n0 + wn * (NI * 8) + ni * 8 + 2 * t + e;
           if (r < p.M && c < p.N) {
             double v = p.alpha * acc[mi][ni][e];
             if (p.beta != 0.0) v += p.beta * C[r + c * p.ldc];
@@ -238,7 +240,7 @@ __global__ void gemm_splitk_reduce_kernel(GemmArgs p) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = idx % p.M, c = idx / p.M;
-    if (p.lower_only && (c / GEMM_BM) > (r / GEMM_BM)) continue;   // lower_only is used with BN = 128 only
+    if (p.lower_only && (c / p.bm) > (r / p.bm)) continue;         // lower_only is used with square tiles only
     double s = 0.0;
     int k0 = 0, k1 = p.splits;
     if (p.tri_skip) {            // the same K clamps the GEMM kernel applied to row tile r / bm

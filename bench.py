@@ -151,6 +151,21 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    if args.only_svm:                   # development aid: just the configs[2] leg (short multi-GPU calls)
+        eng = Engine(local)
+        torch.cuda.synchronize()
+        eng.set_stream(stream.cuda_stream)
+        if world > 1:
+            attach_comm(eng)
+        svm = svm_leg(torch, dist, np, eng, stream, dev, world, rank, barrier, max_over_ranks)
+        if rank == 0:
+            svm["n_gpus"], svm["p2p_mailboxes"] = world, bool(eng.info()["p2p_ready"])
+            print(json.dumps({"svm_c3": svm}))
+        eng.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # The SAME problem at every N (same seed on every rank); rank r keeps rows [lo, hi) of it.
     Dt, s, lam = make_problem_device(torch, dev, M, N_COLS, seed=0)
     lam_max = lam / 0.1
@@ -515,6 +530,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs")
     ap.add_argument("--no-svm", action="store_true", help="skip the configs[2] SVM leg")
+    ap.add_argument("--only-svm", action="store_true", help="only the configs[2] SVM leg")
     ap.add_argument("--light", action="store_true", help="timed steps only (the command profiled under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
