@@ -2413,7 +2413,26 @@ static void run_persist(admm_b200_handle* h, const admm_b200_options& o, const L
   allreduce_sum(h, h->tcur.p, npad);
   ADMM_CUDA(cudaMemcpyAsync(h->tlast.p, h->tcur.p, (size_t)npad * 8, cudaMemcpyDeviceToDevice, h->stream));
 
+  // Tile height: the tallest that fits shared memory streams best (onepass.cuh), but a burst is as long as its
+  // busiest CTA -- ceil(tiles / CTAs) tiles of R rows -- so a slightly lower tile that divides the rows evenly wins
+  // (7500 rows per rank at 8 GPUs: R = 32 gives 2 x 32 row slots per CTA for 50.7 rows of work, R = 28 gives 2 x 28).
   int R = onepass_rows(h, lp);
+  {
+    const size_t budget = 227 * 1024;
+    double best = 1e300;
+    int bestR = R;
+    const int cand[5] = {32, 28, 24, 20, 16};
+    for (int c : cand) {
+      if (c > R) continue;
+      const size_t smem = (size_t)(n * (c + 2) + npad + (OP_THREADS / (c / 2)) * c + 3 * c + (OP_THREADS / 32) * UW_NRED) * 8;
+      if (smem > budget) continue;
+      const int64_t nt = (m + c - 1) / c;
+      const int64_t g = std::min<int64_t>(kNumSM, nt);
+      const double cost = (double)((nt + g - 1) / g) * c * (1.0 + 0.10 * (32 - c) / 16.0);
+      if (cost < best - 1e-9) { best = cost; bestR = c; }
+    }
+    R = bestR;
+  }
   PersistArgs a;
   UwArgs& u = a.uw;
   u.D = h->Qm.p; u.ld = h->ldq; u.m = m; u.n = n; u.x = nullptr; u.z = h->z.p; u.u = h->u.p; u.aux = h->aux.p;
@@ -2426,17 +2445,38 @@ static void run_persist(admm_b200_handle* h, const admm_b200_options& o, const L
   h->uw_partials.ensure((int64_t)grid * UW_NRED);
   a.dpart = h->op_dpart.p; a.partials = h->uw_partials.p; a.tcur = h->tcur.p; a.tlast = h->tlast.p;
   a.mail = h->p2p.dev; a.ctl = h->ctl; a.lp = lp; a.m_total = (double)h->m_total;
+  a.prof = nullptr;
+  static const bool want_prof = getenv("ADMM_B200_PERSIST_PROF") != nullptr;
+  if (want_prof) {
+    ADMM_CUDA(cudaMalloc(&a.prof, (size_t)grid * 8 * sizeof(long long)));
+    ADMM_CUDA(cudaMemsetAsync(a.prof, 0, (size_t)grid * 8 * sizeof(long long), h->stream));
+  }
   const int check = std::max(1, o.check_every);
   int64_t enq = 0;
   while (true) {
     a.burst = (int)std::min<int64_t>(check, N - enq);
     if (R == 32) persist_launch<32>(h, a, grid);
+    else if (R == 28) persist_launch<28>(h, a, grid);
     else if (R == 24) persist_launch<24>(h, a, grid);
+    else if (R == 20) persist_launch<20>(h, a, grid);
     else persist_launch<16>(h, a, grid);
     enq += a.burst;
     ADMM_CUDA(cudaMemcpyAsync(h->h_ctl, h->ctl, sizeof(LoopCtl), cudaMemcpyDeviceToHost, h->stream));
     ADMM_CUDA(cudaStreamSynchronize(h->stream));
     if (h->h_ctl->done != 0 || enq >= N) break;
+  }
+  if (a.prof) {
+    std::vector<long long> hp((size_t)grid * 8);
+    ADMM_CUDA(cudaMemcpy(hp.data(), a.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(a.prof);
+    const double its = std::max<double>(1.0, (double)h->h_ctl->it);
+    const char* names[6] = {"D-phase", "grid.sync", "R sums+stores", "signal", "flag wait", "read t + stop"};
+    fprintf(stderr, "persist profile (rank %d, %d CTAs, %.0f iterations): cycles per iteration, mean / max over CTAs\n", h->rank, grid, its);
+    for (int k = 0; k < 6; ++k) {
+      double mean = 0.0, mx = 0.0;
+      for (int c = 0; c < grid; ++c) { const double v = (double)hp[(size_t)c * 8 + k] / its; mean += v; mx = std::max(mx, v); }
+      fprintf(stderr, "  %-14s %9.0f / %9.0f\n", names[k], mean / grid, mx);
+    }
   }
   // x of the last iteration: x = inv(R)' t = W' t, x_j = column j of W (rows j..n-1) . t
   coldot(h, COLDOT_LOWER, h->W.p, h->ldf, n, n, h->tlast.p, h->x.p);

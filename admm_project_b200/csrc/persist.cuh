@@ -44,6 +44,7 @@ struct PersistArgs {
   LoopParams lp;
   int burst;
   double m_total;
+  long long* prof;           // optional [gridDim.x][8] accumulated SM cycles per phase (ADMM_B200_PERSIST_PROF)
 };
 
 template <int R, int NCH>
@@ -93,6 +94,14 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uw_persist_kernel(PersistArgs a
   const bool rowthread = (tid < 8 * R) && ((tid & 7) == 0);
   const int myrow = tid >> 3;
 
+  long long tk = clock64();
+  auto tick = [&](int k) {
+    if (a.prof && tid == 0) {
+      const long long now = clock64();
+      a.prof[(int64_t)blockIdx.x * 8 + k] += now - tk;
+      tk = now;
+    }
+  };
   for (int b = 0; b < a.burst; ++b) {
     double acc[OP_MAXCOLS];
 #pragma unroll
@@ -182,11 +191,14 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uw_persist_kernel(PersistArgs a
     }
     block_reduce_store<UW_NRED>(racc, a.partials + (int64_t)blockIdx.x * UW_NRED, redsh);
     __threadfence();
+    tick(0);                                   // phase D
     grid.sync();
+    tick(1);                                   // grid barrier (includes waiting for the slowest CTA)
     // ---------------- phase R: fixed-order sums of the CTAs' partials -> every rank's mailbox ----------------
     const int par = (int)(seq & 1);
     const int nparts = (int)gridDim.x, ndparts = 2 * nparts;
-    for (int64_t w = (int64_t)blockIdx.x * (OP_THREADS / 32) + warp; w < n + UW_NRED; w += (int64_t)gridDim.x * (OP_THREADS / 32)) {
+    // output w belongs to (CTA w mod grid, warp w div grid): every CTA gets its ~(n + 10) / grid outputs
+    for (int64_t w = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp; w < n + UW_NRED; w += (int64_t)gridDim.x * (OP_THREADS / 32)) {
       double s = 0.0;
       if (w < n) {
         for (int p = lane; p < ndparts; p += 32) s += __ldcg(a.dpart + (int64_t)p * a.npad + w);
@@ -197,16 +209,19 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uw_persist_kernel(PersistArgs a
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (lane == 0) p2p_store(a.mail, par, (w < n) ? w : a.npad + (w - n), s);
     }
+    tick(2);                                   // phase R sums + stores
     p2p_signal(a.mail, par, seq, gridDim.x);
+    tick(3);                                   // fence + ticket (+ flags in the last CTA)
     // ---------------- phase E: wait for every rank, new t, stop tests ---------------------------------------
     const bool ok = p2p_wait(a.mail, par, seq, /*trap_on_timeout=*/true);   // a CTA must not leave the grid barrier alone
+    tick(4);                                   // wait for the flags
     if (blockIdx.x == 0)                                      // the t this iteration used: x = inv(R)' tlast
       for (int64_t j = tid; j < n; j += OP_THREADS) a.tlast[j] = ts[j];
     __syncthreads();
     for (int64_t j = tid; j < n + UW_NRED; j += OP_THREADS) {
       const int64_t idx = (j < n) ? j : a.npad + (j - n);
       double s = 0.0;
-      for (int r = 0; r < a.mail.nranks; ++r) s += ld_relaxed_sys(a.mail.slot(a.mail.rank, par, r) + idx);
+      for (int r = 0; r < a.mail.nranks; ++r) s += __ldcg(a.mail.slot(a.mail.rank, par, r) + idx);
       if (j < n) ts[j] = s;
       else scal[j - n] = s;
     }
@@ -240,6 +255,7 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uw_persist_kernel(PersistArgs a
     __syncthreads();
     ++seq;
     ++it;
+    tick(5);                                   // read t + stop tests
     if (s_stop) break;
   }
   asm volatile("cp.async.wait_all;" ::: "memory");

@@ -12,7 +12,7 @@
 // visited longest-with-shortest (their lengths sum to ~k+1), so every round moves the same number of bytes and
 // the 148 CTAs finish together.  While round r is being worked on, rounds r+1 and r+2 are in flight (~130 KB
 // per SM).
-// Compute: thread t owns rows {2t, 2t+1} + 1024 q for every column; its y values and its slice of the result
+// Compute: 1024 threads; thread t owns rows {2t, 2t+1} + 2048 q for every column; its y values and its slice of the result
 // live in registers for the whole kernel.  Per round: partial dots from shared memory (conflict-free LDS.128)
 // -> warp shuffle -> per-warp partials in shared memory -> barrier -> every thread sums the 16 partials in the
 // same fixed order -> AXPY from shared memory into the register accumulators -> barrier -> refill the stage.
@@ -24,9 +24,9 @@
 
 namespace admmb200 {
 
-constexpr int ST_THREADS = 512;
+constexpr int ST_THREADS = 1024;
 constexpr int ST_WARPS = ST_THREADS / 32;
-constexpr int ST_Q = 8;                               // row groups of 1024: k <= 8192
+constexpr int ST_Q = 4;                               // row groups of 2048: k <= 8192
 constexpr int ST_MAXK = ST_Q * 2 * ST_THREADS;        // 8192
 constexpr int ST_STAGE = 8192 + 64;                   // doubles per stage: a (longest, shortest) pair + alignment slack
 constexpr int ST_NSTAGE = 3;
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
   double2 yv[ST_Q], acc[ST_Q];
 #pragma unroll
   for (int q = 0; q < ST_Q; ++q) {
-    const int row = 2 * tid + 1024 * q;
+    const int row = 2 * tid + 2 * ST_THREADS * q;
     yv[q] = make_double2(row < a.k ? a.y[row] : 0.0, row + 1 < a.k ? a.y[row + 1] : 0.0);
     acc[q] = make_double2(0.0, 0.0);
   }
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
       double p0 = 0.0, p1 = 0.0;
 #pragma unroll
       for (int q = 0; q < ST_Q; ++q) {
-        const int row = 2 * tid + 1024 * q;
+        const int row = 2 * tid + 2 * ST_THREADS * q;
         if (row < en.len) {                       // len is rounded up with a zero: row + 1 is loaded too
           const double2 v = *reinterpret_cast<const double2*>(col + row);
           p0 = fma(v.x, yv[q].x, p0);
@@ -160,12 +160,23 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
     for (int j = 0; j < ne; ++j) {
       const SymtriEnt en = ent(e0 + j);
       const double* col = sb + en.off;
-      double t = 0.0;
+      double t;
+      {
+        const double2* wp = reinterpret_cast<const double2*>(wsum + j * ST_WARPS);
+        double2 part[ST_WARPS / 2];
 #pragma unroll
-      for (int w = 0; w < ST_WARPS; ++w) t += wsum[j * ST_WARPS + w];      // same order in every thread
+        for (int w = 0; w < ST_WARPS / 2; ++w) part[w] = wp[w];              // broadcast LDS.128, all independent
+#pragma unroll
+        for (int w = 0; w < ST_WARPS / 2; ++w) part[w].x += part[w].y;
+#pragma unroll
+        for (int st = ST_WARPS / 4; st >= 1; st >>= 1)                         // the same fixed tree in every thread
+#pragma unroll
+          for (int w = 0; w < st; ++w) part[w].x += part[w + st].x;
+        t = part[0].x;
+      }
 #pragma unroll
       for (int q = 0; q < ST_Q; ++q) {
-        const int row = 2 * tid + 1024 * q;
+        const int row = 2 * tid + 2 * ST_THREADS * q;
         if (row < en.len) {
           const double2 v = *reinterpret_cast<const double2*>(col + row);
           acc[q].x = fma(v.x, t, acc[q].x);
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
   double* xp = a.xpart + (size_t)blockIdx.x * a.kpad;
 #pragma unroll
   for (int q = 0; q < ST_Q; ++q) {
-    const int row = 2 * tid + 1024 * q;
+    const int row = 2 * tid + 2 * ST_THREADS * q;
     if (row < a.kpad) *reinterpret_cast<double2*>(xp + row) = acc[q];
   }
 }

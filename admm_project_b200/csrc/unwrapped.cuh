@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) uw_epilogue_kernel(UwEpiArgs a) {
     if (ok) {
       for (int64_t i = threadIdx.x; i < a.msg_count; i += blockDim.x) {
         double acc = 0.0;
-        for (int r = 0; r < a.mail.nranks; ++r) acc += ld_relaxed_sys(a.mail.slot(a.mail.rank, par, r) + i);
+        for (int r = 0; r < a.mail.nranks; ++r) acc += __ldcg(a.mail.slot(a.mail.rank, par, r) + i);
         a.msg[i] = acc;
       }
     }
