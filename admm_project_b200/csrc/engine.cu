@@ -1575,7 +1575,7 @@ static void p2p_setup(admm_b200_handle* h) {
   if (R < 2 || R > P2P_MAXRANKS) return;
   p2p_teardown(h);               // a single-rank local mailbox (ensure_mailbox) gives way to the mapped ones
   const bool want = !getenv("ADMM_B200_NO_P2P");
-  P.bytes = (size_t)P2P_FLAG_BYTES + (size_t)2 * R * P2P_CAP * 8;
+  P.bytes = p2p_mailbox_bytes(R);
   ADMM_CUDA(cudaMalloc(&P.local, P.bytes));
   ADMM_CUDA(cudaMemsetAsync(P.local, 0, P.bytes, h->stream));
   void* ctr = nullptr;                       // seq (8) | ticket (4) | ticket2 (4) | err (4)
@@ -2354,7 +2354,7 @@ static void run_bursts(admm_b200_handle* h, const admm_b200_options& o, int64_t 
 static void ensure_mailbox(admm_b200_handle* h) {
   P2PState& P = h->p2p;
   if (P.local) return;
-  P.bytes = (size_t)P2P_FLAG_BYTES + (size_t)2 * P2P_CAP * 8;
+  P.bytes = p2p_mailbox_bytes(1);
   ADMM_CUDA(cudaMalloc(&P.local, P.bytes));
   ADMM_CUDA(cudaMemsetAsync(P.local, 0, P.bytes, h->stream));
   void* ctr = nullptr;
@@ -2373,7 +2373,7 @@ static bool persist_ok(const admm_b200_handle* h, const admm_b200_options& o, co
   if (!is_unwrapped(h->kind) || lp.alg != 0 || !o.nodualerror || o.objevals || history || lp.raw) return false;
   if (!h->have_inverse || h->xsolve_eff != ADMM_B200_XSOLVE_INVFACTOR || o.xsolve != ADMM_B200_XSOLVE_INVFACTOR) return false;
   if (h->nranks > 1 && !h->p2p.ready) return false;
-  if (round_up(h->n, 2) + UW_NRED > P2P_CAP) return false;
+  if (round_up(h->n, 2) + UW_NRED > P2P_LLCAP) return false;
   return onepass_rows(h, lp) != 0;
 }
 
@@ -2470,7 +2470,7 @@ static void run_persist(admm_b200_handle* h, const admm_b200_options& o, const L
     ADMM_CUDA(cudaMemcpy(hp.data(), a.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     cudaFree(a.prof);
     const double its = std::max<double>(1.0, (double)h->h_ctl->it);
-    const char* names[6] = {"D-phase", "grid.sync", "R sums+stores", "signal", "flag wait", "read t + stop"};
+    const char* names[6] = {"D-phase", "grid.sync", "R sums+stores", "(unused)", "values arrive", "stop tests"};
     fprintf(stderr, "persist profile (rank %d, %d CTAs, %.0f iterations): cycles per iteration, mean / max over CTAs\n", h->rank, grid, its);
     for (int k = 0; k < 6; ++k) {
       double mean = 0.0, mx = 0.0;

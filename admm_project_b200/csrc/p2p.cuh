@@ -27,6 +27,7 @@ namespace admmb200 {
 constexpr int P2P_MAXRANKS = 8;
 constexpr int64_t P2P_CAP = 32768;          // doubles per slot (256 KB): n-vector of C2, 16-class batch of C3
 constexpr int P2P_FLAG_BYTES = 256;         // flags[2][8] uint64 = 128 B, padded
+constexpr int64_t P2P_LLCAP = 4096;         // values per slot of the flag-in-data (LL) region
 
 struct P2PDev {
   int rank, nranks;
@@ -41,7 +42,15 @@ struct P2PDev {
   __device__ __forceinline__ double* slot(int r, int par, int src) const {
     return reinterpret_cast<double*>(mail[r] + P2P_FLAG_BYTES) + ((int64_t)par * nranks + src) * cap;
   }
+  // LL region (behind the plain slots): every value travels as two 8-byte words {lo32 | flag<<32, hi32 | flag<<32}
+  __device__ __forceinline__ ulonglong2* ll_slot(int r, int par, int src) const {
+    return reinterpret_cast<ulonglong2*>(mail[r] + P2P_FLAG_BYTES + (size_t)2 * nranks * cap * 8) +
+           ((int64_t)par * nranks + src) * P2P_LLCAP;
+  }
 };
+__host__ __device__ inline size_t p2p_mailbox_bytes(int nranks) {
+  return (size_t)P2P_FLAG_BYTES + (size_t)2 * nranks * P2P_CAP * 8 + (size_t)2 * nranks * P2P_LLCAP * 16;
+}
 
 struct P2PState {
   bool ready = false;
@@ -121,6 +130,46 @@ __device__ __forceinline__ bool p2p_wait(const P2PDev& p, int par, unsigned long
   }
   __syncthreads();
   return p2p_bad == 0;
+}
+
+// ---- flag-in-data exchange (the LL protocol of collective libraries) ------------------------------------------
+// A value and the number of its exchange travel in the SAME 8-byte words: {lo32 | f<<32, hi32 | f<<32}, f = low 32
+// bits of (exchange + 1).  An aligned 8-byte store is atomic, so a reader that sees f in both words has the value of
+// THIS exchange -- no fence, no flag, no election: the writer just stores, the reader spins on the data itself.
+// Used inside the persistent kernel, where the separate fence + ticket + flag cost more than the arithmetic.
+__device__ __forceinline__ void ll_store(ulonglong2* p, double v, unsigned f) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const unsigned long long a = (bits & 0xffffffffull) | ((unsigned long long)f << 32);
+  const unsigned long long b = (bits >> 32) | ((unsigned long long)f << 32);
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ bool ll_load(const ulonglong2* p, unsigned f, double& v) {
+  unsigned long long a, b;
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  v = __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+  return (unsigned)(a >> 32) == f && (unsigned)(b >> 32) == f;
+}
+__device__ __forceinline__ void p2p_ll_store(const P2PDev& p, int par, int64_t idx, double v, unsigned f) {
+#pragma unroll
+  for (int r = 0; r < P2P_MAXRANKS; ++r)
+    if (r < p.nranks) ll_store(p.ll_slot(r, par, p.rank) + idx, v, f);
+}
+// sum over ranks (rank order) of value idx of this exchange; spins until every rank's copy has arrived
+__device__ __forceinline__ double p2p_ll_sum(const P2PDev& p, int par, int64_t idx, unsigned f) {
+  double s = 0.0;
+  const long long t0 = clock64();
+  for (int r = 0; r < p.nranks; ++r) {
+    const ulonglong2* w = p.ll_slot(p.rank, par, r) + idx;
+    double v;
+    while (!ll_load(w, f, v)) {
+      if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer is gone; abort the kernel (loud, and nobody hangs at a grid barrier)
+        *p.err = 1;
+        __trap();
+      }
+    }
+    s += v;
+  }
+  return s;
 }
 
 // ---- generic two-kernel form: buf (count doubles, this rank's device memory) <- sum over ranks ----------

@@ -196,36 +196,43 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uw_persist_kernel(PersistArgs a
     tick(1);                                   // grid barrier (includes waiting for the slowest CTA)
     // ---------------- phase R: fixed-order sums of the CTAs' partials -> every rank's mailbox ----------------
     const int par = (int)(seq & 1);
+    const unsigned fl = (unsigned)(seq + 1);
     const int nparts = (int)gridDim.x, ndparts = 2 * nparts;
     // output w belongs to (CTA w mod grid, warp w div grid): every CTA gets its ~(n + 10) / grid outputs
     for (int64_t w = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp; w < n + UW_NRED; w += (int64_t)gridDim.x * (OP_THREADS / 32)) {
-      double s = 0.0;
-      if (w < n) {
-        for (int p = lane; p < ndparts; p += 32) s += __ldcg(a.dpart + (int64_t)p * a.npad + w);
-      } else {
-        for (int p = lane; p < nparts; p += 32) s += __ldcg(a.partials + (int64_t)p * UW_NRED + (w - n));
+      // all loads first (<= 10 per lane for 2 x 148 partials), then the adds in a fixed order: a `s += load` loop
+      // serialises the L2 round trips (measured 3.4 us per iteration)
+      double v[10];
+      const double* src = (w < n) ? a.dpart + w : a.partials + (w - n);
+      const int64_t stride = (w < n) ? a.npad : UW_NRED;
+      const int cnt = (w < n) ? ndparts : nparts;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+        const int pidx = lane + 32 * i;
+        v[i] = (pidx < cnt) ? __ldcg(src + (int64_t)pidx * stride) : 0.0;
       }
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) s += v[i];
+      for (int pidx = lane + 320; pidx < cnt; pidx += 32) s += __ldcg(src + (int64_t)pidx * stride);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) p2p_store(a.mail, par, (w < n) ? w : a.npad + (w - n), s);
+      if (lane == 0) p2p_ll_store(a.mail, par, (w < n) ? w : a.npad + (w - n), s, fl);   // value + exchange number in one word pair
     }
     tick(2);                                   // phase R sums + stores
-    p2p_signal(a.mail, par, seq, gridDim.x);
-    tick(3);                                   // fence + ticket (+ flags in the last CTA)
-    // ---------------- phase E: wait for every rank, new t, stop tests ---------------------------------------
-    const bool ok = p2p_wait(a.mail, par, seq, /*trap_on_timeout=*/true);   // a CTA must not leave the grid barrier alone
-    tick(4);                                   // wait for the flags
+    // ---------------- phase E: every rank's values (they validate themselves), new t, stop tests ---------------
     if (blockIdx.x == 0)                                      // the t this iteration used: x = inv(R)' tlast
       for (int64_t j = tid; j < n; j += OP_THREADS) a.tlast[j] = ts[j];
     __syncthreads();
     for (int64_t j = tid; j < n + UW_NRED; j += OP_THREADS) {
       const int64_t idx = (j < n) ? j : a.npad + (j - n);
-      double s = 0.0;
-      for (int r = 0; r < a.mail.nranks; ++r) s += __ldcg(a.mail.slot(a.mail.rank, par, r) + idx);
+      const double s = p2p_ll_sum(a.mail, par, idx, fl);
       if (j < n) ts[j] = s;
       else scal[j - n] = s;
     }
     __syncthreads();
+    tick(4);                                   // arrival of every rank's values
+    const bool ok = true;
     if (tid == 0) {
       // admm.m:618-722 with nodualerror: every CTA evaluates the same numbers, CTA 0 records them
       const LoopParams& lp = a.lp;

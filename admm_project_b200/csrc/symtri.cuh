@@ -12,7 +12,7 @@
 // visited longest-with-shortest (their lengths sum to ~k+1), so every round moves the same number of bytes and
 // the 148 CTAs finish together.  While round r is being worked on, rounds r+1 and r+2 are in flight (~130 KB
 // per SM).
-// Compute: 1024 threads; thread t owns rows {2t, 2t+1} + 2048 q for every column; its y values and its slice of the result
+// Compute: 512 threads; thread t owns rows {2t, 2t+1} + 1024 q for every column; its y values and its slice of the result
 // live in registers for the whole kernel.  Per round: partial dots from shared memory (conflict-free LDS.128)
 // -> warp shuffle -> per-warp partials in shared memory -> barrier -> every thread sums the 16 partials in the
 // same fixed order -> AXPY from shared memory into the register accumulators -> barrier -> refill the stage.
@@ -24,9 +24,9 @@
 
 namespace admmb200 {
 
-constexpr int ST_THREADS = 1024;
+constexpr int ST_THREADS = 512;
 constexpr int ST_WARPS = ST_THREADS / 32;
-constexpr int ST_Q = 4;                               // row groups of 2048: k <= 8192
+constexpr int ST_Q = 8;                               // row groups of 1024: k <= 8192 (1024 threads x 4 measured 1.5x slower)
 constexpr int ST_MAXK = ST_Q * 2 * ST_THREADS;        // 8192
 constexpr int ST_STAGE = 8192 + 64;                   // doubles per stage: a (longest, shortest) pair + alignment slack
 constexpr int ST_NSTAGE = 3;
