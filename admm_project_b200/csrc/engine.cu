@@ -24,6 +24,7 @@
 #include "p2p.cuh"
 #include "symtri.cuh"
 #include "persist.cuh"
+#include "persist_batch.cuh"
 #include "gemm_tma.cuh"
 #include <dlfcn.h>
 
@@ -2368,6 +2369,17 @@ static void ensure_mailbox(admm_b200_handle* h) {
   P.ready = false;
 }
 
+// Q_g = D_g * inv(R)' on this rank's rows: one DMMA GEMM per setup (m x n x n), kept next to D
+static void ensure_Q(admm_b200_handle* h) {
+  if (h->have_Q) return;
+  const int64_t n = h->n, m = h->m;
+  h->ldq = round_up(m, 2);
+  h->Qm.ensure(h->ldq * n);
+  GemmOpt g;
+  gemm(h, 0, 1, m, n, n, 1.0, h->dD, h->ldD, h->W.p, h->ldf, 0.0, h->Qm.p, h->ldq, g);
+  h->have_Q = true;
+}
+
 static bool persist_ok(const admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, bool history) {
   if (getenv("ADMM_B200_NO_PERSIST")) return false;
   if (!is_unwrapped(h->kind) || lp.alg != 0 || !o.nodualerror || o.objevals || history || lp.raw) return false;
@@ -2395,14 +2407,7 @@ static void persist_launch(admm_b200_handle* h, PersistArgs& a, int grid) {
 static void run_persist(admm_b200_handle* h, const admm_b200_options& o, const LoopParams& lp, int64_t N) {
   const int64_t n = h->n, m = h->m, npad = round_up(n, 2);
   if (h->nranks == 1) ensure_mailbox(h);
-  if (!h->have_Q) {
-    // Q_g = D_g * inv(R)' on this rank's rows: one DMMA GEMM per setup (m x n x n), kept next to D
-    h->ldq = round_up(m, 2);
-    h->Qm.ensure(h->ldq * n);
-    GemmOpt g;
-    gemm(h, 0, 1, m, n, n, 1.0, h->dD, h->ldD, h->W.p, h->ldf, 0.0, h->Qm.p, h->ldq, g);
-    h->have_Q = true;
-  }
+  ensure_Q(h);
   h->tcur.ensure(npad + 2); h->tlast.ensure(npad + 2);
   // t of the first iteration: sum_g Q_g' r0_g, r0 = z0 - u0 (unwrappedadmm.m:133) or s + z0 - u0 (getProxOps.m:1514)
   uw_first_rhs_kernel<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(m, h->z.p, h->u.p, h->aux.p, uw_kind(h->kind), h->rvec.p);
@@ -2737,6 +2742,39 @@ static void uwb_pass1_t(admm_b200_handle* h, const UwbArgs& a, dim3 grid, size_t
   uwb_gemm_prox_kernel<NB><<<grid, UW_THREADS, smem, h->stream>>>(a);
 }
 
+template <int NBT>
+static void persist_batch_launch(admm_b200_handle* h, PersistBatchArgs& a, int grid) {
+  static PerDevice conf_pd;
+  size_t& conf = conf_pd(h->device);
+  const size_t smem = PersistBatchCfg<NBT>::smem_bytes(a.n, a.npad);
+  if (smem > conf) {
+    ADMM_CUDA(cudaFuncSetAttribute(uwb_persist_kernel<NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  void* args[] = {&a};
+  ADMM_CUDA(cudaLaunchCooperativeKernel((const void*)uwb_persist_kernel<NBT>, dim3(grid), dim3(OP_THREADS), args, smem, h->stream));
+  h->launches++;
+}
+
+static size_t persist_batch_smem(int nbt, int64_t n, int64_t npad) {
+  switch (nbt) {
+    case 2: return PersistBatchCfg<2>::smem_bytes(n, npad);
+    case 4: return PersistBatchCfg<4>::smem_bytes(n, npad);
+    case 8: return PersistBatchCfg<8>::smem_bytes(n, npad);
+    default: return PersistBatchCfg<10>::smem_bytes(n, npad);
+  }
+}
+
+// the class batch as one persistent kernel per burst (persist_batch.cuh)
+static bool persist_batch_ok(const admm_b200_handle* h, const admm_b200_options& o, int nbt, int64_t cbs) {
+  if (getenv("ADMM_B200_NO_PERSIST") || getenv("ADMM_B200_NO_PERSIST_BATCH")) return false;
+  if (nbt > 10 || o.objevals || !h->have_inverse || h->xsolve_eff != ADMM_B200_XSOLVE_INVFACTOR) return false;
+  if (h->nranks > 1 && !h->p2p.ready) return false;
+  if (h->n > (int64_t)PB_MAXCOLS * OP_THREADS || (int64_t)nbt * cbs > P2P_LLCAP) return false;
+  if ((((uintptr_t)h->dD) & 15) != 0 || (h->ldD % 2) != 0) return false;
+  return persist_batch_smem(nbt, h->n, round_up(h->n, 2)) <= (size_t)227 * 1024;
+}
+
 static void solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options& o, int64_t nb, const double* AUX,
                                   int64_t ldaux, const double* X0, const double* Z0, const double* U0,
                                   const UwBatchOut& out) {
@@ -2780,6 +2818,58 @@ static void solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options& 
     lp.pnorm = hist.p; lp.dnorm = hist.p + N * nbt; lp.perr = hist.p + 2 * N * nbt; lp.derr = hist.p + 3 * N * nbt;
     lp.hn = hist.p + 4 * N * nbt; lp.obj = hist.p + 5 * N * nbt;
     lp.dvals = hist.p + 6 * N * nbt; lp.avals = hist.p + 7 * N * nbt; lp.rst = hist.p + 8 * N * nbt;
+    if (persist_batch_ok(h, o, nbt, cbs)) {
+      // ---- persistent path: Q = D inv(R)', t_c = sum_g Q_g' r_{g,c}; no x inside the loop ----
+      if (h->nranks == 1) ensure_mailbox(h);
+      ensure_Q(h);
+      DBuf TL;
+      try {
+        TL.ensure(cbs * nbt);
+        ADMM_CUDA(cudaMemsetAsync(TL.p, 0, (size_t)cbs * nbt * 8, st));
+        ADMM_CUDA(cudaEventRecord(h->ev0, st));
+        uwb_first_rhs_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)nb), 256, 0, st>>>(m, (int)nb, mpad, Z.p, U.p, A.p, uw_kind(h->kind), R.p);
+        ADMM_CUDA(cudaGetLastError());
+        gemvt_strided(h, h->Qm.p, h->ldq, m, n, nbt, R.p, mpad, CB.p, cbs);     // t_c of the first iteration
+        allreduce_sum(h, CB.p, cbs * nbt);
+        ADMM_CUDA(cudaMemcpyAsync(TL.p, CB.p, (size_t)cbs * nbt * 8, cudaMemcpyDeviceToDevice, st));
+        PersistBatchArgs pa;
+        pa.Q = h->Qm.p; pa.ld = h->ldq; pa.m = m; pa.n = n; pa.npad = npad;
+        pa.Z = Z.p; pa.U = U.p; pa.AUX = A.p; pa.ldm = mpad; pa.nb = (int)nb;
+        pa.rho = o.rho; pa.C = h->svmC; pa.kind = uw_kind(h->kind);
+        pa.ntiles = (m + PB_R - 1) / PB_R;
+        const int grid = (int)std::min<int64_t>(kNumSM, pa.ntiles);
+        h->op_dpart.ensure((int64_t)grid * nbt * npad);
+        h->uw_partials.ensure((int64_t)grid * nbt * UW_NRED);
+        pa.dpart = h->op_dpart.p; pa.partials = h->uw_partials.p; pa.tcur = CB.p; pa.tlast = TL.p; pa.cbs = cbs;
+        pa.mail = h->p2p.dev; pa.ctl = ctl; pa.lp = lp; pa.hist_stride = N; pa.done_count = done_count;
+        pa.m_total = (double)h->m_total;
+        const int check = std::max(1, o.check_every);
+        int64_t enq = 0;
+        int hdone = 0;
+        while (true) {
+          pa.burst = (int)std::min<int64_t>(check, N - enq);
+          switch (nbt) {
+            case 2: persist_batch_launch<2>(h, pa, grid); break;
+            case 4: persist_batch_launch<4>(h, pa, grid); break;
+            case 8: persist_batch_launch<8>(h, pa, grid); break;
+            default: persist_batch_launch<10>(h, pa, grid); break;
+          }
+          enq += pa.burst;
+          ADMM_CUDA(cudaMemcpyAsync(&hdone, done_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+          ADMM_CUDA(cudaStreamSynchronize(st));
+          if (hdone >= nb || enq >= N) break;
+        }
+        // x_c of the last iteration each class ran: X = inv(R)' TLAST = W' TLAST
+        GemmOpt gx; gx.a_upper = 1;
+        gemm(h, 1, 0, n, nb, n, 1.0, h->W.p, h->ldf, TL.p, cbs, 0.0, XK.p, npad, gx);
+      } catch (...) {
+        cudaStreamSynchronize(st);
+        TL.release();
+        throw;
+      }
+      cudaStreamSynchronize(st);
+      TL.release();
+    } else {
     // pass-1 launch geometry
     const int64_t rb = (m + UW_ROWS - 1) / UW_ROWS;
     // columns are swept in 128-wide chunks INSIDE a CTA; the grid is split over columns (partials through
@@ -2835,6 +2925,7 @@ static void solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options& 
           ADMM_CUDA(cudaStreamSynchronize(st));
           return hdone >= nb;
         });
+    }
     ADMM_CUDA(cudaEventRecord(h->ev1, st));
     ADMM_CUDA(cudaEventSynchronize(h->ev1));
     p2p_check(h);

@@ -27,7 +27,7 @@ namespace admmb200 {
 constexpr int P2P_MAXRANKS = 8;
 constexpr int64_t P2P_CAP = 32768;          // doubles per slot (256 KB): n-vector of C2, 16-class batch of C3
 constexpr int P2P_FLAG_BYTES = 256;         // flags[2][8] uint64 = 128 B, padded
-constexpr int64_t P2P_LLCAP = 4096;         // values per slot of the flag-in-data (LL) region
+constexpr int64_t P2P_LLCAP = 16384;        // values per slot of the flag-in-data (LL) region (10 classes x 800)
 
 struct P2PDev {
   int rank, nranks;

@@ -73,3 +73,44 @@ def test_persistent_loop_domaxiters_and_small_bursts(engine):
     np.random.seed(8)
     res = linearsvm(D, ELL[:, 1], 0.5, opts, engine=engine)
     compare(res, ref)
+
+
+@pytest.mark.parametrize("rows,cols,classes", [(3000, 300, 4), (20000, 200, 10), (5001, 129, 3), (12000, 784, 10)])
+def test_class_batch_persistent_loop_matches_oracle(engine, rows, cols, classes):
+    """linearsvm_onevsall without the objective: the batch runs as the persistent kernel of csrc/persist_batch.cuh
+    (one 16-row tile of Q per iteration for ALL classes); every class must reproduce its stand-alone oracle run."""
+    from admm_project_b200 import linearsvm_onevsall
+    D, ELL = gen.svm_mnist_like(11, rows, cols, nclass=classes)
+    if cols < 784:
+        D = D + 1e-3 * np.random.RandomState(12).randn(rows, cols)
+    np.random.seed(13)
+    launches = engine.launch_count()
+    outs = linearsvm_onevsall(D, ELL, 0.5, {}, engine=engine)
+    used = engine.launch_count() - launches
+    np.random.seed(13)
+    worst = 0
+    for k in range(classes):
+        ref = oracle.linearsvm(D, ELL[:, k], 0.5, {"history": 0})
+        assert outs[k]["steps"] == ref["steps"], (k, outs[k]["steps"], ref["steps"])
+        for key in ("xopt", "zopt", "uopt", "pnorm", "perr"):
+            assert rel(outs[k][key], ref[key]) < TOL, (k, key, rel(outs[k][key], ref[key]))
+        worst = max(worst, ref["steps"])
+    assert used < 60 + worst // 4          # bursts of the persistent kernel, not ~9 launches per iteration
+
+
+def test_class_batch_c3_size_three_of_ten_classes(engine):
+    """BASELINE.json configs[2] at full size: 60000 x 784, ten one-vs-all classes in one batch; three of the
+    classes are checked against the oracle (each oracle run costs a pinv of D)."""
+    from admm_project_b200 import linearsvm_onevsall
+    D, ELL = gen.svm_mnist_like(0, 60000, 784)
+    np.random.seed(21)
+    outs = linearsvm_onevsall(D, ELL, 0.5, {}, engine=engine)
+    for k in (0, 5, 9):
+        # replay class k's own init: the batch drew rand(n), rand(m), rand(m) per class, in class order
+        np.random.seed(21)
+        for _ in range(k):
+            np.random.rand(784), np.random.rand(60000), np.random.rand(60000)
+        ref = oracle.linearsvm(D, ELL[:, k], 0.5, {"history": 0})
+        assert outs[k]["steps"] == ref["steps"], (k, outs[k]["steps"], ref["steps"])
+        for key in ("xopt", "zopt", "uopt", "pnorm", "perr"):
+            assert rel(outs[k][key], ref[key]) < TOL, (k, key, rel(outs[k][key], ref[key]))

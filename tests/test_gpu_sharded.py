@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("problem,fast", [("svm", ""), ("huber", ""), ("lad", ""), ("huber", "weak"), ("lad", "strong"),
                                           ("huber", "onepass"), ("svm", "onepass"), ("lasso", ""), ("lassopath", ""),
-                                          ("svmbatch", ""), ("svm", "persist")])
+                                          ("svmbatch", ""), ("svm", "persist"), ("svmbatch", "persist")])
 def test_two_rank_run_matches_serial_oracle(problem, fast):
     import torch
     if torch.cuda.device_count() < 2:
