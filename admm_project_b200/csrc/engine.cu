@@ -2770,7 +2770,7 @@ static bool persist_batch_ok(const admm_b200_handle* h, const admm_b200_options&
   if (getenv("ADMM_B200_NO_PERSIST") || getenv("ADMM_B200_NO_PERSIST_BATCH")) return false;
   if (nbt > 10 || o.objevals || !h->have_inverse || h->xsolve_eff != ADMM_B200_XSOLVE_INVFACTOR) return false;
   if (h->nranks > 1 && !h->p2p.ready) return false;
-  if (h->n > (int64_t)PB_MAXCOLS * OP_THREADS || (int64_t)nbt * cbs > P2P_LLCAP) return false;
+  if (h->n > (int64_t)PB_MAXN || (h->n % 4) != 0 || (int64_t)nbt * cbs > P2P_LLCAP) return false;
   if ((((uintptr_t)h->dD) & 15) != 0 || (h->ldD % 2) != 0) return false;
   return persist_batch_smem(nbt, h->n, round_up(h->n, 2)) <= (size_t)227 * 1024;
 }
@@ -2843,6 +2843,12 @@ static void solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options& 
         pa.dpart = h->op_dpart.p; pa.partials = h->uw_partials.p; pa.tcur = CB.p; pa.tlast = TL.p; pa.cbs = cbs;
         pa.mail = h->p2p.dev; pa.ctl = ctl; pa.lp = lp; pa.hist_stride = N; pa.done_count = done_count;
         pa.m_total = (double)h->m_total;
+        pa.prof = nullptr;
+        static const bool want_prof = getenv("ADMM_B200_PERSIST_PROF") != nullptr;
+        if (want_prof) {
+          ADMM_CUDA(cudaMalloc(&pa.prof, (size_t)grid * 8 * sizeof(long long)));
+          ADMM_CUDA(cudaMemsetAsync(pa.prof, 0, (size_t)grid * 8 * sizeof(long long), st));
+        }
         const int check = std::max(1, o.check_every);
         int64_t enq = 0;
         int hdone = 0;
@@ -2858,6 +2864,20 @@ static void solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options& 
           ADMM_CUDA(cudaMemcpyAsync(&hdone, done_count, sizeof(int), cudaMemcpyDeviceToHost, st));
           ADMM_CUDA(cudaStreamSynchronize(st));
           if (hdone >= nb || enq >= N) break;
+        }
+        if (pa.prof) {
+          std::vector<long long> hp((size_t)grid * 8);
+          ADMM_CUDA(cudaMemcpy(hp.data(), pa.prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+          cudaFree(pa.prof);
+          const double its = std::max<double>(1.0, (double)enq);
+          const char* names[7] = {"tile wait + T*t", "shuffles", "proxes", "T'*r", "writes + barrier", "owner sums + exchange", "barrier 2 + stop"};
+          fprintf(stderr, "batch persist profile (rank %d, %d CTAs, %d classes, %.0f iterations): cycles per iteration, mean / max over CTAs\n",
+                  h->rank, grid, (int)nb, its);
+          for (int k = 0; k < 7; ++k) {
+            double mean = 0.0, mx = 0.0;
+            for (int c = 0; c < grid; ++c) { const double v = (double)hp[(size_t)c * 8 + k] / its; mean += v; mx = std::max(mx, v); }
+            fprintf(stderr, "  %-22s %9.0f / %9.0f\n", names[k], mean / grid, mx);
+          }
         }
         // x_c of the last iteration each class ran: X = inv(R)' TLAST = W' TLAST
         GemmOpt gx; gx.a_upper = 1;

@@ -21,12 +21,14 @@
 
 namespace admmb200 {
 
-constexpr int PB_R = 16, PB_RS = PB_R + 2, PB_RP = PB_R / 2, PB_JSTEP = OP_THREADS / PB_RP, PB_RH = PB_R / 2;
-constexpr int PB_MAXCOLS = 2;                         // columns per thread in the T' phase (512 column slots): n <= 1024
+constexpr int PB_R = 16, PB_RS = PB_R + 2, PB_RP = PB_R / 2, PB_JSTEP = OP_THREADS / PB_RP;
+constexpr int PB_TS = 12;                             // row stride of t (shared memory) and of the per-tile rhs: B fragments conflict-free
+constexpr int PB_MT = 4;                              // m-tiles (8 columns) per warp per column chunk in the T' phase: n <= 1024
+constexpr int PB_MAXN = 16 * PB_MT * 8 * 2;           // 1024
 
 template <int NBT> struct PersistBatchCfg {
   static size_t smem_bytes(int64_t n, int64_t npad) {
-    return (size_t)(n * PB_RS + npad * NBT + (OP_THREADS / 32) * PB_R * NBT + NBT * PB_R + PB_R * NBT * UW_NRED + NBT * 16) * 8;
+    return (size_t)(n * PB_RS + npad * PB_TS + (OP_THREADS / 32) * PB_R * NBT + PB_R * PB_TS + 8 + PB_R * NBT * UW_NRED + NBT * 16) * 8;
   }
 };
 
@@ -47,20 +49,22 @@ struct PersistBatchArgs {
   int* done_count;
   int burst;
   double m_total;
+  long long* prof;                                    // optional [gridDim.x][8] SM cycles per phase (ADMM_B200_PERSIST_PROF)
 };
 
 template <int NBT>
 __global__ void __launch_bounds__(OP_THREADS, 1) uwb_persist_kernel(PersistBatchArgs a) {
   namespace cg = cooperative_groups;
   cg::grid_group grid = cg::this_grid();
-  constexpr int R = PB_R, RS = PB_RS, RP = PB_RP, JSTEP = PB_JSTEP, NCH = 2, NW = OP_THREADS / 32;
+  constexpr int R = PB_R, RS = PB_RS, RP = PB_RP, JSTEP = PB_JSTEP, NCH = 2, NW = OP_THREADS / 32, TS = PB_TS;
+  constexpr int NT = (NBT + 7) / 8;                    // n-tiles (8 classes) of the DMMA products
   extern __shared__ __align__(16) double sm[];
   const int64_t n = a.n, m = a.m, npad = a.npad;
   double* T = sm;                                     // [n][RS]
-  double* ts = T + n * RS;                            // [npad][NBT]: t_c[j] at ts[j * NBT + c]
-  double* wpart = ts + npad * NBT;                    // [NW][R][NBT]
-  double* rs = wpart + NW * R * NBT;                  // [NBT][R]: rhs of the tile's rows, per class
-  double* redsm = rs + NBT * R;                       // [R][NBT][UW_NRED]
+  double* ts = T + n * RS;                            // [npad][TS]: t_c[j] at ts[j * TS + c], columns NBT..TS-1 zero
+  double* wpart = ts + npad * TS;                     // [NW][R][NBT]
+  double* rs = wpart + NW * R * NBT;                  // [R][TS] (+8): rhs of the tile's rows, rs[row * TS + class]
+  double* redsm = rs + R * TS + 8;                    // [R][NBT][UW_NRED]
   double* scal = redsm + R * NBT * UW_NRED;           // [NBT][16] (10 used)
   __shared__ int cdone[16], cit[16], s_active;
   __shared__ double chn[16];
@@ -78,14 +82,15 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uwb_persist_kernel(PersistBatch
     if (act == 0) return;                             // uniform over the grid: ctl only changes at the end of a launch
   }
   unsigned long long seq = *a.mail.seq;
-  for (int64_t i = tid; i < npad * NBT; i += OP_THREADS) {
-    const int64_t j = i / NBT;
-    const int c = (int)(i - j * NBT);
-    ts[i] = (j < n) ? a.tcur[(int64_t)c * a.cbs + j] : 0.0;
+  for (int64_t i = tid; i < npad * TS; i += OP_THREADS) {
+    const int64_t j = i / TS;
+    const int c = (int)(i - j * TS);
+    ts[i] = (j < n && c < NBT) ? a.tcur[(int64_t)c * a.cbs + j] : 0.0;
   }
-  const int64_t CW = (n + NCH - 1) / NCH;
+  for (int i = tid; i < R * TS + 8; i += OP_THREADS) rs[i] = 0.0;
+  const int64_t CW = ((n + NCH - 1) / NCH + 7) / 8 * 8;           // column chunks end on an 8-column DMMA tile
   const int q = tid % RP, j0 = tid / RP;              // phase 1: (row pair, column group)
-  const int sc = tid;                                 // phase 2: column slot (columns sc, sc + 512), all R rows
+  const int g = lane >> 2, t = lane & 3;              // DMMA fragment coordinates: a = A[g][t], b = B[t][g], c = C[g][2t..2t+1]
   const int prow = tid % R, pcls = tid / R;           // prox: (row, class) for tid < R * NBT
   const int64_t first = blockIdx.x;
   const bool single_tile = (first + gridDim.x >= a.ntiles);
@@ -108,12 +113,23 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uwb_persist_kernel(PersistBatch
   UwArgs u;                                            // the per-row arithmetic of unwrapped.cuh needs these fields only
   u.rho = a.rho; u.relax = 1.0; u.C = a.C; u.kind = a.kind; u.alg = 0;
 
+  long long tk = clock64();
+  auto tick = [&](int k) {
+    if (a.prof && tid == 0) {
+      const long long now = clock64();
+      a.prof[(int64_t)blockIdx.x * 8 + k] += now - tk;
+      tk = now;
+    }
+  };
   for (int b = 0; b < a.burst; ++b) {
-    double acc[PB_MAXCOLS][NBT];
+    // accumulators of T'*r: [column chunk][m-tile of this warp][n-tile][2]
+    double acc[NCH][PB_MT][NT][2];
 #pragma unroll
-    for (int k = 0; k < PB_MAXCOLS; ++k)
+    for (int c = 0; c < NCH; ++c)
 #pragma unroll
-      for (int c = 0; c < NBT; ++c) acc[k][c] = 0.0;
+      for (int i = 0; i < PB_MT; ++i)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[c][i][nt][0] = acc[c][i][nt][1] = 0.0;
     if (tid < R * NBT)                                 // norm sums of this thread's (row, class), kept in shared memory
 #pragma unroll
       for (int k = 0; k < UW_NRED; ++k) redsm[((int64_t)prow * NBT + pcls) * UW_NRED + k] = 0.0;
@@ -128,9 +144,13 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uwb_persist_kernel(PersistBatch
         const int64_t o = grow + (int64_t)pcls * a.ldm;
         zp = a.Z[o]; uold = a.U[o]; aux = a.AUX[o];
       }
-      double s0[NBT], s1[NBT];
+      // ---- W = T * [t_1 .. t_NB] on DMMA tiles: M = 16 rows (2 m-tiles), N = classes, K = columns of Q.  The K steps
+      // (4 columns) are dealt round-robin to the 16 warps; each warp keeps a 16 x 16 partial W in its C fragments.
+      double wacc[2][NT][2];
 #pragma unroll
-      for (int c = 0; c < NBT; ++c) s0[c] = s1[c] = 0.0;
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) wacc[mt][nt][0] = wacc[mt][nt][1] = 0.0;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         if (!tile_resident) {
@@ -139,42 +159,39 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uwb_persist_kernel(PersistBatch
         }
         __syncthreads();
         const int64_t cbeg = c * CW, cend = min(n, cbeg + CW);
-        const double* tp = T + (cbeg + j0) * RS + 2 * q;
-        const double* tt = ts + (cbeg + j0) * NBT;
-        for (int64_t j = cbeg + j0; j < cend; j += JSTEP) {
-          const double2 t2 = *reinterpret_cast<const double2*>(tp);
+        for (int64_t k0 = cbeg + 4 * warp; k0 < cend; k0 += 4 * NW) {
+          const double* tcol = T + (k0 + t) * RS + g;             // T[row g (+8)][column k0 + t]
+          const double* trow = ts + (k0 + t) * TS + g;            // t_{class g (+8)}[column k0 + t]
+          const double a0 = tcol[0], a1 = tcol[8];
 #pragma unroll
-          for (int c2 = 0; c2 < NBT / 2; ++c2) {
-            const double2 x2 = *reinterpret_cast<const double2*>(tt + 2 * c2);
-            s0[2 * c2] = fma(t2.x, x2.x, s0[2 * c2]);
-            s1[2 * c2] = fma(t2.y, x2.x, s1[2 * c2]);
-            s0[2 * c2 + 1] = fma(t2.x, x2.y, s0[2 * c2 + 1]);
-            s1[2 * c2 + 1] = fma(t2.y, x2.y, s1[2 * c2 + 1]);
+          for (int nt = 0; nt < NT; ++nt) {
+            const double bv = trow[8 * nt];
+            dmma884(wacc[0][nt][0], wacc[0][nt][1], a0, bv);
+            dmma884(wacc[1][nt][0], wacc[1][nt][1], a1, bv);
           }
-          tp += JSTEP * RS;
-          tt += JSTEP * NBT;
         }
       }
-      // the 4 column groups of a warp (lane bits 3, 4) are added by shuffles; lanes 0..7 park the warp's sums
+      tick(0);                                         // tile wait + T*t
+      {
+        double* wp = wpart + (int64_t)warp * R * NBT;
 #pragma unroll
-      for (int c = 0; c < NBT; ++c) {
-        s0[c] += __shfl_xor_sync(0xffffffffu, s0[c], 8);
-        s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], 8);
-        s0[c] += __shfl_xor_sync(0xffffffffu, s0[c], 16);
-        s1[c] += __shfl_xor_sync(0xffffffffu, s1[c], 16);
-      }
-      if (lane < RP) {
-        double* wp = wpart + ((int64_t)warp * R + 2 * lane) * NBT;
+        for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int c = 0; c < NBT; ++c) { wp[c] = s0[c]; wp[NBT + c] = s1[c]; }
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int cl = nt * 8 + 2 * t + e;
+              if (cl < NBT) wp[(mt * 8 + g) * NBT + cl] = wacc[mt][nt][e];
+            }
       }
       __syncthreads();
+      tick(1);                                         // partial W of every warp to shared memory
       if (tid < R * NBT) {
         double rv = 0.0;
         if (pactive) {
           double w = 0.0;
 #pragma unroll
-          for (int g = 0; g < NW; ++g) w += wpart[((int64_t)g * R + prow) * NBT + pcls];   // fixed order over the warps
+          for (int gw = 0; gw < NW; ++gw) w += wpart[((int64_t)gw * R + prow) * NBT + pcls];   // fixed order over the warps
           double rl[UW_NRED];
 #pragma unroll
           for (int k = 0; k < UW_NRED; ++k) rl[k] = 0.0;
@@ -186,37 +203,33 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uwb_persist_kernel(PersistBatch
           a.U[oidx] = o.u;
           rv = (a.kind >= UW_HUBER) ? (aux + o.z - o.u) : (o.z - o.u);
         }
-        rs[pcls * R + prow] = rv;
+        rs[prow * TS + pcls] = rv;
       }
       __syncthreads();
+      tick(2);                                         // proxes
       int64_t next = tile + gridDim.x;
       bool have_next = next < a.ntiles;
       if (!have_next && more && !single_tile) { next = first; have_next = true; }
+      // ---- acc += T' * [r_1 .. r_NB] on DMMA tiles: M = columns of Q (8 per m-tile), N = classes, K = the 16 rows.
+      // The B fragments (the rhs of the tile) are loaded once; warp w takes m-tiles w, w + 16, ... of each column chunk.
+      double bf[4][NT];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) bf[ks][nt] = rs[(ks * 4 + t) * TS + nt * 8 + g];
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int64_t cbeg = c * CW, cend = min(n, cbeg + CW);
 #pragma unroll
-        for (int k = 0; k < PB_MAXCOLS; ++k) {
-          const int64_t j = sc + (int64_t)k * OP_THREADS;
-          if (j >= cbeg && j < cend) {
-            const double* col = T + j * RS;
-            double tc[R];
+        for (int i = 0; i < PB_MT; ++i) {
+          const int64_t jt = cbeg + 8 * (warp + NW * i);
+          if (jt < cend) {
+            const double* tcol = T + (jt + g) * RS + t;             // T[row t (+4 ks)][column jt + g]
 #pragma unroll
-            for (int i = 0; i < R; i += 2) {
-              const double2 t2 = *reinterpret_cast<const double2*>(col + i);
-              tc[i] = t2.x; tc[i + 1] = t2.y;
-            }
+            for (int ks = 0; ks < 4; ++ks) {
+              const double av = tcol[4 * ks];
 #pragma unroll
-            for (int cl = 0; cl < NBT; ++cl) {
-              const double* rr = rs + cl * R;
-              double s = acc[k][cl];
-#pragma unroll
-              for (int i = 0; i < R; i += 2) {
-                const double2 r2 = *reinterpret_cast<const double2*>(rr + i);     // broadcast
-                s = fma(tc[i], r2.x, s);
-                s = fma(tc[i + 1], r2.y, s);
-              }
-              acc[k][cl] = s;
+              for (int nt = 0; nt < NT; ++nt) dmma884(acc[c][i][nt][0], acc[c][i][nt][1], av, bf[ks][nt]);
             }
           }
         }
@@ -224,16 +237,24 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uwb_persist_kernel(PersistBatch
         if (have_next) issue(next, c);
       }
       if (single_tile) tile_resident = true;
+      tick(3);                                         // T'*r
     }
     {
       double* dp = a.dpart + (int64_t)blockIdx.x * NBT * npad;
 #pragma unroll
-      for (int k = 0; k < PB_MAXCOLS; ++k) {
-        const int64_t j = sc + (int64_t)k * OP_THREADS;
-        if (j < n)
+      for (int c = 0; c < NCH; ++c)
 #pragma unroll
-          for (int cl = 0; cl < NBT; ++cl) dp[(int64_t)cl * npad + j] = acc[k][cl];
-      }
+        for (int i = 0; i < PB_MT; ++i) {
+          const int64_t j = c * CW + 8 * (warp + NW * i) + g;
+          if (j < min(n, (c + 1) * CW))
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int cl = nt * 8 + 2 * t + e;
+                if (cl < NBT) dp[(int64_t)cl * npad + j] = acc[c][i][nt][e];
+              }
+        }
     }
     // norm sums per class: the R prox threads of a class, fixed order
     __syncthreads();
@@ -246,61 +267,100 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uwb_persist_kernel(PersistBatch
     }
     __threadfence();
     grid.sync();
+    tick(4);                                           // partial writes + grid barrier
     // ---------------- phase R / E1: the outputs this CTA owns ------------------------------------------------------
     const int par = (int)(seq & 1);
     const unsigned fl = (unsigned)(seq + 1);
-    const int nparts = (int)gridDim.x, ndparts = nparts;
+    const int nparts = (int)gridDim.x;
     const int64_t per = n + UW_NRED, nout = (int64_t)NBT * per;
-    for (int64_t o = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp; o < nout; o += (int64_t)gridDim.x * NW) {
+    // CTA b owns the outputs [b*chunk, (b+1)*chunk).  In blocks of 64 outputs: thread (lane, warp) adds the partials of
+    // CTA group (warp >> 1) for output (warp & 1)*32 + lane -- <= 20 independent L2 loads in flight per thread -- the 8
+    // group sums meet in shared memory and are added in a fixed order; the owner then stores the value into every
+    // rank's mailbox, and 8 lanes per output collect it back from every rank (lane r spins on rank r's word).
+    const int64_t chunk = (nout + gridDim.x - 1) / gridDim.x;
+    const int64_t obeg = (int64_t)blockIdx.x * chunk, oend = min(nout, obeg + chunk);
+    const int pp = (nparts + 7) / 8;
+    double* red = wpart;                                  // [8][64], free between the tile loop and the next iteration
+    auto out_index = [&](int64_t o) {                     // position of output o in the per-rank message / t array
       const int cl = (int)(o / per);
       const int64_t w = o - (int64_t)cl * per;
-      double v[10];
-      const double* src = (w < n) ? a.dpart + (int64_t)cl * npad + w : a.partials + (int64_t)cl * UW_NRED + (w - n);
-      const int64_t stride = (w < n) ? (int64_t)NBT * npad : (int64_t)NBT * UW_NRED;
-      const int cnt = (w < n) ? ndparts : nparts;
-#pragma unroll
-      for (int i = 0; i < 10; ++i) {
-        const int pidx = lane + 32 * i;
-        v[i] = (pidx < cnt) ? __ldcg(src + (int64_t)pidx * stride) : 0.0;
-      }
-      double s = 0.0;
-#pragma unroll
-      for (int i = 0; i < 10; ++i) s += v[i];
-      for (int pidx = lane + 320; pidx < cnt; pidx += 32) s += __ldcg(src + (int64_t)pidx * stride);
-#pragma unroll
-      for (int of = 16; of > 0; of >>= 1) s += __shfl_xor_sync(0xffffffffu, s, of);
-      if (lane == 0) p2p_ll_store(a.mail, par, (int64_t)cl * a.cbs + ((w < n) ? w : npad + (w - n)), s, fl);
-    }
-    if (blockIdx.x == 0) {                             // the t this iteration used, for the classes still running
+      return (int64_t)cl * a.cbs + ((w < n) ? w : npad + (w - n));
+    };
+    if (blockIdx.x == 0) {                                // the t this iteration used, for the classes still running
       for (int64_t i = tid; i < n * NBT; i += OP_THREADS) {
         const int64_t j = i / NBT;
         const int c = (int)(i - j * NBT);
-        if (!cdone[c]) a.tlast[(int64_t)c * a.cbs + j] = ts[i];
+        if (!cdone[c]) a.tlast[(int64_t)c * a.cbs + j] = ts[j * TS + c];
       }
     }
-    for (int64_t o = (int64_t)blockIdx.x + (int64_t)gridDim.x * warp; o < nout; o += (int64_t)gridDim.x * NW) {
-      const int cl = (int)(o / per);
-      const int64_t w = o - (int64_t)cl * per;
-      const int64_t idx = (int64_t)cl * a.cbs + ((w < n) ? w : npad + (w - n));
-      double v = 0.0;
-      if (lane < a.mail.nranks) {                      // lane r collects rank r's copy of this output
-        const ulonglong2* wd = a.mail.ll_slot(a.mail.rank, par, lane) + idx;
-        const long long t0 = clock64();
-        while (!ll_load(wd, fl, v)) {
-          if (clock64() - t0 > 4000000000LL) { *a.mail.err = 1; __trap(); }
+    for (int64_t ob = obeg; ob < oend; ob += 64) {
+      {
+        const int oi = (warp & 1) * 32 + lane, g = warp >> 1;
+        const int64_t o = ob + oi;
+        double s = 0.0;
+        if (o < oend) {
+          const int cl = (int)(o / per);
+          const int64_t w = o - (int64_t)cl * per;
+          const double* src = (w < n) ? a.dpart + (int64_t)cl * npad + w : a.partials + (int64_t)cl * UW_NRED + (w - n);
+          const int64_t stride = (w < n) ? (int64_t)NBT * npad : (int64_t)NBT * UW_NRED;
+          const int p0 = g * pp, p1 = min(nparts, p0 + pp);
+          double v[20];
+#pragma unroll
+          for (int i = 0; i < 20; ++i) v[i] = (p0 + i < p1) ? __ldcg(src + (int64_t)(p0 + i) * stride) : 0.0;
+#pragma unroll
+          for (int i = 0; i < 20; ++i) s += v[i];
+          for (int pidx = p0 + 20; pidx < p1; ++pidx) s += __ldcg(src + (int64_t)pidx * stride);
         }
+        red[g * 64 + oi] = s;
       }
-      double s = 0.0;
-      for (int r = 0; r < a.mail.nranks; ++r) s += __shfl_sync(0xffffffffu, v, r);   // rank order
-      if (lane == 0) a.tcur[idx] = s;
+      __syncthreads();
+      if (tid < 64 && ob + tid < oend) {
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) s += red[g * 64 + tid];
+        p2p_ll_store(a.mail, par, out_index(ob + tid), s, fl);
+      }
+      {
+        const int oi = tid >> 3, r = tid & 7;
+        const int64_t o = ob + oi;
+        double v = 0.0;
+        const bool mine = (o < oend) && (r < a.mail.nranks);
+        const int64_t idx = (o < oend) ? out_index(o) : 0;
+        if (mine) {
+          const ulonglong2* wd = a.mail.ll_slot(a.mail.rank, par, r) + idx;
+          const long long t0 = clock64();
+          while (!ll_load(wd, fl, v)) {
+            if (clock64() - t0 > 4000000000LL) { *a.mail.err = 1; __trap(); }
+          }
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int rr = 0; rr < P2P_MAXRANKS; ++rr) {
+          const double vr = __shfl_sync(0xffffffffu, v, rr, 8);      // rank order inside each group of 8 lanes
+          if (rr < a.mail.nranks) s += vr;
+        }
+        if (r == 0 && o < oend) a.tcur[idx] = s;
+      }
+      __syncthreads();
     }
     __threadfence();
+    tick(5);                                           // owner sums, mailbox stores, collection from every rank
     grid.sync();
     // ---------------- phase E2: the new t of every class, stop tests ------------------------------------------------
-    for (int64_t i = tid; i < n * NBT; i += OP_THREADS) {
-      const int64_t j = i / NBT;
-      const int c = (int)(i - j * NBT);
-      if (!cdone[c]) ts[i] = __ldcg(a.tcur + (int64_t)c * a.cbs + j);
+    for (int64_t i0 = 0; i0 < n * NBT; i0 += 16 * OP_THREADS) {     // 16 independent loads per thread, then the stores
+      double v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int64_t i = i0 + tid + (int64_t)k * OP_THREADS;
+        const int64_t j = i / NBT;
+        const int c = (int)(i - j * NBT);
+        v[k] = (i < n * NBT && !cdone[c]) ? __ldcg(a.tcur + (int64_t)c * a.cbs + j) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int64_t i = i0 + tid + (int64_t)k * OP_THREADS;
+        if (i < n * NBT && !cdone[(int)(i % NBT)]) ts[(i / NBT) * TS + (i % NBT)] = v[k];
+      }
     }
     if (tid < NBT * UW_NRED) {
       const int cl = tid / UW_NRED, k = tid % UW_NRED;
@@ -344,6 +404,7 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uwb_persist_kernel(PersistBatch
     }
     __syncthreads();
     ++seq;
+    tick(6);                                           // second barrier, reload of t, stop tests
     if (s_active == 0) break;
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
