@@ -347,19 +347,23 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uwb_persist_kernel(PersistBatch
     tick(5);                                           // owner sums, mailbox stores, collection from every rank
     grid.sync();
     // ---------------- phase E2: the new t of every class, stop tests ------------------------------------------------
-    for (int64_t i0 = 0; i0 < n * NBT; i0 += 16 * OP_THREADS) {     // 16 independent loads per thread, then the stores
-      double v[16];
+    {
+      const unsigned total = (unsigned)(n * NBT);                     // 32-bit index arithmetic: constant-divisor div / mod
+      const unsigned cbs32 = (unsigned)a.cbs;
+      for (unsigned i0 = 0; i0 < total; i0 += 16u * OP_THREADS) {      // 16 independent loads per thread, then the stores
+        double v[16];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int64_t i = i0 + tid + (int64_t)k * OP_THREADS;
-        const int64_t j = i / NBT;
-        const int c = (int)(i - j * NBT);
-        v[k] = (i < n * NBT && !cdone[c]) ? __ldcg(a.tcur + (int64_t)c * a.cbs + j) : 0.0;
-      }
+        for (int k = 0; k < 16; ++k) {
+          const unsigned i = i0 + (unsigned)tid + (unsigned)k * OP_THREADS;
+          const unsigned j = i / (unsigned)NBT, c = i - j * (unsigned)NBT;
+          v[k] = (i < total && !cdone[c]) ? __ldcg(a.tcur + c * cbs32 + j) : 0.0;
+        }
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int64_t i = i0 + tid + (int64_t)k * OP_THREADS;
-        if (i < n * NBT && !cdone[(int)(i % NBT)]) ts[(i / NBT) * TS + (i % NBT)] = v[k];
+        for (int k = 0; k < 16; ++k) {
+          const unsigned i = i0 + (unsigned)tid + (unsigned)k * OP_THREADS;
+          const unsigned j = i / (unsigned)NBT, c = i - j * (unsigned)NBT;
+          if (i < total && !cdone[c]) ts[j * (unsigned)TS + c] = v[k];
+        }
       }
     }
     if (tid < NBT * UW_NRED) {
