@@ -88,9 +88,10 @@ using namespace admmb200;
 
 struct admm_b200_handle {
   int device = 0;
-  cudaStream_t own_stream = nullptr, stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream_hi = nullptr;   // stream_hi / 2 / 3: Cholesky look-ahead (high / middle / low priority)
+  cudaStream_t own_stream = nullptr, stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr, stream_hi = nullptr;   // stream_hi / 2 / 3: Cholesky look-ahead (high / middle / low priority); 4: the inverse factor trailing it (low)
   std::vector<cudaEvent_t> ev_pool;   // events of the look-ahead Cholesky (created on first use)
   DBuf chol_ws;                       // out-of-place panel solves of the look-ahead Cholesky
+  DBuf inv_ws;                        // L[P, :P] * W[:P, :P] of the inverse factor's block row P
   cudaEvent_t ev_la[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[4] = {nullptr, nullptr, nullptr, nullptr};
   double phase_ms[4] = {0, 0, 0, 0};  // gram (+Dts), cholesky, inverse factor (+transpose), total
@@ -622,24 +623,33 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
   ADMM_CUDA(cudaMemset2DAsync(W, (size_t)ldw * 8, 0, (size_t)k * 8, (size_t)k, h->stream));
   constexpr int64_t NBO = CHOL_NBO;
   const int64_t npan = (k + NBO - 1) / NBO;
-  while ((int64_t)h->ev_pool.size() < 5 * npan + 2) {
+  while ((int64_t)h->ev_pool.size() < 5 * npan + 3) {
     cudaEvent_t e;
     ADMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->ev_pool.push_back(e);
   }
   auto ev = [&](int kind, int64_t P) { return h->ev_pool[(size_t)(kind * npan + P)]; };   // 0 W, 1 top, 2 T, 3 A(col), 4 C(bulk)
   cudaEvent_t ev_start = h->ev_pool[(size_t)(5 * npan)], ev_end = h->ev_pool[(size_t)(5 * npan + 1)];
+  cudaEvent_t ev_inv = h->ev_pool[(size_t)(5 * npan + 2)];
+  // The inverse factor rides one panel behind the factorisation on a fourth (low-priority) stream: block row P of
+  // W = inv(L) is  W[P, :P] = -W_PP * (L[P, :P] * W[:P, :P]),  and L[P, :P] is final once panel P-1 has been solved,
+  // so the big product runs while the chain factors diagonal block P and only the 512-wide product with W_PP comes
+  // after it.  The n^3/3 flops of the inverse fill the SMs the latency-bound chain leaves idle instead of following it.
+  static const bool inv_overlap = getenv("ADMM_B200_NO_INV_OVERLAP") == nullptr;
+  const bool ride = want_inverse && inv_overlap;
+  if (ride) h->inv_ws.ensure(NBO * round_up(k, 2));
   DBuf& T = h->scratch;
   T.ensure(std::max(doubling_scratch(k, NBO), doubling_scratch(NBO, CHOL_NB)));
   const int64_t lds = round_up(k, 2);
   h->chol_ws.ensure(lds * NBO + NBO * NBO);
   double* S2 = h->chol_ws.p;                 // bulk panel solve result (rows below the top block) x 512
   double* S1 = h->chol_ws.p + lds * NBO;     // top block solve result, 512 x 512
-  cudaStream_t user = h->stream, sA = h->stream_hi, sB = h->stream2, sC = h->stream3;
+  cudaStream_t user = h->stream, sA = h->stream_hi, sB = h->stream2, sC = h->stream3, sD = h->stream4;
   ADMM_CUDA(cudaEventRecord(ev_start, user));
   ADMM_CUDA(cudaStreamWaitEvent(sA, ev_start, 0));
   ADMM_CUDA(cudaStreamWaitEvent(sB, ev_start, 0));
   ADMM_CUDA(cudaStreamWaitEvent(sC, ev_start, 0));
+  ADMM_CUDA(cudaStreamWaitEvent(sD, ev_start, 0));
   {
   StreamSwap on_a(h, sA);                  // the chain: every launch below that does not name a stream goes to sA
   for (int64_t P = 0; P < npan; ++P) {
@@ -648,8 +658,26 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
     double* WPP = W + K0 + K0 * ldw;
     // the diagonal block has received the bulk updates of panels <= P-2 on stream C (panel P-1's came on A itself)
     if (P >= 2) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(4, P - 2), 0));
+    if (ride && P >= 1) {
+      // L[P, :P] is final: its last block came from the top solve of panel P-1 (stream A), the others from stream B
+      StreamSwap on_d(h, sD);
+      ADMM_CUDA(cudaStreamWaitEvent(sD, ev(1, P - 1), 0));
+      if (P >= 2) ADMM_CUDA(cudaStreamWaitEvent(sD, ev(2, P - 2), 0));
+      GemmOpt o1;
+      o1.allow_splitk = 0;
+      o1.b_lower = 1;
+      gemm(h, 0, 0, wb, K0, K0, 1.0, A + K0, lda, W, ldw, 0.0, h->inv_ws.p, NBO, o1);
+    }
     potrf_block512(h, APP, lda, wb, WPP, ldw, K0, T);
     ADMM_CUDA(cudaEventRecord(ev(0, P), sA));
+    if (ride && P >= 1) {
+      StreamSwap on_d(h, sD);
+      ADMM_CUDA(cudaStreamWaitEvent(sD, ev(0, P), 0));
+      GemmOpt o2;
+      o2.allow_splitk = 0;
+      o2.a_lower = 1;
+      gemm(h, 0, 0, wb, K0, wb, -1.0, WPP, ldw, h->inv_ws.p, NBO, 0.0, W + K0, ldw, o2);
+    }
     const int64_t rem = k - K1;
     if (rem <= 0) break;
     const int64_t n1 = std::min<int64_t>(NBO, rem), rem2 = rem - n1;
@@ -714,12 +742,14 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
   }
+  ADMM_CUDA(cudaEventRecord(h->evp[2], h->stream));          // factor done; what follows on the timeline is the inverse's tail
+  ADMM_CUDA(cudaEventRecord(ev_inv, sD));
+  ADMM_CUDA(cudaStreamWaitEvent(user, ev_inv, 0));
   int fail = 0;
   ADMM_CUDA(cudaMemcpyAsync(&fail, h->fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   ADMM_CUDA(cudaStreamSynchronize(h->stream));
   ADMM_REQUIRE(fail == 0, ADMM_B200_ERR_NOTPOSDEF, "Matrix must be positive definite. (pivot %d is not positive)", fail);
-  ADMM_CUDA(cudaEventRecord(h->evp[2], h->stream));
-  if (!want_inverse) return;
+  if (!want_inverse || ride) return;
   tri_inverse_doubling(h, k, A, lda, W, ldw, NBO, T);
 }
 
@@ -1070,10 +1100,18 @@ static void symtri_solve(admm_b200_handle* h, const double* WT, int64_t ld, int6
   a.cta_round = pl->d_cta_round; a.round_ent = pl->d_round_ent; a.ents = pl->d_ents;
   symtri_kernel<<<pl->grid, ST_THREADS, ST_SMEM, h->stream>>>(a);
   ADMM_CUDA(cudaGetLastError());
-  symtri_reduce_kernel<<<(unsigned)((k + 31) / 32), 256, 0, h->stream>>>(h->st_part.p, pl->grid, kpad, (int)k, x, 1.0, nullptr, 0.0, done);
+  const int mail_on = (shard && h->p2p.ready && kpad <= P2P_LLCAP) ? 1 : 0;
+  symtri_reduce_kernel<<<(unsigned)((k + 31) / 32), 256, 0, h->stream>>>(h->st_part.p, pl->grid, kpad, (int)k, x, 1.0, nullptr, 0.0, done,
+                                                                         h->p2p.dev, mail_on);
   ADMM_CUDA(cudaGetLastError());
   h->launches += 2;
-  if (shard) allreduce_sum(h, x, kpad, done);
+  if (mail_on) {          // the rank sums are already in every mailbox: one kernel adds them up into x
+    p2p_ll_gather_kernel<<<(unsigned)((k + 255) / 256), 256, 0, h->stream>>>(h->p2p.dev, x, k, done, h->p2p.dev.ticket + 1);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches++;
+  } else if (shard) {
+    allreduce_sum(h, x, kpad, done);
+  }
 }
 
 // x = L' \ (L \ b) with the cached factor (size k); second = the z-update factor of the model problem
@@ -1649,6 +1687,16 @@ static void comm_destroy(admm_b200_handle* h) {
 // every rank); large ones (the n x n Gram) through ncclAllReduce.
 static void allreduce_sum(admm_b200_handle* h, double* buf, int64_t count, const int* done) {
   if (h->nranks <= 1) return;
+  if (h->p2p.ready && count <= P2P_LLCAP && !getenv("ADMM_B200_P2P_FLAGS")) {
+    // flag-in-data words: the writer just stores, the reader spins on the data itself (p2p.cuh)
+    const int grid = (int)std::max<int64_t>(1, (count + 255) / 256);
+    p2p_ll_push_kernel<<<std::min(grid, 64), 256, 0, h->stream>>>(h->p2p.dev, buf, count, done);
+    ADMM_CUDA(cudaGetLastError());
+    p2p_ll_gather_kernel<<<grid, 256, 0, h->stream>>>(h->p2p.dev, buf, count, done, h->p2p.dev.ticket + 1);
+    ADMM_CUDA(cudaGetLastError());
+    h->launches += 2;
+    return;
+  }
   if (h->p2p.ready && count <= P2P_CAP) {
     const int grid = (int)std::max<int64_t>(1, (count + 255) / 256);
     p2p_push_kernel<<<std::min(grid, 32), 256, 0, h->stream>>>(h->p2p.dev, buf, count, done);
@@ -3037,6 +3085,7 @@ int admm_b200_create(int device, admm_b200_handle** out) {
     ADMM_CUDA(cudaStreamCreateWithPriority(&h->stream_hi, cudaStreamNonBlocking, greatest));
     ADMM_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, (least + greatest) / 2));
     ADMM_CUDA(cudaStreamCreateWithPriority(&h->stream3, cudaStreamNonBlocking, least));
+    ADMM_CUDA(cudaStreamCreateWithPriority(&h->stream4, cudaStreamNonBlocking, least));
   }
   for (auto& e : h->ev_la) ADMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   h->stream = h->own_stream;
@@ -3086,6 +3135,7 @@ int admm_b200_destroy(admm_b200_handle* h) {
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream3) cudaStreamDestroy(h->stream3);
+  if (h->stream4) cudaStreamDestroy(h->stream4);
   if (h->stream_hi) cudaStreamDestroy(h->stream_hi);
   for (auto& e : h->ev_pool) cudaEventDestroy(e);
   h->chol_ws.release();

@@ -206,4 +206,46 @@ __global__ void __launch_bounds__(256) p2p_wait_sum_kernel(P2PDev p, double* __r
   }
 }
 
+// ---- generic form on the flag-in-data words: no fence, no flag, no election ---------------------------------------
+__global__ void __launch_bounds__(256) p2p_ll_push_kernel(P2PDev p, const double* __restrict__ buf, int64_t count, const int* done) {
+  if ((done && *done) || *p.err) return;
+  const unsigned long long s = *p.seq;
+  const int par = (int)(s & 1);
+  const unsigned fl = (unsigned)(s + 1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    p2p_ll_store(p, par, i, buf[i], fl);
+}
+
+// buf[i] <- sum over ranks (rank order) of value i of this exchange; the last CTA bumps the exchange counter
+__global__ void __launch_bounds__(256) p2p_ll_gather_kernel(P2PDev p, double* __restrict__ buf, int64_t count, const int* done,
+                                                            unsigned* ticket2) {
+  if ((done && *done) || *p.err) return;
+  const unsigned long long s = *p.seq;
+  const int par = (int)(s & 1);
+  const unsigned fl = (unsigned)(s + 1);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) {
+    double acc = 0.0;
+    const long long t0 = clock64();
+    for (int r = 0; r < p.nranks; ++r) {
+      const ulonglong2* w = p.ll_slot(p.rank, par, r) + i;
+      double v;
+      bool ok;
+      while (!(ok = ll_load(w, fl, v)) && clock64() - t0 <= 4000000000LL) {}
+      if (!ok) { *p.err = 1; v = 0.0; }          // a peer is gone: the host raises after the loop (p2p_check)
+      acc += v;
+    }
+    buf[i] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(ticket2, 1u);
+    if (t == gridDim.x - 1) {
+      *ticket2 = 0;
+      *p.seq = s + 1;
+    }
+  }
+}
+
 }  // namespace admmb200

@@ -21,6 +21,7 @@
 // rank sums then go through the mailbox allreduce.
 #pragma once
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace admmb200 {
 
@@ -196,10 +197,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
 }
 
 // x[r] = scale * sum over CTAs (fixed order) of xpart[cta][r] (+ addscale * addend[r]).  32 rows x 8 CTA groups per block.
+// mail_on: this rank's sums go straight into every rank's mailbox (flag-in-data words) instead of x; a
+// p2p_ll_gather_kernel then adds the ranks up into x (row-sharded lasso, the x-update split by columns over the ranks).
 __global__ void __launch_bounds__(256) symtri_reduce_kernel(const double* __restrict__ xpart, int nparts, int kpad, int k,
                                                             double* __restrict__ x, double scale, const double* addend,
-                                                            double addscale, const int* done) {
+                                                            double addscale, const int* done, P2PDev mail, int mail_on) {
   if (done && *done) return;
+  if (mail_on && *mail.err) return;
+  const unsigned long long seq = mail_on ? *mail.seq : 0ull;
   __shared__ double sh[8][33];
   const int rl = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int row = blockIdx.x * 32 + rl;
@@ -215,7 +220,8 @@ __global__ void __launch_bounds__(256) symtri_reduce_kernel(const double* __rest
     for (int i = 0; i < 8; ++i) t += sh[i][rl];
     t *= scale;
     if (addend) t += addscale * addend[row];
-    x[row] = t;
+    if (mail_on) p2p_ll_store(mail, (int)(seq & 1), row, t, (unsigned)(seq + 1));
+    else x[row] = t;
   }
 }
 
