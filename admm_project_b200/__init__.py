@@ -16,5 +16,6 @@ from .errorcheck import errorcheck                               # noqa: F401
 from . import solvers                                            # noqa: F401
 from . import mnist                                              # noqa: F401
 from . import testers                                            # noqa: F401
+from .showresults import showresults                             # noqa: F401
 from .solvers import linearsvm_onevsall, lasso_path                       # noqa: F401
 from .solvers import lasso, unwrappedadmm, linearsvm, huberfit, lad, basispursuit, totalvariation, quadraticprogram, model   # noqa: F401

@@ -294,7 +294,9 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   const bool small = !no_small && !skinny && !tall_tri && !o.inplace && t128 <= 40 && M >= 64 && N >= 64 &&
                      (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                      (o.strideA % 2 == 0) && (o.strideB % 2 == 0);
-  const int64_t bnsz = (skinny || small) ? 64 : GEMM_BN;
+  // a rank's share of a lambda batch split over several GPUs: 32- or 16-wide tiles (K-major right-hand sides, 16-byte path)
+  const int narrow = (tall_tri && transb == 0 && !getenv("ADMM_B200_NO_NARROW_TRI")) ? (N <= 16 ? 16 : (N <= 32 ? 32 : 0)) : 0;
+  const int64_t bnsz = narrow ? narrow : ((skinny || small) ? 64 : GEMM_BN);
   const int64_t bmsz = tall_tri ? 256 : (small ? 64 : GEMM_BM);
   if (small) g.bm = 64;
   const int64_t tm = (M + bmsz - 1) / bmsz, tn = (N + bnsz - 1) / bnsz;
@@ -364,7 +366,9 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   const bool BK = transb == 0;  // 'N': op(B)[k,j] = B[k + j*ldb]  (K contiguous)
 #define ADMM_GEMM_CASE(a, b)                                     \
   if (AK == a && BK == b) {                                      \
-    if (tall_tri) gemm_launch_t<a, b, 2, 64, 256>(h, g, grid);   \
+    if (tall_tri && narrow == 16 && b) gemm_launch_t<a, true, 2, 16, 256>(h, g, grid);   \
+    else if (tall_tri && narrow == 32 && b) gemm_launch_t<a, true, 2, 32, 256>(h, g, grid);   \
+    else if (tall_tri) gemm_launch_t<a, b, 2, 64, 256>(h, g, grid);   \
     else if (small) gemm_launch_t<a, b, 2, 64, 64>(h, g, grid);  \
     else if (skinny) {                                           \
       if (vec_ok) gemm_launch_t<a, b, 2, 64>(h, g, grid);        \
@@ -636,6 +640,9 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
   // so the big product runs while the chain factors diagonal block P and only the 512-wide product with W_PP comes
   // after it.  The n^3/3 flops of the inverse fill the SMs the latency-bound chain leaves idle instead of following it.
   static const bool inv_overlap = getenv("ADMM_B200_NO_INV_OVERLAP") == nullptr;
+  // timing probe only (tools/chol_probe.py): leave the bulk trailing updates out to see the bare critical chain; the
+  // factor is then WRONG and the pivot check is skipped
+  static const bool probe_nobulk = getenv("ADMM_B200_CHOL_PROBE_NOBULK") != nullptr;
   const bool ride = want_inverse && inv_overlap;
   if (ride) h->inv_ws.ensure(NBO * round_up(k, 2));
   DBuf& T = h->scratch;
@@ -721,7 +728,7 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
         GemmOpt bo;
         bo.lower_only = 1;
         bo.allow_splitk = 0;
-        gemm(h, 0, 1, rem2, rem2, wb, -1.0, A21b, lda, A21b, lda, 1.0, A + (K1 + n1) + (K1 + n1) * lda, lda, bo);
+        if (!probe_nobulk) gemm(h, 0, 1, rem2, rem2, wb, -1.0, A21b, lda, A21b, lda, 1.0, A + (K1 + n1) + (K1 + n1) * lda, lda, bo);
         ADMM_CUDA(cudaEventRecord(ev(4, P), sC));
       }
     } else {
@@ -748,7 +755,7 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
   int fail = 0;
   ADMM_CUDA(cudaMemcpyAsync(&fail, h->fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   ADMM_CUDA(cudaStreamSynchronize(h->stream));
-  ADMM_REQUIRE(fail == 0, ADMM_B200_ERR_NOTPOSDEF, "Matrix must be positive definite. (pivot %d is not positive)", fail);
+  ADMM_REQUIRE(fail == 0 || probe_nobulk, ADMM_B200_ERR_NOTPOSDEF, "Matrix must be positive definite. (pivot %d is not positive)", fail);
   if (!want_inverse || ride) return;
   tri_inverse_doubling(h, k, A, lda, W, ldw, NBO, T);
 }
@@ -2524,12 +2531,18 @@ static void run_persist(admm_b200_handle* h, const admm_b200_options& o, const L
     cudaFree(a.prof);
     const double its = std::max<double>(1.0, (double)h->h_ctl->it);
     const char* names[6] = {"D-phase", "grid.sync", "R sums+stores", "(unused)", "values arrive", "stop tests"};
-    fprintf(stderr, "persist profile (rank %d, %d CTAs, %.0f iterations): cycles per iteration, mean / max over CTAs\n", h->rank, grid, its);
+    char line[256];
+    std::string txt;                     // one write per rank: the ranks' reports must not interleave
+    snprintf(line, sizeof line, "persist profile (rank %d of %d, %lld rows here, %d CTAs, %.0f iterations): cycles per iteration, mean / max over CTAs\n",
+             h->rank, h->nranks, (long long)h->m, grid, its);
+    txt += line;
     for (int k = 0; k < 6; ++k) {
       double mean = 0.0, mx = 0.0;
       for (int c = 0; c < grid; ++c) { const double v = (double)hp[(size_t)c * 8 + k] / its; mean += v; mx = std::max(mx, v); }
-      fprintf(stderr, "  %-14s %9.0f / %9.0f\n", names[k], mean / grid, mx);
+      snprintf(line, sizeof line, "  [r%d] %-14s %9.0f / %9.0f\n", h->rank, names[k], mean / grid, mx);
+      txt += line;
     }
+    fputs(txt.c_str(), stderr);
   }
   // x of the last iteration: x = inv(R)' t = W' t, x_j = column j of W (rows j..n-1) . t
   coldot(h, COLDOT_LOWER, h->W.p, h->ldf, n, n, h->tlast.p, h->x.p);
@@ -2919,13 +2932,18 @@ static void solve_unwrapped_batch(admm_b200_handle* h, const admm_b200_options& 
           cudaFree(pa.prof);
           const double its = std::max<double>(1.0, (double)enq);
           const char* names[7] = {"tile wait + T*t", "shuffles", "proxes", "T'*r", "writes + barrier", "owner sums + exchange", "barrier 2 + stop"};
-          fprintf(stderr, "batch persist profile (rank %d, %d CTAs, %d classes, %.0f iterations): cycles per iteration, mean / max over CTAs\n",
-                  h->rank, grid, (int)nb, its);
+          char line[256];
+          std::string txt;               // one write per rank: the ranks' reports must not interleave
+          snprintf(line, sizeof line, "batch persist profile (rank %d of %d, %lld rows here, %d CTAs, %d classes, %.0f iterations): cycles per iteration, mean / max over CTAs\n",
+                   h->rank, h->nranks, (long long)h->m, grid, (int)nb, its);
+          txt += line;
           for (int k = 0; k < 7; ++k) {
             double mean = 0.0, mx = 0.0;
             for (int c = 0; c < grid; ++c) { const double v = (double)hp[(size_t)c * 8 + k] / its; mean += v; mx = std::max(mx, v); }
-            fprintf(stderr, "  %-22s %9.0f / %9.0f\n", names[k], mean / grid, mx);
+            snprintf(line, sizeof line, "  [r%d] %-22s %9.0f / %9.0f\n", h->rank, names[k], mean / grid, mx);
+            txt += line;
           }
+          fputs(txt.c_str(), stderr);
         }
         // x_c of the last iteration each class ran: X = inv(R)' TLAST = W' TLAST
         GemmOpt gx; gx.a_upper = 1;

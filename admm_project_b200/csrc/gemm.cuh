@@ -43,8 +43,9 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
   if (KMAJOR) {
     if (VEC == 2) {
 #pragma unroll
-      for (int it = 0; it < ROWS / 32; ++it) {
+      for (int it = 0; it < (ROWS + 31) / 32; ++it) {
         int r = (tid >> 3) + 32 * it, c = (tid & 7) * 2;
+        if (ROWS < 32 && r >= ROWS) continue;      // a 16-row tile (few right-hand sides): half the threads load
         int64_t gr = r0 + r, gk = k0 + c;
         int64_t left = (gr < R) ? (Kend - gk) : 0;
         int nb = left >= 2 ? 16 : (left == 1 ? 8 : 0);
@@ -93,7 +94,9 @@ __device__ __forceinline__ void gemm_load_tile(double* s, const double* __restri
 // 64-lambda batch): 8 warps as 4 (M) x 2 (N), warp tile 32 x 32, so no DMMA is spent on padding columns.
 // BM = 256, BN = 64 (tall triangular op(A) times a few right-hand sides: the lambda batch on an 8192-wide factor):
 // 8 warps as 4 (M) x 2 (N) with the full 64 x 32 warp tile, 3 stages; K is cut into uniform chunks so the
-// (row tile, K chunk) units of a triangular operand are equal pieces of work for the 148 SMs.
+// (row tile, K chunk) units of a triangular operand are equal pieces of work for the 148 SMs.  BN = 32 / 16 with
+// BM = 256 (K-major right-hand sides only): the lambda columns of ONE rank when the batch is split over 2 / 4 / 8
+// GPUs -- warp tile 64 x 16 / 64 x 8, so a rank with 8 columns does a quarter of the DMMA work of the 64-wide tile.
 template <int BM> struct GemmCfg {
   static constexpr int STAGES = (BM == 256) ? 3 : GEMM_STAGES;
   static constexpr int LDM = (BM > 128) ? BM + 4 : GEMM_LDM;

@@ -23,9 +23,16 @@ def _solvers(solvers):
     return pkg, {}
 
 
-def _finish(results, test, failed, reason):
+def _finish(results, test, failed, reason, quiet=1, options=None):
     test.update(failed=int(bool(failed)), failreason=reason, steps=results.get("steps"))
+    if not quiet:          # testers/*test.m end with `if ~quiet, showresults(results, test, options); end`
+        from .showresults import showresults
+        test["report"] = showresults(results, test, options or {})
     return results, test
+
+
+def _finish_q(quiet, options, results, test, failed, reason):
+    return _finish(results, test, failed, reason, quiet, options)
 
 
 def lassotest(seed=0, rows=256, cols=64, errtol=1e-3, quiet=1, options=None, solvers=None, **kw):
@@ -38,7 +45,7 @@ def lassotest(seed=0, rows=256, cols=64, errtol=1e-3, quiet=1, options=None, sol
     test = dict(D=D, s=s, lam=lam, testx=testx, trueobjopt=obj(testx), objopt=obj(results["xopt"]),
                 admmopt=results.get("objopt"), errtol=errtol)
     ok = test["objopt"] < test["trueobjopt"]
-    return _finish(results, test, not ok, "ADMM's objective %s the objective of the generating signal" %
+    return _finish_q(quiet, dict(o, solver="lasso"), results, test, not ok, "ADMM's objective %s the objective of the generating signal" %
                    ("is below" if ok else "is NOT below"))
 
 
@@ -63,6 +70,10 @@ def linearsvmtest(seed=0, mpos=128, mneg=128, sep=0.2, errtol=0.05, quiet=1, opt
                           relerror=relerr, failed=int(not (obj(x) < trueobj and relerr <= errtol)), steps=r["steps"]))
     test = dict(D=D, ell=ell, hinge=tests[0], zero_one=tests[1], errtol=errtol, objopt=tests[0]["objopt"],
                 trueobjopt=trueobj)
+    if not quiet:          # linearsvmtest.m:231-237: one report per loss function
+        from .showresults import showresults
+        test["reports"] = [showresults(rh, tests[0], dict(o, tester="linearsvm", lossfunction="hinge")),
+                           showresults(r01, tests[1], dict(o, tester="linearsvm", lossfunction="01"))]
     return _finish(rh, test, tests[0]["failed"] or tests[1]["failed"], "hinge failed=%d, '0-1' failed=%d" %
                    (tests[0]["failed"], tests[1]["failed"]))
 
@@ -75,7 +86,7 @@ def huberfittest(seed=0, rows=2048, cols=128, errtol=1e-3, quiet=1, options=None
     results = S.huberfit(D, s, o, **kw)
     f = lambda x: 0.5 * float(np.sum(_huber1(D @ x - s)))
     test = dict(D=D, s=s, testx=testx, trueobjopt=f(testx), objopt=f(results["xopt"]), admmopt=results.get("objopt"))
-    return _finish(results, test, not (test["objopt"] <= test["trueobjopt"]), "objective vs generating signal")
+    return _finish_q(quiet, dict(o, solver="huberfit"), results, test, not (test["objopt"] <= test["trueobjopt"]), "objective vs generating signal")
 
 
 def ladtest(seed=0, rows=1024, cols=128, errtol=1e-3, quiet=1, options=None, solvers=None, **kw):
@@ -89,7 +100,7 @@ def ladtest(seed=0, rows=1024, cols=128, errtol=1e-3, quiet=1, options=None, sol
     xres = float(np.linalg.norm(xtrue - x))
     test = dict(D=D, s=s, truexopt=xtrue, trueobjopt=trueobj, objopt=obj, xresidual=xres,
                 xerror=float(np.sum(np.abs(xtrue - x)) / x.size), admmopt=results.get("objopt"))
-    return _finish(results, test, not (xres < errtol and abs(obj - trueobj) <= errtol * trueobj),
+    return _finish_q(quiet, dict(o, solver="lad"), results, test, not (xres < errtol and abs(obj - trueobj) <= errtol * trueobj),
                    "xresidual %.3g, objective %.6g vs %.6g" % (xres, obj, trueobj))
 
 
@@ -101,7 +112,7 @@ def totalvariationtest(seed=0, rows=128, errtol=1e-3, quiet=1, options=None, sol
     results = S.totalvariation(s, lam, o, **kw)
     obj = lambda x: 0.5 * float(np.sum((x - s) ** 2)) + lam * float(np.sum(np.abs(np.diff(x))))
     test = dict(s=s, truth=truth, trueobjopt=obj(truth), objopt=obj(results["xopt"]), admmopt=results.get("objopt"))
-    return _finish(results, test, not (test["objopt"] < test["trueobjopt"]), "objective vs the clean signal")
+    return _finish_q(quiet, dict(o, tester="totalvariation"), results, test, not (test["objopt"] < test["trueobjopt"]), "objective vs the clean signal")
 
 
 def basispursuittest(seed=0, rows=64, cols=128, errtol=1e-3, quiet=1, options=None, solvers=None, density=1.0, **kw):
@@ -117,7 +128,7 @@ def basispursuittest(seed=0, rows=64, cols=128, errtol=1e-3, quiet=1, options=No
     cerr = float(np.sum(np.abs((D @ x - s) / (D @ x))) / s.size)           # :119
     test = dict(D=D, s=s, testx=testx, trueobjopt=float(np.sum(np.abs(testx))), objopt=float(np.sum(np.abs(x))),
                 constrainterror=cerr)
-    return _finish(results, test, not (test["trueobjopt"] >= test["objopt"] and cerr <= errtol),
+    return _finish_q(quiet, dict(o, solver="basispursuit"), results, test, not (test["trueobjopt"] >= test["objopt"] and cerr <= errtol),
                    "l1 norm %.6g vs %.6g, constraint error %.3g" % (test["objopt"], test["trueobjopt"], cerr))
 
 
@@ -132,7 +143,7 @@ def modeltest(seed=0, rows=128, cols=128, errtol=1e-3, quiet=1, options=None, so
     objerr, xres = abs(1 - obj(x) / obj(truex)), float(np.linalg.norm(truex - x))
     test = dict(P=P, Q=Q, r=r, s=s, truexopt=truex, trueobjopt=obj(truex), objopt=obj(x), objerror=objerr, xresidual=xres,
                 admmopt=results.get("objopt"))
-    return _finish(results, test, not (objerr <= errtol and xres <= errtol), "objerror %.3g, xresidual %.3g" % (objerr, xres))
+    return _finish_q(quiet, dict(o, solver="model"), results, test, not (objerr <= errtol and xres <= errtol), "objerror %.3g, xresidual %.3g" % (objerr, xres))
 
 
 TESTERS = {"lasso": lassotest, "linearsvm": linearsvmtest, "huberfit": huberfittest, "lad": ladtest,

@@ -65,8 +65,8 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.stop, self.t = index, [], threading.Event(), None
+    def __init__(self, index, enabled=True):
+        self.index, self.rows, self.stop, self.t, self.enabled = index, [], threading.Event(), None, enabled
 
     def _run(self):
         while not self.stop.is_set():
@@ -81,13 +81,15 @@ class ClockSampler:
             self.stop.wait(0.1)
 
     def __enter__(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
+        if self.enabled:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
         return self
 
     def __exit__(self, *a):
         self.stop.set()
-        self.t.join(timeout=6)
+        if self.t is not None:
+            self.t.join(timeout=6)
 
     def summary(self):
         if not self.rows:
@@ -202,7 +204,7 @@ def run_ours(args):
         barrier()
         l0, g0 = eng.launch_count(), eng.graph_replays()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clk:
+        with ClockSampler(local, enabled=(rank == 0)) as clk:   # one sampler per job: eight 10 Hz nvidia-smi loops starve the ranks' host threads
             e0.record(stream)
             for _ in range(args.steps):
                 r = step_resident()
@@ -337,6 +339,14 @@ def run_ours(args):
     tri_bytes = N_COLS * (N_COLS + 1) * 8                # two reads of one triangle per iteration
     xupd_gbs = tri_bytes / (xupd_us * 1e-6) / 1e9
     info = eng.info()
+    # DRAM bytes per launch of the two roofline kernels: counters of the committed ncu --set full captures of THIS command
+    # (profiles/traffic.json names the .ncu-rep each came from); not re-measured in-run -- ncu cannot run inside a timed bench
+    traffic, traffic_src = {}, None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic_src = "profiles/traffic.json (ncu --set full capture of this command, N = 1, full 65536 rows)"
+    except Exception:
+        pass
     out = {
         "metric": "admm_iters_per_s", "value": value, "unit": "iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -350,21 +360,28 @@ def run_ours(args):
         "loop_iters_per_s": 1e6 / iter_us,
         "loop_us_per_iter": {"iteration": iter_us, "x_update": xupd_us, "fused_prox": prox_us},
         "setup_ms": phases,
+        "last_step_ms": {"setup": r["engine"]["setup_ms"], "loop": r["engine"]["loop_ms"],
+                         "loop_us_per_iter": r["engine"]["loop_ms"] / ITERS * 1e3},     # rank 0, the last timed step
         "lambda_batch": batch,
         "svm_c3": svm,
         "svm_c3_weak": svm_weak,
         "time_to_tol": {"reltol": RELTOL, "steps": int(rt["steps"]), "setup_ms": rt["engine"]["setup_ms"],
                         "loop_ms": rt["engine"]["loop_ms"], "wall_ms": tol_wall[-1], "first_call_wall_ms": tol_wall[0]},
-        "roofline": {"kernel": "gemm_f64_dmma_kernel<T,N> (Gram D_g'D_g, lower tiles, this rank's %d rows)" % ml,
+        "roofline": {"kernel": "gemm_tma_kernel (Gram D_g'D_g: FP64 DMMA tiles fed by cp.async.bulk.tensor, lower tiles, this rank's %d rows)" % ml,
                      "bound": "tensor", "achieved": gram_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                      "frac": gram_tflops / fp64_peak,
                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                      "algorithmic_flops": gram_flops,
-                     "traffic": None},          # no in-run DRAM counter; the ncu figure of this round is in profiles/
+                     "traffic": traffic.get("gram_dram_bytes") if world == 1 else None, "traffic_source": traffic_src},
         "roofline_iter": {"kernel": "x-update x = W'(W y) on the cached inverse factor", "bound": "hbm",
                           "achieved": xupd_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": xupd_gbs / hbm_peak,
                           "frac_of_8TBs_nominal": xupd_gbs / 8000.0, "peak_source": peak_src,
-                          "algorithmic_bytes": tri_bytes, "traffic": None},
+                          "note": "algorithmic bytes = the two triangular solves of getProxOps.m:1200 (two reads of one triangle, "
+                                  "SURVEY 8d); symtri_kernel reads the triangle ONCE (x = W'(W y) from one pass), so the bytes really "
+                                  "moved are half: see real_gbs",
+                          "real_bytes": tri_bytes // 2, "real_gbs": xupd_gbs / 2, "real_frac": xupd_gbs / 2 / hbm_peak,
+                          "algorithmic_bytes": tri_bytes,
+                          "traffic": traffic.get("xupdate_dram_bytes") if world == 1 else None, "traffic_source": traffic_src},
         "comm": {"p2p_mailboxes": bool(info["p2p_ready"])} if world > 1 else None,
     }
     if not args.no_cpu and world == 1 and not args.light:          # rank 0 at N = 1 only

@@ -105,6 +105,12 @@ def test_c2_lambda_batch_columns_match_single_solves(engine, c2_problem):
         k = one["steps"]
         assert rel(rb["xopt"][:, j], one["xopt"]) < TOL and rel(rb["zopt"][:, j], one["zopt"]) < TOL
         assert rel(rb["pnorm"][:k, j], one["pnorm"]) < TOL and rel(rb["dnorm"][:k, j], one["dnorm"]) < TOL
+    # a rank's share when the batch is split over 8 / 2 GPUs (8 / 24 columns: the 16- and 32-wide DMMA tiles of gemm.cuh)
+    # must give the same columns as the 64-wide batch
+    for lo, hi in ((16, 24), (20, 44)):
+        sub = engine.solve_lasso_batch(o, lams[lo:hi])
+        assert np.array_equal(sub["steps"], rb["steps"][lo:hi])
+        assert rel(sub["xopt"], rb["xopt"][:, lo:hi]) < TOL and rel(sub["zopt"], rb["zopt"][:, lo:hi]) < TOL
     j = 40                                                  # and one column against the oracle itself
     ref = oracle.lasso(D, s, lams[j], {"reltol": 1e-4, "history": 0})
     assert rb["steps"][j] == ref["steps"]
