@@ -7,6 +7,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/admm_b200.h"
@@ -92,6 +94,13 @@ struct admm_b200_handle {
   std::vector<cudaEvent_t> ev_pool;   // events of the look-ahead Cholesky (created on first use)
   DBuf chol_ws;                       // out-of-place panel solves of the look-ahead Cholesky
   DBuf inv_ws;                        // L[P, :P] * W[:P, :P] of the inverse factor's block row P
+  // pinned staging ring for uploads from PAGEABLE host memory (host threads gather a row panel into it, the DMA
+  // engine takes it from there): allocated on the first such upload
+  static constexpr int kPinBufs = 3;
+  double* pin_buf[kPinBufs] = {nullptr, nullptr, nullptr};
+  cudaEvent_t pin_ev[kPinBufs] = {nullptr, nullptr, nullptr};
+  size_t pin_cap = 0;                 // doubles per buffer
+  int pin_next = 0;
   cudaEvent_t ev_la[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[4] = {nullptr, nullptr, nullptr, nullptr};
   double phase_ms[4] = {0, 0, 0, 0};  // gram (+Dts), cholesky, inverse factor (+transpose), total
@@ -192,6 +201,66 @@ static bool is_device_ptr(const void* p) {
     return false;
   }
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// ordinary (pageable) host memory: the driver would stage such a copy through its own bounce buffer with one thread
+// (~12 GB/s measured for the 4.3 GB matrix of C2, against ~55 GB/s from pinned memory)
+static bool is_pageable_host_ptr(const void* p) {
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+// Rows [r0, r0 + rows) of the column-major HOST matrix D (n columns, ldD) -> dst + r0 (device, leading dimension ld), on
+// `stream`.  Pinned source: one strided DMA.  Pageable source: sub-panels are gathered by a few host threads into a ring
+// of pinned buffers (column segments of a sub-panel are contiguous in the buffer) and the DMA engine copies from there
+// while the threads fill the next buffer -- the upload runs at the PCIe rate instead of the driver's bounce-buffer rate.
+static void upload_rows(admm_b200_handle* h, double* dst, int64_t ld, const double* D, int64_t ldD, int64_t r0, int64_t rows,
+                        int64_t n, cudaStream_t stream, bool pageable) {
+  if (rows <= 0 || n <= 0) return;
+  const bool no_stage = getenv("ADMM_B200_NO_PINNED_STAGING") != nullptr;   // read per call (tests flip it)
+  const size_t bytes = (size_t)rows * (size_t)n * 8;
+  if (!pageable || no_stage || bytes < ((size_t)32 << 20)) {
+    ADMM_CUDA(cudaMemcpy2DAsync(dst + r0, (size_t)ld * 8, D + r0, (size_t)ldD * 8, (size_t)rows * 8, (size_t)n,
+                                cudaMemcpyHostToDevice, stream));
+    return;
+  }
+  constexpr size_t kBufDoubles = (size_t)16 << 20;          // 128 MB per buffer
+  if (!h->pin_buf[0]) {
+    for (int b = 0; b < admm_b200_handle::kPinBufs; ++b) {
+      ADMM_CUDA(cudaHostAlloc((void**)&h->pin_buf[b], kBufDoubles * 8, cudaHostAllocDefault));
+      ADMM_CUDA(cudaEventCreateWithFlags(&h->pin_ev[b], cudaEventDisableTiming));
+    }
+    h->pin_cap = kBufDoubles;
+  }
+  int64_t sub = std::max<int64_t>(1, (int64_t)(h->pin_cap / (size_t)n));
+  if (sub >= 512) sub = sub / 512 * 512;                     // whole pages per column segment
+  ADMM_REQUIRE((size_t)n <= h->pin_cap, ADMM_B200_ERR_UNSUPPORTED, "upload: matrix has too many columns for the staging buffer");
+  const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+  const int nthreads = (int)std::min<unsigned>(8u, std::max(2u, hw / (2u * (unsigned)std::max(1, h->nranks))));
+  for (int64_t s0 = 0; s0 < rows; s0 += sub) {
+    const int64_t sr = std::min(sub, rows - s0);
+    const int b = h->pin_next;
+    h->pin_next = (h->pin_next + 1) % admm_b200_handle::kPinBufs;
+    ADMM_CUDA(cudaEventSynchronize(h->pin_ev[b]));           // the DMA that last read this buffer is done
+    double* stage = h->pin_buf[b];
+    const double* src = D + r0 + s0;
+    auto work = [=](int t) {
+      const int64_t j0 = n * t / nthreads, j1 = n * (t + 1) / nthreads;
+      for (int64_t j = j0; j < j1; ++j) memcpy(stage + j * sr, src + j * ldD, (size_t)sr * 8);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+    ADMM_CUDA(cudaMemcpy2DAsync(dst + r0 + s0, (size_t)ld * 8, stage, (size_t)sr * 8, (size_t)sr * 8, (size_t)n,
+                                cudaMemcpyHostToDevice, stream));
+    ADMM_CUDA(cudaEventRecord(h->pin_ev[b], stream));
+  }
 }
 
 // copy `count` doubles from a host-or-device pointer into a device buffer (async on the stream)
@@ -1195,8 +1264,7 @@ static void stage_matrix(admm_b200_handle* h, int64_t m, int64_t n, const double
   } else {
     int64_t ld = round_up(m, 2);
     h->ownD.ensure(ld * n);
-    ADMM_CUDA(cudaMemcpy2DAsync(h->ownD.p, (size_t)ld * 8, D, (size_t)ldD * 8, (size_t)m * 8, (size_t)n,
-                                cudaMemcpyHostToDevice, h->stream));
+    upload_rows(h, h->ownD.p, ld, D, ldD, 0, m, n, h->stream, is_pageable_host_ptr(D));
     h->dD = h->ownD.p;
     h->ldD = ld;
   }
@@ -1298,21 +1366,34 @@ static void setup_lasso(admm_b200_handle* h, int64_t m, int64_t m_total, int64_t
   GemmOpt o;
   o.lower_only = 1;
   constexpr int64_t kPanelRows = 16384;
-  if (h->tall && !is_device_ptr(D) && m >= 2 * kPanelRows) {
+  if (h->tall && !is_device_ptr(D) && m >= 4096 && m * n >= ((int64_t)32 << 20)) {
     // HOST matrix, tall: pipeline the upload with the Gram.  Row panels of D are copied on the second
     // stream while the previous panel's D_p'D_p (and D_p's_p) accumulate on the compute stream, so the
-    // 4.3 GB H2D of config C2 hides behind the DMMA SYRK instead of preceding it.
+    // 4.3 GB H2D of config C2 hides behind the DMMA SYRK instead of preceding it.  The first panels are small
+    // (2048, 2048, 4096, 8192 rows, then 16384 each): only the first panel's upload is exposed.
     const int64_t ld = round_up(m, 2);
     h->ownD.ensure(ld * n);
     h->dD = h->ownD.p; h->ldD = ld; h->m = m; h->n = n;
     cudaStream_t sC = h->stream, sX = h->stream2;
     ADMM_CUDA(cudaEventRecord(h->ev_la[0], sC));
     ADMM_CUDA(cudaStreamWaitEvent(sX, h->ev_la[0], 0));   // ownD may still be read by earlier work
-    const int64_t npanels = (m + kPanelRows - 1) / kPanelRows;
+    const bool pageable = is_pageable_host_ptr(D);
+    std::vector<int64_t> start;
+    {
+      const int64_t ramp[4] = {2048, 2048, 4096, 8192};
+      int64_t r = 0;
+      for (int i = 0; r < m; ++i) {
+        start.push_back(r);
+        int64_t step = (i < 4) ? ramp[i] : kPanelRows;
+        if (m - (r + step) < 1024) step = m - r;           // no sliver at the end
+        r += step;
+      }
+      start.push_back(m);
+    }
+    const int64_t npanels = (int64_t)start.size() - 1;
     for (int64_t p = 0; p < npanels; ++p) {
-      const int64_t r0 = p * kPanelRows, rows = std::min(kPanelRows, m - r0);
-      ADMM_CUDA(cudaMemcpy2DAsync(h->ownD.p + r0, (size_t)ld * 8, D + r0, (size_t)ldD * 8, (size_t)rows * 8, (size_t)n,
-                                  cudaMemcpyHostToDevice, sX));
+      const int64_t r0 = start[p], rows = start[p + 1] - r0;
+      upload_rows(h, h->ownD.p, ld, D, ldD, r0, rows, n, sX, pageable);
       ADMM_CUDA(cudaEventRecord(h->ev_la[p & 1], sX));
       ADMM_CUDA(cudaStreamWaitEvent(sC, h->ev_la[p & 1], 0));
       o.diag_add = (p == npanels - 1 && !sharded) ? rho : 0.0;
@@ -3154,6 +3235,10 @@ int admm_b200_destroy(admm_b200_handle* h) {
   if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream3) cudaStreamDestroy(h->stream3);
   if (h->stream4) cudaStreamDestroy(h->stream4);
+  for (int b = 0; b < admm_b200_handle::kPinBufs; ++b) {
+    if (h->pin_buf[b]) cudaFreeHost(h->pin_buf[b]);
+    if (h->pin_ev[b]) cudaEventDestroy(h->pin_ev[b]);
+  }
   if (h->stream_hi) cudaStreamDestroy(h->stream_hi);
   for (auto& e : h->ev_pool) cudaEventDestroy(e);
   h->chol_ws.release();

@@ -114,3 +114,31 @@ def test_lasso_tall_host_matrix_pipelined_upload(engine):
     compare(res, ref, hist=False)
     G = D.T @ D + np.eye(48)
     assert rel(engine.get_factor(), np.linalg.cholesky(G)) < 1e-12
+
+
+def test_host_upload_paths_agree(engine, monkeypatch):
+    """A tall HOST matrix goes up in row panels pipelined with the Gram (engine.cu:setup_lasso), and from pageable
+    memory each panel is gathered by host threads into a pinned staging ring first (upload_rows).  Factor and
+    solution must not depend on where D lived: pageable NumPy array (staged), the same array with staging switched off
+    (driver bounce buffer), and a device-resident copy; ragged sizes on purpose."""
+    import torch
+    from admm_project_b200 import DeviceMatrix
+    from admm_project_b200.generators import lasso_problem_big
+    m, n = 18433, 2051                                           # 302 MB: above the panel / staging thresholds; odd m and n
+    D, s, lam, _ = lasso_problem_big(7, m, n)
+    opts = {"reltol": 1e-4, "history": 0}
+    ref = oracle.lasso(D, s, lam, opts)
+    res = lasso(D, s, lam, opts, engine=engine)                   # pageable: pinned staging ring
+    compare(res, ref, hist=False)
+    L_staged = engine.get_factor()
+    ld = m + 1                                                    # device matrices need an even leading dimension
+    Dt = torch.zeros(n, ld, dtype=torch.float64, device="cuda")   # row-major n x ld == column-major ld x n on the device
+    Dt[:, :m] = torch.from_numpy(np.ascontiguousarray(D.T)).cuda()
+    dev = lasso(DeviceMatrix(Dt.data_ptr(), m, n, ld, keepalive=Dt), s, lam, opts, engine=engine)
+    compare(dev, ref, hist=False)
+    L_dev = engine.get_factor()
+    assert rel(L_staged, L_dev) < 1e-12
+    monkeypatch.setenv("ADMM_B200_NO_PINNED_STAGING", "1")       # read at every upload
+    plain = lasso(D, s, lam, opts, engine=engine)
+    compare(plain, ref, hist=False)
+    assert rel(engine.get_factor(), L_dev) < 1e-12
