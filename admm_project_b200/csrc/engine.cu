@@ -9,6 +9,9 @@
 #include <algorithm>
 #include <cstring>
 #include <thread>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 #include <vector>
 
 #include "../../include/admm_b200.h"
@@ -215,6 +218,29 @@ static bool is_pageable_host_ptr(const void* p) {
   return at.type == cudaMemoryTypeUnregistered;
 }
 
+// one column segment into the pinned staging buffer.  Non-temporal stores: the buffer is only read by the DMA engine, so
+// pulling its lines into the cache first (write-allocate) would cost a third of the host memory traffic for nothing.
+static inline void copy_segment_nt(double* dst, const double* src, size_t count) {
+#if defined(__x86_64__)
+  if ((((uintptr_t)dst) & 15) == 0) {
+    size_t i = 0;
+    for (; i + 8 <= count; i += 8) {
+      const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i));
+      const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 2));
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 4));
+      const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + i + 6));
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), a);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 2), b);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 4), c);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 6), d);
+    }
+    for (; i < count; ++i) dst[i] = src[i];
+    return;
+  }
+#endif
+  memcpy(dst, src, count * 8);
+}
+
 // Rows [r0, r0 + rows) of the column-major HOST matrix D (n columns, ldD) -> dst + r0 (device, leading dimension ld), on
 // `stream`.  Pinned source: one strided DMA.  Pageable source: sub-panels are gathered by a few host threads into a ring
 // of pinned buffers (column segments of a sub-panel are contiguous in the buffer) and the DMA engine copies from there
@@ -251,7 +277,10 @@ static void upload_rows(admm_b200_handle* h, double* dst, int64_t ld, const doub
     const double* src = D + r0 + s0;
     auto work = [=](int t) {
       const int64_t j0 = n * t / nthreads, j1 = n * (t + 1) / nthreads;
-      for (int64_t j = j0; j < j1; ++j) memcpy(stage + j * sr, src + j * ldD, (size_t)sr * 8);
+      for (int64_t j = j0; j < j1; ++j) copy_segment_nt(stage + j * sr, src + j * ldD, (size_t)sr);
+#if defined(__x86_64__)
+      _mm_sfence();
+#endif
     };
     std::vector<std::thread> pool;
     for (int t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
@@ -336,6 +365,7 @@ struct GemmOpt {
   int allow_splitk = 1;
   int a_lower = 0, b_lower = 0, a_upper = 0, b_upper = 0;
   int inplace = 0;        // C aliases A: only tilings whose CTAs read nothing another CTA writes (N <= one 128-wide tile column)
+  int max_ctas = 0;       // > 0: at most this many CTAs, each walking several tiles (background work of the look-ahead Cholesky)
 };
 
 static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
@@ -351,6 +381,7 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   g.batch = o.batch; g.strideA = o.strideA; g.strideB = o.strideB; g.strideC = o.strideC;
   g.splits = 1; g.k_per_split = std::max<int64_t>(K, 1); g.ws = nullptr;
   g.bm = GEMM_BM; g.tri_skip = 0;
+  g.persist = 0; g.tm = g.tn = 0; g.nz = 1;
   const bool skinny = (N <= 64) && !o.lower_only;   // 128 x 64 tiles for few right-hand sides
   // tall triangular op(A) x few right-hand sides (the lambda batch on a large factor): 256 x 64 tiles, uniform K chunks
   static const bool no_tall = getenv("ADMM_B200_NO_TALL_TRI") != nullptr;
@@ -403,9 +434,13 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
   const bool vec_ok = (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
                       (o.strideA % 2 == 0) && (o.strideB % 2 == 0);
   dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)(o.batch * g.splits));
+  if (o.max_ctas > 0 && tm * tn * o.batch * g.splits > o.max_ctas) {
+    g.persist = o.max_ctas; g.tm = tm; g.tn = tn; g.nz = o.batch * g.splits;
+    grid = dim3((unsigned)o.max_ctas, 1u, 1u);
+  }
   // Gram-shaped products (both operands K-major, i.e. A'*B on column-major matrices) go through the TMA-fed kernel
   static const bool no_tma = getenv("ADMM_B200_NO_TMA") != nullptr;
-  if (!no_tma && transa != 0 && transb == 0 && vec_ok && o.batch == 1 && !skinny && !tall_tri && !small && !o.a_lower && !o.b_lower &&
+  if (!no_tma && !g.persist && transa != 0 && transb == 0 && vec_ok && o.batch == 1 && !skinny && !tall_tri && !small && !o.a_lower && !o.b_lower &&
       !o.a_upper && !o.b_upper && M >= 128 && N >= 128 && K >= 64 && M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31)) {
     CUtensorMap tmA, tmB;
     if (make_kmajor_tmap(&tmA, A, K, M, lda) && make_kmajor_tmap(&tmB, B, K, N, ldb)) {
@@ -714,6 +749,23 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
   static const bool probe_nobulk = getenv("ADMM_B200_CHOL_PROBE_NOBULK") != nullptr;
   const bool ride = want_inverse && inv_overlap;
   if (ride) h->inv_ws.ensure(NBO * round_up(k, 2));
+  // SMs the background streams (bulk trailing update, riding inverse) leave alone: a chain kernel and a background CTA
+  // cannot share an SM (each wants the whole register file), so without a reserve every launch of the chain waits for
+  // background CTAs to retire (tools/chol_probe.py: 10.8 ms bare chain, 14.4 ms with the bulk behind it).  The
+  // background GEMMs run as capped persistent grids, the cap split by the flops of the two streams at this panel.
+  static const int reserve = getenv("ADMM_B200_CHOL_RESERVE") ? atoi(getenv("ADMM_B200_CHOL_RESERVE")) : 24;
+  auto caps = [&](int64_t bulk_dim, int64_t inv_dim, int& cap_bulk, int& cap_inv) {
+    cap_bulk = cap_inv = 0;
+    if (reserve <= 0 || reserve >= kNumSM - 32) return;
+    const int avail = kNumSM - reserve;
+    const double b = (double)bulk_dim * (double)bulk_dim, v = ride ? (double)inv_dim * (double)inv_dim : 0.0;
+    if (b + v <= 0.0) return;
+    cap_bulk = (int)std::lround(avail * b / (b + v));
+    cap_bulk = std::min(avail - 16, std::max(16, cap_bulk));
+    cap_inv = avail - cap_bulk;
+    if (v == 0.0) { cap_bulk = avail; cap_inv = 0; }
+    if (b == 0.0) { cap_inv = avail; cap_bulk = 0; }
+  };
   DBuf& T = h->scratch;
   T.ensure(std::max(doubling_scratch(k, NBO), doubling_scratch(NBO, CHOL_NB)));
   const int64_t lds = round_up(k, 2);
@@ -742,6 +794,11 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
       GemmOpt o1;
       o1.allow_splitk = 0;
       o1.b_lower = 1;
+      {
+        int cb, ci;
+        caps(std::max<int64_t>(0, k - K0 - 2 * NBO), K0, cb, ci);   // the bulk running beside this product is panel P's
+        o1.max_ctas = ci;
+      }
       gemm(h, 0, 0, wb, K0, K0, 1.0, A + K0, lda, W, ldw, 0.0, h->inv_ws.p, NBO, o1);
     }
     potrf_block512(h, APP, lda, wb, WPP, ldw, K0, T);
@@ -797,6 +854,11 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
         GemmOpt bo;
         bo.lower_only = 1;
         bo.allow_splitk = 0;
+        {
+          int cb, ci;
+          caps(rem2, K1, cb, ci);                                    // the inverse row riding beside it is row P+1
+          bo.max_ctas = cb;
+        }
         if (!probe_nobulk) gemm(h, 0, 1, rem2, rem2, wb, -1.0, A21b, lda, A21b, lda, 1.0, A + (K1 + n1) + (K1 + n1) * lda, lda, bo);
         ADMM_CUDA(cudaEventRecord(ev(4, P), sC));
       }

@@ -34,6 +34,8 @@ struct GemmArgs {
   int splits; int64_t k_per_split; double* ws;   // ws: [batch][splits][M*N]
   int bm;                 // CTA tile height (128 or 256)
   int tri_skip;           // split-K with a triangular op(A): work units whose K range is empty neither run nor get summed
+  int persist;            // > 0: the grid is `persist` CTAs that walk the tm x tn x nz tiles round-robin (background GEMMs of
+  int64_t tm, tn; int nz; //      the look-ahead Cholesky keep off some SMs so the latency-bound chain always finds a free one)
 };
 
 // Loads one ROWS x 16 operand tile (ROWS = 128 or 64).  KMAJOR: element (r,k) at g[k + r*ld]; else at g[r + k*ld].
@@ -118,11 +120,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
   // grouped tile order (GROUP x GROUP super-tiles): the ~148 CTAs resident at any time then share
   // ~12 A panels and ~12 B panels instead of 64 + 3, which cuts the DRAM re-reads of the Gram ~3x
   // (ncu: 69.6 GB for a 4.3 GB matrix with the natural order).
-  int64_t bm = blockIdx.x, bn = blockIdx.y;
+  const int64_t tm = p.persist ? p.tm : (int64_t)gridDim.x, tn = p.persist ? p.tn : (int64_t)gridDim.y;
+  const int64_t per_z = tm * tn, total = p.persist ? per_z * p.nz : 1;
+  bool first_tile = true;
+  for (int64_t lin = p.persist ? (int64_t)blockIdx.x : 0; lin < total; lin += p.persist ? (int64_t)gridDim.x : 1) {
+  if (!first_tile) __syncthreads();     // every warp is done with the shared-memory ring of the tile before
+  first_tile = false;
+  const int bz = p.persist ? (int)(lin / per_z) : (int)blockIdx.z;
+  int64_t bm, bn;
   {
     constexpr int GROUP = 12;
-    const int64_t tm = gridDim.x, tn = gridDim.y;
-    const int64_t pid = (int64_t)blockIdx.y * tm + blockIdx.x;
+    const int64_t pid = p.persist ? lin - (int64_t)bz * per_z : (int64_t)blockIdx.y * tm + blockIdx.x;
     const int64_t per_group = GROUP * tn;
     const int64_t g = pid / per_group, first_m = g * GROUP;
     const int64_t gsz = min((int64_t)GROUP, tm - first_m);
@@ -130,8 +138,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
     bn = (pid % per_group) / gsz;
   }
   const int64_t m0 = bm * GEMM_BM, n0 = bn * BN;
-  if (p.lower_only && n0 > m0) return;  // tile strictly above the diagonal
-  const int bz = blockIdx.z;
+  if (p.lower_only && n0 > m0) continue;  // tile strictly above the diagonal
   const int batch = bz / p.splits, split = bz - batch * p.splits;
   const double* A = p.A + (int64_t)batch * p.strideA;
   const double* B = p.B + (int64_t)batch * p.strideB;
@@ -142,7 +149,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
   if (p.a_upper) kbeg = max(kbeg, m0);                      // op(A)[i][k] = 0 for k < i
   if (p.b_upper) kend = min(kend, n0 + (int64_t)BN);        // op(B)[k][j] = 0 for k > j
   const int nk = (int)((kend - kbeg + GEMM_BK - 1) / GEMM_BK);
-  if (p.tri_skip && nk <= 0) return;      // empty unit of a triangular operand: the reduce pass skips it too
+  if (p.tri_skip && nk <= 0) continue;    // empty unit of a triangular operand: the reduce pass skips it too
 
   double* sA = smem;
   double* sB = smem + GEMM_STAGES * A_TILE;
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_f64_dmma_kernel(GemmArgs
           }
         }
   }
+  }   // tile loop
 }
 
 // second pass of split-K: fixed summation order over the splits (deterministic)
