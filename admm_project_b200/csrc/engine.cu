@@ -749,11 +749,12 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
   static const bool probe_nobulk = getenv("ADMM_B200_CHOL_PROBE_NOBULK") != nullptr;
   const bool ride = want_inverse && inv_overlap;
   if (ride) h->inv_ws.ensure(NBO * round_up(k, 2));
-  // SMs the background streams (bulk trailing update, riding inverse) leave alone: a chain kernel and a background CTA
-  // cannot share an SM (each wants the whole register file), so without a reserve every launch of the chain waits for
-  // background CTAs to retire (tools/chol_probe.py: 10.8 ms bare chain, 14.4 ms with the bulk behind it).  The
-  // background GEMMs run as capped persistent grids, the cap split by the flops of the two streams at this panel.
-  static const int reserve = getenv("ADMM_B200_CHOL_RESERVE") ? atoi(getenv("ADMM_B200_CHOL_RESERVE")) : 24;
+  // Optional SM reserve for the chain (ADMM_B200_CHOL_RESERVE = number of SMs the background streams leave alone; the
+  // background GEMMs then run as capped persistent grids, the cap split by the flops of the two streams at this panel).
+  // Measured on B200 (profiles/r02_chol_probe.txt): it does NOT pay -- factor + inverse 19.5 ms without a reserve,
+  // 23.1 / 24.7 / 26.4 / 28.6 ms with 12 / 24 / 36 / 48 SMs reserved: the chain waits on the bulk update of the panel
+  // before (event 4), so slowing the background slows the chain more than free SMs speed it up.  Default: off.
+  static const int reserve = getenv("ADMM_B200_CHOL_RESERVE") ? atoi(getenv("ADMM_B200_CHOL_RESERVE")) : 0;
   auto caps = [&](int64_t bulk_dim, int64_t inv_dim, int& cap_bulk, int& cap_inv) {
     cap_bulk = cap_inv = 0;
     if (reserve <= 0 || reserve >= kNumSM - 32) return;

@@ -38,11 +38,10 @@ print(json.dumps(best))
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     m = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
-    for name, env in (("full (default reserve)", {}), ("reserve 0 (uncapped background)", {"ADMM_B200_CHOL_RESERVE": "0"}),
+    for name, env in (("full (default: no SM reserve)", {}), ("reserve 24", {"ADMM_B200_CHOL_RESERVE": "24"}),
                       ("reserve 12", {"ADMM_B200_CHOL_RESERVE": "12"}), ("reserve 36", {"ADMM_B200_CHOL_RESERVE": "36"}),
                       ("reserve 48", {"ADMM_B200_CHOL_RESERVE": "48"}),
                       ("no riding inverse", {"ADMM_B200_NO_INV_OVERLAP": "1"}),
-                      ("no riding inverse, reserve 0", {"ADMM_B200_NO_INV_OVERLAP": "1", "ADMM_B200_CHOL_RESERVE": "0"}),
                       ("chain only (no bulk, no riding inverse)", {"ADMM_B200_NO_INV_OVERLAP": "1", "ADMM_B200_CHOL_PROBE_NOBULK": "1"}),
                       ("chain + riding inverse, no bulk", {"ADMM_B200_CHOL_PROBE_NOBULK": "1"}),
                       ("v1 (two streams)", {"ADMM_B200_CHOL_V1": "1"})):
