@@ -96,7 +96,7 @@ struct admm_b200_handle {
   cudaStream_t own_stream = nullptr, stream = nullptr, stream2 = nullptr, stream3 = nullptr, stream4 = nullptr, stream_hi = nullptr;   // stream_hi / 2 / 3: Cholesky look-ahead (high / middle / low priority); 4: the inverse factor trailing it (low)
   std::vector<cudaEvent_t> ev_pool;   // events of the look-ahead Cholesky (created on first use)
   DBuf chol_ws;                       // out-of-place panel solves of the look-ahead Cholesky
-  DBuf inv_ws;                        // L[P, :P] * W[:P, :P] of the inverse factor's block row P
+  DBuf inv_ws, inv_ws2;               // L[P, :P] * W[:P, :P] of the inverse factor's block row P; its split-K workspace
   // pinned staging ring for uploads from PAGEABLE host memory (host threads gather a row panel into it, the DMA
   // engine takes it from there): allocated on the first such upload
   static constexpr int kPinBufs = 3;
@@ -366,6 +366,9 @@ struct GemmOpt {
   int a_lower = 0, b_lower = 0, a_upper = 0, b_upper = 0;
   int inplace = 0;        // C aliases A: only tilings whose CTAs read nothing another CTA writes (N <= one 128-wide tile column)
   int max_ctas = 0;       // > 0: at most this many CTAs, each walking several tiles (background work of the look-ahead Cholesky)
+  int64_t k_chunk = 0;    // > 0: split K into chunks of this length whatever the tile count (short-lived CTAs: a background
+                          //      product must not hold SMs for a millisecond while the chain waits for one)
+  DBuf* ws = nullptr;     // split-K workspace to use instead of the handle's shared one (products on side streams)
 };
 
 static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t N, int64_t K, double alpha,
@@ -422,13 +425,15 @@ static void gemm(admm_b200_handle* h, int transa, int transb, int64_t M, int64_t
     for (int64_t S = 2; S <= 4; ++S)
       if (waste(S) < best - 0.01 && (int64_t)o.batch * S * M * N * 8 <= (int64_t)4 << 30) { best = waste(S); want_splits = S; }
   }
+  if (o.k_chunk > 0 && K > o.k_chunk && !tall_tri) want_splits = (K + o.k_chunk - 1) / o.k_chunk;
   if (want_splits > 1) {
     int64_t splits = want_splits;
     if (splits > 1) {
       g.k_per_split = round_up((K + splits - 1) / splits, GEMM_BK);
       g.splits = (int)((K + g.k_per_split - 1) / g.k_per_split);
-      h->gemm_ws.ensure((int64_t)o.batch * g.splits * M * N);
-      g.ws = h->gemm_ws.p;
+      DBuf& wsb = o.ws ? *o.ws : h->gemm_ws;
+      wsb.ensure((int64_t)o.batch * g.splits * M * N);
+      g.ws = wsb.p;
     }
   }
   const bool vec_ok = (((uintptr_t)A & 15) == 0) && (((uintptr_t)B & 15) == 0) && (lda % 2 == 0) && (ldb % 2 == 0) &&
@@ -731,14 +736,18 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
   ADMM_CUDA(cudaMemset2DAsync(W, (size_t)ldw * 8, 0, (size_t)k * 8, (size_t)k, h->stream));
   constexpr int64_t NBO = CHOL_NBO;
   const int64_t npan = (k + NBO - 1) / NBO;
-  while ((int64_t)h->ev_pool.size() < 5 * npan + 3) {
+  while ((int64_t)h->ev_pool.size() < 6 * npan + 3) {
     cudaEvent_t e;
     ADMM_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     h->ev_pool.push_back(e);
   }
-  auto ev = [&](int kind, int64_t P) { return h->ev_pool[(size_t)(kind * npan + P)]; };   // 0 W, 1 top, 2 T, 3 A(col), 4 C(bulk)
-  cudaEvent_t ev_start = h->ev_pool[(size_t)(5 * npan)], ev_end = h->ev_pool[(size_t)(5 * npan + 1)];
-  cudaEvent_t ev_inv = h->ev_pool[(size_t)(5 * npan + 2)];
+  auto ev = [&](int kind, int64_t P) { return h->ev_pool[(size_t)(kind * npan + P)]; };   // 0 W, 1 top, 2 T, 3 col P+1, 4 bulk, 5 col P+2
+  cudaEvent_t ev_start = h->ev_pool[(size_t)(6 * npan)], ev_end = h->ev_pool[(size_t)(6 * npan + 1)];
+  cudaEvent_t ev_inv = h->ev_pool[(size_t)(6 * npan + 2)];
+  // Look-ahead depth 2 (default): panel P's update of block column P+2 is a separate GEMM on stream B and the bulk starts
+  // at column P+3, so the chain at panel Q waits for the bulk of panel Q-3, not Q-2 -- the bulk of the early panels takes
+  // longer than a chain step, and with depth 1 the chain stalled on it every panel (tools/chol_probe.py).
+  static const int depth = getenv("ADMM_B200_CHOL_DEPTH1") ? 1 : 2;
   // The inverse factor rides one panel behind the factorisation on a fourth (low-priority) stream: block row P of
   // W = inv(L) is  W[P, :P] = -W_PP * (L[P, :P] * W[:P, :P]),  and L[P, :P] is final once panel P-1 has been solved,
   // so the big product runs while the chain factors diagonal block P and only the 512-wide product with W_PP comes
@@ -748,7 +757,11 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
   // factor is then WRONG and the pivot check is skipped
   static const bool probe_nobulk = getenv("ADMM_B200_CHOL_PROBE_NOBULK") != nullptr;
   const bool ride = want_inverse && inv_overlap;
-  if (ride) h->inv_ws.ensure(NBO * round_up(k, 2));
+  if (ride) {
+    h->inv_ws.ensure(NBO * round_up(k, 2));
+    const int64_t kmax = (npan - 1) * NBO;           // the last block row's product: sized once, no reallocation (= device sync) mid-way
+    h->inv_ws2.ensure(((kmax + 1023) / 1024 + 1) * NBO * std::max<int64_t>(kmax, 1));
+  }
   // Optional SM reserve for the chain (ADMM_B200_CHOL_RESERVE = number of SMs the background streams leave alone; the
   // background GEMMs then run as capped persistent grids, the cap split by the flops of the two streams at this panel).
   // Measured on B200 (profiles/r02_chol_probe.txt): it does NOT pay -- factor + inverse 19.5 ms without a reserve,
@@ -785,8 +798,14 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
     const int64_t K0 = P * NBO, wb = std::min<int64_t>(NBO, k - K0), K1 = K0 + wb;
     double* APP = A + K0 + K0 * lda;
     double* WPP = W + K0 + K0 * ldw;
-    // the diagonal block has received the bulk updates of panels <= P-2 on stream C (panel P-1's came on A itself)
-    if (P >= 2) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(4, P - 2), 0));
+    // the diagonal block has received every update of the panels before: P-1's on stream A itself, and (depth 1) the bulk
+    // of <= P-2, or (depth 2) the column-P+2 update of panel P-2 on stream B and the bulk of <= P-3
+    if (depth == 1) {
+      if (P >= 2) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(4, P - 2), 0));
+    } else {
+      if (P >= 2) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(5, P - 2), 0));
+      if (P >= 3) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(4, P - 3), 0));
+    }
     if (ride && P >= 1) {
       // L[P, :P] is final: its last block came from the top solve of panel P-1 (stream A), the others from stream B
       StreamSwap on_d(h, sD);
@@ -800,6 +819,12 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
         caps(std::max<int64_t>(0, k - K0 - 2 * NBO), K0, cb, ci);   // the bulk running beside this product is panel P's
         o1.max_ctas = ci;
       }
+      // K chunks of 1024: a 128 x 128 tile of this product with K = P * 512 would live up to a millisecond on its SM, and
+      // the chain's kernels (high priority, but they need an EMPTY SM) queued behind such tiles: chain 11.2 -> 15.1 ms
+      // with the unsplit product riding along (profiles/r02_chol_probe.txt)
+      static const int64_t inv_chunk = getenv("ADMM_B200_INV_KCHUNK") ? atoll(getenv("ADMM_B200_INV_KCHUNK")) : 1024;
+      o1.k_chunk = inv_chunk;
+      o1.ws = &h->inv_ws2;
       gemm(h, 0, 0, wb, K0, K0, 1.0, A + K0, lda, W, ldw, 0.0, h->inv_ws.p, NBO, o1);
     }
     potrf_block512(h, APP, lda, wb, WPP, ldw, K0, T);
@@ -815,10 +840,12 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
     const int64_t rem = k - K1;
     if (rem <= 0) break;
     const int64_t n1 = std::min<int64_t>(NBO, rem), rem2 = rem - n1;
+    const int64_t n2 = (depth == 2) ? std::min<int64_t>(NBO, rem2) : 0, rem3 = rem2 - n2;   // depth 2: block column P+2 apart
+    const int64_t K2 = K1 + n1, K3 = K2 + n2;
     GemmOpt ts;                              // panel solve as a GEMM with the inverted diagonal block (upper-triangular op(B))
     ts.allow_splitk = 0;
     ts.b_upper = 1;
-    // block row P+1 of block column P: updated by the column update of panel P-1 (stream B) and the bulk of <= P-2 (C)
+    // block row P+1 of block column P: updated by the column updates of panels P-1 / P-2 (stream B) and the bulk before
     if (P >= 1) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(3, P - 1), 0));
     gemm(h, 0, 1, n1, wb, wb, 1.0, A + K1 + K0 * lda, lda, WPP, ldw, 0.0, S1, NBO, ts);
     ADMM_CUDA(cudaMemcpy2DAsync(A + K1 + K0 * lda, (size_t)lda * 8, S1, (size_t)NBO * 8, (size_t)n1 * 8, (size_t)wb,
@@ -827,15 +854,20 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
       GemmOpt so;
       so.lower_only = 1;
       so.allow_splitk = 0;
-      // next diagonal block: bulk of panels <= P-1 must be in (stream C) before this rank-512 update lands on top
-      if (P >= 1) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(4, P - 1), 0));
+      // next diagonal block: everything else that adds into it must be in before this rank-512 update lands on top
+      if (depth == 1) {
+        if (P >= 1) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(4, P - 1), 0));
+      } else {
+        if (P >= 1) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(5, P - 1), 0));
+        if (P >= 2) ADMM_CUDA(cudaStreamWaitEvent(sA, ev(4, P - 2), 0));
+      }
       gemm(h, 0, 1, n1, n1, wb, -1.0, A + K1 + K0 * lda, lda, A + K1 + K0 * lda, lda, 1.0, A + K1 + K1 * lda, lda, so);
     }
     ADMM_CUDA(cudaEventRecord(ev(1, P), sA));
     if (rem2 > 0) {
-      double* A21b = A + (K1 + n1) + K0 * lda;          // rows below the top block, columns of panel P
+      double* A21b = A + K2 + K0 * lda;                  // rows below the top block, columns of panel P
       ADMM_CUDA(cudaStreamWaitEvent(sB, ev(0, P), 0));
-      if (P >= 2) ADMM_CUDA(cudaStreamWaitEvent(sB, ev(4, P - 2), 0));
+      if (P >= depth + 1) ADMM_CUDA(cudaStreamWaitEvent(sB, ev(4, P - depth - 1), 0));
       {
         StreamSwap on_b(h, sB);
         gemm(h, 0, 1, rem2, wb, wb, 1.0, A21b, lda, WPP, ldw, 0.0, S2, lds, ts);
@@ -843,11 +875,18 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
                                     cudaMemcpyDeviceToDevice, sB));
         ADMM_CUDA(cudaEventRecord(ev(2, P), sB));
         ADMM_CUDA(cudaStreamWaitEvent(sB, ev(1, P), 0));                 // L21_top
-        if (P >= 1) ADMM_CUDA(cudaStreamWaitEvent(sB, ev(4, P - 1), 0)); // bulk of panel P-1 touched this block column too
+        if (P >= depth) ADMM_CUDA(cudaStreamWaitEvent(sB, ev(4, P - depth), 0));   // the last bulk that touched block column P+1
         GemmOpt co;
         co.allow_splitk = 0;
-        gemm(h, 0, 1, rem2, n1, wb, -1.0, A21b, lda, A + K1 + K0 * lda, lda, 1.0, A + (K1 + n1) + K1 * lda, lda, co);
+        gemm(h, 0, 1, rem2, n1, wb, -1.0, A21b, lda, A + K1 + K0 * lda, lda, 1.0, A + K2 + K1 * lda, lda, co);
         ADMM_CUDA(cudaEventRecord(ev(3, P), sB));
+        if (depth == 2) {
+          // block column P+2 (diagonal block included; its upper triangle is never read): after the bulk of panel P-1,
+          // which adds into the same block column
+          if (P >= 1) ADMM_CUDA(cudaStreamWaitEvent(sB, ev(4, P - 1), 0));
+          gemm(h, 0, 1, rem2, n2, wb, -1.0, A21b, lda, A21b, lda, 1.0, A + K2 + K2 * lda, lda, co);
+          ADMM_CUDA(cudaEventRecord(ev(5, P), sB));
+        }
       }
       {
         StreamSwap on_c(h, sC);
@@ -857,15 +896,17 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
         bo.allow_splitk = 0;
         {
           int cb, ci;
-          caps(rem2, K1, cb, ci);                                    // the inverse row riding beside it is row P+1
+          caps(rem3, K1, cb, ci);                                    // the inverse row riding beside it is row P+1
           bo.max_ctas = cb;
         }
-        if (!probe_nobulk) gemm(h, 0, 1, rem2, rem2, wb, -1.0, A21b, lda, A21b, lda, 1.0, A + (K1 + n1) + (K1 + n1) * lda, lda, bo);
+        if (!probe_nobulk && rem3 > 0)
+          gemm(h, 0, 1, rem3, rem3, wb, -1.0, A + K3 + K0 * lda, lda, A + K3 + K0 * lda, lda, 1.0, A + K3 + K3 * lda, lda, bo);
         ADMM_CUDA(cudaEventRecord(ev(4, P), sC));
       }
     } else {
       ADMM_CUDA(cudaEventRecord(ev(3, P), sA));
       ADMM_CUDA(cudaEventRecord(ev(4, P), sA));
+      ADMM_CUDA(cudaEventRecord(ev(5, P), sA));
     }
   }
   }

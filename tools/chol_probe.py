@@ -38,9 +38,10 @@ print(json.dumps(best))
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     m = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
-    for name, env in (("full (default: no SM reserve)", {}), ("reserve 24", {"ADMM_B200_CHOL_RESERVE": "24"}),
-                      ("reserve 12", {"ADMM_B200_CHOL_RESERVE": "12"}), ("reserve 36", {"ADMM_B200_CHOL_RESERVE": "36"}),
-                      ("reserve 48", {"ADMM_B200_CHOL_RESERVE": "48"}),
+    for name, env in (("full (default: no SM reserve)", {}), ("look-ahead depth 1", {"ADMM_B200_CHOL_DEPTH1": "1"}),
+                      ("riding inverse unsplit (K chunk off)", {"ADMM_B200_INV_KCHUNK": "1000000"}),
+                      ("riding inverse, K chunk 512", {"ADMM_B200_INV_KCHUNK": "512"}),
+                      ("riding inverse, K chunk 2048", {"ADMM_B200_INV_KCHUNK": "2048"}),
                       ("no riding inverse", {"ADMM_B200_NO_INV_OVERLAP": "1"}),
                       ("chain only (no bulk, no riding inverse)", {"ADMM_B200_NO_INV_OVERLAP": "1", "ADMM_B200_CHOL_PROBE_NOBULK": "1"}),
                       ("chain + riding inverse, no bulk", {"ADMM_B200_CHOL_PROBE_NOBULK": "1"}),
