@@ -127,6 +127,8 @@ struct admm_b200_handle {
   int64_t k = 0, ldf = 0;
   DBuf L, W, WT;
   bool have_factor = false, have_inverse = false;
+  int64_t subst_bs = 128;        // width of the inverted diagonal blocks W holds (512 after the look-ahead Cholesky)
+  DBuf subst_t;                  // W_PP y_P of the substitution path
 
   // iterates and work vectors
   DBuf x, z, u, y, t1, t2;
@@ -1321,31 +1323,46 @@ static void factor_solve(admm_b200_handle* h, const double* b, double* tmp, doub
     // x = W' t : x_j = column j of W (rows j..k-1) . t
     coldot(h, COLDOT_LOWER, h->W.p, h->ldf, h->k, h->k, tmp, x, 1.0, nullptr, 0.0, done);
   } else if (xsolve == ADMM_B200_XSOLVE_SUBST) {
-    // Blocked forward / back substitution on the factor L itself (128-wide blocks, the inverted
-    // diagonal blocks are the diagonal blocks of W).  2 x (k/128) dependent steps of small launches:
-    // the exact-semantics reference path, not the fast one.
+    // Blocked forward / back substitution on the factor L itself: x = L' \ (L \ b) as the reference writes it
+    // (getProxOps.m:1200).  The inverted diagonal blocks are the diagonal blocks of W -- 512 wide when the look-ahead
+    // Cholesky built them (k > 512: 16 dependent steps per solve at k = 8192), 128 wide otherwise -- so the critical
+    // path is products only: y_P = W_PP y_P, then the panel below is streamed by all SMs (y[below] -= L[below, P] y_P);
+    // backwards with the transposes.  Every entry of L is read once per solve.  The exact-semantics path: it is what
+    // runs when the conditioning guard fires.
     ADMM_REQUIRE(h->W.p != nullptr, ADMM_B200_ERR_STATE, "xsolve = SUBST needs the inverted diagonal blocks");
-    const int64_t k = h->k, ld = h->ldf;
+    const int64_t k = h->k, ld = h->ldf, bs = h->subst_bs;
     double* y = tmp;
+    h->subst_t.ensure(round_up(bs, 2) + 2);
+    double* t = h->subst_t.p;
     vec_copy_kernel<<<(unsigned)((k + 255) / 256), 256, 0, h->stream>>>(y, b, k, done);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
-    for (int64_t k0 = 0; k0 < k; k0 += CHOL_NB) {          // L y = b
-      const int nb = (int)std::min<int64_t>(CHOL_NB, k - k0);
-      tri_block_mv_kernel<<<1, 128, 0, h->stream>>>(h->W.p + k0 + k0 * ld, ld, nb, y + k0, 0, done);
+    auto diag_apply = [&](int64_t k0, int nb, int trans) {     // y_P <- W_PP y_P  or  W_PP' y_P
+      const double* Wkk = h->W.p + k0 + k0 * ld;
+      if (nb <= 128) {
+        tri_block_mv_kernel<<<1, 128, 0, h->stream>>>(Wkk, ld, nb, y + k0, trans, done);
+        ADMM_CUDA(cudaGetLastError());
+        h->launches++;
+        return;
+      }
+      if (!trans) gemvn(h, Wkk, ld, nb, nb, y + k0, t, 1.0, 0.0, nullptr, done);
+      else coldot(h, COLDOT_FULL, Wkk, ld, nb, nb, y + k0, t, 1.0, nullptr, 0.0, done);
+      vec_copy_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, h->stream>>>(y + k0, t, nb, done);
       ADMM_CUDA(cudaGetLastError());
       h->launches++;
+    };
+    for (int64_t k0 = 0; k0 < k; k0 += bs) {          // L y = b
+      const int nb = (int)std::min<int64_t>(bs, k - k0);
+      diag_apply(k0, nb, 0);
       const int64_t rem = k - k0 - nb;
       if (rem > 0)   // y[k0+nb:] -= L[k0+nb:, k0:k0+nb] * y_k
         gemvn(h, h->L.p + (k0 + nb) + k0 * ld, ld, rem, nb, y + k0, y + k0 + nb, -1.0, 1.0, y + k0 + nb, done);
     }
-    const int64_t nblk = (k + CHOL_NB - 1) / CHOL_NB;
+    const int64_t nblk = (k + bs - 1) / bs;
     for (int64_t bi = nblk - 1; bi >= 0; --bi) {           // L' x = y
-      const int64_t k0 = bi * CHOL_NB;
-      const int nb = (int)std::min<int64_t>(CHOL_NB, k - k0);
-      tri_block_mv_kernel<<<1, 128, 0, h->stream>>>(h->W.p + k0 + k0 * ld, ld, nb, y + k0, 1, done);
-      ADMM_CUDA(cudaGetLastError());
-      h->launches++;
+      const int64_t k0 = bi * bs;
+      const int nb = (int)std::min<int64_t>(bs, k - k0);
+      diag_apply(k0, nb, 1);
       if (k0 > 0)    // y[0:k0] -= L[k0:k0+nb, 0:k0]' * x_k
         coldot(h, COLDOT_FULL, h->L.p + k0, ld, nb, k0, y + k0, y, -1.0, y, 1.0, done);
     }
@@ -1426,6 +1443,7 @@ static void factor_current(admm_b200_handle* h, int64_t k, bool want_inverse) {
   h->k = k;
   h->have_factor = true;
   h->have_inverse = want_inverse;
+  h->subst_bs = (k > CHOL_NBO && !getenv("ADMM_B200_CHOL_V1") && !getenv("ADMM_B200_SUBST_128")) ? CHOL_NBO : CHOL_NB;
 }
 
 // the x-update realisation a solve uses: the caller's choice, except that INVFACTOR gives way to SUBST when the

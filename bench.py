@@ -220,12 +220,13 @@ def run_ours(args):
         o = eng.default_options()
         eng.set_lambda(lam)
 
-        def timed_raw(which, reps):
-            eng.iterate_raw(o, which, 5)
+        def timed_raw(which, reps, oo=None):
+            oo = o if oo is None else oo
+            eng.iterate_raw(oo, which, 5)
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            eng.iterate_raw(o, which, reps)
+            eng.iterate_raw(oo, which, reps)
             b.record(stream)
             torch.cuda.synchronize()
             return a.elapsed_time(b) / reps * 1e3       # us
@@ -233,6 +234,11 @@ def run_ours(args):
         xupd_us = max_over_ranks(timed_raw(1, reps))
         prox_us = max_over_ranks(timed_raw(2, reps))
         iter_us = max_over_ranks(timed_raw(0, reps))
+        # the reference's own formulation, x = U \ (L \ y) by blocked substitution on L (options.xsolve = SUBST): what runs
+        # when the conditioning guard fires; 16 dependent 512-wide steps per solve at n = 8192
+        osub = eng.default_options()
+        osub.xsolve = L.XSOLVE_SUBST
+        xsub_us = max_over_ranks(timed_raw(1, max(2, reps // 10), osub))
 
         # ---- time to tolerance (reltol 1e-4) from resident D ----------------------------------
         tol_opts = dict(opts, domaxiters=0, maxiters=(3 if args.light else 1000), check_every=8)
@@ -358,7 +364,8 @@ def run_ours(args):
         "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": int(launches), "graph_replays": int(graph_replays),
         "clocks": clk.summary(),
         "loop_iters_per_s": 1e6 / iter_us,
-        "loop_us_per_iter": {"iteration": iter_us, "x_update": xupd_us, "fused_prox": prox_us},
+        "loop_us_per_iter": {"iteration": iter_us, "x_update": xupd_us, "fused_prox": prox_us,
+                             "x_update_substitution": xsub_us},
         "setup_ms": phases,
         "last_step_ms": {"setup": r["engine"]["setup_ms"], "loop": r["engine"]["loop_ms"],
                          "loop_us_per_iter": r["engine"]["loop_ms"] / ITERS * 1e3},     # rank 0, the last timed step

@@ -88,6 +88,13 @@ def test_c2_factor_matches_lapack(engine, c2_problem):
     Lc = np.linalg.cholesky(G)
     assert rel(Lg, Lc) < 1e-12
     assert engine.info()["diag_ratio"] < 10.0              # column-normalised Gaussian design: cond(D'D + I) ~ 2-3
+    # both x-update realisations against LAPACK's two triangular solves (getProxOps.m:1200) at n = 8192
+    import scipy.linalg as sla
+    from admm_project_b200 import _lib as L
+    b = np.random.RandomState(3).randn(8192)
+    xref = sla.solve_triangular(Lc.T, sla.solve_triangular(Lc, b, lower=True), lower=False)
+    assert rel(engine.factor_solve(b, L.XSOLVE_INVFACTOR), xref) < 1e-12
+    assert rel(engine.factor_solve(b, L.XSOLVE_SUBST), xref) < 1e-12
 
 
 def test_c2_lambda_batch_columns_match_single_solves(engine, c2_problem):

@@ -107,7 +107,7 @@ def test_lasso_runs_in_substitution_mode(engine):
     from admm_project_b200 import lasso
     from admm_project_b200.generators import lasso_problem
     from admm_project_b200 import _lib as L
-    for rows, cols in ((600, 260), (150, 400)):
+    for rows, cols in ((600, 260), (150, 400), (3000, 1300)):      # 1300: three 512-wide steps (512, 512, 276) per solve
         D, s, lam, _ = lasso_problem(0, rows, cols)
         ref = oracle.lasso(D, s, lam, {"history": 0})
         res = lasso(D, s, lam, {"history": 0, "xsolve": L.XSOLVE_SUBST}, engine=engine)
