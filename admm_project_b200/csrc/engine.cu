@@ -158,6 +158,8 @@ struct admm_b200_handle {
   // total variation: double-buffered z/u, pivot table of the constant tridiagonal
   DBuf zz, uu, tvtab;
   int tv_par = 0, tv_ntab = 0, tv_halo = 0;
+  bool tv_exact = false;         // rho too large for the windowed solve: segments chained through their aggregates (tv.cuh)
+  DBuf tv_y, tv_seg;             // exact path: y (n) and [segA | segB | cin] (3 x nseg)
   double tv_inv_star = 0.0;
   double tv_rho = -1.0;
   // row-sharded runs: one NCCL communicator per handle (one process per GPU)
@@ -1741,21 +1743,26 @@ static void tv_prepare(admm_b200_handle* h, double rho) {
   if (h->tv_rho == rho) return;
   // pivots of I + rho*D'D: delta_0 = 1 + rho, delta_i = 1 + 2 rho - rho^2/delta_{i-1}; contraction
   std::vector<double> inv;
-  const int64_t cap = std::min<int64_t>(n, 1 << 18);
   double d = 1.0 + rho;
   inv.push_back(1.0 / d);
-  for (int64_t i = 1; i < cap; ++i) {
+  for (int64_t i = 1; i < n; ++i) {             // until the pivots reach their fixed point (or the end of the chain)
     const double dn = (1.0 + 2.0 * rho) - rho * rho / d;
     inv.push_back(1.0 / dn);
     if (dn == d) break;
     d = dn;
   }
   const double astar = rho * inv.back();       // forward/backward multiplier at the fixed point
-  int64_t K = (astar > 0.0) ? (int64_t)ceil(40.0 / -log(astar)) : 1;
+  int64_t K = (astar > 0.0 && astar < 1.0) ? (int64_t)std::min(1e15, ceil(40.0 / -log(astar))) : 1;
   K = round_up(std::max<int64_t>(K, 16), 16);
-  ADMM_REQUIRE(4 * K <= TvCfg<16>::SEG, ADMM_B200_ERR_UNSUPPORTED,
-               "totalvariation: rho = %g needs a %lld-element halo, more than the windowed tridiagonal solve carries",
-               rho, (long long)K);
+  // a halo the windowed kernels cannot carry (rho >~ 2500): the exact chained solve takes over -- any rho runs,
+  // as in the reference (getProxOps.m:1047)
+  h->tv_exact = (4 * K > TvCfg<16>::SEG) || getenv("ADMM_B200_TV_EXACT") != nullptr;
+  if (h->tv_exact) {
+    const int64_t nseg = (n + TvCfg<16>::SEG - 1) / TvCfg<16>::SEG;
+    h->tv_y.ensure(round_up(n, 2));
+    h->tv_seg.ensure(3 * nseg);
+    K = 16;
+  }
   h->tvtab.ensure((int64_t)inv.size());
   ADMM_CUDA(cudaMemcpyAsync(h->tvtab.p, inv.data(), inv.size() * 8, cudaMemcpyHostToDevice, h->stream));
   ADMM_CUDA(cudaStreamSynchronize(h->stream));
@@ -2081,7 +2088,7 @@ static void load_init(admm_b200_handle* h) {
 static inline int64_t tv_stride(int64_t n) { return round_up(n, 4); }
 // CTA size of the fused iteration kernel, 0 when the halo is too wide for it (overhead > 25 %)
 static int tv_fused_threads(const admm_b200_handle* h) {
-  if (getenv("ADMM_B200_TV_UNFUSED")) return 0;
+  if (getenv("ADMM_B200_TV_UNFUSED") || h->tv_exact) return 0;
   static const int pref = getenv("ADMM_B200_TVF_T") ? atoi(getenv("ADMM_B200_TVF_T")) : 128;
   if (pref == 128 && 8 * h->tv_halo <= 128 * TVF_E) return 128;
   if (8 * h->tv_halo <= 256 * TVF_E) return 256;
@@ -2209,7 +2216,30 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     const int64_t npad = tv_stride(n);
     const double* zc = h->zz.p + (int64_t)h->tv_par * npad;
     const double* uc = h->uu.p + (int64_t)h->tv_par * npad;
-    if (which != 2) {
+    if (which != 2 && h->tv_exact) {
+      // any rho: forward aggregates -> chain -> y + backward aggregates -> chain -> x (tv.cuh, tv_exact_kernel)
+      static PerDevice conf_pd;
+      size_t& conf = conf_pd(h->device);
+      if (!conf) {
+        ADMM_CUDA(cudaFuncSetAttribute(tv_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TvCfg<16>::SMEM_BYTES));
+        ADMM_CUDA(cudaFuncSetAttribute(tv_exact_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TvCfg<16>::SMEM_BYTES));
+        ADMM_CUDA(cudaFuncSetAttribute(tv_exact_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TvCfg<16>::SMEM_BYTES));
+        conf = 1;
+      }
+      const int64_t nseg = (n + TvCfg<16>::SEG - 1) / TvCfg<16>::SEG;
+      TvExactArgs a;
+      a.n = n; a.s = h->s.p; a.z = zc; a.u = uc; a.y = h->tv_y.p; a.x = h->x.p; a.rho = o.rho; a.invdelta = h->tvtab.p;
+      a.inv_star = h->tv_inv_star; a.ntab = h->tv_ntab; a.done = done;
+      a.segA = h->tv_seg.p; a.segB = h->tv_seg.p + nseg; a.cin = h->tv_seg.p + 2 * nseg;
+      double* cin = h->tv_seg.p + 2 * nseg;
+      tv_exact_kernel<1><<<(unsigned)nseg, TV_THREADS, TvCfg<16>::SMEM_BYTES, h->stream>>>(a);
+      tv_chain_kernel<<<1, 32, 0, h->stream>>>(a.segA, a.segB, nseg, cin, 0, done);
+      tv_exact_kernel<2><<<(unsigned)nseg, TV_THREADS, TvCfg<16>::SMEM_BYTES, h->stream>>>(a);
+      tv_chain_kernel<<<1, 32, 0, h->stream>>>(a.segA, a.segB, nseg, cin, 1, done);
+      tv_exact_kernel<3><<<(unsigned)nseg, TV_THREADS, TvCfg<16>::SMEM_BYTES, h->stream>>>(a);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches += 5;
+    } else if (which != 2) {
       TvSolveArgs a;
       a.n = n; a.s = h->s.p; a.z = zc; a.u = uc; a.x = h->x.p; a.rho = o.rho; a.invdelta = h->tvtab.p;
       a.inv_star = h->tv_inv_star; a.ntab = h->tv_ntab; a.halo = h->tv_halo; a.done = done;

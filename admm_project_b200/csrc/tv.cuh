@@ -166,6 +166,179 @@ __global__ void __launch_bounds__(TV_THREADS, (TV_E == 8 ? 2 : 1)) tv_solve_kern
 #undef TV_PAD
 }
 
+// ---------------------------------------------------------------------------------------------
+// Exact x-update for ANY rho (the windowed kernels above need the recurrences to forget their carry within a
+// halo of ~40 sqrt(rho) elements; the reference accepts any rho, getProxOps.m:1047).  The two Thomas recurrences
+// are scans of affine maps, and affine maps compose exactly, so the segments are chained through their
+// aggregates instead of through a halo:
+//   pass 1   every CTA composes the forward maps of its 8192-element segment            -> (A_b, B_b)
+//   chain    carry into segment b:  c_b = B_{b-1} + A_{b-1} c_{b-1}                       (one thread, nseg steps)
+//   pass 2   the forward recurrence again, now from the true carry: y (kept) -- and the aggregate of the
+//            segment's backward maps
+//   chain    from the right
+//   pass 3   the backward recurrence from the true carry: x
+// 9 vector passes instead of 4; used only when the halo does not fit (rho >~ 2500).
+// ---------------------------------------------------------------------------------------------
+struct TvExactArgs {
+  int64_t n;
+  const double *s, *z, *u;
+  double *y, *x;
+  double rho;
+  const double* invdelta; double inv_star; int ntab;
+  double *segA, *segB;        // [nseg] aggregates of the pass being run
+  const double* cin;          // [nseg] carry into each segment (passes 2 and 3)
+  const int* done;
+};
+
+// exclusive prefix (as a map) of this thread's affine map over the CTA in thread order, and the CTA total
+__device__ __forceinline__ Affine block_affine_prefix(Affine mine, double* shA, double* shB, Affine& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Affine inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double pa = __shfl_up_sync(0xffffffffu, inc.A, d);
+    const double pb = __shfl_up_sync(0xffffffffu, inc.B, d);
+    if (lane >= d) inc = compose(inc, Affine{pa, pb});
+  }
+  if (lane == 31) { shA[warp] = inc.A; shB[warp] = inc.B; }
+  __syncthreads();
+  if (warp == 0) {
+    Affine w = (lane < TV_THREADS / 32) ? Affine{shA[lane], shB[lane]} : Affine{1.0, 0.0};
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double pa = __shfl_up_sync(0xffffffffu, w.A, d);
+      const double pb = __shfl_up_sync(0xffffffffu, w.B, d);
+      if (lane >= d) w = compose(w, Affine{pa, pb});
+    }
+    if (lane < TV_THREADS / 32) { shA[32 + lane] = w.A; shB[32 + lane] = w.B; }
+  }
+  __syncthreads();
+  const double pa = __shfl_up_sync(0xffffffffu, inc.A, 1);
+  const double pb = __shfl_up_sync(0xffffffffu, inc.B, 1);
+  Affine excl = (lane > 0) ? Affine{pa, pb} : Affine{1.0, 0.0};
+  if (warp > 0) excl = compose(excl, Affine{shA[32 + warp - 1], shB[32 + warp - 1]});
+  total = Affine{shA[32 + TV_THREADS / 32 - 1], shB[32 + TV_THREADS / 32 - 1]};
+  __syncthreads();
+  return excl;
+}
+
+// PASS 1: forward aggregates.  PASS 2: y from the true carry + backward aggregates.  PASS 3: x from the true carry.
+template <int PASS>
+__global__ void __launch_bounds__(TV_THREADS, 1) tv_exact_kernel(TvExactArgs a) {
+  if (a.done && *a.done) return;
+  constexpr int TV_E = 16;
+  constexpr int TV_SEG = TvCfg<TV_E>::SEG;
+  constexpr int TV_SMEM_DOUBLES = TvCfg<TV_E>::SMEM_DOUBLES;
+#define TV_PAD(i) TV_PAD<TV_E>(i)
+  extern __shared__ __align__(16) double sm[];
+  double* bufA = sm;
+  double* bufB = sm + TV_SMEM_DOUBLES;
+  double* shA = sm + 2 * TV_SMEM_DOUBLES;
+  double* shB = shA + 64;
+  const int tid = threadIdx.x;
+  const int64_t g0 = (int64_t)blockIdx.x * TV_SEG;        // global index of local element 0
+  const double rho = a.rho;
+  auto invd = [&](int64_t i) -> double { return i < a.ntab ? a.invdelta[i] : a.inv_star; };
+  const int j0 = tid * TV_E;
+  Affine total;
+  if (PASS <= 2) {
+    for (int j = tid; j < TV_SEG + 1; j += TV_THREADS) {
+      const int64_t i = g0 + j - 1;
+      double w = 0.0;
+      if (i >= 0 && i < a.n) w = a.z[i] - a.u[i];
+      bufA[TV_PAD(j)] = w;
+    }
+    for (int j = tid; j < TV_SEG; j += TV_THREADS) {
+      const int64_t i = g0 + j;
+      bufB[TV_PAD(j)] = (i < a.n) ? a.s[i] : 0.0;
+    }
+    __syncthreads();
+    double r[TV_E], fa[TV_E];
+#pragma unroll
+    for (int e = 0; e < TV_E; ++e) {
+      const int j = j0 + e;
+      const int64_t i = g0 + j;
+      const bool in = (i < a.n);
+      const double w = bufA[TV_PAD(j + 1)], wl = bufA[TV_PAD(j)];
+      r[e] = in ? fma(rho, w - wl, bufB[TV_PAD(j)]) : 0.0;
+      fa[e] = (in && i > 0) ? rho * invd(i - 1) : (in ? 0.0 : 1.0);   // past the end: identity maps, so the aggregate is the segment's
+      if (!in) r[e] = 0.0;
+    }
+    Affine m{1.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < TV_E; ++e) m = Affine{fa[e] * m.A, fma(fa[e], m.B, r[e])};
+    __syncthreads();
+    const Affine excl = block_affine_prefix(m, shA, shB, total);
+    if (PASS == 1) {
+      if (tid == 0) { a.segA[blockIdx.x] = total.A; a.segB[blockIdx.x] = total.B; }
+      return;
+    }
+    double carry = fma(excl.A, a.cin[blockIdx.x], excl.B);
+#pragma unroll
+    for (int e = 0; e < TV_E; ++e) {
+      carry = fma(fa[e], carry, r[e]);
+      bufA[TV_PAD(j0 + e)] = carry;                        // y_i
+    }
+    __syncthreads();
+    for (int j = tid; j < TV_SEG; j += TV_THREADS) {
+      const int64_t i = g0 + j;
+      if (i < a.n) a.y[i] = bufA[TV_PAD(j)];
+    }
+  } else {
+    for (int j = tid; j < TV_SEG; j += TV_THREADS) {
+      const int64_t i = g0 + j;
+      bufA[TV_PAD(j)] = (i < a.n) ? a.y[i] : 0.0;
+    }
+    __syncthreads();
+  }
+  // ---- backward maps in reversed local order: x_i = invd_i*y_i + (rho*invd_i) x_{i+1}
+  double bb[TV_E], ba[TV_E];
+#pragma unroll
+  for (int e = 0; e < TV_E; ++e) {
+    const int j = TV_SEG - 1 - (j0 + e);
+    const int64_t i = g0 + j;
+    const bool in = (i < a.n);
+    const double id = in ? invd(i) : 0.0;
+    bb[e] = id * bufA[TV_PAD(j)];
+    ba[e] = (in && i < a.n - 1) ? rho * id : (in ? 0.0 : 1.0);      // past the end: identity
+  }
+  Affine mb{1.0, 0.0};
+#pragma unroll
+  for (int e = 0; e < TV_E; ++e) mb = Affine{ba[e] * mb.A, fma(ba[e], mb.B, bb[e])};
+  __syncthreads();
+  const Affine exclb = block_affine_prefix(mb, shA, shB, total);
+  if (PASS == 2) {
+    if (tid == 0) { a.segA[blockIdx.x] = total.A; a.segB[blockIdx.x] = total.B; }
+    return;
+  }
+  double carry = fma(exclb.A, a.cin[blockIdx.x], exclb.B);
+#pragma unroll
+  for (int e = 0; e < TV_E; ++e) {
+    carry = fma(ba[e], carry, bb[e]);
+    bufB[TV_PAD(TV_SEG - 1 - (j0 + e))] = carry;           // x_i
+  }
+  __syncthreads();
+  for (int j = tid; j < TV_SEG; j += TV_THREADS) {
+    const int64_t i = g0 + j;
+    if (i < a.n) a.x[i] = bufB[TV_PAD(j)];
+  }
+#undef TV_PAD
+}
+
+// carry into every segment from the aggregates: forward (reverse = 0: c_0 = 0, c_b = B_{b-1} + A_{b-1} c_{b-1}) or from the
+// right (reverse = 1).  One warp; lane 0 walks the chain (nseg = n / 8192 steps of one FMA).
+__global__ void tv_chain_kernel(const double* __restrict__ segA, const double* __restrict__ segB, int64_t nseg, double* cin,
+                                int reverse, const int* done) {
+  if (done && *done) return;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double c = 0.0;
+  if (!reverse) {
+    for (int64_t b = 0; b < nseg; ++b) { cin[b] = c; c = fma(segA[b], c, segB[b]); }
+  } else {
+    for (int64_t b = nseg - 1; b >= 0; --b) { cin[b] = c; c = fma(segA[b], c, segB[b]); }
+  }
+}
+
 constexpr int TVP_THREADS = 256;
 constexpr int TVP_E = 4;
 
