@@ -2208,7 +2208,8 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
       ADMM_CUDA(cudaFuncSetAttribute(tv_solve_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TvCfg<16>::SMEM_BYTES));
       configured = 1;
     }
-    if (which == 0 && tv_fused_ok(h)) {          // small halo: the whole iteration is one kernel (tv.cuh)
+    const bool fastmode = lp.alg != 0;            // fast / accelerated ADMM: x-update from (v, uhat), stepwise kernels
+    if (which == 0 && !fastmode && tv_fused_ok(h)) {          // small halo: the whole iteration is one kernel (tv.cuh)
       tv_fused_launch(h, o, lp, h->tv_par, false, history);
       h->tv_par ^= 1;
       return;
@@ -2216,6 +2217,8 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     const int64_t npad = tv_stride(n);
     const double* zc = h->zz.p + (int64_t)h->tv_par * npad;
     const double* uc = h->uu.p + (int64_t)h->tv_par * npad;
+    const double* zsolve = fastmode ? h->fv.p : zc;       // admm.m:506: x = xminf(x, v, uhat, rho)
+    const double* usolve = fastmode ? h->fuhat.p : uc;
     if (which != 2 && h->tv_exact) {
       // any rho: forward aggregates -> chain -> y + backward aggregates -> chain -> x (tv.cuh, tv_exact_kernel)
       static PerDevice conf_pd;
@@ -2228,7 +2231,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
       }
       const int64_t nseg = (n + TvCfg<16>::SEG - 1) / TvCfg<16>::SEG;
       TvExactArgs a;
-      a.n = n; a.s = h->s.p; a.z = zc; a.u = uc; a.y = h->tv_y.p; a.x = h->x.p; a.rho = o.rho; a.invdelta = h->tvtab.p;
+      a.n = n; a.s = h->s.p; a.z = zsolve; a.u = usolve; a.y = h->tv_y.p; a.x = h->x.p; a.rho = o.rho; a.invdelta = h->tvtab.p;
       a.inv_star = h->tv_inv_star; a.ntab = h->tv_ntab; a.done = done;
       a.segA = h->tv_seg.p; a.segB = h->tv_seg.p + nseg; a.cin = h->tv_seg.p + 2 * nseg;
       double* cin = h->tv_seg.p + 2 * nseg;
@@ -2241,7 +2244,7 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
       h->launches += 5;
     } else if (which != 2) {
       TvSolveArgs a;
-      a.n = n; a.s = h->s.p; a.z = zc; a.u = uc; a.x = h->x.p; a.rho = o.rho; a.invdelta = h->tvtab.p;
+      a.n = n; a.s = h->s.p; a.z = zsolve; a.u = usolve; a.x = h->x.p; a.rho = o.rho; a.invdelta = h->tvtab.p;
       a.inv_star = h->tv_inv_star; a.ntab = h->tv_ntab; a.halo = h->tv_halo; a.done = done;
       if (8 * h->tv_halo <= TvCfg<8>::SEG) {      // halo overhead <= 25 %: small segments, 3 CTAs per SM
         const int64_t S = TvCfg<8>::SEG - 2 * h->tv_halo;
@@ -2260,14 +2263,24 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     p.unew = h->uu.p + (int64_t)(1 - h->tv_par) * npad;
     p.lambda = h->lambda;
     const int grid = (int)std::min<int64_t>(2 * kNumSM, std::max<int64_t>(1, (n + TVP_THREADS * TVP_E - 1) / (TVP_THREADS * TVP_E)));
-    h->partials.ensure((int64_t)grid * 8);
+    h->partials.ensure((int64_t)grid * TVP_NRED);
     p.partials = h->partials.p; p.ctl = h->ctl; p.lp = lp;
     p.xvals = history ? h->xvals.p : nullptr;
     p.zvals = history ? h->zvals.p : nullptr;
     p.uvals = history ? h->uvals.p : nullptr;
-    tv_prox_kernel<<<grid, TVP_THREADS, 0, h->stream>>>(p);
+    p.v = h->fv.p; p.uhat = h->fuhat.p;
+    if (fastmode) tv_prox_kernel<true><<<grid, TVP_THREADS, 0, h->stream>>>(p);
+    else tv_prox_kernel<false><<<grid, TVP_THREADS, 0, h->stream>>>(p);
     ADMM_CUDA(cudaGetLastError());
     h->launches++;
+    if (fastmode) {      // acceleration pass (admm.m:562-600) + scalar epilogue; z / u of the step before = the half just read
+      TvAccelArgs b;
+      b.n = n; b.z = p.znew; b.u = p.unew; b.zprev = zc; b.uprev = uc; b.v = h->fv.p; b.uhat = h->fuhat.p;
+      b.partials = h->partials.p; b.ctl = h->ctl; b.lp = lp;
+      tv_accel_kernel<<<grid, 256, 0, h->stream>>>(b);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches++;
+    }
     h->tv_par ^= 1;
   } else if (h->kind == ADMM_B200_BASISPURSUIT) {
     const int64_t n = h->n, m = h->m;
@@ -2540,9 +2553,6 @@ static void validate_options(admm_b200_handle* h, const admm_b200_options& o) {
   ADMM_REQUIRE(h->kind != 0, ADMM_B200_ERR_STATE, "no problem set up on this handle");
   ADMM_REQUIRE(o.rho > 0, ADMM_B200_ERR_INVALID, "Argument options.rho is not a positive real number!");
   ADMM_REQUIRE(o.stopcond >= 0 && o.stopcond <= 2, ADMM_B200_ERR_INVALID, "invalid stopcond %d", o.stopcond);
-  if (o.fast)
-    ADMM_REQUIRE(h->kind != ADMM_B200_TOTALVARIATION, ADMM_B200_ERR_UNSUPPORTED,
-                 "options.fast is not built for totalvariation");
   if (h->kind == ADMM_B200_SVM_HINGE || h->kind == ADMM_B200_SVM_01)
     ADMM_REQUIRE(o.relax == 1.0, ADMM_B200_ERR_INVALID,
                  "Inner matrix dimensions must agree. (linearsvm with relax ~= 1: the reference's zminLinearSVM "
@@ -2813,7 +2823,7 @@ static void solve(admm_b200_handle* h, const admm_b200_options& o, admm_b200_res
     h->tv_par = (int)half;
     // the fused iteration keeps x in registers: materialise the x of the last iteration from the
     // half it read (untouched since: later launches exit on ctl->done)
-    if (tv_fused_ok(h) && h->h_ctl->it >= 1) tv_fused_launch(h, o, lp, (int)(1 - half), true, false);
+    if (lp.alg == 0 && tv_fused_ok(h) && h->h_ctl->it >= 1) tv_fused_launch(h, o, lp, (int)(1 - half), true, false);
   }
   if (!res) return;
   const int64_t steps = h->h_ctl->it;

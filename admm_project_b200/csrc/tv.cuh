@@ -348,23 +348,29 @@ struct TvProxArgs {
   const double *z, *u;     // current iterates (read by neighbours too, hence double-buffered)
   double *znew, *unew;
   double lambda;
-  double* partials;     // [gridDim.x][8]
+  double* partials;     // [gridDim.x][TVP_NRED]
   LoopCtl* ctl;
   LoopParams lp;
   double *xvals, *zvals, *uvals;
+  const double *v, *uhat;  // fast / accelerated ADMM (admm.m:503-529): the prox and the u-update start from uhat
 };
+constexpr int TVP_NRED = 10;
 
+// FAST: the fast / accelerated variants (admm.m:267-298, 503-600).  z and u of the previous iteration are simply the
+// half of the double buffer this kernel reads, so nothing is copied; the residual norms need the NEW v, so the scalar
+// epilogue moves to tv_accel_kernel and the last CTA here only fixes the predictor weight / restart.
+template <bool FAST>
 __global__ void __launch_bounds__(TVP_THREADS, 2) tv_prox_kernel(TvProxArgs a) {
   LoopCtl* ctl = a.ctl;
   if (ctl->done) return;
-  __shared__ double sh[(TVP_THREADS / 32) * 8];
+  __shared__ double sh[(TVP_THREADS / 32) * TVP_NRED];
   __shared__ bool is_last;
   const int it = ctl->it;
   const double rho = a.lp.rho, relax = a.lp.relax, thr = a.lambda / rho;
   const int64_t n = a.n;
-  double r[8];
+  double r[TVP_NRED];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) r[k] = 0.0;
+  for (int k = 0; k < TVP_NRED; ++k) r[k] = 0.0;
 
   for (int64_t base = ((int64_t)blockIdx.x * TVP_THREADS + threadIdx.x) * TVP_E; base < n;
        base += (int64_t)gridDim.x * TVP_THREADS * TVP_E) {
@@ -397,6 +403,17 @@ __global__ void __launch_bounds__(TVP_THREADS, 2) tv_prox_kernel(TvProxArgs a) {
 #pragma unroll
       for (int k = 0; k < TVP_E; ++k) { const int64_t i = base + k; sr[k] = (i < n) ? a.s[i] : 0.0; }
     }
+    double uo[TVP_E + 1], vr[TVP_E + 1];      // FAST: u of the previous iteration (ur then holds uhat), v
+    if (FAST) {
+#pragma unroll
+      for (int k = 0; k < TVP_E + 1; ++k) {
+        const int64_t i = base - 1 + k;
+        const bool in = (i >= 0 && i < n);
+        uo[k] = ur[k];
+        ur[k] = in ? a.uhat[i] : 0.0;
+        vr[k] = in ? a.v[i] : 0.0;
+      }
+    }
     // element i = base - 1 + k; k = 0 is the left neighbour, recomputed only for the D' stencils of
     // the dual residual.  Values of the previous element are carried in scalars (few live registers).
     double zl = 0.0, ul = 0.0, dzl = 0.0;
@@ -421,8 +438,13 @@ __global__ void __launch_bounds__(TVP_THREADS, 2) tv_prox_kernel(TvProxArgs a) {
       const double un = up + (Axh + (-zn) - 0.0);
       const double dz = zn - zp;
       if (k >= 1 && i < n) {
-        const double du = un - up;
+        const double du = un - (FAST ? uo[k] : up);
         const double pr = Dx + (-zn) - 0.0;
+        if (FAST) {
+          const double e1 = un - up, e2 = zn - vr[k];
+          r[8] = fma(e1, e1, r[8]);                 // ||u - uhat||^2
+          r[9] = fma(e2, e2, r[9]);                 // ||B(z - v)||^2, B = -I
+        }
         const double dtdz = rho * ((i > 0) ? (dz - dzl) : dz);       // rho*At(B(z-zprev)) up to sign
         const double dtu = rho * ((i > 0) ? (un - ul) : un);         // rho*At(u)
         const double xs = x0 - sr[k - 1];
@@ -448,7 +470,7 @@ __global__ void __launch_bounds__(TVP_THREADS, 2) tv_prox_kernel(TvProxArgs a) {
     }
     (void)zl;
   }
-  block_reduce_store<8>(r, a.partials + (int64_t)blockIdx.x * 8, sh);
+  block_reduce_store<TVP_NRED>(r, a.partials + (int64_t)blockIdx.x * TVP_NRED, sh);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -458,17 +480,76 @@ __global__ void __launch_bounds__(TVP_THREADS, 2) tv_prox_kernel(TvProxArgs a) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (threadIdx.x < 8) {
+  if (threadIdx.x < TVP_NRED) {
     double s = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(a.partials + (int64_t)b * 8 + threadIdx.x);
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(a.partials + (int64_t)b * TVP_NRED + threadIdx.x);
     sh[threadIdx.x] = s;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double red[8] = {sh[0], sh[1], sh[2], 0.0, sh[3], sh[4], sh[5], sh[6]};
     ctl->ticket = 0;
+    if (FAST) {
+      // kept for tv_accel_kernel: ||Ax - z||^2, ||Ax||^2, ||z||^2, ||rho At(u)||^2, ||dz||^2, ||du||^2, -, objective
+      ctl->sums[0] = sh[0]; ctl->sums[1] = sh[1]; ctl->sums[2] = sh[2]; ctl->sums[3] = sh[4];
+      ctl->sums[4] = sh[5]; ctl->sums[5] = sh[6]; ctl->sums[6] = 0.0; ctl->sums[7] = sh[7];
+      accel_decide(ctl, a.lp, sh[8], sh[9]);
+      return;
+    }
+    double red[8] = {sh[0], sh[1], sh[2], 0.0, sh[3], sh[4], sh[5], sh[6]};
     loop_epilogue(ctl, a.lp, red, (double)n, (double)n, sh[7]);
   }
+}
+
+// Acceleration pass of the fast variants for total variation (admm.m:562-600): v = z + gamma (z - zprev),
+// uhat = u + gamma (u - uprev), or v = zprev, uhat = uprev on a restart; the dual residual of the fast variant,
+// rho * ||At(B(z - v))|| with At = D' (admm.m:629-633: (D'e)_i = e_i - e_{i-1}); last CTA: the scalar epilogue.
+struct TvAccelArgs {
+  int64_t n;
+  const double *z, *u, *zprev, *uprev;    // new half / old half of the double buffers
+  double *v, *uhat;
+  double* partials;                       // [gridDim.x]
+  LoopCtl* ctl;
+  LoopParams lp;
+};
+
+__global__ void __launch_bounds__(256) tv_accel_kernel(TvAccelArgs a) {
+  LoopCtl* ctl = a.ctl;
+  if (ctl->done) return;
+  __shared__ double sh[256 / 32];
+  __shared__ bool is_last;
+  const double gamma = ctl->gamma, rho = a.lp.rho;
+  const int restart = ctl->restart;
+  double r1[1] = {0.0};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double z = a.z[i], u = a.u[i], zp = a.zprev[i], up = a.uprev[i];
+    const double v = restart ? zp : z + gamma * (z - zp);
+    const double uh = restart ? up : u + gamma * (u - up);
+    a.v[i] = v;
+    a.uhat[i] = uh;
+    double e = z - v;
+    if (i > 0) {                          // the left neighbour's z - v, recomputed (its thread may sit in another CTA)
+      const double zl = a.z[i - 1], zpl = a.zprev[i - 1];
+      const double vl = restart ? zpl : zl + gamma * (zl - zpl);
+      e -= zl - vl;
+    }
+    r1[0] = fma(e, e, r1[0]);
+  }
+  block_reduce_store<1>(r1, a.partials + blockIdx.x, sh);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(&ctl->ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  double sdt = 0.0;
+  for (unsigned b = 0; b < gridDim.x; ++b) sdt += __ldcg(a.partials + b);
+  ctl->ticket = 0;
+  const double* sm = ctl->sums;
+  double red[8] = {sm[0], sm[1], sm[2], 0.0, rho * rho * sdt, sm[3], sm[4], sm[5]};
+  loop_epilogue(ctl, a.lp, red, (double)a.n, (double)a.n, sm[7]);
 }
 
 // ---------------------------------------------------------------------------------------------

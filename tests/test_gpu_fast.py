@@ -74,3 +74,18 @@ def test_svm_and_bp_fast(engine):
     assert res["steps"] == ref["steps"]
     for k in ("xopt", "zopt", "uopt", "avals", "pnorm", "dnorm"):
         assert rel(res[k], ref[k]) < TOL, (k, rel(res[k], ref[k]))
+
+
+@pytest.mark.parametrize("fasttype", ["weak", "strong"])
+@pytest.mark.parametrize("n,rho,relax", [(1000, 1.0, 1.0), (20001, 2.0, 1.0), (6000, 1.0, 1.3), (9001, 5000.0, 1.0)])
+def test_totalvariation_fast_variants(engine, fasttype, n, rho, relax):
+    """Total variation under the fast / accelerated variants: the x-update starts from (v, uhat), the stencil prox from
+    uhat, and the fast dual residual is rho*||D'(z - v)|| (admm.m:503-529, 562-600, 629-633).  rho = 5000 takes the
+    chained exact x-update.  A fixed number of early iterations (see test_lasso_fast_variants)."""
+    from admm_project_b200 import totalvariation
+    s, _ = gen.tv_problem(2, n)
+    opts = {"fast": 1, "fasttype": fasttype, "objevals": 1, "rho": rho, "relax": relax, "history": 0, "maxiters": 25,
+            "restart": 0.9}
+    ref = oracle.totalvariation(s, 2.0, opts)
+    res = totalvariation(s, 2.0, opts, engine=engine)
+    compare(res, ref, fasttype)
