@@ -1281,6 +1281,10 @@ static void symtri_solve(admm_b200_handle* h, const double* WT, int64_t ld, int6
   h->st_part.ensure((int64_t)pl->grid * kpad);
   SymtriArgs a;
   a.WT = WT; a.ld = ld; a.k = (int)k; a.kpad = kpad; a.y = b; a.xpart = h->st_part.p; a.done = done;
+  static const int chunk = getenv("ADMM_B200_SYMTRI_CHUNK") ? std::max(64, atoi(getenv("ADMM_B200_SYMTRI_CHUNK")) & ~1) : (1 << 20);   // default: one copy per column (measured: 1024 / 2048 / 4096-double pieces 78 / 75 / 74 us, whole columns 71 us)
+  a.chunk = chunk;
+  static const int probe = getenv("ADMM_B200_SYMTRI_PROBE") ? 1 : 0;     // data movement only (timing experiment, wrong x)
+  a.probe = probe;
   a.cta_round = pl->d_cta_round; a.round_ent = pl->d_round_ent; a.ents = pl->d_ents;
   symtri_kernel<<<pl->grid, ST_THREADS, ST_SMEM, h->stream>>>(a);
   ADMM_CUDA(cudaGetLastError());

@@ -34,7 +34,7 @@ constexpr int ST_NSTAGE = 3;
 constexpr int ST_CPR = 16;                            // columns per round at most (small factors pack several pairs)
 constexpr int ST_MAXENT = 448;                        // plan entries / rounds of a CTA kept in shared memory
 constexpr int ST_MAXROUND = 127;
-constexpr size_t ST_SMEM = (size_t)ST_NSTAGE * ST_STAGE * 8 + (size_t)ST_CPR * ST_WARPS * 8 + 64 + (size_t)ST_MAXENT * 16 +
+constexpr size_t ST_SMEM = (size_t)ST_NSTAGE * ST_STAGE * 8 + (size_t)2 * ST_CPR * ST_WARPS * 8 + 64 + (size_t)ST_MAXENT * 16 +
                            (size_t)(ST_MAXROUND + 1) * 4;
 
 struct SymtriEnt { int col, off, len, pad; };        // column, offset in the stage (doubles, even), rows 0..len-1
@@ -42,6 +42,8 @@ struct SymtriEnt { int col, off, len, pad; };        // column, offset in the st
 struct SymtriArgs {
   const double* WT; int64_t ld;
   int k, kpad;
+  int chunk;                       // doubles per bulk copy (even)
+  int probe;                       // timing probe: 1 = move the data, skip the arithmetic (WRONG result)
   const double* y;
   double* xpart;                   // [gridDim.x][kpad]
   const int* done;
@@ -84,8 +86,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
   if (a.done && *a.done) return;
   extern __shared__ __align__(128) unsigned char st_raw[];
   double* stage = reinterpret_cast<double*>(st_raw);                                  // [NSTAGE][ST_STAGE]
-  double* wsum = stage + (size_t)ST_NSTAGE * ST_STAGE;                                // [ST_CPR][ST_WARPS]
-  uint64_t* full = reinterpret_cast<uint64_t*>(wsum + ST_CPR * ST_WARPS);             // [NSTAGE] (+ padding to 64 bytes)
+  double* wsum = stage + (size_t)ST_NSTAGE * ST_STAGE;                                // [2][ST_CPR][ST_WARPS]: partial dots of two rounds
+  uint64_t* full = reinterpret_cast<uint64_t*>(wsum + 2 * ST_CPR * ST_WARPS);         // [NSTAGE] (+ padding to 64 bytes)
   SymtriEnt* s_ents = reinterpret_cast<SymtriEnt*>(full + 8);                         // [ST_MAXENT]
   int* s_rent = reinterpret_cast<int*>(s_ents + ST_MAXENT);                           // [ST_MAXROUND + 1]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -117,8 +119,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
     mbar_expect_tx(full + s, total);
     for (int e = e0; e < e1; ++e) {
       const SymtriEnt en = ent(e);
-      tma_bulk_g2s(stage + (size_t)s * ST_STAGE + en.off, a.WT + (int64_t)en.col * a.ld, (unsigned)((en.len + 1) & ~1) * 8u,
-                   full + s);
+      // a column can go up as several bulk copies of a.chunk doubles (ADMM_B200_SYMTRI_CHUNK); measured on B200, pieces
+      // are SLOWER than one copy per column, so the default chunk is larger than any column
+      const int padded = (en.len + 1) & ~1;
+      double* dst = stage + (size_t)s * ST_STAGE + en.off;
+      const double* src = a.WT + (int64_t)en.col * a.ld;
+      for (int o = 0; o < padded; o += a.chunk) {
+        const int c = min(a.chunk, padded - o);
+        tma_bulk_g2s(dst + o, src + o, (unsigned)c * 8u, full + s);
+      }
     }
   };
   if (tid == 0)
@@ -133,14 +142,50 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
     acc[q] = make_double2(0.0, 0.0);
   }
 
-  for (int round = r0; round < r1; ++round) {
+  // Skewed by one round: an iteration does the DOTS of round r+1 and the AXPYs of round r, then ONE barrier -- the
+  // partial dots of r+1 are complete for the next iteration, everybody is done with the stage of round r (refilled at
+  // once) and with the partial-dot buffer the iteration after next overwrites.  Half the barriers of the straight
+  // dot / barrier / AXPY / barrier form, and the shared-memory sweep of one round overlaps the shuffle / tree-sum
+  // latency of the other.
+  auto dots = [&](int round) {
     const int s = (round - r0) % ST_NSTAGE;
     const unsigned parity = (unsigned)(((round - r0) / ST_NSTAGE) & 1);
     const double* sb = stage + (size_t)s * ST_STAGE;
+    double* ws = wsum + (size_t)((round - r0) & 1) * ST_CPR * ST_WARPS;
     const int e0 = rent(round), ne = rent(round + 1) - e0;
     mbar_wait(full + s, parity);
-    // ---- partial dots w_i . y
-    for (int j = 0; j < ne; ++j) {
+    if (a.probe) return;
+    // two columns at a time (a round of a large factor is a long and a short column): two independent chains of
+    // LDS -> DFMA -> shuffles per thread instead of one -- the kernel is bound by instruction latency at 16 warps per SM
+    int j = 0;
+    for (; j + 1 < ne; j += 2) {
+      const SymtriEnt ea = ent(e0 + j), eb = ent(e0 + j + 1);
+      const double* ca = sb + ea.off;
+      const double* cb = sb + eb.off;
+      double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+      for (int q = 0; q < ST_Q; ++q) {
+        const int row = 2 * tid + 2 * ST_THREADS * q;
+        if (row < ea.len) {
+          const double2 v = *reinterpret_cast<const double2*>(ca + row);
+          a0 = fma(v.x, yv[q].x, a0);
+          a1 = fma(v.y, yv[q].y, a1);
+        }
+        if (row < eb.len) {
+          const double2 v = *reinterpret_cast<const double2*>(cb + row);
+          b0 = fma(v.x, yv[q].x, b0);
+          b1 = fma(v.y, yv[q].y, b1);
+        }
+      }
+      double pa = a0 + a1, pb = b0 + b1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        pa += __shfl_xor_sync(0xffffffffu, pa, o);
+        pb += __shfl_xor_sync(0xffffffffu, pb, o);
+      }
+      if (lane == 0) { ws[j * ST_WARPS + warp] = pa; ws[(j + 1) * ST_WARPS + warp] = pb; }
+    }
+    for (; j < ne; ++j) {
       const SymtriEnt en = ent(e0 + j);
       const double* col = sb + en.off;
       double p0 = 0.0, p1 = 0.0;
@@ -154,27 +199,53 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
         }
       }
       const double p = warp_sum(p0 + p1);
-      if (lane == 0) wsum[j * ST_WARPS + warp] = p;
+      if (lane == 0) ws[j * ST_WARPS + warp] = p;
     }
-    __syncthreads();
-    // ---- x += w_i * t_i
-    for (int j = 0; j < ne; ++j) {
+  };
+  auto tree = [&](const double* ws, int j) {        // sum of the 16 warp partials of column j: the same fixed tree in every thread
+    const double2* wp = reinterpret_cast<const double2*>(ws + j * ST_WARPS);
+    double2 part[ST_WARPS / 2];
+#pragma unroll
+    for (int w = 0; w < ST_WARPS / 2; ++w) part[w] = wp[w];              // broadcast LDS.128, all independent
+#pragma unroll
+    for (int w = 0; w < ST_WARPS / 2; ++w) part[w].x += part[w].y;
+#pragma unroll
+    for (int st = ST_WARPS / 4; st >= 1; st >>= 1)
+#pragma unroll
+      for (int w = 0; w < st; ++w) part[w].x += part[w + st].x;
+    return part[0].x;
+  };
+  auto axpys = [&](int round) {
+    const int s = (round - r0) % ST_NSTAGE;
+    const double* sb = stage + (size_t)s * ST_STAGE;
+    const double* ws = wsum + (size_t)((round - r0) & 1) * ST_CPR * ST_WARPS;
+    const int e0 = rent(round), ne = rent(round + 1) - e0;
+    if (a.probe) return;
+    int j = 0;
+    for (; j + 1 < ne; j += 2) {                      // two columns at a time, accumulated in column order
+      const SymtriEnt ea = ent(e0 + j), eb = ent(e0 + j + 1);
+      const double* ca = sb + ea.off;
+      const double* cb = sb + eb.off;
+      const double ta = tree(ws, j), tb = tree(ws, j + 1);
+#pragma unroll
+      for (int q = 0; q < ST_Q; ++q) {
+        const int row = 2 * tid + 2 * ST_THREADS * q;
+        if (row < ea.len) {
+          const double2 v = *reinterpret_cast<const double2*>(ca + row);
+          acc[q].x = fma(v.x, ta, acc[q].x);
+          acc[q].y = fma(v.y, ta, acc[q].y);
+        }
+        if (row < eb.len) {
+          const double2 v = *reinterpret_cast<const double2*>(cb + row);
+          acc[q].x = fma(v.x, tb, acc[q].x);
+          acc[q].y = fma(v.y, tb, acc[q].y);
+        }
+      }
+    }
+    for (; j < ne; ++j) {
       const SymtriEnt en = ent(e0 + j);
       const double* col = sb + en.off;
-      double t;
-      {
-        const double2* wp = reinterpret_cast<const double2*>(wsum + j * ST_WARPS);
-        double2 part[ST_WARPS / 2];
-#pragma unroll
-        for (int w = 0; w < ST_WARPS / 2; ++w) part[w] = wp[w];              // broadcast LDS.128, all independent
-#pragma unroll
-        for (int w = 0; w < ST_WARPS / 2; ++w) part[w].x += part[w].y;
-#pragma unroll
-        for (int st = ST_WARPS / 4; st >= 1; st >>= 1)                         // the same fixed tree in every thread
-#pragma unroll
-          for (int w = 0; w < st; ++w) part[w].x += part[w + st].x;
-        t = part[0].x;
-      }
+      const double t = tree(ws, j);
 #pragma unroll
       for (int q = 0; q < ST_Q; ++q) {
         const int row = 2 * tid + 2 * ST_THREADS * q;
@@ -185,7 +256,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) symtri_kernel(SymtriArgs a) {
         }
       }
     }
-    __syncthreads();                              // everybody is done with stage s and with wsum
+  };
+  if (r0 < r1) {
+    dots(r0);
+    __syncthreads();
+  }
+  for (int round = r0; round < r1; ++round) {
+    if (round + 1 < r1) dots(round + 1);
+    axpys(round);
+    __syncthreads();
     if (tid == 0 && round + ST_NSTAGE < r1) issue(round + ST_NSTAGE);
   }
   double* xp = a.xpart + (size_t)blockIdx.x * a.kpad;
