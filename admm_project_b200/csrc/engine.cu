@@ -903,8 +903,16 @@ static void potrf_lookahead(admm_b200_handle* h, int64_t k, double* A, int64_t l
           caps(rem3, K1, cb, ci);                                    // the inverse row riding beside it is row P+1
           bo.max_ctas = cb;
         }
-        if (!probe_nobulk && rem3 > 0)
-          gemm(h, 0, 1, rem3, rem3, wb, -1.0, A + K3 + K0 * lda, lda, A + K3 + K0 * lda, lda, 1.0, A + K3 + K3 * lda, lda, bo);
+        if (!probe_nobulk && rem3 > 0) {
+          // the rank-512 update in K pieces (ADMM_B200_BULK_PIECES): shorter-lived background CTAs free SMs for the chain sooner
+          static const int pieces = getenv("ADMM_B200_BULK_PIECES") ? std::max(1, atoi(getenv("ADMM_B200_BULK_PIECES"))) : 1;
+          const int64_t step = round_up((wb + pieces - 1) / pieces, 16);
+          for (int64_t kk = 0; kk < wb; kk += step) {
+            const int64_t kw = std::min(step, wb - kk);
+            const double* Lp = A + K3 + (K0 + kk) * lda;
+            gemm(h, 0, 1, rem3, rem3, kw, -1.0, Lp, lda, Lp, lda, 1.0, A + K3 + K3 * lda, lda, bo);
+          }
+        }
         ADMM_CUDA(cudaEventRecord(ev(4, P), sC));
       }
     } else {

@@ -39,9 +39,8 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
     m = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
     for name, env in (("full (default: no SM reserve)", {}), ("look-ahead depth 1", {"ADMM_B200_CHOL_DEPTH1": "1"}),
-                      ("riding inverse unsplit (K chunk off)", {"ADMM_B200_INV_KCHUNK": "1000000"}),
-                      ("riding inverse, K chunk 512", {"ADMM_B200_INV_KCHUNK": "512"}),
-                      ("riding inverse, K chunk 2048", {"ADMM_B200_INV_KCHUNK": "2048"}),
+                      ("bulk in 2 K pieces", {"ADMM_B200_BULK_PIECES": "2"}), ("bulk in 4 K pieces", {"ADMM_B200_BULK_PIECES": "4"}),
+                      ("bulk in 2 K pieces, inverse K chunk 512", {"ADMM_B200_BULK_PIECES": "2", "ADMM_B200_INV_KCHUNK": "512"}),
                       ("no riding inverse", {"ADMM_B200_NO_INV_OVERLAP": "1"}),
                       ("chain only (no bulk, no riding inverse)", {"ADMM_B200_NO_INV_OVERLAP": "1", "ADMM_B200_CHOL_PROBE_NOBULK": "1"}),
                       ("chain + riding inverse, no bulk", {"ADMM_B200_CHOL_PROBE_NOBULK": "1"}),
