@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <sched.h>
 #include <thread>
 #if defined(__x86_64__)
 #include <emmintrin.h>
@@ -104,6 +105,7 @@ struct admm_b200_handle {
   cudaEvent_t pin_ev[kPinBufs] = {nullptr, nullptr, nullptr};
   size_t pin_cap = 0;                 // doubles per buffer
   int pin_next = 0;
+  bool pin_failed = false;            // pinned allocation refused once: uploads go through the driver's own staging from then on
   cudaEvent_t ev_la[2] = {nullptr, nullptr};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evp[4] = {nullptr, nullptr, nullptr, nullptr};
   double phase_ms[4] = {0, 0, 0, 0};  // gram (+Dts), cholesky, inverse factor (+transpose), total
@@ -260,17 +262,36 @@ static void upload_rows(admm_b200_handle* h, double* dst, int64_t ld, const doub
     return;
   }
   constexpr size_t kBufDoubles = (size_t)16 << 20;          // 128 MB per buffer
-  if (!h->pin_buf[0]) {
-    for (int b = 0; b < admm_b200_handle::kPinBufs; ++b) {
-      ADMM_CUDA(cudaHostAlloc((void**)&h->pin_buf[b], kBufDoubles * 8, cudaHostAllocDefault));
-      ADMM_CUDA(cudaEventCreateWithFlags(&h->pin_ev[b], cudaEventDisableTiming));
+  if (!h->pin_buf[0] && !h->pin_failed) {
+    for (int b = 0; b < admm_b200_handle::kPinBufs && !h->pin_failed; ++b) {
+      if (cudaHostAlloc((void**)&h->pin_buf[b], kBufDoubles * 8, cudaHostAllocDefault) != cudaSuccess ||
+          cudaEventCreateWithFlags(&h->pin_ev[b], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();                         // no pinned memory to be had (locked-memory limit): the driver's path still works
+        h->pin_failed = true;
+      }
     }
-    h->pin_cap = kBufDoubles;
+    if (h->pin_failed) {
+      for (int b = 0; b < admm_b200_handle::kPinBufs; ++b) {
+        if (h->pin_buf[b]) cudaFreeHost(h->pin_buf[b]);
+        if (h->pin_ev[b]) cudaEventDestroy(h->pin_ev[b]);
+        h->pin_buf[b] = nullptr; h->pin_ev[b] = nullptr;
+      }
+    } else {
+      h->pin_cap = kBufDoubles;
+    }
+  }
+  if (h->pin_failed || (size_t)n > h->pin_cap) {
+    ADMM_CUDA(cudaMemcpy2DAsync(dst + r0, (size_t)ld * 8, D + r0, (size_t)ldD * 8, (size_t)rows * 8, (size_t)n,
+                                cudaMemcpyHostToDevice, stream));
+    return;
   }
   int64_t sub = std::max<int64_t>(1, (int64_t)(h->pin_cap / (size_t)n));
   if (sub >= 512) sub = sub / 512 * 512;                     // whole pages per column segment
-  ADMM_REQUIRE((size_t)n <= h->pin_cap, ADMM_B200_ERR_UNSUPPORTED, "upload: matrix has too many columns for the staging buffer");
-  const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+  unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+  {
+    cpu_set_t cpus;                                  // the cores this process may run on (containers, taskset)
+    if (sched_getaffinity(0, sizeof(cpus), &cpus) == 0 && CPU_COUNT(&cpus) > 0) hw = std::max(2u, (unsigned)CPU_COUNT(&cpus));
+  }
   const int nthreads = (int)std::min<unsigned>(8u, std::max(2u, hw / (2u * (unsigned)std::max(1, h->nranks))));
   for (int64_t s0 = 0; s0 < rows; s0 += sub) {
     const int64_t sr = std::min(sub, rows - s0);
