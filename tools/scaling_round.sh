@@ -1,3 +1,4 @@
+# One 8-GPU box: bench.py at N = 8, 4, 2, 1 back to back (the curve of profiles/r02_scaling.txt) and the two-rank parity cases.
 set -u
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
