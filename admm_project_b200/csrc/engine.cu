@@ -1290,7 +1290,10 @@ static SymtriPlan* symtri_plan(admm_b200_handle* h, int64_t k, int64_t c_lo, int
 
 static bool symtri_ok(const admm_b200_handle* h, int64_t k, int64_t ld, const double* WT) {
   static const bool off = getenv("ADMM_B200_NO_SYMTRI") != nullptr;
-  return !off && k <= ST_MAXK && k >= 2 && (ld % 2 == 0) && (((uintptr_t)WT & 15) == 0);
+  // small factors stay on the two coldot passes: at k = 1500 (C1) the one-pass kernel's fixed cost (148 CTAs each loading
+  // y and writing a partial x) makes the iteration 90 us against 79 us
+  static const int64_t mink = getenv("ADMM_B200_SYMTRI_MINK") ? atoll(getenv("ADMM_B200_SYMTRI_MINK")) : 2048;
+  return !off && k <= ST_MAXK && k >= std::max<int64_t>(2, mink) && (ld % 2 == 0) && (((uintptr_t)WT & 15) == 0);
 }
 
 // x = WT * (WT' * b) = W'(W b) in one pass over WT (upper triangular, columns contiguous).  shard: this rank
