@@ -74,6 +74,8 @@ SYMBOLS = {
     "admm_b200_get_unique_id": (_int, [_vp]),
     "admm_b200_comm_init": (_int, [_vp, _int, _int, _vp]),
     "admm_b200_comm_destroy": (_int, [_vp]),
+    "admm_b200_comm_ipc_export": (_int, [_vp, _int, _int, _vp]),
+    "admm_b200_comm_ipc_attach": (_int, [_vp, _vp]),
     "admm_b200_allreduce": (_int, [_vp, _vp, _i64]),
     "admm_b200_set_lambda": (_int, [_vp, _d]),
     "admm_b200_set_init": (_int, [_vp, _vp, _vp, _vp]),

@@ -1857,14 +1857,15 @@ static void p2p_teardown(admm_b200_handle* h) {
   P = P2PState();
 }
 
-// Called by every rank right after the NCCL communicator exists.  Allocates and zeroes this rank's mailbox,
-// exchanges the CUDA IPC handles through ncclAllGather and maps every peer's mailbox.  When the peers cannot
-// be mapped (no peer access between the devices, IPC disabled in the container, ADMM_B200_NO_P2P=1) the small
-// allreduces stay on NCCL; admm_b200_comm_info reports which transport is in use.
-static void p2p_setup(admm_b200_handle* h) {
+struct P2PSlot { cudaIpcMemHandle_t hd; int ok; int pad[3]; };
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+
+// Allocates and zeroes this rank's mailbox and exports its CUDA IPC handle (ok = 0 when IPC is unavailable or
+// ADMM_B200_NO_P2P=1).  The stream is drained before returning: a peer may store into the mailbox as soon as
+// it has the handle.
+static P2PSlot p2p_alloc_local(admm_b200_handle* h) {
   P2PState& P = h->p2p;
   const int R = h->nranks;
-  if (R < 2 || R > P2P_MAXRANKS) return;
   p2p_teardown(h);               // a single-rank local mailbox (ensure_mailbox) gives way to the mapped ones
   const bool want = !getenv("ADMM_B200_NO_P2P");
   P.bytes = p2p_mailbox_bytes(R);
@@ -1877,25 +1878,18 @@ static void p2p_setup(admm_b200_handle* h) {
   P.dev.ticket = (unsigned*)((char*)ctr + 8);
   P.dev.err = (int*)((char*)ctr + 16);
   P.dev.rank = h->rank; P.dev.nranks = R; P.dev.cap = P2P_CAP;
-  // handle exchange: [R][64 bytes + 1 flag byte]
-  struct Slot { cudaIpcMemHandle_t hd; int ok; int pad[3]; };
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  Slot mine{};
+  ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  P2PSlot mine{};
   mine.ok = 0;
   if (want && cudaIpcGetMemHandle(&mine.hd, P.local) == cudaSuccess) mine.ok = 1;
   else cudaGetLastError();
-  Slot* dall = nullptr;
-  ADMM_CUDA(cudaMalloc(&dall, sizeof(Slot) * (R + 1)));
-  std::vector<Slot> all(R);
-  try {
-    ADMM_CUDA(cudaMemcpyAsync(dall + R, &mine, sizeof(Slot), cudaMemcpyHostToDevice, h->stream));
-    ADMM_NCCL(g_nccl.AllGather(dall + R, dall, sizeof(Slot), /*ncclInt8*/ 0, h->comm, h->stream));
-    ADMM_CUDA(cudaMemcpyAsync(all.data(), dall, sizeof(Slot) * R, cudaMemcpyDeviceToHost, h->stream));
-    ADMM_CUDA(cudaStreamSynchronize(h->stream));
-  } catch (...) {
-    cudaFree(dall);
-    throw;
-  }
+  return mine;
+}
+
+// Maps every peer's mailbox into this process; false when a handle is missing or cannot be opened.
+static bool p2p_map_peers(admm_b200_handle* h, const P2PSlot* all) {
+  P2PState& P = h->p2p;
+  const int R = h->nranks;
   int ok = 1;
   for (int r = 0; r < R; ++r) ok &= all[r].ok;
   for (int r = 0; r < R && ok; ++r) {
@@ -1909,6 +1903,32 @@ static void p2p_setup(admm_b200_handle* h) {
     P.opened[r] = ptr;
     P.dev.mail[r] = (unsigned char*)ptr;
   }
+  return ok != 0;
+}
+
+// Called by every rank right after the NCCL communicator exists: the IPC handles of the mailboxes travel through
+// ncclAllGather.  When the peers cannot be mapped (no peer access between the devices, IPC disabled in the
+// container, ADMM_B200_NO_P2P=1) the small allreduces stay on NCCL; admm_b200_comm_info reports which transport
+// is in use.
+static void p2p_setup(admm_b200_handle* h) {
+  P2PState& P = h->p2p;
+  const int R = h->nranks;
+  if (R < 2 || R > P2P_MAXRANKS) return;
+  const bool want = !getenv("ADMM_B200_NO_P2P");
+  P2PSlot mine = p2p_alloc_local(h);
+  P2PSlot* dall = nullptr;
+  ADMM_CUDA(cudaMalloc(&dall, sizeof(P2PSlot) * (R + 1)));
+  std::vector<P2PSlot> all(R);
+  try {
+    ADMM_CUDA(cudaMemcpyAsync(dall + R, &mine, sizeof(P2PSlot), cudaMemcpyHostToDevice, h->stream));
+    ADMM_NCCL(g_nccl.AllGather(dall + R, dall, sizeof(P2PSlot), /*ncclInt8*/ 0, h->comm, h->stream));
+    ADMM_CUDA(cudaMemcpyAsync(all.data(), dall, sizeof(P2PSlot) * R, cudaMemcpyDeviceToHost, h->stream));
+    ADMM_CUDA(cudaStreamSynchronize(h->stream));
+  } catch (...) {
+    cudaFree(dall);
+    throw;
+  }
+  const int ok = p2p_map_peers(h, all.data()) ? 1 : 0;
   // every rank must agree on the transport: min over ranks of `ok` (1 double through NCCL)
   double* dok = (double*)dall;
   double hok = ok;
@@ -1957,6 +1977,20 @@ static void allreduce_sum(admm_b200_handle* h, double* buf, int64_t count, const
     p2p_wait_sum_kernel<<<grid, 256, 0, h->stream>>>(h->p2p.dev, buf, count, done, h->p2p.dev.ticket + 1);
     ADMM_CUDA(cudaGetLastError());
     h->launches += 2;
+    return;
+  }
+  if (!h->comm) {
+    // mailbox-only transport (admm_b200_comm_init_ipc): a large message goes through the plain slots in pieces
+    ADMM_REQUIRE(h->p2p.ready, ADMM_B200_ERR_COMM, "allreduce: the handle has neither a communicator nor mapped mailboxes");
+    for (int64_t off = 0; off < count; off += P2P_CAP) {
+      const int64_t cnt = std::min<int64_t>(P2P_CAP, count - off);
+      const int grid = (int)((cnt + 255) / 256);
+      p2p_push_kernel<<<std::min(grid, 32), 256, 0, h->stream>>>(h->p2p.dev, buf + off, cnt, done);
+      ADMM_CUDA(cudaGetLastError());
+      p2p_wait_sum_kernel<<<grid, 256, 0, h->stream>>>(h->p2p.dev, buf + off, cnt, done, h->p2p.dev.ticket + 1);
+      ADMM_CUDA(cudaGetLastError());
+      h->launches += 2;
+    }
     return;
   }
   ADMM_NCCL(g_nccl.AllReduce(buf, buf, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->comm, h->stream));
@@ -3540,6 +3574,41 @@ int admm_b200_comm_init(admm_b200_handle* h, int rank, int nranks, const void* u
   h->rank = rank;
   h->nranks = nranks;
   p2p_setup(h);     // also performs the first collectives, so NCCL's lazy channel setup is not inside a timed setup
+  ADMM_API_END
+}
+
+int admm_b200_comm_ipc_export(admm_b200_handle* h, int rank, int nranks, void* out_handle64) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(nranks >= 2 && nranks <= admmb200::P2P_MAXRANKS && rank >= 0 && rank < nranks && out_handle64, ADMM_B200_ERR_INVALID,
+               "comm_ipc_export: bad arguments (2 <= nranks <= %d)", admmb200::P2P_MAXRANKS);
+  comm_destroy(h);
+  h->rank = rank;
+  h->nranks = nranks;
+  const P2PSlot mine = p2p_alloc_local(h);
+  if (!mine.ok) {
+    comm_destroy(h);
+    ADMM_REQUIRE(false, ADMM_B200_ERR_COMM, "comm_ipc_export: CUDA IPC is not available for the mailbox (or ADMM_B200_NO_P2P is set)");
+  }
+  memcpy(out_handle64, &mine.hd, 64);
+  ADMM_API_END
+}
+
+int admm_b200_comm_ipc_attach(admm_b200_handle* h, const void* handles) {
+  ADMM_API_BEGIN
+  check_handle(h);
+  ADMM_REQUIRE(handles && h->nranks >= 2 && h->p2p.local && !h->comm && !h->p2p.ready, ADMM_B200_ERR_STATE,
+               "comm_ipc_attach: call admm_b200_comm_ipc_export on this handle first");
+  std::vector<P2PSlot> all(h->nranks);
+  for (int r = 0; r < h->nranks; ++r) {
+    memcpy(&all[r].hd, (const char*)handles + 64 * r, 64);
+    all[r].ok = 1;
+  }
+  if (!p2p_map_peers(h, all.data())) {
+    comm_destroy(h);
+    ADMM_REQUIRE(false, ADMM_B200_ERR_COMM, "comm_ipc_attach: a peer's mailbox could not be mapped (cudaIpcOpenMemHandle)");
+  }
+  h->p2p.ready = true;
   ADMM_API_END
 }
 

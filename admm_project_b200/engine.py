@@ -172,6 +172,21 @@ class Engine:
         L.check(self._lib.admm_b200_comm_init(self._h, int(rank), int(nranks), buf))
         self.rank, self.nranks = int(rank), int(nranks)
 
+    def comm_ipc_export(self, rank, nranks):
+        """Mailbox-only transport, step 1: allocate this rank's mailbox, return its 64-byte CUDA IPC handle."""
+        buf = (C.c_char * 64)()
+        L.check(self._lib.admm_b200_comm_ipc_export(self._h, int(rank), int(nranks), buf))
+        self.rank, self.nranks = int(rank), int(nranks)
+        return bytes(buf.raw)
+
+    def comm_ipc_attach(self, handles):
+        """Step 2: map every rank's mailbox (handles in rank order)."""
+        blob = b"".join(bytes(hd) for hd in handles)
+        if len(blob) != 64 * self.nranks:
+            raise ValueError("comm_ipc_attach: need one 64-byte handle per rank")
+        buf = (C.c_char * len(blob)).from_buffer_copy(blob)
+        L.check(self._lib.admm_b200_comm_ipc_attach(self._h, buf))
+
     def comm_destroy(self):
         L.check(self._lib.admm_b200_comm_destroy(self._h))
         self.rank, self.nranks = 0, 1

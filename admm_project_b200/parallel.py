@@ -30,15 +30,38 @@ def row_range(m, rank, world):
     return lo, lo + int(sizes[rank])
 
 
-def attach_comm(engine):
-    """Create the engine's NCCL communicator over the default torch.distributed group: rank 0
-    makes the id, everybody receives it (works over gloo or nccl)."""
+def _device_key(engine):
+    """(host, GPU uuid) of the engine's device: two ranks with the same key share one GPU."""
+    import socket
     import torch
+    try:
+        uuid = str(torch.cuda.get_device_properties(engine.device).uuid)
+    except Exception:  # older torch without .uuid
+        uuid = "cuda:%d" % engine.device
+    return socket.gethostname(), uuid
+
+
+def attach_comm(engine):
+    """Connect the engine to the ranks of the default torch.distributed group (which only carries the bootstrap
+    bytes, over gloo or nccl).  One rank per GPU: rank 0 makes the NCCL id, everybody receives it
+    (admm_b200_comm_init: NCCL for the Gram, peer mailboxes for the per-iteration messages).  When several ranks
+    SHARE a device -- NCCL refuses that -- or ADMM_B200_TRANSPORT=ipc is set, the mailbox-only transport is used:
+    the ranks exchange the CUDA IPC handles of their mailboxes here (admm_b200_comm_ipc_export / _attach)."""
+    import os
     import torch.distributed as dist
     rank, world = dist_info()
     if world == 1:
         return rank, world
     if engine.nranks == world and engine.rank == rank:
+        return rank, world
+    keys = [None] * world
+    dist.all_gather_object(keys, _device_key(engine))
+    shared = len(set(keys)) < world
+    if shared or os.environ.get("ADMM_B200_TRANSPORT", "") == "ipc":
+        handles = [None] * world
+        dist.all_gather_object(handles, engine.comm_ipc_export(rank, world))
+        engine.comm_ipc_attach(handles)
+        dist.barrier()      # nobody stores into a mailbox before every rank has mapped all of them
         return rank, world
     payload = [engine.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(payload, src=0)

@@ -202,6 +202,14 @@ int admm_b200_setup_model(admm_b200_handle* h, int64_t m, int64_t n, const doubl
 int admm_b200_get_unique_id(void* out128);
 int admm_b200_comm_init(admm_b200_handle* h, int rank, int nranks, const void* unique_id128);
 int admm_b200_comm_destroy(admm_b200_handle* h);
+/* The same worker pool WITHOUT NCCL (mailbox-only transport): every rank exports the CUDA IPC handle of its
+ * mailbox (64 bytes), the host side all-gathers the handles in rank order (nranks x 64 bytes) and every rank
+ * attaches them.  All sums over ranks -- the Gram in pieces of 32768 doubles too -- then go through the mailboxes.
+ * It is what lets several ranks share ONE device (NCCL refuses two ranks on a GPU): the reference's parfor runs
+ * its slices on however many workers the pool has (admm.m:343-408), and the 2-rank parity tests run on a 1-GPU
+ * box this way (the ranks' kernels are time-sliced by the driver; the waits are bounded, p2p.cuh).  2..8 ranks. */
+int admm_b200_comm_ipc_export(admm_b200_handle* h, int rank, int nranks, void* out_handle64);
+int admm_b200_comm_ipc_attach(admm_b200_handle* h, const void* handles_nranks_x_64);
 /* comm_init also maps every peer's MAILBOX (CUDA IPC over NVLink): messages of up to 32768 doubles -- the one
  * exchange per iteration of the row-sharded loops -- are summed by a one-shot peer-memory allreduce inside the
  * engine's own kernels (p2p.cuh) instead of a library collective; larger ones (the n x n Gram) use ncclAllReduce.

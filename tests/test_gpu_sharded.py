@@ -1,5 +1,8 @@
-"""Row-sharded solvers on 2 GPUs (skipped on a 1-GPU box): the sharded run must reproduce the
-SERIAL oracle -- same steps, iterates within 1e-9."""
+"""Row-sharded solvers with 2 ranks: the sharded run must reproduce the SERIAL oracle -- same steps, iterates
+within 1e-9.  On a box with 2 GPUs: one rank per GPU (NCCL for the Gram, peer mailboxes over
+NVLink per iteration).  On a 1-GPU box the two ranks SHARE the device through the mailbox-only transport
+(admm_b200_comm_ipc_export / _attach): same kernels, same in-kernel exchange, the driver time-slices the two
+processes -- slow, but it is the whole sharded data path."""
 import json
 import os
 import subprocess
@@ -16,8 +19,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
                                           ("svmbatch", ""), ("svm", "persist"), ("svmbatch", "persist")])
 def test_two_rank_run_matches_serial_oracle(problem, fast):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < 1:
+        pytest.skip("needs a GPU")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "run_sharded.py"), "--check",
            "--problem", problem, "--rows", "5001", "--cols", "64"] + (["--fast", fast] if fast else [])

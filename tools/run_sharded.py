@@ -29,11 +29,16 @@ def main():
     ap.add_argument("--fast", default="", help="'' | weak | strong: fast / accelerated ADMM variant")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
+    ndev = torch.cuda.device_count()
+    dev = local % ndev                 # more ranks than GPUs: ranks share a device (mailbox-only transport, parallel.attach_comm)
+    torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    eng = Engine(local)
-    out = {"problem": args.problem, "world": world, "rows": args.rows, "cols": args.cols}
+        if world > ndev:
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    eng = Engine(dev)
+    out = {"problem": args.problem, "world": world, "rows": args.rows, "cols": args.cols, "devices": min(world, ndev)}
     if args.problem == "lasso":
         # row-sharded setup (admm_b200_setup_lasso_sharded): every rank hands the FULL host matrix to lasso(), which
         # keeps its own rows; the result must be the serial oracle's on every rank
