@@ -8,7 +8,7 @@ import numpy as np
 from ..engine import DeviceMatrix, Engine, acquire_engine
 from ..errorcheck import MatlabError, errorcheck
 from ..getproxops import getproxops
-from .unwrappedadmm import unwrappedadmm
+from .unwrappedadmm import check_single_column, unwrappedadmm
 from ..parallel import attach_comm, gather_rows, row_range, shared_draw
 
 
@@ -27,6 +27,7 @@ def linearsvm(D, ell, C, options, engine=None):
         m = D.shape[0]
     else:
         m = int(getattr(D, "m_total", D.shape[0]))
+    check_single_column(m, D.shape[1])      # raised by admm.m at the end of the reference's call chain; same text, before device work
     loss = options.get("lossfunction", "hinge")                             # :154-158
     eng = acquire_engine(engine, options)
     args = {"engine": eng, "D": D, "ell": ell, "C": float(C), "lossfunction": loss}   # :210-214
@@ -65,6 +66,7 @@ def linearsvm_onevsall(D, ELL, C, options, engine=None):
         raise L.EngineError(L.ERR_UNSUPPORTED, "linearsvm_onevsall: the class batch is built for the hinge loss")
     m, n = D.shape
     K = ELL.shape[1]
+    check_single_column(m, n)
     eng = acquire_engine(engine, options)
     # Under torch.distributed every rank keeps its row block of D / ELL (errorcheck.m:249-259) and the batch
     # exchanges ONE allreduce of K x [D'r ; scalars] per iteration.  Rank 0 draws the initial iterates for all.

@@ -23,6 +23,9 @@ def totalvariation(s, lam, options, engine=None):
         raise MatlabError("Given options is not a struct! At least pass empty struct!")
     options = dict(options)
     n = s.shape[0]
+    if n == 1:      # D = spdiags(.., 1, 1) is a scalar to admm.m:113-161 and totalvariation.m passes no options.nA
+        raise MatlabError("Given scalar as matrix A with no number of columnsnA specified in options struct; cannot "
+                          "infer nA - please specify nA in options!")
     eng = acquire_engine(engine, options)
     # :127-131 build D = spdiags([1 -1],0:1,n,n), Dt, DtD, Id; the engine keeps them implicit
     xmin, zmin, _ = getproxops("TotalVariation", {"engine": eng, "s": s, "lambda": float(lam)})   # :148

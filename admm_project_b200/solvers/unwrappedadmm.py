@@ -18,6 +18,16 @@ from ..getproxops import EngineProx
 from ..parallel import shared_draw
 
 
+def check_single_column(m, n):
+    """unwrappedadmm.m:81-82 hands A = D, At = D' to admm() WITHOUT options.nA, and admm.m:113-201 cannot infer nA from
+    a single column: a one-feature D is a reference error, not a supported shape."""
+    if n == 1:
+        raise MatlabError("Given scalar as matrix A with no number of columnsnA specified in options struct; cannot "
+                          "infer nA - please specify nA in options!" if m == 1 else
+                          "Number of rows in At (A transpose) do not match number of columns in A, in constraint "
+                          "Ax + Bz = c")
+
+
 def unwrappedadmm(zming, D, options):
     t0 = time.perf_counter()
     if not isinstance(options, dict):
@@ -31,6 +41,7 @@ def unwrappedadmm(zming, D, options):
         m, n = int(getattr(D, "m_total", D.shape[0])), D.shape[1]
     else:
         m, n = np.asarray(D).shape                                          # :43
+    check_single_column(m, n)
     if options.get("parallel") in ("xminf", "zming", "both"):               # :45-74
         workers = max(int(options.get("workers", eng.nranks)), 1)
         slices = options.get("slices", 0)

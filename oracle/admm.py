@@ -58,6 +58,8 @@ def _shape2(a):
 def _as_operator(a):
     """``A = @(v) A*v`` (admm.m:120,164,204) for a scalar, dense or sparse matrix."""
     if isinstance(a, (int, float, np.integer, np.floating)) or getattr(a, "shape", None) in ((), (1, 1), (1,)):
+        if hasattr(a, "toarray"):      # a 1 x 1 sparse matrix (total variation with n = 1) is a scalar to MATLAB
+            a = a.toarray()
         s = float(np.asarray(a).reshape(-1)[0]) if hasattr(a, "shape") else float(a)
         return lambda v: s * v
     return lambda v: a @ v

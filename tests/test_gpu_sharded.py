@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.parametrize("problem,fast", [("svm", ""), ("huber", ""), ("lad", ""), ("huber", "weak"), ("lad", "strong"),
                                           ("huber", "onepass"), ("svm", "onepass"), ("lasso", ""), ("lassopath", ""),
-                                          ("svmbatch", ""), ("svm", "persist"), ("svmbatch", "persist")])
+                                          ("svmbatch", ""), ("svm", "persist"), ("svmbatch", "persist"), ("lasso", "wide")])
 def test_two_rank_run_matches_serial_oracle(problem, fast):
     import torch
     if torch.cuda.device_count() < 1:
@@ -28,6 +28,9 @@ def test_two_rank_run_matches_serial_oracle(problem, fast):
     if fast == "onepass":          # the single-pass tile kernel (csrc/onepass.cuh) on every rank's row block
         cmd = cmd[:-2]
         env["ADMM_B200_FORCE_ONEPASS"] = "1"
+    if fast == "wide":             # a 208 x 200 Gram (41600 doubles) is larger than a mailbox slot: NCCL on 2 GPUs, two pieces
+        cmd = cmd[:-2]             # through the mailboxes when the ranks share a device
+        cmd[cmd.index("--rows") + 1], cmd[cmd.index("--cols") + 1] = "3001", "200"
     if fast == "persist":          # the persistent kernel with its in-kernel mailbox exchange (csrc/persist.cuh)
         cmd[cmd.index("--rows") + 1], cmd[cmd.index("--cols") + 1] = "20001", "160"
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
@@ -35,4 +38,4 @@ def test_two_rank_run_matches_serial_oracle(problem, fast):
     assert line, p.stdout[-2000:] + p.stderr[-2000:]
     out = json.loads(line[-1][8:])
     assert out["ok"], out
-    assert out["zopt_len"] == (20001 if fast == "persist" else 5001)
+    assert out["zopt_len"] == {"persist": 20001, "wide": 3001}.get(fast, 5001)

@@ -18,6 +18,9 @@ CASES = [
     ("lad", lambda S: S.lad(D, np.ones(3), {}), "do not match size of s"),
     ("linearsvm", lambda S: S.linearsvm(D, np.ones(3), 0.5, {}), "Product ell\\*D is not possible"),
     ("linearsvm", lambda S: S.linearsvm(D, np.ones(4), -1.0, {}), "C is not a nonnegative number"),
+    ("linearsvm", lambda S: S.linearsvm(D[:, :1], np.array([1.0, -1, 1, -1]), 0.5, {}), "Number of rows in At"),
+    ("linearsvm", lambda S: S.linearsvm(np.ones((1, 1)), np.ones(1), 0.5, {}), "Given scalar as matrix A"),
+    ("totalvariation", lambda S: S.totalvariation(np.ones(1), 1.0, {}), "Given scalar as matrix A"),
     ("totalvariation", lambda S: S.totalvariation(np.ones(5), -2.0, {}), "lambda parameter is not a nonnegative number"),
     ("totalvariation", lambda S: S.totalvariation(np.ones((3, 3)), 1.0, {}), "Argument s is not a vector"),
     ("basispursuit", lambda S: S.basispursuit(np.eye(3), np.ones(3), {}), "Square matrix problem"),
