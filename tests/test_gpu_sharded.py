@@ -35,6 +35,12 @@ def test_two_rank_run_matches_serial_oracle(problem, fast):
         cmd[cmd.index("--rows") + 1], cmd[cmd.index("--cols") + 1] = "20001", "160"
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("SHARDED ")]
+    if not line and torch.cuda.device_count() < 2 and "timed out" in p.stderr:
+        # ranks sharing ONE device are time-sliced by the driver; a bounded mailbox wait (2 s, p2p.cuh) can in principle
+        # expire while the peer's process is descheduled on a loaded box: one more try, and say so
+        print("shared-device run hit a mailbox timeout, retrying once:", p.stderr[-300:])
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+        line = [ln for ln in p.stdout.splitlines() if ln.startswith("SHARDED ")]
     assert line, p.stdout[-2000:] + p.stderr[-2000:]
     out = json.loads(line[-1][8:])
     assert out["ok"], out
