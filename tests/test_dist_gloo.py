@@ -82,6 +82,45 @@ def _worker(rank, world, port, q):
         both = [None, None]
         dist.all_gather_object(both, x0)
         assert np.array_equal(both[0], both[1])
+        # transport choice of attach_comm (recording stand-in for the engine, no GPU): ranks on DIFFERENT devices get the
+        # NCCL id rank 0 made; ranks that SHARE a device exchange their mailbox handles in rank order instead
+        from admm_project_b200 import parallel
+
+        class FakeEngine:
+            def __init__(self, key):
+                self.rank, self.nranks, self.key, self.calls = 0, 1, key, []
+
+            def unique_id(self):
+                return bytes([7]) * 128
+
+            def comm_init(self, r, w, uid):
+                self.calls.append(("nccl", r, w, uid))
+                self.rank, self.nranks = r, w
+
+            def comm_ipc_export(self, r, w):
+                self.calls.append(("export", r, w))
+                self.rank, self.nranks = r, w
+                return bytes([r + 1]) * 64
+
+            def comm_ipc_attach(self, handles):
+                self.calls.append(("attach", list(handles)))
+        real_key = parallel._device_key
+        try:
+            parallel._device_key = lambda e: e.key
+            apart = FakeEngine(("host", "GPU-%d" % rank))
+            assert parallel.attach_comm(apart) == (rank, world)
+            assert apart.calls == [("nccl", rank, world, bytes([7]) * 128)]
+            assert parallel.attach_comm(apart) == (rank, world) and len(apart.calls) == 1      # already attached: no-op
+            shared = FakeEngine(("host", "GPU-0"))
+            assert parallel.attach_comm(shared) == (rank, world)
+            assert shared.calls == [("export", rank, world), ("attach", [bytes([1]) * 64, bytes([2]) * 64])]
+            os.environ["ADMM_B200_TRANSPORT"] = "ipc"                                            # forced, one rank per device
+            forced = FakeEngine(("host", "GPU-%d" % rank))
+            parallel.attach_comm(forced)
+            assert [c[0] for c in forced.calls] == ["export", "attach"]
+        finally:
+            parallel._device_key = real_key
+            os.environ.pop("ADMM_B200_TRANSPORT", None)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
