@@ -12,6 +12,12 @@
  *         admm_b200_mex('setup_quadratic', h, kind, P, q, r, rho, lb, ub)   quadraticprogram.m:210-216 (kind 9 = box, 8 = nonneg)
  *         admm_b200_mex('set_lambda', h, lambda)                   getProxOps.m:455
  *         admm_b200_mex('set_init', h, x0, z0, u0)                 admm.m:252-254 ([] = zeros)
+ *   id  = admm_b200_mex('unique_id')                               uint8(1,128), made by rank 0 (replaces the PCT pool, admm.m:343-408)
+ *         admm_b200_mex('comm_init', h, rank, nranks, id)          one MATLAB process per GPU; see solvers/b200_comm.m
+ *         admm_b200_mex('comm_destroy', h)
+ *   sl  = admm_b200_mex('slicemaker', len, workers)                errorcheck.m:249-259 (balanced row blocks)
+ *         admm_b200_mex('setup_lasso_sharded', h, Drows, srows, rho, m_total)
+ *         admm_b200_mex('setup_unwrapped', h, kind, Drows, auxrows, C, m_total)   (m_total optional: row-sharded form)
  *   res = admm_b200_mex('solve', h, opts)                          admm.m:496-767
  *   res = admm_b200_mex('solve_lasso_batch', h, opts, lambdas)
  *
@@ -164,10 +170,34 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     check(admm_b200_setup_lasso(get_handle(prhs[1]), (int64_t)mxGetM(prhs[2]), (int64_t)mxGetN(prhs[2]),
                                 dense(prhs[2], "D"), (int64_t)mxGetM(prhs[2]), dense(prhs[3], "s"),
                                 mxGetScalar(prhs[4]), ADMM_B200_XSOLVE_INVFACTOR));
-  } else if (!strcmp(cmd, "setup_unwrapped")) {          /* (h, kind, D, aux, C) */
+  } else if (!strcmp(cmd, "setup_unwrapped")) {          /* (h, kind, D, aux, C [, m_total]) */
     int64_t m = (int64_t)mxGetM(prhs[3]);
-    check(admm_b200_setup_unwrapped(get_handle(prhs[1]), (int32_t)mxGetScalar(prhs[2]), m, m, (int64_t)mxGetN(prhs[3]),
+    int64_t mt = nrhs > 6 ? (int64_t)mxGetScalar(prhs[6]) : m;      /* row-sharded: D holds this rank's rows of an mt-row matrix */
+    check(admm_b200_setup_unwrapped(get_handle(prhs[1]), (int32_t)mxGetScalar(prhs[2]), m, mt, (int64_t)mxGetN(prhs[3]),
                                     dense(prhs[3], "D"), m, dense(prhs[4], "ell/s"), nrhs > 5 ? mxGetScalar(prhs[5]) : 0.0));
+  } else if (!strcmp(cmd, "setup_lasso_sharded")) {      /* (h, Drows, srows, rho, m_total) */
+    int64_t m = (int64_t)mxGetM(prhs[2]);
+    check(admm_b200_setup_lasso_sharded(get_handle(prhs[1]), m, (int64_t)mxGetScalar(prhs[5]), (int64_t)mxGetN(prhs[2]),
+                                        dense(prhs[2], "D"), m, dense(prhs[3], "s"), mxGetScalar(prhs[4]),
+                                        ADMM_B200_XSOLVE_INVFACTOR));
+  } else if (!strcmp(cmd, "unique_id")) {                /* rank 0: the 128-byte id every rank needs for comm_init */
+    plhs[0] = mxCreateNumericMatrix(1, 128, mxUINT8_CLASS, mxREAL);
+    check(admm_b200_get_unique_id(mxGetData(plhs[0])));
+  } else if (!strcmp(cmd, "comm_init")) {                /* (h, rank, nranks, id) */
+    if (nrhs < 5 || mxGetNumberOfElements(prhs[4]) != 128 || mxGetClassID(prhs[4]) != mxUINT8_CLASS)
+      mexErrMsgIdAndTxt("admm_b200:args", "comm_init needs (h, rank, nranks, id) with id = uint8(1,128) from 'unique_id'");
+    check(admm_b200_comm_init(get_handle(prhs[1]), (int)mxGetScalar(prhs[2]), (int)mxGetScalar(prhs[3]), mxGetData(prhs[4])));
+  } else if (!strcmp(cmd, "comm_destroy")) {
+    check(admm_b200_comm_destroy(get_handle(prhs[1])));
+  } else if (!strcmp(cmd, "slicemaker")) {               /* (len, workers) -> row counts, errorcheck.m:249-259 */
+    int64_t w = (int64_t)mxGetScalar(prhs[2]), i;
+    int64_t* tmp;
+    if (w < 1 || w > 65536) mexErrMsgIdAndTxt("admm_b200:args", "slicemaker: workers out of range");
+    tmp = (int64_t*)mxMalloc((size_t)w * sizeof(int64_t));
+    check(admm_b200_slicemaker((int64_t)mxGetScalar(prhs[1]), w, tmp));
+    plhs[0] = mxCreateDoubleMatrix(1, (mwSize)w, mxREAL);
+    for (i = 0; i < w; ++i) mxGetPr(plhs[0])[i] = (double)tmp[i];
+    mxFree(tmp);
   } else if (!strcmp(cmd, "setup_basispursuit")) {       /* (h, D, s) */
     check(admm_b200_setup_basispursuit(get_handle(prhs[1]), (int64_t)mxGetM(prhs[2]), (int64_t)mxGetN(prhs[2]),
                                        dense(prhs[2], "D"), (int64_t)mxGetM(prhs[2]), dense(prhs[3], "s")));

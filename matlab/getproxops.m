@@ -20,11 +20,11 @@ switch problem
         admm_b200_mex('setup_totalvariation', args.h, args.s, args.lambda);
     case 'linearsvm'
         kind = 4 + strcmp(args.lossfunction, '01');        % only the exact string '01' is the 0-1 loss (getProxOps.m:1094)
-        admm_b200_mex('setup_unwrapped', args.h, kind, args.D, args.ell, args.C);
+        admm_b200_mex('setup_unwrapped', args.h, kind, args.D, args.ell, args.C, b200_mtotal(args));
     case 'huberfit'
-        admm_b200_mex('setup_unwrapped', args.h, 6, args.D, args.s, 0);
+        admm_b200_mex('setup_unwrapped', args.h, 6, args.D, args.s, 0, b200_mtotal(args));
     case 'lad'
-        admm_b200_mex('setup_unwrapped', args.h, 7, args.D, args.s, 0);
+        admm_b200_mex('setup_unwrapped', args.h, 7, args.D, args.s, 0, b200_mtotal(args));
     case 'model'                                           % P, Q, r, s instead of PtP .. Qts (model.m:123-128): Grams on the device
         rho = 1; if isfield(args, 'rho'), rho = args.rho; end
         admm_b200_mex('setup_model', args.h, args.P, args.Q, args.r, args.s, rho);
@@ -42,6 +42,10 @@ end
 desc = struct('h', args.h, 'problem', problem);
 minx = @(x, z, u, rho) b200_nohost(desc);
 minz = @(x, z, u, rho) b200_nohost(desc);
+end
+
+function mt = b200_mtotal(args)      % global row count of a row-sharded A = D problem (solvers/b200_comm.m); default: all rows here
+mt = size(args.D, 1); if isfield(args, 'm_total'), mt = args.m_total; end
 end
 
 function b200_nohost(desc) %#ok<INUSD>

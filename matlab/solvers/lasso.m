@@ -11,8 +11,13 @@ if isfield(options, 'parallel') && any(strcmp(options.parallel, {'both', 'zming'
     error('admm_b200: the parfor consensus LASSO branch (lasso.m:193-224) is out of scope.');
 end
 h = b200_engine(options);
-admm_b200_mex('setup_lasso', h, D, s(:), rho);
-n = size(D, 2);
+[m, n] = size(D); s = s(:);
+[~, world, lo, hi] = b200_comm(h, m);                  % one MATLAB per GPU: Gram of this rank's rows, ONE allreduce (lasso.m:160,168)
+if world > 1 && m >= n
+    admm_b200_mex('setup_lasso_sharded', h, D(lo:hi, :), s(lo:hi), rho, m);
+else
+    admm_b200_mex('setup_lasso', h, D, s, rho);
+end
 args = struct('h', h, 'lambda', lambda, 'm', size(D, 1), 'n', n, 'rho', rho, 'parallel', 0);
 [minx, minz] = getproxops('LASSO', args);
 options.A = 1; options.At = 1; options.B = -1; options.c = 0; options.m = n; options.nA = n; options.nB = n;

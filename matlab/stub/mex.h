@@ -10,7 +10,7 @@ typedef struct mxArray_tag mxArray;
 typedef size_t mwSize;
 typedef size_t mwIndex;
 typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
-typedef enum { mxUNKNOWN_CLASS = 0, mxDOUBLE_CLASS = 6, mxUINT64_CLASS = 13 } mxClassID;
+typedef enum { mxUNKNOWN_CLASS = 0, mxDOUBLE_CLASS = 6, mxUINT8_CLASS = 9, mxUINT64_CLASS = 13 } mxClassID;
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -32,6 +32,8 @@ int mxIsStruct(const mxArray* a);
 int mxIsEmpty(const mxArray* a);
 char* mxArrayToString(const mxArray* a);
 void mxFree(void* p);
+void* mxMalloc(size_t n);
+mxClassID mxGetClassID(const mxArray* a);
 mxArray* mxGetField(const mxArray* s, mwIndex i, const char* name);
 mxArray* mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c);
 mxArray* mxCreateDoubleScalar(double v);
