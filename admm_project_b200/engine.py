@@ -185,7 +185,11 @@ class Engine:
         if len(blob) != 64 * self.nranks:
             raise ValueError("comm_ipc_attach: need one 64-byte handle per rank")
         buf = (C.c_char * len(blob)).from_buffer_copy(blob)
-        L.check(self._lib.admm_b200_comm_ipc_attach(self._h, buf))
+        try:
+            L.check(self._lib.admm_b200_comm_ipc_attach(self._h, buf))
+        except L.EngineError:
+            self.rank, self.nranks = 0, 1       # the library detached the handle (a peer's mailbox could not be mapped)
+            raise
 
     def comm_destroy(self):
         L.check(self._lib.admm_b200_comm_destroy(self._h))

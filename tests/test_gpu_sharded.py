@@ -45,3 +45,28 @@ def test_two_rank_run_matches_serial_oracle(problem, fast):
     out = json.loads(line[-1][8:])
     assert out["ok"], out
     assert out["zopt_len"] == {"persist": 20001, "wide": 3001}.get(fast, 5001)
+
+
+def test_mailbox_only_transport_argument_and_state_checks():
+    """admm_b200_comm_ipc_export / _attach fail loudly on misuse and leave the handle usable for single-GPU work."""
+    import numpy as np
+    from admm_project_b200 import Engine, lasso
+    from admm_project_b200._lib import EngineError
+    eng = Engine(0)
+    try:
+        with pytest.raises(EngineError, match="comm_ipc_attach"):
+            eng.comm_ipc_attach([b"\0" * 64])                        # nothing exported yet
+        with pytest.raises(EngineError, match="bad arguments"):
+            eng.comm_ipc_export(0, 9)                                 # more ranks than mailboxes (8)
+        with pytest.raises(EngineError, match="bad arguments"):
+            eng.comm_ipc_export(2, 2)
+        hd = eng.comm_ipc_export(0, 2)
+        assert len(hd) == 64 and any(hd)
+        with pytest.raises(EngineError, match="could not be mapped"):
+            eng.comm_ipc_attach([hd, b"\0" * 64])                     # a peer handle that is not one
+        assert (eng.rank, eng.nranks) == (0, 1)                       # detached again, on both sides of the ABI
+        rs = np.random.RandomState(0)
+        D, s = rs.randn(40, 8), rs.randn(40)
+        assert lasso(D, s, 0.1, {}, engine=eng)["steps"] > 0
+    finally:
+        eng.close()
