@@ -112,6 +112,44 @@ def test_lasso_kkt_and_tester_criterion(rows, cols):        # lassotest.m:143-14
     assert obj(r["xopt"]) < obj(testx)
 
 
+@pytest.mark.parametrize("seed,rows,cols", [(2, 200, 50), (3, 60, 150)])
+def test_lasso_optimum_matches_coordinate_descent(seed, rows, cols):   # lasso.m:227: 1/2||Dx - s||^2 + lambda||x||_1
+    """An independent ALGORITHM on the same objective: scikit-learn's coordinate descent minimises
+    1/(2m)||s - Dw||^2 + alpha||w||_1, i.e. alpha = lambda/m.  Tall (Cholesky of D'D + rho I) and fat (Woodbury) branch."""
+    lm = pytest.importorskip("sklearn.linear_model")
+    D, s, lam, _ = gen.lasso_problem(seed, rows, cols)
+    r = oracle.lasso(D, s, lam, {"abstol": 1e-12, "reltol": 1e-12, "maxiters": 200000})
+    sk = lm.Lasso(alpha=lam / rows, fit_intercept=False, tol=1e-14, max_iter=5000000).fit(D, s)
+    assert np.abs(sk.coef_ - r["zopt"]).max() < 1e-8
+    assert np.array_equal(sk.coef_ != 0, np.abs(r["zopt"]) > 1e-10)     # same support
+    obj = lambda x: 0.5 * np.sum((D @ x - s) ** 2) + lam * np.sum(np.abs(x))
+    assert abs(obj(r["zopt"]) - obj(sk.coef_)) <= 1e-10 * obj(sk.coef_)
+
+
+def test_huberfit_optimum_matches_quasi_newton():           # huberfit.m:180: 1/2*sum(huber(Dx - s))
+    D, s, _ = gen.huber_problem(1, 300, 8)
+    r = oracle.huberfit(D, s, {"abstol": 1e-11, "reltol": 1e-11, "maxiters": 20000})
+    f = lambda x: 0.5 * np.sum(oracle.huber(D @ x - s))
+    g = lambda x: D.T @ np.clip(D @ x - s, -1.0, 1.0)
+    o = sopt.minimize(f, np.zeros(D.shape[1]), jac=g, method="BFGS", options={"gtol": 1e-11})
+    assert np.abs(o.x - r["xopt"]).max() < 1e-6 and abs(f(o.x) - f(r["xopt"])) <= 1e-10 * f(o.x)
+
+
+def test_bounded_qp_optimum_matches_lbfgsb():                # quadraticprogram.m:210-216, getProxOps.m:1441-1474
+    rs = np.random.RandomState(4)
+    n = 25
+    Mx = rs.randn(n, n)
+    P, q = Mx @ Mx.T + 0.5 * np.eye(n), rs.randn(n)
+    lb, ub = -0.3 * np.ones(n), 0.2 * np.ones(n)
+    r = oracle.quadraticprogram(P, q, 0.0, lb, ub, {"abstol": 1e-12, "reltol": 1e-12, "maxiters": 50000})
+    f = lambda x: 0.5 * x @ P @ x + q @ x
+    o = sopt.minimize(f, np.zeros(n), jac=lambda x: P @ x + q, method="L-BFGS-B", bounds=list(zip(lb, ub)),
+                      options={"ftol": 1e-15, "gtol": 1e-12, "maxiter": 10000})
+    assert np.abs(o.x - r["zopt"]).max() < 1e-6 and f(r["zopt"]) <= f(o.x) + 1e-10
+    assert np.all(r["zopt"] >= lb - 1e-12) and np.all(r["zopt"] <= ub + 1e-12)
+    assert np.any(r["zopt"] == lb) and np.any(r["zopt"] == ub)          # both bounds active somewhere: a real projection
+
+
 def test_lasso_fat_and_tall_branches_agree_on_square_problem():  # getProxOps.m:1199-1205 (Woodbury)
     D, s, lam, _ = gen.lasso_problem(1, 50, 50)
     tall = oracle.lasso(D, s, lam, {"domaxiters": 1, "maxiters": 25})
