@@ -2017,6 +2017,7 @@ static void setup_unwrapped(admm_b200_handle* h, int kind, int64_t m_local, int6
                "setup_unwrapped: bad dimensions or null input");
   if (kind == ADMM_B200_SVM_HINGE || kind == ADMM_B200_SVM_01)
     ADMM_REQUIRE(C >= 0, ADMM_B200_ERR_INVALID, "Given regularization parameter C is not a nonnegative number!");
+  if (is_device_ptr(D)) h->ownD.release();      // a staged copy of an earlier problem's matrix: its cudaFree is not setup time
   ADMM_CUDA(cudaEventRecord(h->ev0, h->stream));
   h->have_factor = false; h->lasso_sharded = false; h->zero_cols = 0; h->xshard = false; h->have_Q = false;
   stage_matrix(h, m_local, n, D, ldD);
@@ -2223,28 +2224,6 @@ static int onepass_rows(const admm_b200_handle* h, const LoopParams& lp) {
   if (OnepassCfg<24>::smem_bytes(n, npad) <= budget) return 24;
   if (OnepassCfg<16>::smem_bytes(n, npad) <= budget) return 16;
   return 0;
-}
-
-// cluster form (two tile buffers per CTA): tile height under the same shared-memory budget
-static int onepass2_rows(int64_t n) {
-  const int64_t nh = (n + 1) / 2 + (((n + 1) / 2) & 1);
-  const size_t budget = 227 * 1024;
-  if (Onepass2Cfg<32>::smem_bytes(nh) <= budget) return 32;
-  if (Onepass2Cfg<24>::smem_bytes(nh) <= budget) return 24;
-  if (Onepass2Cfg<16>::smem_bytes(nh) <= budget) return 16;
-  return 0;
-}
-template <int R>
-static void onepass2_launch(admm_b200_handle* h, const OnepassArgs& a, int grid) {
-  static PerDevice conf_pd;
-  size_t& conf = conf_pd(h->device);
-  const int64_t n = a.uw.n, nh = (n + 1) / 2 + (((n + 1) / 2) & 1);
-  const size_t smem = Onepass2Cfg<R>::smem_bytes(nh);
-  if (smem > conf) {
-    ADMM_CUDA(cudaFuncSetAttribute(uw_onepass2_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conf = smem;
-  }
-  uw_onepass2_kernel<R><<<grid, OP_THREADS, smem, h->stream>>>(a);   // __cluster_dims__(2,1,1): grid is even
 }
 
 template <int R, int NCH>
@@ -2508,33 +2487,19 @@ static void enqueue_iteration(admm_b200_handle* h, const admm_b200_options& o, c
     a.zvals = history ? h->zvals.p : nullptr;
     a.uvals = history ? h->uvals.p : nullptr;
     a.alg = lp.alg; a.v = h->fv.p; a.uhat = h->fuhat.p; a.zprev = h->fzprev.p; a.uprev = h->fuprev.p;
-    if (int R = onepass_rows(h, lp)) {
+    if (const int R = onepass_rows(h, lp)) {
       // D read once: D_g*x, the prox and D_g'*[rhs, dz, u] from one shared-memory tile (onepass.cuh)
       OnepassArgs op;
       op.uw = a; op.nv = nv; op.npad = npad;
-      // The 2-CTA cluster form (two tile buffers per CTA) is parity-green but measured SLOWER on B200 (C3 143 vs
-      // 128 us, C4 10.1 vs 8.8 ms per iteration): the kernel is bound by the LSU / shared-memory pipe (LDGSTS
-      // 8 cycles per warp instruction + the LDS of both phases), not by missing overlap -- profiles/r01_notes.md.
-      // It stays opt-in (ADMM_B200_ONEPASS_CLUSTER=1) as the base for a TMA-fed version.
-      const int R2 = getenv("ADMM_B200_ONEPASS_CLUSTER") ? onepass2_rows(n) : 0;
-      int grid1, ndparts;
-      if (R2 >= R) {            // 2-CTA clusters, two tile buffers per CTA
-        R = R2;
-        op.ntiles = (m + R - 1) / R;
-        const int nclusters = (int)std::min<int64_t>(kNumSM / 2, op.ntiles);
-        grid1 = 2 * nclusters; ndparts = 2 * nclusters;
-      } else {
-        op.ntiles = (m + R - 1) / R;
-        grid1 = (int)std::min<int64_t>(kNumSM, op.ntiles); ndparts = 2 * grid1;
-      }
+      // (A 2-CTA cluster form with two tile buffers per CTA was parity-green but measured SLOWER on B200 -- C3 143 vs
+      // 128 us, C4 10.1 vs 8.8 ms per iteration: the kernel is bound by the LSU / shared-memory pipe, not by missing
+      // overlap, profiles/r01_notes.md -- and was removed in round 2.)
+      op.ntiles = (m + R - 1) / R;
+      const int grid1 = (int)std::min<int64_t>(kNumSM, op.ntiles), ndparts = 2 * grid1;
       h->op_dpart.ensure((int64_t)ndparts * nv * npad);
       h->uw_partials.ensure((int64_t)grid1 * UW_NRED);
       op.dpart = h->op_dpart.p; op.partials = h->uw_partials.p;
-      if (R2 >= R) {
-        if (R == 32) onepass2_launch<32>(h, op, grid1);
-        else if (R == 24) onepass2_launch<24>(h, op, grid1);
-        else onepass2_launch<16>(h, op, grid1);
-      } else if (R == 32) onepass_launch<32>(h, op, grid1);
+      if (R == 32) onepass_launch<32>(h, op, grid1);
       else if (R == 24) onepass_launch<24>(h, op, grid1);
       else onepass_launch<16>(h, op, grid1);
       ADMM_CUDA(cudaGetLastError());

@@ -205,205 +205,6 @@ __global__ void __launch_bounds__(OP_THREADS, 1) uw_onepass_kernel(OnepassArgs a
   block_reduce_store<UW_NRED>(racc, a.partials + (int64_t)blockIdx.x * UW_NRED, redsh);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Cluster form: a 2-CTA thread-block cluster shares every tile.  CTA `rank` keeps columns
-// [rank*nh, rank*nh + nh) of the tile, so a whole tile now takes half the shared memory of one SM and
-// each CTA holds TWO tile buffers: tile k+1 streams in while tile k is being worked on (the single-CTA
-// kernel has one buffer and ~25 % of its time no load in flight).  The only exchange is the R partial
-// row dots: each CTA writes its half-sums into both CTAs' shared memory (DSMEM) and one cluster barrier
-// per tile (~380 cycles) makes them visible; both CTAs then evaluate the R proxes redundantly with
-// identical arithmetic (rank 0 alone stores z, u and keeps the norm sums), and each does the D' phase
-// for its own columns.
-// ---------------------------------------------------------------------------------------------
-template <int R> struct Onepass2Cfg {
-  static constexpr int RS = R + 2, RP = R / 2, JSTEP = OP_THREADS / RP, ACTIVE = JSTEP * RP;
-  static size_t smem_bytes(int64_t nh) {     // nh = columns per CTA (even)
-    return (size_t)(2 * nh * RS + nh + JSTEP * R + 2 * 2 * R + 3 * R + (OP_THREADS / 32) * UW_NRED) * 8;
-  }
-};
-
-__device__ __forceinline__ unsigned cluster_ctarank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// store a double into the shared memory of CTA `rank` of this cluster at the address `p` has locally
-__device__ __forceinline__ void st_shared_cluster(double* p, unsigned rank, double v) {
-  unsigned local = (unsigned)__cvta_generic_to_shared(p), remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
-}
-
-template <int R>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OP_THREADS, 1) uw_onepass2_kernel(OnepassArgs a) {
-  const UwArgs& u = a.uw;
-  if (u.ctl->done) return;                                // the same flag for both CTAs of a cluster
-  using Cfg = Onepass2Cfg<R>;
-  constexpr int RS = Cfg::RS, RP = Cfg::RP, JSTEP = Cfg::JSTEP, ACTIVE = Cfg::ACTIVE, RH = R / 2;
-  extern __shared__ __align__(16) double sm[];
-  const int64_t n = u.n, m = u.m;
-  const unsigned rank = cluster_ctarank();
-  const int64_t nh = (n + 1) / 2 + (((n + 1) / 2) & 1);    // columns per CTA, even
-  const int64_t c0 = (int64_t)rank * nh;                   // first column of this CTA
-  const int64_t nc = max((int64_t)0, min(nh, n - c0));     // columns it really has
-  double* Tb = sm;                                         // [2][nh][RS]
-  double* xs = Tb + 2 * nh * RS;                           // x[c0 .. c0+nc)
-  double* wpart = xs + nh;                                 // [JSTEP][R]
-  double* wx = wpart + JSTEP * R;                          // [2 parities][2 ranks][R] half-sums of the row dots
-  double* rs = wx + 4 * R;                                 // [3][R]
-  double* redsh = rs + 3 * R;
-  const int tid = threadIdx.x, it = u.ctl->it;
-  for (int64_t j = tid; j < nc; j += OP_THREADS) xs[j] = u.x[c0 + j];
-  const int q = tid % RP, j0 = tid / RP;
-  const int sc = tid % OP_SLOTS, hh = tid / OP_SLOTS;
-  const int64_t nclusters = gridDim.x / 2, cid = blockIdx.x / 2;
-
-  auto issue = [&](int64_t tile, int buf) {                // this CTA's columns of `tile` -> buffer `buf`
-    if (tid < ACTIVE) {
-      const int64_t row = tile * R + 2 * q;
-      const int bytes = (int)min((int64_t)16, max((int64_t)0, (m - row) * 8));
-      const double* src = u.D + (bytes > 0 ? row : 0) + (c0 + j0) * u.ld;
-      double* dst = Tb + (int64_t)buf * nh * RS + j0 * RS + 2 * q;
-      for (int64_t j = j0; j < nc; j += JSTEP) {
-        cp_async16_zfill(dst, src, bytes);
-        src += (int64_t)JSTEP * u.ld;
-        dst += JSTEP * RS;
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  int64_t tile = cid;
-  if (tile < a.ntiles) issue(tile, 0);
-  if (tile + nclusters < a.ntiles) issue(tile + nclusters, 1);
-  else asm volatile("cp.async.commit_group;" ::: "memory");   // keep the group count uniform
-  double acc[3][OP_MAXCOLS / 2];
-#pragma unroll
-  for (int k = 0; k < 3; ++k)
-#pragma unroll
-    for (int c = 0; c < OP_MAXCOLS / 2; ++c) acc[k][c] = 0.0;
-  double racc[UW_NRED];
-#pragma unroll
-  for (int k = 0; k < UW_NRED; ++k) racc[k] = 0.0;
-  const bool rowthread = (tid < 8 * R) && ((tid & 7) == 0);
-  const int myrow = tid >> 3;
-  cluster_sync_all();                                      // both CTAs are resident before any DSMEM store
-
-  int buf = 0, par = 0;
-  for (; tile < a.ntiles; tile += nclusters, buf ^= 1, par ^= 1) {
-    const double* T = Tb + (int64_t)buf * nh * RS;
-    const int64_t row = tile * R + myrow;
-    double zp = 0.0, uold = 0.0, aux = 0.0;
-    if (rowthread && row < m) { zp = u.z[row]; uold = u.u[row]; aux = u.aux[row]; }
-    cp_async_wait<1>();                                    // this tile has landed; the next one may still be in flight
-    __syncthreads();
-    // ---- half row dots over this CTA's columns
-    double s0 = 0.0, s1 = 0.0;
-    if (tid < ACTIVE) {
-      const double* tp = T + j0 * RS + 2 * q;
-#pragma unroll 4
-      for (int64_t j = j0; j < nc; j += JSTEP) {
-        const double2 t = *reinterpret_cast<const double2*>(tp);
-        const double xj = xs[j];
-        s0 = fma(t.x, xj, s0);
-        s1 = fma(t.y, xj, s1);
-        tp += JSTEP * RS;
-      }
-      *reinterpret_cast<double2*>(wpart + j0 * R + 2 * q) = make_double2(s0, s1);
-    }
-    __syncthreads();
-    if (tid < 8 * R) {
-      double w = 0.0;
-      for (int g = tid & 7; g < JSTEP; g += 8) w += wpart[g * R + myrow];
-      w += __shfl_xor_sync(0xffffffffu, w, 4);
-      w += __shfl_xor_sync(0xffffffffu, w, 2);
-      w += __shfl_xor_sync(0xffffffffu, w, 1);
-      if ((tid & 7) == 0) {                                // my half-sum goes to both CTAs
-        double* slot = wx + (par * 2 + rank) * R + myrow;
-        *slot = w;
-        st_shared_cluster(slot, rank ^ 1u, w);
-      }
-    }
-    cluster_sync_all();
-    if (rowthread) {
-      const double w = wx[(par * 2 + 0) * R + myrow] + wx[(par * 2 + 1) * R + myrow];   // same order on both CTAs
-      double rv = 0.0, dzv = 0.0, uv = 0.0;
-      if (row < m) {
-        const UwRowOut o = uw_row_core(u, zp, uold, uold, aux, 0.0, w, racc);
-        if (rank == 0) {
-          u.z[row] = o.z;
-          u.u[row] = o.u;
-          if (u.zvals) {
-            u.zvals[(int64_t)it * m + row] = o.z;
-            u.uvals[(int64_t)it * m + row] = o.u;
-          }
-        }
-        rv = (u.kind >= UW_HUBER) ? (aux + o.z - o.u) : (o.z - o.u);
-        dzv = o.dz;
-        uv = o.u;
-      }
-      rs[myrow] = rv; rs[R + myrow] = dzv; rs[2 * R + myrow] = uv;
-    }
-    __syncthreads();
-    // ---- d += T'[rhs, dz, u] for this CTA's columns, this thread's half of the rows
-#pragma unroll
-    for (int k = 0; k < OP_MAXCOLS / 2; ++k) {
-      const int64_t j = sc + (int64_t)k * OP_SLOTS;
-      if (j < nc) {
-        const double* col = T + j * RS + hh * RH;
-        const double* rr = rs + hh * RH;
-        if (a.nv == 3) {
-          double a0 = acc[0][k], a1 = acc[1][k], a2 = acc[2][k];
-#pragma unroll
-          for (int i = 0; i < RH; i += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(col + i);
-            const double2 r0 = *reinterpret_cast<const double2*>(rr + i);
-            const double2 r1 = *reinterpret_cast<const double2*>(rr + R + i);
-            const double2 r2 = *reinterpret_cast<const double2*>(rr + 2 * R + i);
-            a0 = fma(t.x, r0.x, a0); a0 = fma(t.y, r0.y, a0);
-            a1 = fma(t.x, r1.x, a1); a1 = fma(t.y, r1.y, a1);
-            a2 = fma(t.x, r2.x, a2); a2 = fma(t.y, r2.y, a2);
-          }
-          acc[0][k] = a0; acc[1][k] = a1; acc[2][k] = a2;
-        } else {
-          double a0 = acc[0][k];
-#pragma unroll
-          for (int i = 0; i < RH; i += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(col + i);
-            const double2 r0 = *reinterpret_cast<const double2*>(rr + i);
-            a0 = fma(t.x, r0.x, a0); a0 = fma(t.y, r0.y, a0);
-          }
-          acc[0][k] = a0;
-        }
-      }
-    }
-    __syncthreads();                                       // buffer `buf` is free: refill it with the tile after next
-    const int64_t nxt = tile + 2 * nclusters;
-    if (nxt < a.ntiles) issue(nxt, buf);
-    else asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  cp_async_wait<0>();
-  // per-cluster, per-row-half partials: the two CTAs of a cluster fill disjoint column ranges of one row
-  double* dp = a.dpart + ((int64_t)cid * 2 + hh) * a.nv * a.npad + c0;
-#pragma unroll
-  for (int k = 0; k < OP_MAXCOLS / 2; ++k) {
-    const int64_t j = sc + (int64_t)k * OP_SLOTS;
-    if (j < nc) {
-      dp[j] = acc[0][k];
-      if (a.nv == 3) { dp[a.npad + j] = acc[1][k]; dp[2 * a.npad + j] = acc[2][k]; }
-    }
-  }
-  if (rank != 0) {
-#pragma unroll
-    for (int k = 0; k < UW_NRED; ++k) racc[k] = 0.0;       // the row sums are rank 0's
-  }
-  block_reduce_store<UW_NRED>(racc, a.partials + (int64_t)blockIdx.x * UW_NRED, redsh);
-  cluster_sync_all();                                      // no CTA exits while its partner may still store into it
-}
-
 // d_k = sum over the CTAs' partials, scalars likewise.  One WARP per output: lane l adds parts l, l+32, ...
 // in order, then a fixed xor tree -- a thread per output would walk ~300 dependent L2 loads (20+ us).
 __global__ void __launch_bounds__(256) uw_onepass_finish_kernel(const double* dpart, int ndparts, int nparts, int nv, int64_t n,

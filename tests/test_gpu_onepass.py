@@ -77,13 +77,3 @@ def test_onepass_is_the_default_at_size_and_agrees_with_two_pass(engine, monkeyp
     for k in ("xopt", "zopt", "uopt", "pnorm", "dnorm", "objevals"):
         assert rel(one[k], two[k]) < 1e-11, k
     compare(one, oracle.huberfit(D, s, opts))
-
-
-@pytest.mark.parametrize("rows,cols,relax", [(2049, 130, 1.0), (333, 21, 1.5), (3000, 1000, 1.0)])
-def test_cluster_form_matches_oracle(engine, force, monkeypatch, rows, cols, relax):
-    # opt-in 2-CTA cluster kernel: each CTA holds half the columns of two tile buffers, the row dots are
-    # exchanged through distributed shared memory (onepass.cuh: uw_onepass2_kernel)
-    monkeypatch.setenv("ADMM_B200_ONEPASS_CLUSTER", "1")
-    D, s, _ = gen.huber_problem(3, rows, cols)
-    opts = {"objevals": 1, "relax": relax, "history": int(cols < 200), "maxiters": 60}
-    compare(huberfit(D, s, opts, engine=engine), oracle.huberfit(D, s, opts))
