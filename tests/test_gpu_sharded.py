@@ -5,6 +5,7 @@ NVLink per iteration).  On a 1-GPU box the two ranks SHARE the device through th
 processes -- slow, but it is the whole sharded data path."""
 import json
 import os
+import socket
 import subprocess
 import sys
 
@@ -12,6 +13,14 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
 
 
 @pytest.mark.parametrize("problem,fast", [("svm", ""), ("huber", ""), ("lad", ""), ("huber", "weak"), ("lad", "strong"),
@@ -22,7 +31,7 @@ def test_two_rank_run_matches_serial_oracle(problem, fast):
     if torch.cuda.device_count() < 1:
         pytest.skip("needs a GPU")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "run_sharded.py"), "--check",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "run_sharded.py"), "--check",
            "--problem", problem, "--rows", "5001", "--cols", "64"] + (["--fast", fast] if fast else [])
     env = dict(os.environ)
     if fast == "onepass":          # the single-pass tile kernel (csrc/onepass.cuh) on every rank's row block
@@ -35,10 +44,11 @@ def test_two_rank_run_matches_serial_oracle(problem, fast):
         cmd[cmd.index("--rows") + 1], cmd[cmd.index("--cols") + 1] = "20001", "160"
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     line = [ln for ln in p.stdout.splitlines() if ln.startswith("SHARDED ")]
-    if not line and torch.cuda.device_count() < 2 and "timed out" in p.stderr:
+    if not line and torch.cuda.device_count() < 2:
         # ranks sharing ONE device are time-sliced by the driver; a bounded mailbox wait (2 s, p2p.cuh) can in principle
         # expire while the peer's process is descheduled on a loaded box: one more try, and say so
-        print("shared-device run hit a mailbox timeout, retrying once:", p.stderr[-300:])
+        print("shared-device run produced no result, retrying once:", p.stderr[-400:])
+        cmd[cmd.index("--master-port") + 1] = str(_free_port())
         p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
         line = [ln for ln in p.stdout.splitlines() if ln.startswith("SHARDED ")]
     assert line, p.stdout[-2000:] + p.stderr[-2000:]
