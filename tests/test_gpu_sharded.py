@@ -23,6 +23,16 @@ def _free_port():
     return port
 
 
+def _device_is_shareable():
+    """False only when nvidia-smi positively reports an Exclusive / Prohibited compute mode (two ranks need two contexts)."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", "0", "--query-gpu=compute_mode", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return True
+    return not ("Exclusive" in out or "Prohibited" in out)
+
+
 @pytest.mark.parametrize("problem,fast", [("svm", ""), ("huber", ""), ("lad", ""), ("huber", "weak"), ("lad", "strong"),
                                           ("huber", "onepass"), ("svm", "onepass"), ("lasso", ""), ("lassopath", ""),
                                           ("svmbatch", ""), ("svm", "persist"), ("svmbatch", "persist"), ("lasso", "wide")])
@@ -30,6 +40,8 @@ def test_two_rank_run_matches_serial_oracle(problem, fast):
     import torch
     if torch.cuda.device_count() < 1:
         pytest.skip("needs a GPU")
+    if torch.cuda.device_count() < 2 and not _device_is_shareable():
+        pytest.skip("one GPU in an exclusive compute mode: two processes cannot share it")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "run_sharded.py"), "--check",
            "--problem", problem, "--rows", "5001", "--cols", "64"] + (["--fast", fast] if fast else [])
