@@ -49,6 +49,12 @@ def admm(xminf, zming, options):
     if setopt(options, "adaptive", 0):
         raise L.EngineError(L.ERR_UNSUPPORTED, "options.adaptive is an unfinished experiment in the reference "
                             "(admm.m:724-741) and is not built")
+    # admm.m:556-558, 612-616: host handles evaluated INSIDE every iteration -- the device loop cannot call back
+    for name in ("altu", "specialnorms"):
+        if callable(options.get(name)):
+            raise L.EngineError(L.ERR_UNSUPPORTED, "options.%s is a host function handle evaluated in every iteration "
+                                "(admm.m:%s); the device-resident loop has no CPU path for it" %
+                                (name, "556-558" if name == "altu" else "612-616"))
     quiet = setopt(options, "quiet", 1)
     o = eng.default_options()
     o.rho = float(setopt(options, "rho", 1.0))
@@ -107,6 +113,8 @@ def admm(xminf, zming, options):
         results["Hnormtol"] = o.hnormtol
 
     start = time.perf_counter()
+    if callable(options.get("preprocess")):     # admm.m:473-476: one host call before the loop (after the timer started, :319)
+        options["preprocess"]()
     try:
         r = eng.solve(o, want_history=bool(o.history))
     finally:

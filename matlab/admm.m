@@ -15,6 +15,11 @@ end
 if getopt(options, 'adaptive', 0)
     error('admm_b200: options.adaptive is not built (unfinished experiment in the reference, admm.m:724-741).');
 end
+for f = {'altu', 'specialnorms'}          % admm.m:556-558, 612-616: host handles evaluated inside every iteration
+    if isfield(options, f{1}) && isa(options.(f{1}), 'function_handle')
+        error('admm_b200: options.%s is a host function handle evaluated in every iteration; the device loop cannot call back.', f{1});
+    end
+end
 stopnames = {'standard', 'hnorm', 'both'};
 o = struct();
 o.rho = getopt(options, 'rho', 1.0);            o.relax = getopt(options, 'relax', 1);
@@ -38,6 +43,7 @@ for f = {'A', 'B'}
 end
 admm_b200_mex('set_init', dx.h, getopt(options, 'x0', []), getopt(options, 'z0', []), getopt(options, 'u0', []));
 t = tic;
+if isfield(options, 'preprocess') && isa(options.preprocess, 'function_handle'), options.preprocess(); end   % admm.m:473-476
 r = admm_b200_mex('solve', dx.h, o);
 k = r.steps;
 if alg == 2     % accelerated ADMM records d, alpha and restarts instead of residual norms (admm.m:586-599)

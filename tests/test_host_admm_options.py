@@ -103,6 +103,14 @@ def test_reference_error_texts_and_refusals():
         run({"adaptive": 1})
     with pytest.raises(EngineError, match="consensus"):
         run({"parallel": "both"})
+    # host handles the reference evaluates inside every iteration (admm.m:556-558, 612-616) are refused, not ignored
+    with pytest.raises(EngineError, match="options.altu"):
+        run({"altu": lambda u, ax, bz, c: u})
+    with pytest.raises(EngineError, match="options.specialnorms"):
+        run({"specialnorms": lambda x, z, u, rho: (0.0, 0.0)})
+    calls = []
+    res, eng = run({"preprocess": lambda: calls.append(1)})         # admm.m:473-476: called once, before the loop
+    assert calls == [1] and res["steps"] == 3
     with pytest.raises(EngineError, match="different problems"):
         e = RecordingEngine()
         admm(EngineProx("xminf", "lasso", "x", e, {}), EngineProx("zming", "lad", "z", e, {}), {})
